@@ -1,0 +1,172 @@
+/* ptap.h - C ABI of libptap.so, the B200-native render core behind PathTracerAP's API.
+ *
+ * The reference (purvakulkarni15/PathTracerAP) has no FFI: its boundary is the C++ surface
+ * main.cpp:8-22 uses (Scene.h:21-39, Renderer.h:46-55, GPUMemoryPool.h:10-46).  Every entry
+ * point below names the reference interface it replaces; include/PathTracerAP/*.h wraps
+ * this ABI back into those C++ classes so that the reference's main.cpp compiles unchanged
+ * (INTEGRATION.md).
+ *
+ * Conventions: plain pointers and sizes only; every call returns 0 on success, a negative
+ * PTAP_E_* code or a positive cudaError_t otherwise, with text in ptap_last_error().
+ * One context per GPU; a context is not thread-safe; no global state; the caller owns all
+ * host buffers, the library owns the device arena.  There is no CPU fallback: every compute
+ * entry fails with PTAP_E_NO_DEVICE when no sm_100 device is usable.
+ */
+#ifndef PTAP_H
+#define PTAP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTAP_VERSION 1
+
+enum {
+    PTAP_OK = 0,
+    PTAP_E_INVALID = -1,      /* bad argument / call order */
+    PTAP_E_NO_DEVICE = -2,    /* no usable CUDA device (never falls back to the CPU) */
+    PTAP_E_NOMEM = -3,        /* device arena exhausted */
+    PTAP_E_IO = -4,           /* file could not be read / written */
+    PTAP_E_PARSE = -5,        /* malformed OBJ / Config.txt */
+    PTAP_E_STATE = -6         /* scene / accel / render parameters missing */
+};
+
+/* ---- PODs with the reference's exact layouts (Primitive.h:10-179) ----------------------- */
+
+typedef struct { int32_t type; float refractive_index, reflectivity; float color[3]; } PtapMaterial;   /* Primitive.h:68-83, 24 B */
+typedef struct { int32_t grid_index, mesh_index; float model_to_world[16], world_to_model[16]; PtapMaterial mat; } PtapModel; /* :93-100, 160 B, column-major */
+typedef struct { int32_t v_start, v_end, t_start, t_end; float bb_min[3], bb_max[3]; } PtapMesh;       /* :85-90, 40 B */
+typedef struct { float position[3], normal[3], uv[2]; } PtapVertex;                                    /* :23-28, 32 B */
+typedef struct { int32_t v[3]; } PtapTriangle;                                                         /* :30-33, 12 B */
+typedef struct { int32_t v_start, v_end; float width[3]; int32_t entity_type, entity_index; } PtapGrid;/* :126-137, 28 B */
+typedef struct { int32_t start, end, entity_type; } PtapVoxel;                                         /* :120-124, 12 B */
+
+enum { PTAP_DIFFUSE = 0, PTAP_SPECULAR, PTAP_REFLECTIVE, PTAP_REFRACTIVE, PTAP_EMISSIVE, PTAP_COAT, PTAP_METAL }; /* Primitive.h:70-79 */
+
+/* The seven public vectors of the reference's Scene (Scene.h:26-32) as raw arrays. */
+typedef struct {
+    const PtapModel* models; int32_t nmodels;
+    const PtapMesh* meshes; int32_t nmeshes;
+    const PtapVertex* vertices; int32_t nvertices;
+    const PtapTriangle* triangles; int32_t ntriangles;
+    const PtapGrid* grids; int32_t ngrids;            /* may be NULL/0 when only the BVH is used */
+    const PtapVoxel* voxels; int32_t nvoxels;
+    const int32_t* refs; int32_t nrefs;               /* Scene::per_voxel_data_pool */
+    int32_t grid_dim[3];                              /* GRID_X/Y/Z (Config.h:8-10) */
+} PtapSceneView;
+
+/* Closest-hit record of the parity entry point.  The reference's IntersectionData (Primitive.h:150-156)
+ * has no primitive id; these fields are what BASELINE.json's parity contract compares. */
+typedef struct {
+    int32_t model, tri;       /* winning model, GLOBAL triangle index; -1 = miss */
+    float t_model, dist;      /* model-space t; world distance (9999999.0f = miss) */
+    float u, v;
+    float normal[3];          /* world-space flat shading normal */
+    int32_t mat_type;
+} PtapHit;                    /* 40 B */
+
+/* One path of a caller-supplied wavefront (parity entry point for the shade kernel). */
+typedef struct {
+    float orig[3], dir[3], color[3];
+    int32_t ipixel;
+    int32_t model, tri;       /* closest hit of this ray (-1, -1 = miss) */
+    float dist;
+} PtapPathIn;                 /* 52 B */
+typedef struct {
+    float orig[3], dir[3], color[3];
+    int32_t ipixel;
+    int32_t alive;            /* 1: continues to the next bounce */
+} PtapPathOut;                /* 44 B */
+
+typedef struct {
+    int64_t rays_traced;          /* sum of active rays over closest-hit launches (BASELINE.md metric) */
+    int64_t paths;                /* camera paths started */
+    int64_t kernel_launches;      /* this library's kernels launched by render calls */
+    int64_t active_per_round[16]; /* last iteration: active rays entering each round */
+    float ms_render;              /* device time of the last ptap_render call (CUDA events on the context stream) */
+    float ms_trace, ms_shade, ms_generate;  /* per-kernel split of that call when profiling is enabled, else 0 */
+    float avg_nodes, avg_tris, avg_cells, avg_refs;  /* per traced ray, when built with counting enabled (ptap_trace_count) */
+} PtapStats;
+
+typedef struct ptap_scene ptap_scene;   /* host-side scene: replaces class Scene (Scene.h:21-39) */
+typedef struct ptap_ctx ptap_ctx;       /* per-GPU render context: replaces class Renderer + RenderData (Renderer.h:19-55) */
+
+/* ---- host scene: replaces Scene (Scene.h:21-39, Scene.cpp) ------------------------------ */
+
+/* Scene::Scene as coded at Scene.cpp:3-224 (its `config` argument is ignored there): the 3 bundled meshes, 11 models.
+ * `root` is the directory containing "Input data/". */
+int ptap_scene_create_builtin(const char* root, ptap_scene** out);
+/* Scene(config) for the schema sketched in Config.txt:1-31 (the reference never parses it). */
+int ptap_scene_create_from_config(const char* config_path, ptap_scene** out);
+int ptap_scene_create_empty(ptap_scene** out);
+int ptap_scene_create_from_view(const PtapSceneView* view, ptap_scene** out);
+/* Scene::loadAndProcessMeshFile (Scene.cpp:226-291) with an in-repo Wavefront reader (Assimp is not vendored):
+ * one vertex per face corner, positions and normals scaled by BASE_MODEL_SCALE (Config.h:17). */
+int ptap_scene_add_obj(ptap_scene* s, const char* path, int32_t* mesh_index);
+int ptap_scene_add_mesh(ptap_scene* s, const PtapVertex* vertices, int32_t nvertices, const int32_t* indices, int32_t ntriangles, int32_t* mesh_index);
+/* synthetic displaced icosphere: 20*4^level triangles, radius `radius` model units */
+int ptap_scene_add_icosphere(ptap_scene* s, int32_t level, float radius, float displacement, uint32_t seed, int32_t* mesh_index);
+/* models.push_back(Model{...}) (Scene.cpp:32-221): world_to_model is computed from model_to_world when NULL */
+int ptap_scene_add_model(ptap_scene* s, int32_t mesh_index, const float model_to_world[16], const float* world_to_model, const PtapMaterial* mat, int32_t* model_index);
+/* glm::translate * glm::rotate(Y) * glm::scale as every model of Scene.cpp composes it; writes model_to_world, world_to_model */
+void ptap_compose_trs(const float translate[3], float rotate_y_degrees, const float scale[3], float model_to_world[16], float world_to_model[16]);
+/* Scene::addMeshesToGrid (Scene.cpp:318-396) */
+int ptap_scene_build_grids(ptap_scene* s, int32_t gx, int32_t gy, int32_t gz);
+int ptap_scene_view(const ptap_scene* s, PtapSceneView* out);     /* pointers stay owned by the scene */
+PtapModel* ptap_scene_models(ptap_scene* s);                      /* mutable, like the public vector */
+void ptap_scene_destroy(ptap_scene* s);
+const char* ptap_scene_last_error(const ptap_scene* s);
+/* RESOLUTION / ITER / DEPTH keys of a parsed Config.txt (0 when absent): out4 = {W, H, iters, depth} */
+int ptap_scene_config_params(const ptap_scene* s, int32_t out4[4]);
+
+/* ---- device context: replaces Renderer (Renderer.h:46-55) -------------------------------- */
+
+enum { PTAP_ACCEL_GRID_COMPAT = 0,  /* the reference's per-mesh uniform grid walked exactly as Renderer.cpp:238-360 (oracle tier R0) */
+       PTAP_ACCEL_BVH = 1 };        /* two-level BVH, exact closest hit under the reference's triangle predicate (oracle tier R1) */
+
+enum { PTAP_FLAG_FIRST_HIT_CACHE = 1,   /* Renderer.cpp:580,594-613 */
+       PTAP_FLAG_PROFILE = 2 };         /* per-kernel CUDA-event split in PtapStats (adds event records) */
+
+int ptap_create(int device, size_t arena_bytes /* 0 = sized on demand */, ptap_ctx** out);
+void ptap_destroy(ptap_ctx* ctx);                                   /* Renderer::free (Renderer.cpp:132-148) */
+const char* ptap_last_error(const ptap_ctx* ctx);
+
+/* Renderer::allocateOnGPU (Renderer.cpp:65-130): copies the scene into the device arena (repacked). */
+int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* view);
+int ptap_build_accel(ptap_ctx* ctx, int kind);
+int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, uint32_t flags);
+/* Renderer::renderLoop (Renderer.cpp:567-648) for iterations [iter_begin, iter_end); the film accumulates.
+ * Asynchronous on the context stream; ptap_sync / ptap_read_film / ptap_get_stats wait for it. */
+int ptap_render(ptap_ctx* ctx, int32_t iter_begin, int32_t iter_end);
+int ptap_film_reset(ptap_ctx* ctx);                                /* initImageKernel (Renderer.cpp:557-565) */
+int ptap_sync(ptap_ctx* ctx);
+/* render_data.dev_image_data->pool (Renderer.cpp:49): the un-normalised sum over iterations, W*H*3 floats */
+int ptap_read_film(ptap_ctx* ctx, float* rgb);
+int ptap_film_device_ptr(ptap_ctx* ctx, void** dev_ptr, size_t* nfloats);   /* for the NCCL reduce */
+int ptap_film_add(ptap_ctx* ctx, const float* rgb);                /* host film += (multi-rank emulation / resume) */
+/* Renderer::renderImage (Renderer.cpp:15-63): 24-bpp BMP, bottom-up, bytes (uint8)(sum/iters*255) */
+int ptap_write_bmp(ptap_ctx* ctx, const char* path, int32_t iters);
+int ptap_get_stats(ptap_ctx* ctx, PtapStats* out);
+void* ptap_stream(ptap_ctx* ctx);                                  /* cudaStream_t of the context */
+
+/* ---- parity entry points (what BASELINE.json's contract measures) ------------------------- */
+
+/* computeRaySceneIntersectionKernel (Renderer.cpp:363-409) on a caller ray set: n x 6 host floats (origin, direction). */
+int ptap_trace(ptap_ctx* ctx, const float* rays_od, int32_t n, PtapHit* out);
+/* same, also returning per-ray traversal counts (nodes or cells, refs, triangle tests): n x 4 int32 */
+int ptap_trace_count(ptap_ctx* ctx, const float* rays_od, int32_t n, PtapHit* out, int32_t* counts);
+/* shadeRayKernel + compaction (Renderer.cpp:411-479, 506-519, 628-630) on a caller wavefront whose slot i is paths[i];
+ * `remaining` is Ray::meta_data.remaining_bounces of every path.  out[i] is the post-shade state of slot i;
+ * order[k] is the slot that the stable compaction moved to position k (k < *n_alive). */
+int ptap_shade(ptap_ctx* ctx, const PtapPathIn* paths, int32_t n, int32_t iter, int32_t remaining, PtapPathOut* out, int32_t* order, int32_t* n_alive);
+
+/* device-resident timing helpers for bench.py (inputs already in HBM): trace the active queue of a primed wavefront `reps` times */
+int ptap_bench_trace(ptap_ctx* ctx, const float* rays_od, int32_t n, int32_t reps, float* ms_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -92,7 +92,7 @@ class OracleScene:
             "models": np.ascontiguousarray(arrays["models"], MODEL), "meshes": np.ascontiguousarray(arrays["meshes"], MESH),
             "vertices": np.ascontiguousarray(arrays["vertices"], VERTEX), "triangles": np.ascontiguousarray(arrays["triangles"], TRIANGLE),
         }
-        if "grids" in arrays and arrays["grids"] is not None:
+        if arrays.get("voxels") is not None and arrays.get("refs") is not None and arrays.get("grids") is not None:
             self.a["grids"] = np.ascontiguousarray(arrays["grids"], GRID)
             self.a["voxels"] = np.ascontiguousarray(arrays["voxels"], VOXEL)
             self.a["refs"] = np.ascontiguousarray(arrays["refs"], np.int32)

@@ -107,16 +107,13 @@ void* ref_scene_builtin(const char* root)
 void* ref_scene_from_arrays(const void* models, int nmodels, const void* meshes, int nmeshes,
                             const void* vertices, int nvertices, const void* triangles, int ntriangles)
 {
-    char cwd[4096];
-    if (!getcwd(cwd, sizeof cwd)) return nullptr;
-    if (chdir("/") != 0) return nullptr;          // no "Input data/" here: all six loads fail
-    Scene* s;
-    {
-        fflush(stderr); int saved = dup(2); int nul = ::open("/dev/null", 1); dup2(nul, 2); ::close(nul);
-        s = new Scene(std::string(""));
-        fflush(stderr); dup2(saved, 2); ::close(saved);
-    }
-    if (chdir(cwd) != 0) { delete s; return nullptr; }
+    // Scene has no default constructor and its only constructor hard-codes a scene (Scene.cpp:3-224) and, when the
+    // OBJ files are absent, walks uninitialised Mesh ranges.  The class is exactly seven std::vectors (Scene.h:26-32),
+    // so build the members in place instead of running that constructor.
+    Scene* s = static_cast<Scene*>(::operator new(sizeof(Scene)));
+    new (&s->models) std::vector<Model>(); new (&s->meshes) std::vector<Mesh>(); new (&s->vertices) std::vector<Vertex>();
+    new (&s->triangles) std::vector<Triangle>(); new (&s->grids) std::vector<Grid>(); new (&s->voxels) std::vector<Voxel>();
+    new (&s->per_voxel_data_pool) std::vector<EntityIndex>();
     s->models.assign((const Model*)models, (const Model*)models + nmodels);
     s->meshes.assign((const Mesh*)meshes, (const Mesh*)meshes + nmeshes);
     s->vertices.assign((const Vertex*)vertices, (const Vertex*)vertices + nvertices);

@@ -1,0 +1,613 @@
+// api.cu - the C ABI of libptap.so (include/ptap.h): device context, arena, scene upload, render loop.
+//
+// Replaces Renderer::allocateOnGPU / renderLoop / renderImage / free (Renderer.cpp:15-148, 567-648) and
+// GPUMemoryPool<T> (GPUMemoryPool.h:10-46).  Where the reference makes 12 cudaMallocManaged calls plus a managed
+// copy of each pool object, and reaches every element through two dependent loads, this context owns ONE device
+// arena per lifetime class (scene, frame), bump-allocated at 256 B alignment, and passes raw pointers by value.
+// A whole iteration is enqueued without a host round trip: the active-ray count of every bounce lives in device
+// memory (FrameState) and all kernels are persistent grids sized from the SM count.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bvh_build.h"
+#include "host_math.h"
+#include "kernels.cuh"
+
+using namespace ptap;
+
+namespace {
+
+struct Arena {
+    char* base = nullptr;
+    size_t cap = 0, used = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        used = 0;
+        if (bytes <= cap) return cudaSuccess;
+        if (base) cudaFree(base);
+        base = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&base, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    template <typename T> T* alloc(size_t count)
+    {
+        size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+        if (used + bytes > cap) return nullptr;
+        T* p = reinterpret_cast<T*>(base + used);
+        used += bytes;
+        return p;
+    }
+    static size_t need(size_t count, size_t elem) { return (count * elem + 255) & ~size_t(255); }
+    void release() { if (base) cudaFree(base); base = nullptr; cap = used = 0; }
+};
+
+}  // namespace
+
+struct ptap_ctx {
+    int device = 0;
+    int sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> prof_events;
+    std::vector<int> prof_kind;      // 0 generate, 1 trace, 2 shade  (pairs)
+    size_t prof_used = 0;
+    Arena scene_arena, frame_arena, scratch;
+    SceneDev sc{};
+    WaveDev wv{};
+    // host copies kept for the acceleration-structure builds
+    std::vector<TriRec> h_tris;
+    std::vector<PtapMesh> h_meshes;
+    std::vector<PtapModel> h_models;
+    bool have_scene = false, have_grid = false, have_bvh = false, have_frame = false;
+    int accel = PTAP_ACCEL_GRID_COMPAT;
+    uint32_t flags = 0;
+    bool cache_valid = false;
+    int grid_trace = 0, grid_shade = 0, grid_gen = 0;
+    PtapStats stats{};
+    bool render_pending = false;
+    std::string err;
+};
+
+namespace {
+
+int fail(ptap_ctx* c, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return fail(ctx, (int)e_, "%s: %s", #call, cudaGetErrorString(e_));   \
+    } while (0)
+
+float4 row(const float* m, int r) { return make_float4(m[0 + r], m[4 + r], m[8 + r], m[12 + r]); }
+
+void launchTrace(ptap_ctx* c, FrameState* st, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, int round, int n_fixed)
+{
+    if (c->accel == PTAP_ACCEL_BVH) launchTraceBvh(c->sc, O, D, hit, uv, counts, st, round, n_fixed, c->grid_trace, c->stream);
+    else launchTraceGrid(c->sc, O, D, hit, uv, counts, st, round, n_fixed, c->grid_trace, c->stream);
+}
+
+void profMark(ptap_ctx* c, int kind)
+{
+    if (!(c->flags & PTAP_FLAG_PROFILE)) return;
+    if (c->prof_used == c->prof_events.size()) {
+        cudaEvent_t e; cudaEventCreate(&e); c->prof_events.push_back(e); c->prof_kind.push_back(0);
+    }
+    c->prof_kind[c->prof_used] = kind;
+    cudaEventRecord(c->prof_events[c->prof_used++], c->stream);
+}
+
+int collect(ptap_ctx* ctx)
+{
+    if (!ctx->render_pending) return PTAP_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->render_pending = false;
+    CK(cudaEventElapsedTime(&ctx->stats.ms_render, ctx->ev0, ctx->ev1));
+    FrameState fs;
+    CK(cudaMemcpy(&fs, ctx->wv.st, sizeof fs, cudaMemcpyDeviceToHost));
+    ctx->stats.rays_traced = (int64_t)fs.rays_traced;
+    ctx->stats.paths = (int64_t)fs.paths;
+    for (int i = 0; i < 16; ++i) ctx->stats.active_per_round[i] = i <= kMaxDepth ? fs.n_active[i] : 0;
+    ctx->stats.ms_generate = ctx->stats.ms_trace = ctx->stats.ms_shade = 0.f;
+    for (size_t i = 0; i + 1 < ctx->prof_used; ++i) {          // event i -> i+1 spans the kernel of kind[i]
+        float ms = 0.f;
+        if (ctx->prof_kind[i] < 0) continue;
+        cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]);
+        if (ctx->prof_kind[i] == 0) ctx->stats.ms_generate += ms;
+        else if (ctx->prof_kind[i] == 1) ctx->stats.ms_trace += ms;
+        else ctx->stats.ms_shade += ms;
+    }
+    ctx->prof_used = 0;
+    return PTAP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ptap_create(int device, size_t arena_bytes, ptap_ctx** out)
+{
+    if (!out) return PTAP_E_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return PTAP_E_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PTAP_E_NO_DEVICE;
+    if (prop.major < 10) return PTAP_E_NO_DEVICE;              // sm_100a code only; no fallback path exists
+    ptap_ctx* ctx = new ptap_ctx();
+    ctx->device = device;
+    ctx->sms = prop.multiProcessorCount;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx; return PTAP_E_NO_DEVICE;
+    }
+    cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+    if (arena_bytes) {                                          // caller-sized arena: split 1/4 scene, 3/4 frame
+        if (ctx->scene_arena.reserve(arena_bytes / 4) != cudaSuccess || ctx->frame_arena.reserve(arena_bytes - arena_bytes / 4) != cudaSuccess) {
+            ptap_destroy(ctx); return PTAP_E_NOMEM;
+        }
+    }
+    *out = ctx;
+    return PTAP_OK;
+}
+
+void ptap_destroy(ptap_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    ctx->scene_arena.release(); ctx->frame_arena.release(); ctx->scratch.release();
+    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* ptap_last_error(const ptap_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+void* ptap_stream(ptap_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
+{
+    if (!ctx || !v || !v->models || !v->meshes || !v->vertices || !v->triangles || v->nmodels <= 0) return fail(ctx, PTAP_E_INVALID, "upload_scene: missing arrays");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
+    const int nm = v->nmodels, nt = v->ntriangles;
+    const bool grid = v->grids && v->voxels && v->refs && v->ngrids > 0;
+    for (int i = 0; i < nm; ++i) {
+        const PtapModel& m = v->models[i];
+        if (m.mesh_index < 0 || m.mesh_index >= v->nmeshes) return fail(ctx, PTAP_E_INVALID, "model %d: mesh_index %d out of range", i, m.mesh_index);
+        if (grid && (m.grid_index < 0 || m.grid_index >= v->ngrids)) return fail(ctx, PTAP_E_INVALID, "model %d: grid_index %d out of range", i, m.grid_index);
+    }
+    for (int t = 0; t < nt; ++t)
+        for (int k = 0; k < 3; ++k)
+            if (v->triangles[t].v[k] < 0 || v->triangles[t].v[k] >= v->nvertices) return fail(ctx, PTAP_E_INVALID, "triangle %d: vertex index out of range", t);
+
+    // ---- repack on the host (DESIGN.md "Data layout")
+    std::vector<InstanceTrace> inst(nm);
+    std::vector<InstanceShade> shade(nm);
+    for (int i = 0; i < nm; ++i) {
+        const PtapModel& m = v->models[i];
+        InstanceTrace& it = inst[i];
+        for (int r = 0; r < 3; ++r) { it.w2m[r] = row(m.world_to_model, r); it.m2w[r] = row(m.model_to_world, r); }
+        it.bb_min = make_float4(0, 0, 0, 1); it.bb_max = make_float4(0, 0, 0, 1); it.grid = make_float4(1, 0, 0, 0);
+        if (grid) {
+            const PtapGrid& g = v->grids[m.grid_index];
+            // the bbox is reached through the grid's creating model, not the traced one (Renderer.cpp:245-249)
+            int owner = g.entity_index;
+            if (owner < 0 || owner >= nm) return fail(ctx, PTAP_E_INVALID, "grid %d: entity_index %d out of range", m.grid_index, owner);
+            const PtapMesh& mesh = v->meshes[v->models[owner].mesh_index];
+            it.bb_min = make_float4(mesh.bb_min[0], mesh.bb_min[1], mesh.bb_min[2], g.width[0]);
+            it.bb_max = make_float4(mesh.bb_max[0], mesh.bb_max[1], mesh.bb_max[2], g.width[1]);
+            it.grid.x = g.width[2];
+            it.grid.y = __builtin_bit_cast(float, (int)g.v_start);
+        }
+        float nmx[9];
+        hm::normal_matrix(m.model_to_world, nmx);
+        shade[i].nm0 = make_float4(nmx[0], nmx[1], nmx[2], m.mat.color[0]);
+        shade[i].nm1 = make_float4(nmx[3], nmx[4], nmx[5], m.mat.color[1]);
+        shade[i].nm2 = make_float4(nmx[6], nmx[7], nmx[8], m.mat.color[2]);
+        shade[i].mat = make_int4(m.mat.type, 0, 0, 0);
+    }
+    ctx->h_tris.resize(nt);
+    for (int t = 0; t < nt; ++t) {
+        const PtapVertex& a = v->vertices[v->triangles[t].v[0]];
+        const PtapVertex& b = v->vertices[v->triangles[t].v[1]];
+        const PtapVertex& c = v->vertices[v->triangles[t].v[2]];
+        const hm::V3 v0 = hm::v3(a.position);
+        const hm::V3 e1 = hm::sub(hm::v3(b.position), v0), e2 = hm::sub(hm::v3(c.position), v0);     // Renderer.cpp:183-184
+        const hm::V3 n = hm::normalize(hm::scale(hm::add(hm::add(hm::v3(a.normal), hm::v3(b.normal)), hm::v3(c.normal)), 1 / 3.0f));   // :203
+        ctx->h_tris[t].v0 = make_float4(v0.x, v0.y, v0.z, n.x);
+        ctx->h_tris[t].e1 = make_float4(e1.x, e1.y, e1.z, n.y);
+        ctx->h_tris[t].e2 = make_float4(e2.x, e2.y, e2.z, n.z);
+    }
+    ctx->h_meshes.assign(v->meshes, v->meshes + v->nmeshes);
+    ctx->h_models.assign(v->models, v->models + nm);
+
+    std::vector<int2> cells;
+    if (grid) {
+        cells.resize(v->nvoxels);
+        for (int i = 0; i < v->nvoxels; ++i) {
+            // a voxel whose entity_type is not TRIANGLE is never tested (Renderer.cpp:226): store an empty range
+            const bool tri = v->voxels[i].entity_type == 2;
+            cells[i] = tri ? make_int2(v->voxels[i].start, v->voxels[i].end) : make_int2(0, 0);
+            if (tri && (v->voxels[i].start < 0 || v->voxels[i].end > v->nrefs)) return fail(ctx, PTAP_E_INVALID, "voxel %d: ref range out of bounds", i);
+        }
+        for (int i = 0; i < v->nrefs; ++i)
+            if (v->refs[i] < 0 || v->refs[i] >= nt) return fail(ctx, PTAP_E_INVALID, "ref %d: triangle index out of range", i);
+    }
+
+    // ---- one arena for everything scene-lifetime; BVH storage is reserved up front (2T-1 nodes bound)
+    size_t need = Arena::need(nm, sizeof(InstanceTrace)) + Arena::need(nm, sizeof(InstanceCull)) + Arena::need(nm, sizeof(InstanceShade)) +
+                  Arena::need(nt, sizeof(TriRec)) * 2 + Arena::need(nt, sizeof(int)) + Arena::need((size_t)std::max(nt, 1) * 2, sizeof(BvhNode)) +
+                  (grid ? Arena::need(v->nvoxels, sizeof(int2)) + Arena::need(v->nrefs, sizeof(int)) : 0) + 4096;
+    if (need > ctx->scene_arena.cap) CK(ctx->scene_arena.reserve(need)); else ctx->scene_arena.used = 0;
+    Arena& A = ctx->scene_arena;
+    InstanceTrace* d_inst = A.alloc<InstanceTrace>(nm);
+    InstanceCull* d_cull = A.alloc<InstanceCull>(nm);
+    InstanceShade* d_shade = A.alloc<InstanceShade>(nm);
+    TriRec* d_tris = A.alloc<TriRec>(nt);
+    TriRec* d_btris = A.alloc<TriRec>(nt);
+    int* d_btid = A.alloc<int>(nt);
+    BvhNode* d_nodes = A.alloc<BvhNode>((size_t)std::max(nt, 1) * 2);
+    int2* d_cells = grid ? A.alloc<int2>(v->nvoxels) : nullptr;
+    int* d_refs = grid ? A.alloc<int>(v->nrefs) : nullptr;
+    if (!d_inst || !d_cull || !d_shade || !d_tris || !d_btris || !d_btid || !d_nodes || (grid && (!d_cells || !d_refs))) return fail(ctx, PTAP_E_NOMEM, "scene arena exhausted");
+    CK(cudaMemcpyAsync(d_inst, inst.data(), nm * sizeof(InstanceTrace), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_shade, shade.data(), nm * sizeof(InstanceShade), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_tris, ctx->h_tris.data(), nt * sizeof(TriRec), cudaMemcpyHostToDevice, ctx->stream));
+    if (grid) {
+        CK(cudaMemcpyAsync(d_cells, cells.data(), cells.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_refs, v->refs, v->nrefs * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->sc.inst = d_inst; ctx->sc.cull = d_cull; ctx->sc.shade = d_shade; ctx->sc.tris = d_tris;
+    ctx->sc.cells = d_cells; ctx->sc.refs = d_refs; ctx->sc.nodes = d_nodes; ctx->sc.bvh_tris = d_btris; ctx->sc.bvh_tri_id = d_btid;
+    ctx->sc.nmodels = nm; ctx->sc.gx = v->grid_dim[0]; ctx->sc.gy = v->grid_dim[1]; ctx->sc.gz = v->grid_dim[2];
+    ctx->have_scene = true; ctx->have_grid = grid; ctx->have_bvh = false; ctx->cache_valid = false;
+    ctx->accel = PTAP_ACCEL_GRID_COMPAT;
+    return PTAP_OK;
+}
+
+int ptap_build_accel(ptap_ctx* ctx, int kind)
+{
+    if (!ctx || !ctx->have_scene) return fail(ctx, PTAP_E_STATE, "build_accel: no scene uploaded");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
+    if (kind == PTAP_ACCEL_GRID_COMPAT) {
+        if (!ctx->have_grid) return fail(ctx, PTAP_E_STATE, "build_accel: the uploaded scene carries no grids (call ptap_scene_build_grids first)");
+    } else if (kind == PTAP_ACCEL_BVH) {
+        if (!ctx->have_bvh) {
+            BvhBuildResult res;
+            buildSceneBvh(ctx->h_tris, ctx->h_meshes, ctx->h_models, res);
+            const int nm = (int)ctx->h_models.size();
+            std::vector<InstanceTrace> inst(nm);
+            CK(cudaMemcpy(inst.data(), ctx->sc.inst, nm * sizeof(InstanceTrace), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < nm; ++i) {
+                inst[i].grid.z = __builtin_bit_cast(float, res.mesh_root[ctx->h_models[i].mesh_index]);
+                inst[i].grid.w = 0.0f;
+            }
+            if (res.nodes.size() > (size_t)std::max<size_t>(ctx->h_tris.size(), 1) * 2) return fail(ctx, PTAP_E_NOMEM, "BVH larger than reserved");
+            CK(cudaMemcpy((void*)ctx->sc.inst, inst.data(), nm * sizeof(InstanceTrace), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy((void*)ctx->sc.cull, res.cull.data(), nm * sizeof(InstanceCull), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy((void*)ctx->sc.nodes, res.nodes.data(), res.nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy((void*)ctx->sc.bvh_tris, res.tris.data(), res.tris.size() * sizeof(TriRec), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy((void*)ctx->sc.bvh_tri_id, res.tri_id.data(), res.tri_id.size() * sizeof(int), cudaMemcpyHostToDevice));
+            ctx->have_bvh = true;
+        }
+    } else return fail(ctx, PTAP_E_INVALID, "build_accel: unknown kind %d", kind);
+    ctx->accel = kind;
+    ctx->cache_valid = false;
+    int occ = kind == PTAP_ACCEL_BVH ? traceBvhOccupancy() : traceGridOccupancy();
+    ctx->grid_trace = ctx->sms * std::max(occ, 1);
+    return PTAP_OK;
+}
+
+int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, uint32_t flags)
+{
+    if (!ctx || W <= 0 || H <= 0 || depth <= 0 || depth > kMaxDepth) return fail(ctx, PTAP_E_INVALID, "set_render_params: W,H > 0 and 1 <= depth <= %d required", kMaxDepth);
+    if ((long long)W * H > (1ll << 30)) return fail(ctx, PTAP_E_INVALID, "set_render_params: too many pixels");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
+    const int N = W * H;
+    const int ntiles = (N + kShadeBlock - 1) / kShadeBlock;
+    size_t need = Arena::need(N, sizeof(float4)) * 8 + Arena::need(N, sizeof(float2)) + Arena::need((size_t)N * 3, sizeof(float)) +
+                  Arena::need((size_t)ntiles * kMaxDepth, sizeof(unsigned long long)) + Arena::need(1, sizeof(FrameState)) + 4096;
+    if (need > ctx->frame_arena.cap) CK(ctx->frame_arena.reserve(need)); else ctx->frame_arena.used = 0;
+    Arena& A = ctx->frame_arena;
+    WaveDev& wv = ctx->wv;
+    for (int k = 0; k < 2; ++k) { wv.O[k] = A.alloc<float4>(N); wv.D[k] = A.alloc<float4>(N); wv.C[k] = A.alloc<float4>(N); }
+    wv.hit = A.alloc<float4>(N); wv.hit_cache = A.alloc<float4>(N); wv.uv = A.alloc<float2>(N);
+    wv.film = A.alloc<float>((size_t)N * 3);
+    wv.tile_status = A.alloc<unsigned long long>((size_t)ntiles * kMaxDepth);
+    wv.st = A.alloc<FrameState>(1);
+    if (!wv.st || !wv.tile_status || !wv.film) return fail(ctx, PTAP_E_NOMEM, "frame arena exhausted");
+    wv.W = W; wv.H = H; wv.N = N; wv.depth = depth; wv.ntiles = ntiles;
+    wv.step_x = (float)(20.0 / (double)W);                       // Renderer.cpp:538-539 (SAMPLESX = SAMPLESY = 1)
+    wv.step_y = (float)(16.0 / (double)H);
+    CK(cudaMemsetAsync(wv.film, 0, (size_t)N * 3 * sizeof(float), ctx->stream));   // initImageKernel, Renderer.cpp:557-565
+    CK(cudaMemsetAsync(wv.st, 0, sizeof(FrameState), ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->flags = flags; ctx->cache_valid = false; ctx->have_frame = true;
+    ctx->grid_shade = ctx->sms * std::max(shadeOccupancy(), 1);
+    ctx->grid_gen = ctx->sms * 8;
+    if (!ctx->grid_trace) {
+        int occ = ctx->accel == PTAP_ACCEL_BVH ? traceBvhOccupancy() : traceGridOccupancy();
+        ctx->grid_trace = ctx->sms * std::max(occ, 1);
+    }
+    ctx->stats = PtapStats{};
+    return PTAP_OK;
+}
+
+int ptap_render(ptap_ctx* ctx, int32_t iter_begin, int32_t iter_end)
+{
+    if (!ctx || !ctx->have_scene || !ctx->have_frame) return fail(ctx, PTAP_E_STATE, "render: scene and render parameters required");
+    if (ctx->accel == PTAP_ACCEL_GRID_COMPAT && !ctx->have_grid) return fail(ctx, PTAP_E_STATE, "render: no grid in the uploaded scene; build the BVH");
+    if (iter_end < iter_begin) return fail(ctx, PTAP_E_INVALID, "render: empty iteration range");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
+    const WaveDev& wv = ctx->wv;
+    const bool cache = ctx->flags & PTAP_FLAG_FIRST_HIT_CACHE;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    launchSetIter(wv.st, iter_begin, ctx->stream);
+    int64_t launches = 1;
+    for (int it = iter_begin; it < iter_end; ++it) {
+        profMark(ctx, 0);
+        launchGenerate(wv, ctx->grid_gen, ctx->stream); ++launches;
+        int in = 0;
+        for (int round = 0; round < wv.depth; ++round) {
+            float4* hitbuf = (round == 0 && cache) ? wv.hit_cache : wv.hit;
+            if (!(round == 0 && cache && ctx->cache_valid)) {                    // Renderer.cpp:594-620
+                profMark(ctx, 1);
+                launchTrace(ctx, wv.st, wv.O[in], wv.D[in], hitbuf, nullptr, nullptr, round, -1); ++launches;
+            }
+            profMark(ctx, 2);
+            launchShade(ctx->sc, wv, round, in, hitbuf, wv.depth - round, -1, 0, nullptr, ctx->grid_shade, ctx->stream); ++launches;
+            in ^= 1;
+        }
+        if (cache) ctx->cache_valid = true;
+    }
+    profMark(ctx, -1);
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaGetLastError());
+    ctx->stats.kernel_launches += launches;
+    ctx->render_pending = true;
+    return PTAP_OK;
+}
+
+int ptap_sync(ptap_ctx* ctx)
+{
+    if (!ctx) return PTAP_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc = collect(ctx); if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PTAP_OK;
+}
+
+int ptap_film_reset(ptap_ctx* ctx)
+{
+    if (!ctx || !ctx->have_frame) return fail(ctx, PTAP_E_STATE, "film_reset: no render parameters");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->wv.film, 0, (size_t)ctx->wv.N * 3 * sizeof(float), ctx->stream));
+    return PTAP_OK;
+}
+
+int ptap_read_film(ptap_ctx* ctx, float* rgb)
+{
+    if (!ctx || !ctx->have_frame || !rgb) return fail(ctx, PTAP_E_STATE, "read_film: no render parameters");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(rgb, ctx->wv.film, (size_t)ctx->wv.N * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    return ptap_sync(ctx);
+}
+
+int ptap_film_device_ptr(ptap_ctx* ctx, void** dev_ptr, size_t* nfloats)
+{
+    if (!ctx || !ctx->have_frame || !dev_ptr) return fail(ctx, PTAP_E_STATE, "film_device_ptr: no render parameters");
+    *dev_ptr = ctx->wv.film;
+    if (nfloats) *nfloats = (size_t)ctx->wv.N * 3;
+    return PTAP_OK;
+}
+
+int ptap_film_add(ptap_ctx* ctx, const float* rgb)
+{
+    if (!ctx || !ctx->have_frame || !rgb) return fail(ctx, PTAP_E_STATE, "film_add: no render parameters");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->wv.N * 3;
+    if (Arena::need(n, sizeof(float)) > ctx->scratch.cap) CK(ctx->scratch.reserve(Arena::need(n, sizeof(float)))); else ctx->scratch.used = 0;
+    float* tmp = ctx->scratch.alloc<float>(n);
+    CK(cudaMemcpyAsync(tmp, rgb, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    launchFilmAdd(ctx->wv.film, tmp, n, ctx->stream);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return PTAP_OK;
+}
+
+int ptap_get_stats(ptap_ctx* ctx, PtapStats* out)
+{
+    if (!ctx || !out) return PTAP_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc = collect(ctx); if (rc) return rc;
+    *out = ctx->stats;
+    return PTAP_OK;
+}
+
+// Renderer::renderImage (Renderer.cpp:15-63)
+int ptap_write_bmp(ptap_ctx* ctx, const char* path, int32_t iters)
+{
+    if (!ctx || !ctx->have_frame || !path || iters <= 0) return fail(ctx, PTAP_E_INVALID, "write_bmp: bad arguments");
+    const int W = ctx->wv.W, H = ctx->wv.H;
+    std::vector<float> film((size_t)W * H * 3);
+    int rc = ptap_read_film(ctx, film.data()); if (rc) return rc;
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(ctx, PTAP_E_IO, "write_bmp: cannot open %s", path);
+    unsigned char hdr[54] = {0};
+    hdr[0] = 'B'; hdr[1] = 'M'; hdr[10] = 54; hdr[14] = 40; hdr[26] = 1; hdr[28] = 24;
+    const int32_t fileSize = 54 + 3 * W * H, imageSize = 3 * W * H;
+    memcpy(hdr + 2, &fileSize, 4); memcpy(hdr + 18, &W, 4); memcpy(hdr + 22, &H, 4); memcpy(hdr + 34, &imageSize, 4);
+    fwrite(hdr, 1, 54, f);
+    // rows bottom-up as stored, no padding, bytes written in (x, y, z) order exactly as the reference does (Renderer.cpp:45-53)
+    std::vector<unsigned char> rowbuf((size_t)3 * W);
+    const float div = 1 / (float)iters;
+    for (int y = 0; y < H; ++y) {
+        for (int x = 0; x < W; ++x)
+            for (int k = 0; k < 3; ++k) {
+                const float c = (film[3 * ((size_t)x + (size_t)y * W) + k] * div) * 255.0f;
+                rowbuf[3 * x + k] = (unsigned char)(int)c;
+            }
+        fwrite(rowbuf.data(), 1, rowbuf.size(), f);
+    }
+    fclose(f);
+    return PTAP_OK;
+}
+
+// ---- parity entry points -------------------------------------------------------------------------------------
+
+static int traceImpl(ptap_ctx* ctx, const float* rays_od, int32_t n, PtapHit* out, int32_t* counts)
+{
+    if (!ctx || !ctx->have_scene || !rays_od || !out || n < 0) return fail(ctx, PTAP_E_STATE, "trace: scene and buffers required");
+    if (ctx->accel == PTAP_ACCEL_GRID_COMPAT && !ctx->have_grid) return fail(ctx, PTAP_E_STATE, "trace: no grid in the uploaded scene");
+    if (n == 0) return PTAP_OK;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
+    size_t need = Arena::need(n, sizeof(float4)) * 3 + Arena::need(n, sizeof(float2)) + Arena::need(n, sizeof(PtapHit)) + Arena::need(n, sizeof(int4)) +
+                  Arena::need((size_t)n * 6, sizeof(float)) + Arena::need(1, sizeof(FrameState)) + 4096;
+    if (need > ctx->scratch.cap) CK(ctx->scratch.reserve(need)); else ctx->scratch.used = 0;
+    Arena& A = ctx->scratch;
+    float4* O = A.alloc<float4>(n); float4* D = A.alloc<float4>(n); float4* hit = A.alloc<float4>(n);
+    float2* uv = A.alloc<float2>(n); PtapHit* dout = A.alloc<PtapHit>(n); int4* dcnt = A.alloc<int4>(n);
+    FrameState* st = A.alloc<FrameState>(1);
+    std::vector<float4> hO(n), hD(n);
+    for (int i = 0; i < n; ++i) {
+        hO[i] = make_float4(rays_od[6 * (size_t)i], rays_od[6 * (size_t)i + 1], rays_od[6 * (size_t)i + 2], 0.f);
+        hD[i] = make_float4(rays_od[6 * (size_t)i + 3], rays_od[6 * (size_t)i + 4], rays_od[6 * (size_t)i + 5], 0.f);
+    }
+    CK(cudaMemcpyAsync(O, hO.data(), n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(D, hD.data(), n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(st, 0, sizeof(FrameState), ctx->stream));
+    if (!ctx->grid_trace) {
+        int occ = ctx->accel == PTAP_ACCEL_BVH ? traceBvhOccupancy() : traceGridOccupancy();
+        ctx->grid_trace = ctx->sms * std::max(occ, 1);
+    }
+    launchTrace(ctx, st, O, D, hit, uv, counts ? dcnt : nullptr, 0, n);
+    launchResolveHits(ctx->sc, hit, uv, n, dout, ctx->stream);
+    CK(cudaMemcpyAsync(out, dout, n * sizeof(PtapHit), cudaMemcpyDeviceToHost, ctx->stream));
+    if (counts) CK(cudaMemcpyAsync(counts, dcnt, n * sizeof(int4), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return PTAP_OK;
+}
+
+int ptap_trace(ptap_ctx* ctx, const float* rays_od, int32_t n, PtapHit* out) { return traceImpl(ctx, rays_od, n, out, nullptr); }
+int ptap_trace_count(ptap_ctx* ctx, const float* rays_od, int32_t n, PtapHit* out, int32_t* counts) { return traceImpl(ctx, rays_od, n, out, counts); }
+
+int ptap_shade(ptap_ctx* ctx, const PtapPathIn* paths, int32_t n, int32_t iter, int32_t remaining, PtapPathOut* out, int32_t* order, int32_t* n_alive)
+{
+    if (!ctx || !ctx->have_scene || !paths || !out || n <= 0 || remaining <= 0) return fail(ctx, PTAP_E_STATE, "shade: scene and buffers required");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
+    const int ntiles = (n + kShadeBlock - 1) / kShadeBlock;
+    size_t need = Arena::need(n, sizeof(float4)) * 7 + Arena::need((size_t)n * 3, sizeof(float)) + Arena::need(n, sizeof(int)) +
+                  Arena::need(ntiles, sizeof(unsigned long long)) + Arena::need(1, sizeof(FrameState)) + 4096;
+    if (need > ctx->scratch.cap) CK(ctx->scratch.reserve(need)); else ctx->scratch.used = 0;
+    Arena& A = ctx->scratch;
+    WaveDev wv{};
+    for (int k = 0; k < 2; ++k) { wv.O[k] = A.alloc<float4>(n); wv.D[k] = A.alloc<float4>(n); wv.C[k] = A.alloc<float4>(n); }
+    float4* hit = A.alloc<float4>(n);
+    wv.film = A.alloc<float>((size_t)n * 3);
+    int* slot_pos = A.alloc<int>(n);
+    wv.tile_status = A.alloc<unsigned long long>(ntiles);
+    wv.st = A.alloc<FrameState>(1);
+    wv.N = n; wv.W = n; wv.H = 1; wv.depth = 1; wv.ntiles = ntiles;
+    std::vector<float4> hO(n), hD(n), hC(n), hH(n);
+    for (int i = 0; i < n; ++i) {
+        const PtapPathIn& p = paths[i];
+        hO[i] = make_float4(p.orig[0], p.orig[1], p.orig[2], __builtin_bit_cast(float, i));   // film slot = path index
+        hD[i] = make_float4(p.dir[0], p.dir[1], p.dir[2], 0.f);
+        hC[i] = make_float4(p.color[0], p.color[1], p.color[2], 0.f);
+        const bool miss = p.model < 0 || p.tri < 0;
+        if (!miss && (p.model >= ctx->sc.nmodels || p.tri >= (int)ctx->h_tris.size())) return fail(ctx, PTAP_E_INVALID, "shade: path %d has ids out of range", i);
+        hH[i] = make_float4(miss ? kFloatMax : p.dist, __builtin_bit_cast(float, p.tri), __builtin_bit_cast(float, p.model), 0.f);
+    }
+    CK(cudaMemcpyAsync(wv.O[0], hO.data(), n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(wv.D[0], hD.data(), n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(wv.C[0], hC.data(), n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(hit, hH.data(), n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(wv.film, 0, (size_t)n * 3 * sizeof(float), ctx->stream));
+    CK(cudaMemsetAsync(wv.tile_status, 0, ntiles * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(wv.st, 0, sizeof(FrameState), ctx->stream));
+    const int grid = ctx->sms * std::max(shadeOccupancy(), 1);
+    launchShade(ctx->sc, wv, 0, 0, hit, remaining, n, iter, slot_pos, grid, ctx->stream);
+    std::vector<float4> oO(n), oD(n), oC(n);
+    std::vector<float> film((size_t)n * 3);
+    std::vector<int> pos(n);
+    FrameState fs;
+    CK(cudaMemcpyAsync(oO.data(), wv.O[1], n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(oD.data(), wv.D[1], n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(oC.data(), wv.C[1], n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(film.data(), wv.film, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(pos.data(), slot_pos, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&fs, wv.st, sizeof fs, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    const int alive = fs.n_active[kMaxDepth + 1];
+    if (n_alive) *n_alive = alive;
+    for (int i = 0; i < n; ++i) {
+        PtapPathOut& o = out[i];
+        o.ipixel = paths[i].ipixel;
+        if (pos[i] >= 0) {
+            const int k = pos[i];
+            if (k >= alive) return fail(ctx, PTAP_E_INVALID, "shade: compaction position out of range");
+            o.alive = 1;
+            o.orig[0] = oO[k].x; o.orig[1] = oO[k].y; o.orig[2] = oO[k].z;
+            o.dir[0] = oD[k].x; o.dir[1] = oD[k].y; o.dir[2] = oD[k].z;
+            o.color[0] = oC[k].x; o.color[1] = oC[k].y; o.color[2] = oC[k].z;
+            if (__builtin_bit_cast(int, oO[k].w) != i) return fail(ctx, PTAP_E_INVALID, "shade: compaction lost the pixel id");
+            if (order) order[k] = i;
+        } else {
+            o.alive = 0;
+            memcpy(o.orig, paths[i].orig, 12); memcpy(o.dir, paths[i].dir, 12);
+            o.color[0] = film[3 * (size_t)i]; o.color[1] = film[3 * (size_t)i + 1]; o.color[2] = film[3 * (size_t)i + 2];   // sqrt(throughput): the film contribution
+        }
+    }
+    return PTAP_OK;
+}
+
+int ptap_bench_trace(ptap_ctx* ctx, const float* rays_od, int32_t n, int32_t reps, float* ms_per_launch)
+{
+    if (!ctx || !ctx->have_scene || !rays_od || n <= 0 || reps <= 0 || !ms_per_launch) return fail(ctx, PTAP_E_INVALID, "bench_trace: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
+    size_t need = Arena::need(n, sizeof(float4)) * 3 + Arena::need(1, sizeof(FrameState)) + 4096;
+    if (need > ctx->scratch.cap) CK(ctx->scratch.reserve(need)); else ctx->scratch.used = 0;
+    Arena& A = ctx->scratch;
+    float4* O = A.alloc<float4>(n); float4* D = A.alloc<float4>(n); float4* hit = A.alloc<float4>(n);
+    FrameState* st = A.alloc<FrameState>(1);
+    std::vector<float4> hO(n), hD(n);
+    for (int i = 0; i < n; ++i) {
+        hO[i] = make_float4(rays_od[6 * (size_t)i], rays_od[6 * (size_t)i + 1], rays_od[6 * (size_t)i + 2], 0.f);
+        hD[i] = make_float4(rays_od[6 * (size_t)i + 3], rays_od[6 * (size_t)i + 4], rays_od[6 * (size_t)i + 5], 0.f);
+    }
+    CK(cudaMemcpy(O, hO.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(D, hD.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
+    CK(cudaMemset(st, 0, sizeof(FrameState)));
+    for (int w = 0; w < 3; ++w) launchTrace(ctx, st, O, D, hit, nullptr, nullptr, 0, n);
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    for (int r = 0; r < reps; ++r) launchTrace(ctx, st, O, D, hit, nullptr, nullptr, 0, n);
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    *ms_per_launch = ms / reps;
+    return PTAP_OK;
+}
+
+}  // extern "C"

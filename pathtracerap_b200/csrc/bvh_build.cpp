@@ -1,0 +1,196 @@
+// bvh_build.cpp - binned-SAH BVH2 builder, one BLAS per mesh (instances share it, as they share the reference's grid).
+//
+// Leaf bounds are CONSERVATIVE FOR THE REFERENCE'S PREDICATE, not for the exact triangle: computeRayTriangleIntersection
+// (Renderer.cpp:188-201) accepts u,v >= -0.005, u+v <= 1.005 in barycentric units, i.e. hits up to 0.5 % of an edge
+// length outside the triangle.  Each triangle is therefore bounded by its fattened version with corners at
+// (u,v) = (-e,-e), (1+2e,-e), (-e,1+2e), e slightly above 0.005, plus a floating-point slack proportional to the
+// mesh extent.  With exact bounds a BVH silently drops the hits the reference finds in the tolerance band
+// (SURVEY.md 0.5 third hazard / hard part 2).
+#include "bvh_build.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <thread>
+
+namespace ptap {
+
+namespace {
+
+constexpr int kBins = 16;
+constexpr int kMaxLeaf = 4;          // SAH may stop earlier; hard cap 8 by the link encoding
+constexpr double kBandEps = 0.0056;  // > EPSILON (Config.h:4) to absorb rounding of u, v
+
+struct Box {
+    float lo[3], hi[3];
+    void reset() { for (int k = 0; k < 3; ++k) { lo[k] = FLT_MAX; hi[k] = -FLT_MAX; } }
+    void grow(const Box& b) { for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], b.lo[k]); hi[k] = std::max(hi[k], b.hi[k]); } }
+    void grow(const float* p) { for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); } }
+    float area() const
+    {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        return dx < 0 ? 0.f : 2.f * (dx * dy + dy * dz + dz * dx);
+    }
+};
+
+struct Prim { Box box; float c[3]; int id; };
+
+struct Builder {
+    std::vector<Prim>& prims;
+    std::vector<BvhNode>& nodes;
+    std::vector<int>& order;      // leaf-order list of prim ids (local to the mesh), appended
+    int leaf_base;                // leaf-order offset of this mesh in the global arrays
+    int max_depth = 0;
+
+    static int leafLink(int first, int count) { return ~((first << 3) | (count - 1)); }
+
+    // returns link (node index >= 0 or leaf < 0) and the bounds of the subtree
+    int build(int begin, int end, Box& bounds, int depth)
+    {
+        max_depth = std::max(max_depth, depth);
+        bounds.reset();
+        Box cb; cb.reset();
+        for (int i = begin; i < end; ++i) { bounds.grow(prims[i].box); cb.grow(prims[i].c); }
+        const int n = end - begin;
+        auto makeLeaf = [&]() {
+            int first = leaf_base + (int)order.size();
+            for (int i = begin; i < end; ++i) order.push_back(prims[i].id);
+            return leafLink(first, n);
+        };
+        if (n <= 1) return makeLeaf();
+        // binned SAH over the largest centroid axis first, then the others if it fails
+        int best_axis = -1, best_bin = -1; float best_cost = FLT_MAX;
+        for (int axis = 0; axis < 3; ++axis) {
+            const float lo = cb.lo[axis], ext = cb.hi[axis] - cb.lo[axis];
+            if (!(ext > 0.f)) continue;
+            Box bb[kBins]; int cnt[kBins];
+            for (int b = 0; b < kBins; ++b) { bb[b].reset(); cnt[b] = 0; }
+            const float scale = kBins / ext;
+            for (int i = begin; i < end; ++i) {
+                int b = std::min(kBins - 1, std::max(0, (int)((prims[i].c[axis] - lo) * scale)));
+                bb[b].grow(prims[i].box); cnt[b]++;
+            }
+            float rightArea[kBins]; int rightCnt[kBins];
+            Box acc; acc.reset(); int c = 0;
+            for (int b = kBins - 1; b > 0; --b) { acc.grow(bb[b]); c += cnt[b]; rightArea[b] = acc.area(); rightCnt[b] = c; }
+            acc.reset(); c = 0;
+            for (int b = 0; b < kBins - 1; ++b) {
+                acc.grow(bb[b]); c += cnt[b];
+                if (c == 0 || rightCnt[b + 1] == 0) continue;
+                float cost = acc.area() * c + rightArea[b + 1] * rightCnt[b + 1];
+                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
+            }
+        }
+        const float leaf_cost = bounds.area() * n;
+        if (n <= kMaxLeaf && (best_axis < 0 || best_cost + bounds.area() * 1.0f >= leaf_cost)) return makeLeaf();
+        int mid;
+        if (best_axis < 0) {
+            if (n <= 8) return makeLeaf();
+            mid = begin + n / 2;         // identical centroids: split by count
+        } else {
+            const float lo = cb.lo[best_axis], scale = kBins / (cb.hi[best_axis] - cb.lo[best_axis]);
+            auto it = std::partition(prims.begin() + begin, prims.begin() + end, [&](const Prim& p) {
+                int b = std::min(kBins - 1, std::max(0, (int)((p.c[best_axis] - lo) * scale)));
+                return b <= best_bin;
+            });
+            mid = (int)(it - prims.begin());
+            if (mid == begin || mid == end) mid = begin + n / 2;
+        }
+        const int me = (int)nodes.size();
+        nodes.emplace_back();
+        Box b0, b1;
+        const int l0 = build(begin, mid, b0, depth + 1);
+        const int l1 = build(mid, end, b1, depth + 1);
+        BvhNode& nd = nodes[me];
+        nd.xy0 = make_float4(b0.lo[0], b0.hi[0], b0.lo[1], b0.hi[1]);
+        nd.xy1 = make_float4(b1.lo[0], b1.hi[0], b1.lo[1], b1.hi[1]);
+        nd.z01 = make_float4(b0.lo[2], b0.hi[2], b1.lo[2], b1.hi[2]);
+        nd.link = make_int4(l0, l1, 0, 0);
+        return me;
+    }
+};
+
+}  // namespace
+
+void buildSceneBvh(const std::vector<TriRec>& tris, const std::vector<PtapMesh>& meshes, const std::vector<PtapModel>& models,
+                   BvhBuildResult& out)
+{
+    out.nodes.clear(); out.tris.clear(); out.tri_id.clear(); out.cull.clear();
+    out.mesh_root.assign(meshes.size(), -1);
+    out.max_depth = 0;
+    std::vector<Box> mesh_box(meshes.size());
+    for (size_t mi = 0; mi < meshes.size(); ++mi) {
+        const PtapMesh& mesh = meshes[mi];
+        mesh_box[mi].reset();
+        const int t0 = mesh.t_start, t1 = mesh.t_end;
+        if (t1 <= t0 || t0 < 0 || t1 > (int)tris.size()) continue;
+        // extent of the mesh for the floating-point slack
+        double ext = 0;
+        for (int t = t0; t < t1; ++t) {
+            const TriRec& r = tris[t];
+            const double v[3][3] = {{r.v0.x, r.v0.y, r.v0.z}, {(double)r.v0.x + r.e1.x, (double)r.v0.y + r.e1.y, (double)r.v0.z + r.e1.z},
+                                    {(double)r.v0.x + r.e2.x, (double)r.v0.y + r.e2.y, (double)r.v0.z + r.e2.z}};
+            for (auto& p : v) for (double c : p) ext = std::max(ext, std::fabs(c));
+        }
+        const float slack = (float)(ext * 4e-6 + 1e-6);
+        std::vector<Prim> prims((size_t)(t1 - t0));
+        for (int t = t0; t < t1; ++t) {
+            const TriRec& r = tris[t];
+            Prim& p = prims[t - t0];
+            p.id = t; p.box.reset();
+            const double uv[3][2] = {{-kBandEps, -kBandEps}, {1 + 2 * kBandEps, -kBandEps}, {-kBandEps, 1 + 2 * kBandEps}};
+            double cx = 0, cy = 0, cz = 0;
+            for (auto& c : uv) {
+                const double x = r.v0.x + c[0] * r.e1.x + c[1] * r.e2.x, y = r.v0.y + c[0] * r.e1.y + c[1] * r.e2.y, z = r.v0.z + c[0] * r.e1.z + c[1] * r.e2.z;
+                const float lo[3] = {std::nextafter((float)x, -FLT_MAX) - slack, std::nextafter((float)y, -FLT_MAX) - slack, std::nextafter((float)z, -FLT_MAX) - slack};
+                const float hi[3] = {std::nextafter((float)x, FLT_MAX) + slack, std::nextafter((float)y, FLT_MAX) + slack, std::nextafter((float)z, FLT_MAX) + slack};
+                p.box.grow(lo); p.box.grow(hi);
+                cx += x; cy += y; cz += z;
+            }
+            p.c[0] = (float)(cx / 3); p.c[1] = (float)(cy / 3); p.c[2] = (float)(cz / 3);
+        }
+        std::vector<int> order; order.reserve(prims.size());
+        const int root = (int)out.nodes.size();
+        Builder b{prims, out.nodes, order, (int)out.tri_id.size()};
+        Box bounds;
+        const int link = b.build(0, (int)prims.size(), bounds, 0);
+        if (link < 0) {
+            // the whole mesh fits one leaf: give it a root whose second child can never be hit
+            BvhNode nd;
+            nd.xy0 = make_float4(bounds.lo[0], bounds.hi[0], bounds.lo[1], bounds.hi[1]);
+            nd.xy1 = make_float4(FLT_MAX, -FLT_MAX, FLT_MAX, -FLT_MAX);
+            nd.z01 = make_float4(bounds.lo[2], bounds.hi[2], FLT_MAX, -FLT_MAX);
+            nd.link = make_int4(link, link, 0, 0);
+            out.nodes.push_back(nd);
+        }
+        out.mesh_root[mi] = root;
+        out.max_depth = std::max(out.max_depth, b.max_depth);
+        mesh_box[mi] = bounds;
+        for (int id : order) { out.tri_id.push_back(id); out.tris.push_back(tris[id]); }
+    }
+    // world-space cull boxes: the 8 corners of the (already fattened) mesh bounds through model_to_world, padded
+    out.cull.resize(models.size());
+    for (size_t i = 0; i < models.size(); ++i) {
+        const PtapModel& m = models[i];
+        const Box& mb = mesh_box[m.mesh_index];
+        Box wb; wb.reset();
+        if (out.mesh_root[m.mesh_index] >= 0) {
+            for (int c = 0; c < 8; ++c) {
+                const double p[3] = {(c & 1) ? mb.hi[0] : mb.lo[0], (c & 2) ? mb.hi[1] : mb.lo[1], (c & 4) ? mb.hi[2] : mb.lo[2]};
+                float w[3];
+                for (int r = 0; r < 3; ++r)
+                    w[r] = (float)(m.model_to_world[0 + r] * p[0] + m.model_to_world[4 + r] * p[1] + m.model_to_world[8 + r] * p[2] + m.model_to_world[12 + r]);
+                wb.grow(w);
+            }
+            double ext = 0;
+            for (int k = 0; k < 3; ++k) ext = std::max(ext, std::max(std::fabs((double)wb.lo[k]), std::fabs((double)wb.hi[k])));
+            const float pad = (float)(ext * 1e-4 + 1e-3);
+            for (int k = 0; k < 3; ++k) { wb.lo[k] -= pad; wb.hi[k] += pad; }
+        }
+        out.cull[i].lo = make_float4(wb.lo[0], wb.lo[1], wb.lo[2], 0.f);
+        out.cull[i].hi = make_float4(wb.hi[0], wb.hi[1], wb.hi[2], 0.f);
+    }
+}
+
+}  // namespace ptap

@@ -1,0 +1,97 @@
+// device_types.h - layouts of everything libptap keeps in HBM (see DESIGN.md "Data layout").
+// All records are multiples of 16 B and fetched with 16-byte vector loads.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ptap {
+
+constexpr float kEpsilon = 0.005f;          // Config.h:4
+constexpr float kFloatMax = 9999999.0f;     // Config.h:5
+constexpr float kFloatMin = -9999990.0f;    // Config.h:6
+constexpr int kMaxDepth = 16;               // rounds per iteration the context reserves state for
+
+// Per-model record read by the closest-hit kernels: 9 x float4 = 144 B.
+// Rows 0..2 of the reference's column-major mat4s (the w row is never used by
+// transformPosition/transformDirection, utility.h:71-80).
+struct InstanceTrace {
+    float4 w2m[3];      // w2m[r] = (m[0][r], m[1][r], m[2][r], m[3][r]) of world_to_model
+    float4 m2w[3];      // same for model_to_world
+    float4 bb_min;      // mesh bbox min (through the grid's creating model, Renderer.cpp:245-249); .w = voxel width x
+    float4 bb_max;      // mesh bbox max; .w = voxel width y
+    float4 grid;        // .x = voxel width z, .y = bits(first voxel of the grid), .z = bits(BLAS root node), .w = bits(first BVH triangle)
+};
+
+// World-space cull box of a model for the BVH path (2 x float4).
+struct InstanceCull {
+    float4 lo;          // .w = bits(mesh t_start)
+    float4 hi;          // .w = bits(mesh t_end)
+};
+
+// Per-model record read by the shade kernel: 4 x float4 = 64 B.
+struct InstanceShade {
+    float4 nm0;         // rows of transpose(inverse(mat3(model_to_world))) (utility.h:82-88): nm0 = (r0.x, r0.y, r0.z, color.r)
+    float4 nm1;         // (r1.x, r1.y, r1.z, color.g)
+    float4 nm2;         // (r2.x, r2.y, r2.z, color.b)
+    int4 mat;           // .x = material type (Primitive.h:70-79)
+};
+
+// Triangle, model space: 3 x float4 = 48 B.  e1 = v1 - v0 and e2 = v2 - v0 are the same fp32 subtractions the
+// reference performs per test (Renderer.cpp:183-184); the .w lanes carry the flat shading normal
+// normalize((n0+n1+n2)*(1/3.0f)) (Renderer.cpp:203), read only by the shade kernel.
+struct TriRec {
+    float4 v0;          // (v0.xyz, n.x)
+    float4 e1;          // (e1.xyz, n.y)
+    float4 e2;          // (e2.xyz, n.z)
+};
+
+// BVH2 node, 64 B: both children's bounds and links in one record.
+struct BvhNode {
+    float4 xy0;         // child0: (lo.x, hi.x, lo.y, hi.y)
+    float4 xy1;         // child1: (lo.x, hi.x, lo.y, hi.y)
+    float4 z01;         // (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
+    int4 link;          // (child0, child1, 0, 0); >= 0: node index, < 0: leaf ~((first << 3) | (count - 1))
+};
+
+// Device-resident frame state: lets a whole iteration run without a host round trip.
+struct FrameState {
+    int n_active[kMaxDepth + 2];        // rays entering round r
+    unsigned int ticket[kMaxDepth + 2]; // tile tickets of the shade kernel, per round
+    unsigned int fetch[kMaxDepth + 2];  // work-stealing cursors of the trace kernel, per round
+    int iter_cur, iter_next;
+    int cache_valid;                    // first-hit cache holds round-0 hits
+    int pad;
+    unsigned long long rays_traced;
+    unsigned long long paths;
+    unsigned long long count_nodes, count_tris, count_cells, count_refs;   // counting build only
+};
+
+struct SceneDev {
+    const InstanceTrace* inst;
+    const InstanceCull* cull;
+    const InstanceShade* shade;
+    const TriRec* tris;         // indexed by GLOBAL triangle id (reference order)
+    const int2* cells;          // grid voxels: (start, end) into refs
+    const int* refs;            // global triangle ids
+    const BvhNode* nodes;       // all BLAS nodes
+    const TriRec* bvh_tris;     // triangles in BVH leaf order; v0.w..: see bvh_tri_id
+    const int* bvh_tri_id;      // leaf-order position -> global triangle id
+    int nmodels;
+    int gx, gy, gz;
+};
+
+struct WaveDev {
+    float4* O[2];               // (orig.xyz, bits(ipixel)) ping-pong
+    float4* D[2];               // (dir.xyz, unused)
+    float4* C[2];               // (throughput rgb, unused)
+    float4* hit;                // (dist, bits(tri), bits(model), t_model) per slot
+    float4* hit_cache;          // round-0 hits (first-hit cache, Renderer.cpp:594-613)
+    float2* uv;                 // parity entry only
+    float* film;                // W*H*3 running sum (Pixel, Primitive.h:145-148)
+    unsigned long long* tile_status;   // shade look-back words: rounds x tiles
+    FrameState* st;
+    int W, H, N, depth, ntiles;
+    float step_x, step_y;
+};
+
+}  // namespace ptap

@@ -1,0 +1,30 @@
+// kernels.cuh - launch wrappers of the wavefront kernels (one translation unit per kernel family).
+#pragma once
+#include "device_types.h"
+#include "exact_math.cuh"
+#include "../../include/ptap.h"
+
+namespace ptap {
+
+constexpr int kTraceBlock = 128;
+constexpr int kShadeBlock = 256;     // one look-back tile = one CTA = 256 consecutive slots
+constexpr int kGenBlock = 256;
+
+// closest hit, grid-compat (trace_grid.cu) and BVH (trace_bvh.cu).  n_fixed < 0: read the count from st->n_active[round].
+void launchTraceGrid(const SceneDev& sc, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts,
+                     FrameState* st, int round, int n_fixed, int grid, cudaStream_t stream);
+int traceGridOccupancy();
+void launchTraceBvh(const SceneDev& sc, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts,
+                    FrameState* st, int round, int n_fixed, int grid, cudaStream_t stream);
+int traceBvhOccupancy();
+
+// wavefront.cu
+void launchGenerate(const WaveDev& wv, int grid, cudaStream_t stream);
+void launchShade(const SceneDev& sc, const WaveDev& wv, int round, int in_buf, const float4* hit, int remaining, int n_fixed,
+                 int iter_fixed, int* slot_pos, int grid, cudaStream_t stream);
+int shadeOccupancy();
+void launchResolveHits(const SceneDev& sc, const float4* hit, const float2* uv, int n, PtapHit* out, cudaStream_t stream);
+void launchSetIter(FrameState* st, int iter, cudaStream_t stream);
+void launchFilmAdd(float* film, const float* add, size_t n, cudaStream_t stream);
+
+}  // namespace ptap

@@ -1,0 +1,320 @@
+// wavefront.cu - ray generation, shading + stable compaction + film accumulation, hit resolve.
+//
+// Replaces generateRaysKernel (Renderer.cpp:521-555), shadeRayKernel (:411-479), compactStencilKernel +
+// thrust::stable_partition (:506-519, :628-630), gatherImageDataKernel (:481-496) and initImageKernel (:557-565).
+//
+// Design (DESIGN.md "Wavefront"): path state is SoA float4 (origin+pixel, direction, throughput) in ping-pong
+// queues.  One kernel per bounce shades a slot, decides whether the path survives, and writes survivors straight
+// to their compacted position in the other queue; terminated paths add sqrt(throughput) to the film on the spot
+// (each pixel owns exactly one path per iteration, so this equals the reference's end-of-iteration gather).
+// The compaction is ORDER-PRESERVING, as thrust::stable_partition is, because the reference seeds its RNG with the
+// slot index after compaction (Renderer.cpp:435, utility.h:57-62): same slots => same random streams => the same
+// image, sample for sample.  It is a single-pass decoupled look-back scan over 256-slot tiles: warp ballots give
+// the in-tile ranks, one 64-bit status word per tile carries (flag, count) between CTAs.  No 80-byte struct is
+// moved twice, no temporary is allocated, no count is read back by the host.
+#include "kernels.cuh"
+
+namespace ptap {
+
+namespace {
+
+constexpr float kTwoPi = 6.2831853071795864769252867665590057683943f;          // utility.h:20
+constexpr float kSqrtOneThird = 0.5773502691896257645091487805019574556476f;   // utility.h:21
+
+// utility.h:43-53
+__device__ __forceinline__ unsigned utilHash(unsigned a)
+{
+    a = (a + 0x7ed55d16u) + (a << 12);
+    a = (a ^ 0xc761c23cu) ^ (a >> 19);
+    a = (a + 0x165667b1u) + (a << 5);
+    a = (a + 0xd3a2646cu) ^ (a << 9);
+    a = (a + 0xfd7046c5u) + (a << 3);
+    a = (a ^ 0xb55a4f09u) ^ (a >> 16);
+    return a;
+}
+
+// thrust::minstd_rand seeded as utility.h:57-62 does; uniform_real_distribution<float>(0,1) draws.
+struct Lcg {
+    unsigned x;
+    __device__ __forceinline__ Lcg(int iter, int index, int depth)
+    {
+        const unsigned h = utilHash(0x80000000u | ((unsigned)depth << 22) | (unsigned)iter) ^ utilHash((unsigned)index);
+        x = h % 2147483647u;
+        if (x == 0u) x = 1u;
+    }
+    __device__ __forceinline__ float u01()
+    {
+        x = (unsigned)(((unsigned long long)x * 48271ull) % 2147483647ull);
+        return xdiv((float)(x - 1u), 2147483648.0f);
+    }
+};
+
+// utility.h:64-69: n - 2 (i.n) n  (the reference's "mirror" keeps the normal as base vector)
+__device__ __forceinline__ V3 reflectRay(V3 i, V3 n) { return xsub(n, xscale(n, xmul(2.0f, xdot(i, n)))); }
+
+// utility.h:91-123
+__device__ __forceinline__ V3 hemisphere(V3 n, Lcg& rng)
+{
+    const float up = xsqrt(rng.u01());
+    const float over = xsqrt(xsub(1.0f, xmul(up, up)));
+    const float around = xmul(rng.u01(), kTwoPi);
+    V3 nn;
+    if (xabs(n.x) < kSqrtOneThird) nn = v3(1, 0, 0);
+    else if (xabs(n.y) < kSqrtOneThird) nn = v3(0, 1, 0);
+    else nn = v3(0, 0, 1);
+    const V3 p1 = xnormalize(xcross(n, nn));
+    const V3 p2 = xnormalize(xcross(n, p1));
+    float s, c;
+    s = sinf(around); c = cosf(around);
+    return xadd(xadd(xscale(n, up), xscale(p1, xmul(c, over))), xscale(p2, xmul(s, over)));
+}
+
+// utility.h:145-170
+__device__ __forceinline__ V3 metal(V3 n, V3 dir, Lcg& rng)
+{
+    rng.u01(); rng.u01();                                   // `up`/`around` are drawn but unused (utility.h:150-152)
+    const float phi = xmul(kTwoPi, rng.u01());
+    const float r2 = rng.u01();
+    const float cosTheta = powf(xsub(1.0f, r2), xdiv(1.0f, xadd(30.0f, 1.0f)));
+    const float sinTheta = xsqrt(xsub(1.0f, xmul(cosTheta, cosTheta)));
+    const V3 w = xnormalize(xsub(dir, xscale(xscale(n, 2.0f), xdot(n, dir))));
+    const V3 a = ((double)xabs(w.x) > .1) ? v3(0, 1, 0) : v3(1, 0, 0);
+    const V3 u = xnormalize(xcross(a, w));
+    const V3 v = xcross(w, u);
+    return xadd(xadd(xscale(xscale(u, cosf(phi)), sinTheta), xscale(xscale(v, sinf(phi)), sinTheta)), xscale(w, cosTheta));
+}
+
+// utility.h:125-143
+__device__ __forceinline__ V3 coat(V3 n, V3 dir, Lcg& rng)
+{
+    if (rng.u01() < 0.5f) return reflectRay(dir, n);
+    return hemisphere(n, rng);
+}
+
+// world-space shading normal of (model, tri): normalize(transpose(inverse(mat3(M))) * flat_normal)
+// (Renderer.cpp:203,397; utility.h:82-88); matrix rows and flat normal are precomputed at upload with the same arithmetic.
+__device__ __forceinline__ V3 worldNormal(const SceneDev& sc, int model, int tri, float4& nm0, float4& nm1, float4& nm2)
+{
+    const TriRec* t = &sc.tris[tri];
+    const V3 n = v3(__ldg(&t->v0.w), __ldg(&t->e1.w), __ldg(&t->e2.w));
+    nm0 = ldg4(&sc.shade[model].nm0); nm1 = ldg4(&sc.shade[model].nm1); nm2 = ldg4(&sc.shade[model].nm2);
+    const V3 r = v3(xadd(xadd(xmul(nm0.x, n.x), xmul(nm0.y, n.y)), xmul(nm0.z, n.z)),
+                    xadd(xadd(xmul(nm1.x, n.x), xmul(nm1.y, n.y)), xmul(nm1.z, n.z)),
+                    xadd(xadd(xmul(nm2.x, n.x), xmul(nm2.y, n.y)), xmul(nm2.z, n.z)));
+    return xnormalize(r);
+}
+
+constexpr unsigned long long kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kValueMask = 0xFFFFFFFFull;
+
+__device__ __forceinline__ unsigned long long ldVolatile(const unsigned long long* p)
+{
+    return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+__device__ __forceinline__ void stVolatile(unsigned long long* p, unsigned long long v)
+{
+    *reinterpret_cast<volatile unsigned long long*>(p) = v;
+}
+
+}  // namespace
+
+// generateRaysKernel (Renderer.cpp:521-555) + per-iteration reset of the device-side frame state.
+__global__ void __launch_bounds__(kGenBlock) k_generate(WaveDev wv)
+{
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stride = gridDim.x * blockDim.x;
+    FrameState* st = wv.st;
+    if (tid == 0) {
+        st->iter_cur = st->iter_next; st->iter_next = st->iter_cur + 1;
+        st->n_active[0] = wv.N;
+        st->paths += (unsigned long long)wv.N;
+    }
+    if (tid >= 1 && tid <= kMaxDepth + 1) st->n_active[tid] = 0;
+    if (tid < kMaxDepth + 2) { st->ticket[tid] = 0u; st->fetch[tid] = 0u; }
+    const int nwords = wv.ntiles * wv.depth;
+    for (int i = tid; i < nwords; i += stride) wv.tile_status[i] = 0ull;
+    for (int i = tid; i < wv.N; i += stride) {
+        const int y = i / wv.W, x = i % wv.W;
+        // float world_x = -10.0 + x * step_x  (double add of a float product, Renderer.cpp:541-542)
+        const float wx = (float)(-10.0 + (double)xmul((float)x, wv.step_x));
+        const float wy = (float)(-4.0 + (double)xmul((float)y, wv.step_y));
+        wv.O[0][i] = make_float4(0.0f, 0.0f, 920.0f, __int_as_float(i));
+        wv.D[0][i] = make_float4(xsub(wx, 0.0f), xsub(wy, 0.0f), xsub(900.0f, 920.0f), 0.0f);
+        wv.C[0][i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+    }
+}
+
+// shadeRayKernel + stable compaction + film accumulation for one bounce.
+// Slot i of queue `in` holds a path with `remaining` bounces left (every live path of a round has the same count).
+__global__ void __launch_bounds__(kShadeBlock)
+k_shade(SceneDev sc, WaveDev wv, int round, int in, const float4* __restrict__ hit, int remaining, int n_fixed, int iter_fixed,
+        int* __restrict__ slot_pos)
+{
+    __shared__ int s_warp_off[kShadeBlock / 32];
+    __shared__ int s_excl;
+    __shared__ unsigned s_tile;
+    FrameState* st = wv.st;
+    const int n = n_fixed >= 0 ? n_fixed : st->n_active[round];
+    const int iter = n_fixed >= 0 ? iter_fixed : st->iter_cur;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float4* __restrict__ Oi = wv.O[in]; const float4* __restrict__ Di = wv.D[in]; const float4* __restrict__ Ci = wv.C[in];
+    float4* __restrict__ Oo = wv.O[in ^ 1]; float4* __restrict__ Do = wv.D[in ^ 1]; float4* __restrict__ Co = wv.C[in ^ 1];
+    unsigned long long* status = wv.tile_status + (size_t)round * wv.ntiles;
+
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(&st->ticket[round], 1u);
+        __syncthreads();
+        const int tile = (int)s_tile;
+        const int base = tile * kShadeBlock;
+        if (base >= n) break;
+        const int i = base + threadIdx.x;
+        bool alive = false;
+        float4 o4, d4, c4;
+        if (i < n) {
+            o4 = Oi[i]; d4 = Di[i]; c4 = Ci[i];
+            const float4 h = hit[i];
+            V3 col = v3(c4);
+            if (h.x < kFloatMax) {                                               // Renderer.cpp:426
+                const int tri = __float_as_int(h.y), model = __float_as_int(h.z);
+                float4 nm0, nm1, nm2;
+                const V3 nrm = worldNormal(sc, model, tri, nm0, nm1, nm2);
+                const int type = __ldg(&sc.shade[model].mat.x);
+                const V3 albedo = v3(nm0.w, nm1.w, nm2.w);
+                const V3 dir = xnormalize(v3(d4));                               // Renderer.cpp:428
+                const V3 pt = xadd(v3(o4), xscale(dir, h.x));                    // Renderer.cpp:429
+                alive = remaining > 1;                                           // bounces-- leaves > 0 (Renderer.cpp:478, 512)
+                if (type == PTAP_DIFFUSE || type == PTAP_METAL || type == PTAP_COAT) {   // Renderer.cpp:433-453
+                    if (alive) {
+                        Lcg rng(iter, i, remaining);
+                        const V3 nd = type == PTAP_DIFFUSE ? hemisphere(nrm, rng) : type == PTAP_METAL ? metal(nrm, dir, rng) : coat(nrm, dir, rng);
+                        const V3 no = xadd(pt, xscale(nrm, 0.1f));
+                        o4.x = no.x; o4.y = no.y; o4.z = no.z; d4.x = nd.x; d4.y = nd.y; d4.z = nd.z;
+                    }
+                    col = xmul(col, albedo);
+                } else if (type == PTAP_EMISSIVE) {                              // Renderer.cpp:454-460
+                    col = xmul(col, albedo);
+                    alive = false;
+                } else if (type == PTAP_REFLECTIVE) {                            // Renderer.cpp:461-467
+                    col = xmul(col, albedo);
+                    const V3 nd = reflectRay(dir, nrm);
+                    const V3 no = xadd(pt, xscale(nrm, 0.1f));
+                    o4.x = no.x; o4.y = no.y; o4.z = no.z; d4.x = nd.x; d4.y = nd.y; d4.z = nd.z;
+                }                                                                // SPECULAR / REFRACTIVE: no branch, ray unchanged
+            } else {                                                             // Renderer.cpp:471-477
+                col = xmul(col, v3(0.01f, 0.01f, 0.01f));
+            }
+            c4.x = col.x; c4.y = col.y; c4.z = col.z;
+            if (!alive) {                                                        // gatherImageDataKernel, Renderer.cpp:481-496
+                float* px = wv.film + 3 * (size_t)__float_as_int(o4.w);
+                px[0] = xadd(px[0], xsqrt(col.x)); px[1] = xadd(px[1], xsqrt(col.y)); px[2] = xadd(px[2], xsqrt(col.z));
+            }
+        }
+        // ---- order-preserving compaction: ranks inside the tile by ballot, tile offsets by decoupled look-back
+        const unsigned ballot = __ballot_sync(0xffffffffu, alive);
+        const int rank = __popc(ballot & ((1u << lane) - 1u));
+        if (lane == 0) s_warp_off[warp] = __popc(ballot);
+        __syncthreads();
+        if (warp == 0) {
+            const int wt = lane < kShadeBlock / 32 ? s_warp_off[lane] : 0;
+            int incl = wt;
+#pragma unroll
+            for (int d = 1; d < kShadeBlock / 32; d <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += up;
+            }
+            const int block_total = __shfl_sync(0xffffffffu, incl, kShadeBlock / 32 - 1);
+            if (lane < kShadeBlock / 32) s_warp_off[lane] = incl - wt;
+            int excl = 0;
+            if (tile == 0) {
+                if (lane == 0) stVolatile(&status[0], kFlagPrefix | (unsigned long long)block_total);
+            } else {
+                if (lane == 0) stVolatile(&status[tile], kFlagAgg | (unsigned long long)block_total);
+                int look = tile - 1;
+                for (;;) {
+                    const int idx = look - lane;
+                    unsigned long long w = idx >= 0 ? ldVolatile(&status[idx]) : kFlagPrefix;
+                    const unsigned has_prefix = __ballot_sync(0xffffffffu, (w >> 62) == 2ull);
+                    const unsigned is_empty = __ballot_sync(0xffffffffu, (w >> 62) == 0ull);
+                    const int p = has_prefix ? __ffs(has_prefix) - 1 : 32;       // nearest tile with an inclusive prefix
+                    const unsigned need = p >= 31 ? 0xffffffffu : ((2u << p) - 1u);
+                    if (is_empty & need) continue;                               // a needed predecessor has not published yet
+                    int v = (lane <= p) ? (int)(w & kValueMask) : 0;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                    excl += v;
+                    if (p < 32) break;
+                    look -= 32;
+                }
+                if (lane == 0) stVolatile(&status[tile], kFlagPrefix | (unsigned long long)(excl + block_total));
+            }
+            if (lane == 0) {
+                s_excl = excl;
+                if (base + kShadeBlock >= n && n_fixed < 0) st->n_active[round + 1] = excl + block_total;
+                if (base + kShadeBlock >= n && n_fixed >= 0) st->n_active[kMaxDepth + 1] = excl + block_total;
+            }
+        }
+        __syncthreads();
+        if (i < n) {
+            const int pos = alive ? s_excl + s_warp_off[warp] + rank : -1;
+            if (alive) { Oo[pos] = o4; Do[pos] = d4; Co[pos] = c4; }
+            if (slot_pos) slot_pos[i] = pos;
+        }
+        __syncthreads();
+    }
+}
+
+// (dist, tri, model, t) + (u, v) -> PtapHit with the world normal and material the reference would have stored
+__global__ void k_resolve_hits(SceneDev sc, const float4* __restrict__ hit, const float2* __restrict__ uv, int n, PtapHit* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 h = hit[i];
+    PtapHit r;
+    r.tri = __float_as_int(h.y); r.model = __float_as_int(h.z); r.t_model = h.w; r.dist = h.x;
+    r.u = 0.0f; r.v = 0.0f; r.normal[0] = r.normal[1] = r.normal[2] = 0.0f; r.mat_type = -1;
+    if (h.x < kFloatMax && r.model >= 0) {
+        float4 a, b, c;
+        const V3 nrm = worldNormal(sc, r.model, r.tri, a, b, c);
+        r.normal[0] = nrm.x; r.normal[1] = nrm.y; r.normal[2] = nrm.z;
+        r.mat_type = sc.shade[r.model].mat.x;
+        if (uv) { r.u = uv[i].x; r.v = uv[i].y; }
+    } else {
+        r.model = -1; r.tri = -1; r.t_model = 0.0f;
+    }
+    out[i] = r;
+}
+
+__global__ void k_set_iter(FrameState* st, int iter) { st->iter_next = iter; }
+
+__global__ void k_film_add(float* __restrict__ film, const float* __restrict__ add, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) film[i] += add[i];
+}
+
+void launchGenerate(const WaveDev& wv, int grid, cudaStream_t stream) { k_generate<<<grid, kGenBlock, 0, stream>>>(wv); }
+
+void launchShade(const SceneDev& sc, const WaveDev& wv, int round, int in_buf, const float4* hit, int remaining, int n_fixed,
+                 int iter_fixed, int* slot_pos, int grid, cudaStream_t stream)
+{
+    k_shade<<<grid, kShadeBlock, 0, stream>>>(sc, wv, round, in_buf, hit, remaining, n_fixed, iter_fixed, slot_pos);
+}
+
+int shadeOccupancy()
+{
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade, kShadeBlock, 0);
+    return nb;
+}
+
+void launchResolveHits(const SceneDev& sc, const float4* hit, const float2* uv, int n, PtapHit* out, cudaStream_t stream)
+{
+    if (n > 0) k_resolve_hits<<<(n + 255) / 256, 256, 0, stream>>>(sc, hit, uv, n, out);
+}
+
+void launchSetIter(FrameState* st, int iter, cudaStream_t stream) { k_set_iter<<<1, 1, 0, stream>>>(st, iter); }
+
+void launchFilmAdd(float* film, const float* add, size_t n, cudaStream_t stream)
+{
+    if (n) k_film_add<<<148 * 4, 256, 0, stream>>>(film, add, n);
+}
+
+}  // namespace ptap

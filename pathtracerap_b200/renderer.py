@@ -1,0 +1,131 @@
+"""Device-side renderer: the Python mirror of the reference's `Renderer` (Renderer.h:46-55) over the C ABI.
+
+`allocateOnGPU / renderLoop / renderImage / free` keep the reference's names and meaning; the remaining
+methods expose what the reference hard-codes (resolution, iterations, depth) and the parity entry points.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from .scene import Scene
+
+
+class Renderer:
+    # Config.h:12-13,19 and Renderer.cpp:550
+    RESOLUTION_X, RESOLUTION_Y, ITER, DEPTH = 1000, 800, 500, 5
+
+    def __init__(self, device: int = 0, width: int | None = None, height: int | None = None, iters: int | None = None,
+                 depth: int | None = None, accel: int = N.ACCEL_GRID_COMPAT, first_hit_cache: bool = True, profile: bool = False,
+                 arena_bytes: int = 0):
+        self.W = width or self.RESOLUTION_X; self.H = height or self.RESOLUTION_Y
+        self.iters = iters or self.ITER; self.depth = depth or self.DEPTH
+        self.accel = accel
+        self.flags = (N.FLAG_FIRST_HIT_CACHE if first_hit_cache else 0) | (N.FLAG_PROFILE if profile else 0)
+        self._iters_done = 0
+        h = C.c_void_p()
+        rc = N.lib().ptap_create(device, arena_bytes, C.byref(h))
+        if rc != 0:
+            raise N.PtapError(f"ptap_create(device={device}) failed with {rc}: a CUDA sm_100 device is required (no CPU fallback)")
+        self.h = h
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise N.PtapError(f"{what}: error {rc}: {N.lib().ptap_last_error(self.h).decode()}")
+
+    # -- the reference's four methods ----------------------------------------------------------------------------
+    def allocateOnGPU(self, scene: Scene):
+        v = scene.view()
+        self._check(N.lib().ptap_upload_scene(self.h, C.byref(v)), "allocateOnGPU/upload_scene")
+        self._check(N.lib().ptap_build_accel(self.h, self.accel), "allocateOnGPU/build_accel")
+        self._check(N.lib().ptap_set_render_params(self.h, self.W, self.H, self.depth, self.flags), "allocateOnGPU/set_render_params")
+        self._iters_done = 0
+
+    def renderLoop(self):
+        self.render(0, self.iters)
+        self.sync()
+
+    def renderImage(self, path: str = "Render.bmp"):
+        self._check(N.lib().ptap_write_bmp(self.h, path.encode(), max(self._iters_done, 1)), "renderImage")
+
+    def free(self):
+        if getattr(self, "h", None):
+            N.lib().ptap_destroy(self.h)
+            self.h = None
+
+    # -- finer control -------------------------------------------------------------------------------------------
+    def set_accel(self, accel: int):
+        self.accel = accel
+        self._check(N.lib().ptap_build_accel(self.h, accel), "build_accel")
+
+    def set_params(self, width, height, depth, first_hit_cache=True, profile=False):
+        self.W, self.H, self.depth = width, height, depth
+        self.flags = (N.FLAG_FIRST_HIT_CACHE if first_hit_cache else 0) | (N.FLAG_PROFILE if profile else 0)
+        self._check(N.lib().ptap_set_render_params(self.h, width, height, depth, self.flags), "set_render_params")
+        self._iters_done = 0
+
+    def render(self, iter_begin: int, iter_end: int):
+        """Enqueue iterations [iter_begin, iter_end) (asynchronous)."""
+        self._check(N.lib().ptap_render(self.h, iter_begin, iter_end), "render")
+        self._iters_done += iter_end - iter_begin
+
+    def sync(self):
+        self._check(N.lib().ptap_sync(self.h), "sync")
+
+    def film_reset(self):
+        self._check(N.lib().ptap_film_reset(self.h), "film_reset")
+        self._iters_done = 0
+
+    def film(self) -> np.ndarray:
+        """Un-normalised running sum, H x W x 3 (render_data.dev_image_data->pool, Renderer.cpp:49)."""
+        out = np.zeros((self.H, self.W, 3), np.float32)
+        self._check(N.lib().ptap_read_film(self.h, N.ptr(out)), "read_film")
+        return out
+
+    def film_add(self, rgb: np.ndarray):
+        rgb = np.ascontiguousarray(rgb, np.float32)
+        assert rgb.size == self.W * self.H * 3
+        self._check(N.lib().ptap_film_add(self.h, N.ptr(rgb)), "film_add")
+
+    def film_device_ptr(self):
+        p = C.c_void_p(); n = C.c_size_t()
+        self._check(N.lib().ptap_film_device_ptr(self.h, C.byref(p), C.byref(n)), "film_device_ptr")
+        return p.value, n.value
+
+    def stats(self) -> dict:
+        s = N.Stats()
+        self._check(N.lib().ptap_get_stats(self.h, C.byref(s)), "get_stats")
+        d = {k: getattr(s, k) for k, _ in N.Stats._fields_ if k != "active_per_round"}
+        d["active_per_round"] = [int(x) for x in s.active_per_round]
+        return d
+
+    # -- parity entry points -------------------------------------------------------------------------------------
+    def trace(self, rays_od, counts: bool = False):
+        rays_od = np.ascontiguousarray(rays_od, np.float32).reshape(-1, 6)
+        out = np.zeros(len(rays_od), N.HIT)
+        if counts:
+            cnt = np.zeros((len(rays_od), 4), np.int32)
+            self._check(N.lib().ptap_trace_count(self.h, N.ptr(rays_od), len(rays_od), N.ptr(out), N.ptr(cnt)), "trace_count")
+            return out, cnt
+        self._check(N.lib().ptap_trace(self.h, N.ptr(rays_od), len(rays_od), N.ptr(out)), "trace")
+        return out
+
+    def shade(self, paths, it: int, remaining: int):
+        paths = np.ascontiguousarray(paths, N.PATH_IN)
+        out = np.zeros(len(paths), N.PATH_OUT); order = np.full(len(paths), -1, np.int32); n_alive = C.c_int32(0)
+        self._check(N.lib().ptap_shade(self.h, N.ptr(paths), len(paths), it, remaining, N.ptr(out), N.ptr(order), C.byref(n_alive)), "shade")
+        return out, order[:n_alive.value]
+
+    def bench_trace(self, rays_od, reps: int = 10) -> float:
+        rays_od = np.ascontiguousarray(rays_od, np.float32).reshape(-1, 6)
+        ms = C.c_float(0)
+        self._check(N.lib().ptap_bench_trace(self.h, N.ptr(rays_od), len(rays_od), reps, C.byref(ms)), "bench_trace")
+        return ms.value
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
