@@ -46,6 +46,15 @@ typedef struct { int32_t start, end, entity_type; } PtapVoxel;                  
 
 enum { PTAP_DIFFUSE = 0, PTAP_SPECULAR, PTAP_REFLECTIVE, PTAP_REFRACTIVE, PTAP_EMISSIVE, PTAP_COAT, PTAP_METAL }; /* Primitive.h:70-79 */
 
+/* BVH2 node (new; the reference has no BVH): both children's bounds and links in one 64-byte record.
+ * link >= 0: child node index; link < 0: leaf, ~link = (first_leaf_triangle << 3) | (count - 1). */
+typedef struct {
+    float xy0[4];   /* child 0: lo.x, hi.x, lo.y, hi.y */
+    float xy1[4];   /* child 1: lo.x, hi.x, lo.y, hi.y */
+    float z01[4];   /* c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z */
+    int32_t link[4];/* child0, child1, 0, 0 */
+} PtapBvhNode;
+
 /* The seven public vectors of the reference's Scene (Scene.h:26-32) as raw arrays. */
 typedef struct {
     const PtapModel* models; int32_t nmodels;
@@ -56,6 +65,10 @@ typedef struct {
     const PtapVoxel* voxels; int32_t nvoxels;
     const int32_t* refs; int32_t nrefs;               /* Scene::per_voxel_data_pool */
     int32_t grid_dim[3];                              /* GRID_X/Y/Z (Config.h:8-10) */
+    /* optional prebuilt BVH (ptap_scene_build_bvh); NULL/0: ptap_build_accel(PTAP_ACCEL_BVH) builds it from the triangles */
+    const PtapBvhNode* bvh_nodes; int32_t n_bvh_nodes;
+    const int32_t* bvh_tri_id; int32_t n_bvh_tris;    /* leaf-order position -> global triangle index */
+    const int32_t* bvh_mesh_root; int32_t n_bvh_roots;/* per mesh: root node, -1 if empty */
 } PtapSceneView;
 
 /* Closest-hit record of the parity entry point.  The reference's IntersectionData (Primitive.h:150-156)
@@ -88,7 +101,9 @@ typedef struct {
     int64_t active_per_round[16]; /* last iteration: active rays entering each round */
     float ms_render;              /* device time of the last ptap_render call (CUDA events on the context stream) */
     float ms_trace, ms_shade, ms_generate;  /* per-kernel split of that call when profiling is enabled, else 0 */
-    float avg_nodes, avg_tris, avg_cells, avg_refs;  /* per traced ray, when built with counting enabled (ptap_trace_count) */
+    float avg_nodes, avg_tris, avg_cells, avg_refs;  /* per traced ray, PTAP_FLAG_COUNT renders only */
+    int64_t trace_launches;       /* closest-hit launches inside the last ptap_render call */
+    int64_t scene_bytes;          /* bytes copied host->device by the last ptap_upload_scene */
 } PtapStats;
 
 typedef struct ptap_scene ptap_scene;   /* host-side scene: replaces class Scene (Scene.h:21-39) */
@@ -115,6 +130,9 @@ int ptap_scene_add_model(ptap_scene* s, int32_t mesh_index, const float model_to
 void ptap_compose_trs(const float translate[3], float rotate_y_degrees, const float scale[3], float model_to_world[16], float world_to_model[16]);
 /* Scene::addMeshesToGrid (Scene.cpp:318-396) */
 int ptap_scene_build_grids(ptap_scene* s, int32_t gx, int32_t gy, int32_t gz);
+/* Builds one BVH per mesh on the host (binned SAH); part of scene construction like addMeshesToGrid, so that
+ * Renderer::allocateOnGPU only uploads.  Bounds are conservative for the reference's tolerance band. */
+int ptap_scene_build_bvh(ptap_scene* s);
 int ptap_scene_view(const ptap_scene* s, PtapSceneView* out);     /* pointers stay owned by the scene */
 PtapModel* ptap_scene_models(ptap_scene* s);                      /* mutable, like the public vector */
 void ptap_scene_destroy(ptap_scene* s);
@@ -128,7 +146,8 @@ enum { PTAP_ACCEL_GRID_COMPAT = 0,  /* the reference's per-mesh uniform grid wal
        PTAP_ACCEL_BVH = 1 };        /* two-level BVH, exact closest hit under the reference's triangle predicate (oracle tier R1) */
 
 enum { PTAP_FLAG_FIRST_HIT_CACHE = 1,   /* Renderer.cpp:580,594-613 */
-       PTAP_FLAG_PROFILE = 2 };         /* per-kernel CUDA-event split in PtapStats (adds event records) */
+       PTAP_FLAG_PROFILE = 2,           /* per-kernel CUDA-event split in PtapStats (adds event records) */
+       PTAP_FLAG_COUNT = 4 };           /* counting build of the closest-hit kernel: avg_* in PtapStats (slower; not for timing) */
 
 int ptap_create(int device, size_t arena_bytes /* 0 = sized on demand */, ptap_ctx** out);
 void ptap_destroy(ptap_ctx* ctx);                                   /* Renderer::free (Renderer.cpp:132-148) */
@@ -141,8 +160,13 @@ int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, u
 /* Renderer::renderLoop (Renderer.cpp:567-648) for iterations [iter_begin, iter_end); the film accumulates.
  * Asynchronous on the context stream; ptap_sync / ptap_read_film / ptap_get_stats wait for it. */
 int ptap_render(ptap_ctx* ctx, int32_t iter_begin, int32_t iter_end);
+/* start of a new renderLoop: zero film (initImageKernel), forget the first-hit cache, zero the stats counters */
+int ptap_frame_begin(ptap_ctx* ctx);
 int ptap_film_reset(ptap_ctx* ctx);                                /* initImageKernel (Renderer.cpp:557-565) */
 int ptap_sync(ptap_ctx* ctx);
+/* CUDA-event timer on the context stream (device time of everything enqueued between the two calls) */
+int ptap_timer_start(ptap_ctx* ctx);
+int ptap_timer_stop(ptap_ctx* ctx, float* ms);
 /* render_data.dev_image_data->pool (Renderer.cpp:49): the un-normalised sum over iterations, W*H*3 floats */
 int ptap_read_film(ptap_ctx* ctx, float* rgb);
 int ptap_film_device_ptr(ptap_ctx* ctx, void** dev_ptr, size_t* nfloats);   /* for the NCCL reduce */

@@ -35,30 +35,32 @@ assert GRID.itemsize == 28 and VOXEL.itemsize == 12 and HIT.itemsize == 40 and P
 FLOAT_MAX = np.float32(9999999.0)
 DIFFUSE, SPECULAR, REFLECTIVE, REFRACTIVE, EMISSIVE, COAT, METAL = range(7)
 ACCEL_GRID_COMPAT, ACCEL_BVH = 0, 1
-FLAG_FIRST_HIT_CACHE, FLAG_PROFILE = 1, 2
+FLAG_FIRST_HIT_CACHE, FLAG_PROFILE, FLAG_COUNT = 1, 2, 4
 
 
 class SceneView(C.Structure):
     _fields_ = [("models", C.c_void_p), ("nmodels", C.c_int32), ("meshes", C.c_void_p), ("nmeshes", C.c_int32),
                 ("vertices", C.c_void_p), ("nvertices", C.c_int32), ("triangles", C.c_void_p), ("ntriangles", C.c_int32),
                 ("grids", C.c_void_p), ("ngrids", C.c_int32), ("voxels", C.c_void_p), ("nvoxels", C.c_int32),
-                ("refs", C.c_void_p), ("nrefs", C.c_int32), ("grid_dim", C.c_int32 * 3)]
+                ("refs", C.c_void_p), ("nrefs", C.c_int32), ("grid_dim", C.c_int32 * 3),
+                ("bvh_nodes", C.c_void_p), ("n_bvh_nodes", C.c_int32), ("bvh_tri_id", C.c_void_p), ("n_bvh_tris", C.c_int32),
+                ("bvh_mesh_root", C.c_void_p), ("n_bvh_roots", C.c_int32)]
 
 
 class Stats(C.Structure):
     _fields_ = [("rays_traced", C.c_int64), ("paths", C.c_int64), ("kernel_launches", C.c_int64),
                 ("active_per_round", C.c_int64 * 16), ("ms_render", C.c_float), ("ms_trace", C.c_float),
                 ("ms_shade", C.c_float), ("ms_generate", C.c_float), ("avg_nodes", C.c_float), ("avg_tris", C.c_float),
-                ("avg_cells", C.c_float), ("avg_refs", C.c_float)]
+                ("avg_cells", C.c_float), ("avg_refs", C.c_float), ("trace_launches", C.c_int64), ("scene_bytes", C.c_int64)]
 
 
 EXPORTS = [
     "ptap_scene_create_builtin", "ptap_scene_create_from_config", "ptap_scene_create_empty", "ptap_scene_create_from_view",
     "ptap_scene_add_obj", "ptap_scene_add_mesh", "ptap_scene_add_icosphere", "ptap_scene_add_model", "ptap_compose_trs",
-    "ptap_scene_build_grids", "ptap_scene_view", "ptap_scene_models", "ptap_scene_destroy", "ptap_scene_last_error",
+    "ptap_scene_build_grids", "ptap_scene_build_bvh", "ptap_scene_view", "ptap_scene_models", "ptap_scene_destroy", "ptap_scene_last_error",
     "ptap_scene_config_params",
     "ptap_create", "ptap_destroy", "ptap_last_error", "ptap_upload_scene", "ptap_build_accel", "ptap_set_render_params",
-    "ptap_render", "ptap_film_reset", "ptap_sync", "ptap_read_film", "ptap_film_device_ptr", "ptap_film_add",
+    "ptap_render", "ptap_timer_start", "ptap_timer_stop", "ptap_frame_begin", "ptap_film_reset", "ptap_sync", "ptap_read_film", "ptap_film_device_ptr", "ptap_film_add",
     "ptap_write_bmp", "ptap_get_stats", "ptap_stream", "ptap_trace", "ptap_trace_count", "ptap_shade", "ptap_bench_trace",
 ]
 
@@ -89,6 +91,7 @@ def lib():
         L.ptap_compose_trs.argtypes = [vp, C.c_float, vp, vp, vp]; L.ptap_compose_trs.restype = None
         L.ptap_scene_build_grids.argtypes = [vp, ci, ci, ci]
         L.ptap_scene_view.argtypes = [vp, C.POINTER(SceneView)]
+        L.ptap_scene_build_bvh.argtypes = [vp]
         L.ptap_scene_models.argtypes = [vp]; L.ptap_scene_models.restype = vp
         L.ptap_scene_destroy.argtypes = [vp]; L.ptap_scene_destroy.restype = None
         L.ptap_scene_last_error.argtypes = [vp]; L.ptap_scene_last_error.restype = C.c_char_p
@@ -101,6 +104,9 @@ def lib():
         L.ptap_set_render_params.argtypes = [vp, ci, ci, ci, cu]
         L.ptap_render.argtypes = [vp, ci, ci]
         L.ptap_film_reset.argtypes = [vp]
+        L.ptap_frame_begin.argtypes = [vp]
+        L.ptap_timer_start.argtypes = [vp]
+        L.ptap_timer_stop.argtypes = [vp, C.POINTER(C.c_float)]
         L.ptap_sync.argtypes = [vp]
         L.ptap_read_film.argtypes = [vp, vp]
         L.ptap_film_device_ptr.argtypes = [vp, pp, C.POINTER(C.c_size_t)]

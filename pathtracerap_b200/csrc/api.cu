@@ -7,6 +7,7 @@
 // A whole iteration is enqueued without a host round trip: the active-ray count of every bounce lives in device
 // memory (FrameState) and all kernels are persistent grids sized from the SM count.
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -52,7 +53,7 @@ struct ptap_ctx {
     int device = 0;
     int sms = 148;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, tm0 = nullptr, tm1 = nullptr;
     std::vector<cudaEvent_t> prof_events;
     std::vector<int> prof_kind;      // 0 generate, 1 trace, 2 shade  (pairs)
     size_t prof_used = 0;
@@ -63,6 +64,8 @@ struct ptap_ctx {
     std::vector<TriRec> h_tris;
     std::vector<PtapMesh> h_meshes;
     std::vector<PtapModel> h_models;
+    std::vector<InstanceTrace> h_inst;
+    InstanceTrace* d_inst = nullptr; InstanceCull* d_cull = nullptr; BvhNode* d_nodes = nullptr; TriRec* d_btris = nullptr; int* d_btid = nullptr;
     bool have_scene = false, have_grid = false, have_bvh = false, have_frame = false;
     int accel = PTAP_ACCEL_GRID_COMPAT;
     uint32_t flags = 0;
@@ -91,10 +94,11 @@ int fail(ptap_ctx* c, int code, const char* fmt, ...)
 
 float4 row(const float* m, int r) { return make_float4(m[0 + r], m[4 + r], m[8 + r], m[12 + r]); }
 
-void launchTrace(ptap_ctx* c, FrameState* st, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, int round, int n_fixed)
+void launchTrace(ptap_ctx* c, FrameState* st, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, int round, int n_fixed,
+                 bool count_totals = false)
 {
-    if (c->accel == PTAP_ACCEL_BVH) launchTraceBvh(c->sc, O, D, hit, uv, counts, st, round, n_fixed, c->grid_trace, c->stream);
-    else launchTraceGrid(c->sc, O, D, hit, uv, counts, st, round, n_fixed, c->grid_trace, c->stream);
+    if (c->accel == PTAP_ACCEL_BVH) launchTraceBvh(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, c->stream);
+    else launchTraceGrid(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, c->stream);
 }
 
 void profMark(ptap_ctx* c, int kind)
@@ -118,6 +122,9 @@ int collect(ptap_ctx* ctx)
     ctx->stats.rays_traced = (int64_t)fs.rays_traced;
     ctx->stats.paths = (int64_t)fs.paths;
     for (int i = 0; i < 16; ++i) ctx->stats.active_per_round[i] = i <= kMaxDepth ? fs.n_active[i] : 0;
+    const double rt = fs.rays_traced ? (double)fs.rays_traced : 1.0;
+    ctx->stats.avg_nodes = (float)(fs.count_nodes / rt); ctx->stats.avg_tris = (float)(fs.count_tris / rt);
+    ctx->stats.avg_cells = (float)(fs.count_cells / rt); ctx->stats.avg_refs = (float)(fs.count_refs / rt);
     ctx->stats.ms_generate = ctx->stats.ms_trace = ctx->stats.ms_shade = 0.f;
     for (size_t i = 0; i + 1 < ctx->prof_used; ++i) {          // event i -> i+1 spans the kernel of kind[i]
         float ms = 0.f;
@@ -128,6 +135,60 @@ int collect(ptap_ctx* ctx)
         else ctx->stats.ms_shade += ms;
     }
     ctx->prof_used = 0;
+    return PTAP_OK;
+}
+
+// Copies a BVH (nodes, leaf order) into the scene arena, gathers the leaf-ordered triangle records, points every model at
+// its mesh's root and derives the world-space cull boxes from the root node's child bounds.
+int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id, const int* mesh_root, size_t* bytes)
+{
+    const int nt = (int)ctx->h_tris.size(), nm = (int)ctx->h_models.size();
+    if ((size_t)nnodes > (size_t)std::max(nt, 1) * 2) return fail(ctx, PTAP_E_NOMEM, "BVH has more nodes than reserved (2 per triangle)");
+    for (int i = 0; i < nnodes; ++i)
+        for (int k = 0; k < 2; ++k) {
+            const int l = k ? nodes[i].link.y : nodes[i].link.x;
+            if (l >= nnodes) return fail(ctx, PTAP_E_INVALID, "BVH node %d: child index out of range", i);
+            if (l < 0) { const int code = ~l, first = code >> 3, cnt = (code & 7) + 1; if (first < 0 || first + cnt > nt) return fail(ctx, PTAP_E_INVALID, "BVH node %d: leaf range out of bounds", i); }
+        }
+    std::vector<TriRec> btris(nt);
+    for (int k = 0; k < nt; ++k) {
+        if (tri_id[k] < 0 || tri_id[k] >= nt) return fail(ctx, PTAP_E_INVALID, "BVH leaf order entry %d out of range", k);
+        btris[k] = ctx->h_tris[tri_id[k]];
+    }
+    std::vector<InstanceCull> cull(nm);
+    for (int i = 0; i < nm; ++i) {
+        const PtapModel& m = ctx->h_models[i];
+        const int root = mesh_root[m.mesh_index];
+        if (root >= nnodes) return fail(ctx, PTAP_E_INVALID, "mesh %d: BVH root out of range", m.mesh_index);
+        ctx->h_inst[i].grid.z = __builtin_bit_cast(float, root);
+        float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+        if (root >= 0) {
+            const BvhNode& r = nodes[root];
+            const float blo[2][3] = {{r.xy0.x, r.xy0.z, r.z01.x}, {r.xy1.x, r.xy1.z, r.z01.z}}, bhi[2][3] = {{r.xy0.y, r.xy0.w, r.z01.y}, {r.xy1.y, r.xy1.w, r.z01.w}};
+            float mlo[3], mhi[3];
+            for (int k = 0; k < 3; ++k) { mlo[k] = std::min(blo[0][k], blo[1][k] > bhi[1][k] ? blo[0][k] : blo[1][k]); mhi[k] = std::max(bhi[0][k], blo[1][k] > bhi[1][k] ? bhi[0][k] : bhi[1][k]); }
+            for (int c = 0; c < 8; ++c) {
+                const double p[3] = {(c & 1) ? mhi[0] : mlo[0], (c & 2) ? mhi[1] : mlo[1], (c & 4) ? mhi[2] : mlo[2]};
+                for (int rr = 0; rr < 3; ++rr) {
+                    const float w = (float)(m.model_to_world[0 + rr] * p[0] + m.model_to_world[4 + rr] * p[1] + m.model_to_world[8 + rr] * p[2] + m.model_to_world[12 + rr]);
+                    lo[rr] = std::min(lo[rr], w); hi[rr] = std::max(hi[rr], w);
+                }
+            }
+            float ext = 0.f;
+            for (int k = 0; k < 3; ++k) ext = std::max(ext, std::max(std::fabs(lo[k]), std::fabs(hi[k])));
+            const float pad = ext * 1e-4f + 1e-3f;
+            for (int k = 0; k < 3; ++k) { lo[k] -= pad; hi[k] += pad; }
+        }
+        cull[i].lo = make_float4(lo[0], lo[1], lo[2], 0.f); cull[i].hi = make_float4(hi[0], hi[1], hi[2], 0.f);
+    }
+    CK(cudaMemcpyAsync(ctx->d_inst, ctx->h_inst.data(), nm * sizeof(InstanceTrace), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_cull, cull.data(), nm * sizeof(InstanceCull), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_nodes, nodes, (size_t)nnodes * sizeof(BvhNode), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_btris, btris.data(), (size_t)nt * sizeof(TriRec), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_btid, tri_id, (size_t)nt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));      // btris / cull are stack-owned
+    if (bytes) *bytes = nm * (sizeof(InstanceTrace) + sizeof(InstanceCull)) + (size_t)nnodes * sizeof(BvhNode) + (size_t)nt * (sizeof(TriRec) + sizeof(int));
+    ctx->have_bvh = true;
     return PTAP_OK;
 }
 
@@ -168,6 +229,7 @@ void ptap_destroy(ptap_ctx* ctx)
     ctx->scene_arena.release(); ctx->frame_arena.release(); ctx->scratch.release();
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->tm0) { cudaEventDestroy(ctx->tm0); cudaEventDestroy(ctx->tm1); }
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -219,17 +281,7 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
         shade[i].mat = make_int4(m.mat.type, 0, 0, 0);
     }
     ctx->h_tris.resize(nt);
-    for (int t = 0; t < nt; ++t) {
-        const PtapVertex& a = v->vertices[v->triangles[t].v[0]];
-        const PtapVertex& b = v->vertices[v->triangles[t].v[1]];
-        const PtapVertex& c = v->vertices[v->triangles[t].v[2]];
-        const hm::V3 v0 = hm::v3(a.position);
-        const hm::V3 e1 = hm::sub(hm::v3(b.position), v0), e2 = hm::sub(hm::v3(c.position), v0);     // Renderer.cpp:183-184
-        const hm::V3 n = hm::normalize(hm::scale(hm::add(hm::add(hm::v3(a.normal), hm::v3(b.normal)), hm::v3(c.normal)), 1 / 3.0f));   // :203
-        ctx->h_tris[t].v0 = make_float4(v0.x, v0.y, v0.z, n.x);
-        ctx->h_tris[t].e1 = make_float4(e1.x, e1.y, e1.z, n.y);
-        ctx->h_tris[t].e2 = make_float4(e2.x, e2.y, e2.z, n.z);
-    }
+    makeTriRecs(v->vertices, v->triangles, nt, ctx->h_tris.data());
     ctx->h_meshes.assign(v->meshes, v->meshes + v->nmeshes);
     ctx->h_models.assign(v->models, v->models + nm);
 
@@ -269,12 +321,26 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
         CK(cudaMemcpyAsync(d_cells, cells.data(), cells.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(d_refs, v->refs, v->nrefs * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     }
+    size_t bytes = nm * (sizeof(InstanceTrace) + sizeof(InstanceShade)) + (size_t)nt * sizeof(TriRec) +
+                   (grid ? cells.size() * sizeof(int2) + (size_t)v->nrefs * sizeof(int) : 0);
+    ctx->h_inst = inst;
+    ctx->d_inst = d_inst; ctx->d_cull = d_cull; ctx->d_nodes = d_nodes; ctx->d_btris = d_btris; ctx->d_btid = d_btid;
+    ctx->have_bvh = false;
+    if (v->bvh_nodes && v->n_bvh_nodes > 0 && v->bvh_tri_id && v->bvh_mesh_root) {
+        if (v->n_bvh_tris != nt || v->n_bvh_roots != v->nmeshes) return fail(ctx, PTAP_E_INVALID, "upload_scene: prebuilt BVH does not match the triangle / mesh counts");
+        size_t bb = 0;
+        int rc = uploadBvh(ctx, reinterpret_cast<const BvhNode*>(v->bvh_nodes), v->n_bvh_nodes, v->bvh_tri_id, v->bvh_mesh_root, &bb);
+        if (rc) return rc;
+        bytes += bb;
+    }
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.scene_bytes = (int64_t)bytes;
     ctx->sc.inst = d_inst; ctx->sc.cull = d_cull; ctx->sc.shade = d_shade; ctx->sc.tris = d_tris;
     ctx->sc.cells = d_cells; ctx->sc.refs = d_refs; ctx->sc.nodes = d_nodes; ctx->sc.bvh_tris = d_btris; ctx->sc.bvh_tri_id = d_btid;
     ctx->sc.nmodels = nm; ctx->sc.gx = v->grid_dim[0]; ctx->sc.gy = v->grid_dim[1]; ctx->sc.gz = v->grid_dim[2];
-    ctx->have_scene = true; ctx->have_grid = grid; ctx->have_bvh = false; ctx->cache_valid = false;
-    ctx->accel = PTAP_ACCEL_GRID_COMPAT;
+    ctx->have_scene = true; ctx->have_grid = grid; ctx->cache_valid = false;
+    ctx->accel = grid ? PTAP_ACCEL_GRID_COMPAT : PTAP_ACCEL_BVH;
+    ctx->grid_trace = 0;
     return PTAP_OK;
 }
 
@@ -288,21 +354,10 @@ int ptap_build_accel(ptap_ctx* ctx, int kind)
     } else if (kind == PTAP_ACCEL_BVH) {
         if (!ctx->have_bvh) {
             BvhBuildResult res;
-            buildSceneBvh(ctx->h_tris, ctx->h_meshes, ctx->h_models, res);
-            const int nm = (int)ctx->h_models.size();
-            std::vector<InstanceTrace> inst(nm);
-            CK(cudaMemcpy(inst.data(), ctx->sc.inst, nm * sizeof(InstanceTrace), cudaMemcpyDeviceToHost));
-            for (int i = 0; i < nm; ++i) {
-                inst[i].grid.z = __builtin_bit_cast(float, res.mesh_root[ctx->h_models[i].mesh_index]);
-                inst[i].grid.w = 0.0f;
-            }
-            if (res.nodes.size() > (size_t)std::max<size_t>(ctx->h_tris.size(), 1) * 2) return fail(ctx, PTAP_E_NOMEM, "BVH larger than reserved");
-            CK(cudaMemcpy((void*)ctx->sc.inst, inst.data(), nm * sizeof(InstanceTrace), cudaMemcpyHostToDevice));
-            CK(cudaMemcpy((void*)ctx->sc.cull, res.cull.data(), nm * sizeof(InstanceCull), cudaMemcpyHostToDevice));
-            CK(cudaMemcpy((void*)ctx->sc.nodes, res.nodes.data(), res.nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
-            CK(cudaMemcpy((void*)ctx->sc.bvh_tris, res.tris.data(), res.tris.size() * sizeof(TriRec), cudaMemcpyHostToDevice));
-            CK(cudaMemcpy((void*)ctx->sc.bvh_tri_id, res.tri_id.data(), res.tri_id.size() * sizeof(int), cudaMemcpyHostToDevice));
-            ctx->have_bvh = true;
+            buildSceneBvh(ctx->h_tris.data(), (int)ctx->h_tris.size(), ctx->h_meshes.data(), (int)ctx->h_meshes.size(), res);
+            int rc = uploadBvh(ctx, res.nodes.data(), (int)res.nodes.size(), res.tri_id.data(), res.mesh_root.data(), nullptr);
+            if (rc) return rc;
+            CK(cudaStreamSynchronize(ctx->stream));
         }
     } else return fail(ctx, PTAP_E_INVALID, "build_accel: unknown kind %d", kind);
     ctx->accel = kind;
@@ -344,7 +399,7 @@ int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, u
         int occ = ctx->accel == PTAP_ACCEL_BVH ? traceBvhOccupancy() : traceGridOccupancy();
         ctx->grid_trace = ctx->sms * std::max(occ, 1);
     }
-    ctx->stats = PtapStats{};
+    { const int64_t sb = ctx->stats.scene_bytes; ctx->stats = PtapStats{}; ctx->stats.scene_bytes = sb; }
     return PTAP_OK;
 }
 
@@ -359,7 +414,7 @@ int ptap_render(ptap_ctx* ctx, int32_t iter_begin, int32_t iter_end)
     const bool cache = ctx->flags & PTAP_FLAG_FIRST_HIT_CACHE;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     launchSetIter(wv.st, iter_begin, ctx->stream);
-    int64_t launches = 1;
+    int64_t launches = 1, trace_launches = 0;
     for (int it = iter_begin; it < iter_end; ++it) {
         profMark(ctx, 0);
         launchGenerate(wv, ctx->grid_gen, ctx->stream); ++launches;
@@ -368,7 +423,7 @@ int ptap_render(ptap_ctx* ctx, int32_t iter_begin, int32_t iter_end)
             float4* hitbuf = (round == 0 && cache) ? wv.hit_cache : wv.hit;
             if (!(round == 0 && cache && ctx->cache_valid)) {                    // Renderer.cpp:594-620
                 profMark(ctx, 1);
-                launchTrace(ctx, wv.st, wv.O[in], wv.D[in], hitbuf, nullptr, nullptr, round, -1); ++launches;
+                launchTrace(ctx, wv.st, wv.O[in], wv.D[in], hitbuf, nullptr, nullptr, round, -1, (ctx->flags & PTAP_FLAG_COUNT) != 0); ++launches; ++trace_launches;
             }
             profMark(ctx, 2);
             launchShade(ctx->sc, wv, round, in, hitbuf, wv.depth - round, -1, 0, nullptr, ctx->grid_shade, ctx->stream); ++launches;
@@ -380,6 +435,7 @@ int ptap_render(ptap_ctx* ctx, int32_t iter_begin, int32_t iter_end)
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaGetLastError());
     ctx->stats.kernel_launches += launches;
+    ctx->stats.trace_launches = trace_launches;
     ctx->render_pending = true;
     return PTAP_OK;
 }
@@ -390,6 +446,40 @@ int ptap_sync(ptap_ctx* ctx)
     CK(cudaSetDevice(ctx->device));
     int rc = collect(ctx); if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
+    return PTAP_OK;
+}
+
+int ptap_frame_begin(ptap_ctx* ctx)
+{
+    if (!ctx || !ctx->have_frame) return fail(ctx, PTAP_E_STATE, "frame_begin: no render parameters");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
+    CK(cudaMemsetAsync(ctx->wv.film, 0, (size_t)ctx->wv.N * 3 * sizeof(float), ctx->stream));
+    CK(cudaMemsetAsync(ctx->wv.st, 0, sizeof(FrameState), ctx->stream));
+    ctx->cache_valid = false;
+    const int64_t sb = ctx->stats.scene_bytes;
+    ctx->stats = PtapStats{};
+    ctx->stats.scene_bytes = sb;
+    return PTAP_OK;
+}
+
+// Device timer on the context stream: bench.py brackets its timed region with these.
+int ptap_timer_start(ptap_ctx* ctx)
+{
+    if (!ctx) return PTAP_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->tm0) { CK(cudaEventCreate(&ctx->tm0)); CK(cudaEventCreate(&ctx->tm1)); }
+    CK(cudaEventRecord(ctx->tm0, ctx->stream));
+    return PTAP_OK;
+}
+
+int ptap_timer_stop(ptap_ctx* ctx, float* ms)
+{
+    if (!ctx || !ms || !ctx->tm0) return PTAP_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->tm1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->tm1));
+    CK(cudaEventElapsedTime(ms, ctx->tm0, ctx->tm1));
     return PTAP_OK;
 }
 

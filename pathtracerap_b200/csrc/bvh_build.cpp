@@ -7,6 +7,7 @@
 // mesh extent.  With exact bounds a BVH silently drops the hits the reference finds in the tolerance band
 // (SURVEY.md 0.5 third hazard / hard part 2).
 #include "bvh_build.h"
+#include "host_math.h"
 
 #include <algorithm>
 #include <cfloat>
@@ -113,18 +114,30 @@ struct Builder {
 
 }  // namespace
 
-void buildSceneBvh(const std::vector<TriRec>& tris, const std::vector<PtapMesh>& meshes, const std::vector<PtapModel>& models,
-                   BvhBuildResult& out)
+void makeTriRecs(const PtapVertex* vertices, const PtapTriangle* triangles, int ntris, TriRec* out)
 {
-    out.nodes.clear(); out.tris.clear(); out.tri_id.clear(); out.cull.clear();
-    out.mesh_root.assign(meshes.size(), -1);
+    for (int t = 0; t < ntris; ++t) {
+        const PtapVertex& a = vertices[triangles[t].v[0]];
+        const PtapVertex& b = vertices[triangles[t].v[1]];
+        const PtapVertex& c = vertices[triangles[t].v[2]];
+        const hm::V3 v0 = hm::v3(a.position);
+        const hm::V3 e1 = hm::sub(hm::v3(b.position), v0), e2 = hm::sub(hm::v3(c.position), v0);     // Renderer.cpp:183-184
+        const hm::V3 n = hm::normalize(hm::scale(hm::add(hm::add(hm::v3(a.normal), hm::v3(b.normal)), hm::v3(c.normal)), 1 / 3.0f));   // :203
+        out[t].v0 = make_float4(v0.x, v0.y, v0.z, n.x);
+        out[t].e1 = make_float4(e1.x, e1.y, e1.z, n.y);
+        out[t].e2 = make_float4(e2.x, e2.y, e2.z, n.z);
+    }
+}
+
+void buildSceneBvh(const TriRec* tris, int ntris, const PtapMesh* meshes, int nmeshes, BvhBuildResult& out)
+{
+    out.nodes.clear(); out.tri_id.clear();
+    out.mesh_root.assign(nmeshes, -1);
     out.max_depth = 0;
-    std::vector<Box> mesh_box(meshes.size());
-    for (size_t mi = 0; mi < meshes.size(); ++mi) {
+    for (int mi = 0; mi < nmeshes; ++mi) {
         const PtapMesh& mesh = meshes[mi];
-        mesh_box[mi].reset();
         const int t0 = mesh.t_start, t1 = mesh.t_end;
-        if (t1 <= t0 || t0 < 0 || t1 > (int)tris.size()) continue;
+        if (t1 <= t0 || t0 < 0 || t1 > ntris) continue;
         // extent of the mesh for the floating-point slack
         double ext = 0;
         for (int t = t0; t < t1; ++t) {
@@ -166,30 +179,7 @@ void buildSceneBvh(const std::vector<TriRec>& tris, const std::vector<PtapMesh>&
         }
         out.mesh_root[mi] = root;
         out.max_depth = std::max(out.max_depth, b.max_depth);
-        mesh_box[mi] = bounds;
-        for (int id : order) { out.tri_id.push_back(id); out.tris.push_back(tris[id]); }
-    }
-    // world-space cull boxes: the 8 corners of the (already fattened) mesh bounds through model_to_world, padded
-    out.cull.resize(models.size());
-    for (size_t i = 0; i < models.size(); ++i) {
-        const PtapModel& m = models[i];
-        const Box& mb = mesh_box[m.mesh_index];
-        Box wb; wb.reset();
-        if (out.mesh_root[m.mesh_index] >= 0) {
-            for (int c = 0; c < 8; ++c) {
-                const double p[3] = {(c & 1) ? mb.hi[0] : mb.lo[0], (c & 2) ? mb.hi[1] : mb.lo[1], (c & 4) ? mb.hi[2] : mb.lo[2]};
-                float w[3];
-                for (int r = 0; r < 3; ++r)
-                    w[r] = (float)(m.model_to_world[0 + r] * p[0] + m.model_to_world[4 + r] * p[1] + m.model_to_world[8 + r] * p[2] + m.model_to_world[12 + r]);
-                wb.grow(w);
-            }
-            double ext = 0;
-            for (int k = 0; k < 3; ++k) ext = std::max(ext, std::max(std::fabs((double)wb.lo[k]), std::fabs((double)wb.hi[k])));
-            const float pad = (float)(ext * 1e-4 + 1e-3);
-            for (int k = 0; k < 3; ++k) { wb.lo[k] -= pad; wb.hi[k] += pad; }
-        }
-        out.cull[i].lo = make_float4(wb.lo[0], wb.lo[1], wb.lo[2], 0.f);
-        out.cull[i].hi = make_float4(wb.hi[0], wb.hi[1], wb.hi[2], 0.f);
+        for (int id : order) out.tri_id.push_back(id);
     }
 }
 

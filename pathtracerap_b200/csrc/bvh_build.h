@@ -10,15 +10,14 @@ namespace ptap {
 
 struct BvhBuildResult {
     std::vector<BvhNode> nodes;      // all BLASes back to back
-    std::vector<TriRec> tris;        // triangles in leaf order (all meshes)
     std::vector<int> tri_id;         // leaf-order position -> global triangle id
     std::vector<int> mesh_root;      // per mesh: index of its BLAS root node, -1 if the mesh has no triangles
-    std::vector<InstanceCull> cull;  // per model: conservative world bounds
     int max_depth = 0;
 };
 
-// tris: global triangle table as uploaded (v0, e1, e2 in .xyz).  One BLAS per mesh over [t_start, t_end).
-void buildSceneBvh(const std::vector<TriRec>& tris, const std::vector<PtapMesh>& meshes, const std::vector<PtapModel>& models,
-                   BvhBuildResult& out);
+// tris: global triangle table (v0, e1, e2 in .xyz).  One BLAS per mesh over [t_start, t_end).
+void buildSceneBvh(const TriRec* tris, int ntris, const PtapMesh* meshes, int nmeshes, BvhBuildResult& out);
+// (v0, e1 = v1 - v0, e2 = v2 - v0, flat normal in .w lanes) with the reference's arithmetic (Renderer.cpp:183-184, 203)
+void makeTriRecs(const PtapVertex* vertices, const PtapTriangle* triangles, int ntris, TriRec* out);
 
 }  // namespace ptap

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../../include/ptap.h"
+#include "bvh_build.h"
 
 namespace {
 
@@ -38,6 +39,9 @@ struct ptap_scene {
     int32_t grid_dim[3] = {25, 25, 25};
     // Config.txt extensions (not part of the reference's Scene)
     int32_t cfg_width = 0, cfg_height = 0, cfg_iter = 0, cfg_depth = 0;
+    // optional BVH (ptap_scene_build_bvh); invalidated by any mesh edit
+    ptap::BvhBuildResult bvh;
+    bool have_bvh = false;
     std::string err;
 };
 
@@ -157,6 +161,7 @@ int appendMesh(ptap_scene* s, const PtapVertex* verts, int nverts, const int32_t
     }
     mesh.t_end = (int)s->triangles.size();
     s->meshes.push_back(mesh);
+    s->have_bvh = false;
     return (int)s->meshes.size() - 1;
 }
 
@@ -672,9 +677,26 @@ int ptap_scene_create_from_view(const PtapSceneView* v, ptap_scene** out)
     return PTAP_OK;
 }
 
+int ptap_scene_build_bvh(ptap_scene* s)
+{
+    if (!s || s->triangles.empty()) return PTAP_E_INVALID;
+    std::vector<ptap::TriRec> recs(s->triangles.size());
+    ptap::makeTriRecs(s->vertices.data(), s->triangles.data(), (int)s->triangles.size(), recs.data());
+    ptap::buildSceneBvh(recs.data(), (int)recs.size(), s->meshes.data(), (int)s->meshes.size(), s->bvh);
+    s->have_bvh = true;
+    return PTAP_OK;
+}
+
 int ptap_scene_view(const ptap_scene* s, PtapSceneView* out)
 {
     if (!s || !out) return PTAP_E_INVALID;
+    static_assert(sizeof(PtapBvhNode) == sizeof(ptap::BvhNode), "public and device BVH node layouts must agree");
+    out->bvh_nodes = nullptr; out->n_bvh_nodes = 0; out->bvh_tri_id = nullptr; out->n_bvh_tris = 0; out->bvh_mesh_root = nullptr; out->n_bvh_roots = 0;
+    if (s->have_bvh) {
+        out->bvh_nodes = reinterpret_cast<const PtapBvhNode*>(s->bvh.nodes.data()); out->n_bvh_nodes = (int)s->bvh.nodes.size();
+        out->bvh_tri_id = s->bvh.tri_id.data(); out->n_bvh_tris = (int)s->bvh.tri_id.size();
+        out->bvh_mesh_root = s->bvh.mesh_root.data(); out->n_bvh_roots = (int)s->bvh.mesh_root.size();
+    }
     out->models = s->models.data(); out->nmodels = (int)s->models.size();
     out->meshes = s->meshes.data(); out->nmeshes = (int)s->meshes.size();
     out->vertices = s->vertices.data(); out->nvertices = (int)s->vertices.size();

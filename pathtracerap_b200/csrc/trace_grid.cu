@@ -133,6 +133,7 @@ k_trace_grid(SceneDev sc, const float4* __restrict__ O, const float4* __restrict
 {
     const int n = n_fixed >= 0 ? n_fixed : st->n_active[round];
     if (blockIdx.x == 0 && threadIdx.x == 0 && n_fixed < 0) st->rays_traced += (unsigned long long)n;
+    unsigned long long tot_x = 0, tot_y = 0, tot_z = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const float4 o4 = O[i], d4 = D[i];
         const V3 bo = v3(o4), bd = v3(d4);
@@ -164,15 +165,24 @@ k_trace_grid(SceneDev sc, const float4* __restrict__ O, const float4* __restrict
         }
         const bool found = g_dist < kFloatMax;                                   // Renderer.cpp:402-408
         hit[i] = make_float4(found ? g_dist : last_dist, __int_as_float(found ? g_tri : -1), __int_as_float(found ? g_model : -1), g_t);
-        if (UV) uv[i] = make_float2(g_u, g_v);
-        if (COUNT) counts[i] = cnt;
+        if (UV && uv) uv[i] = make_float2(g_u, g_v);
+        if (COUNT) { if (counts) counts[i] = cnt; tot_x += cnt.x; tot_y += cnt.y; tot_z += cnt.z; }
+    }
+    if (COUNT) {        // counting build: per-warp totals into the frame state (never used for timing)
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            tot_x += __shfl_xor_sync(0xffffffffu, tot_x, d); tot_y += __shfl_xor_sync(0xffffffffu, tot_y, d); tot_z += __shfl_xor_sync(0xffffffffu, tot_z, d);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&st->count_cells, tot_x); atomicAdd(&st->count_refs, tot_y); atomicAdd(&st->count_tris, tot_z);
+        }
     }
 }
 
-void launchTraceGrid(const SceneDev& sc, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts,
+void launchTraceGrid(const SceneDev& sc, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, bool count_totals,
                      FrameState* st, int round, int n_fixed, int grid, cudaStream_t stream)
 {
-    if (counts) k_trace_grid<true, true><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed);
+    if (counts || count_totals) k_trace_grid<true, true><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed);
     else if (uv) k_trace_grid<true, false><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed);
     else k_trace_grid<false, false><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed);
 }

@@ -60,9 +60,9 @@ class Renderer:
         self.accel = accel
         self._check(N.lib().ptap_build_accel(self.h, accel), "build_accel")
 
-    def set_params(self, width, height, depth, first_hit_cache=True, profile=False):
+    def set_params(self, width, height, depth, first_hit_cache=True, profile=False, count=False):
         self.W, self.H, self.depth = width, height, depth
-        self.flags = (N.FLAG_FIRST_HIT_CACHE if first_hit_cache else 0) | (N.FLAG_PROFILE if profile else 0)
+        self.flags = (N.FLAG_FIRST_HIT_CACHE if first_hit_cache else 0) | (N.FLAG_PROFILE if profile else 0) | (N.FLAG_COUNT if count else 0)
         self._check(N.lib().ptap_set_render_params(self.h, width, height, depth, self.flags), "set_render_params")
         self._iters_done = 0
 
@@ -73,6 +73,25 @@ class Renderer:
 
     def sync(self):
         self._check(N.lib().ptap_sync(self.h), "sync")
+
+    def upload(self, scene: Scene):
+        """ptap_upload_scene only (host -> device copy of the scene arrays, including a prebuilt BVH when the scene has one)."""
+        v = scene.view()
+        self._check(N.lib().ptap_upload_scene(self.h, C.byref(v)), "upload_scene")
+        self._check(N.lib().ptap_build_accel(self.h, self.accel), "build_accel")
+
+    def frame_begin(self):
+        """Start of a renderLoop: zero film, forget the first-hit cache, zero the counters."""
+        self._check(N.lib().ptap_frame_begin(self.h), "frame_begin")
+        self._iters_done = 0
+
+    def timer_start(self):
+        self._check(N.lib().ptap_timer_start(self.h), "timer_start")
+
+    def timer_stop(self) -> float:
+        ms = C.c_float(0)
+        self._check(N.lib().ptap_timer_stop(self.h, C.byref(ms)), "timer_stop")
+        return ms.value
 
     def film_reset(self):
         self._check(N.lib().ptap_film_reset(self.h), "film_reset")

@@ -111,6 +111,10 @@ class Scene:
     def build_grids(self, gx=25, gy=25, gz=25):
         self._check(N.lib().ptap_scene_build_grids(self.h, gx, gy, gz), "build_grids")
 
+    def build_bvh(self):
+        """One BVH per mesh, built on the host as part of scene construction (like addMeshesToGrid for the grid)."""
+        self._check(N.lib().ptap_scene_build_bvh(self.h), "build_bvh")
+
     # -- the seven public vectors (Scene.h:26-32) as numpy copies -----------------------------------------------
     def view(self) -> N.SceneView:
         v = N.SceneView()
