@@ -2,7 +2,7 @@
  *
  * The reference (purvakulkarni15/PathTracerAP) has no FFI: its boundary is the C++ surface
  * main.cpp:8-22 uses (Scene.h:21-39, Renderer.h:46-55, GPUMemoryPool.h:10-46).  Every entry
- * point below names the reference interface it replaces; include/PathTracerAP/*.h wraps
+ * point below names the reference interface it replaces; the headers under include/PathTracerAP/ wrap
  * this ABI back into those C++ classes so that the reference's main.cpp compiles unchanged
  * (INTEGRATION.md).
  *

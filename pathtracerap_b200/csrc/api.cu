@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -65,12 +66,13 @@ struct ptap_ctx {
     std::vector<PtapMesh> h_meshes;
     std::vector<PtapModel> h_models;
     std::vector<InstanceTrace> h_inst;
-    InstanceTrace* d_inst = nullptr; InstanceCull* d_cull = nullptr; BvhNode* d_nodes = nullptr; TriRec* d_btris = nullptr; int* d_btid = nullptr;
+    InstanceTrace* d_inst = nullptr; BvhNode* d_nodes = nullptr; size_t nodes_cap = 0; TriRec* d_btris = nullptr; int* d_btid = nullptr;
     bool have_scene = false, have_grid = false, have_bvh = false, have_frame = false;
     int accel = PTAP_ACCEL_GRID_COMPAT;
     uint32_t flags = 0;
     bool cache_valid = false;
     int grid_trace = 0, grid_shade = 0, grid_gen = 0;
+    int trace_ctas = 0;              // PTAP_TRACE_CTAS: CTAs per SM of the closest-hit kernels (0 = occupancy query)
     PtapStats stats{};
     bool render_pending = false;
     std::string err;
@@ -111,6 +113,13 @@ void profMark(ptap_ctx* c, int kind)
     cudaEventRecord(c->prof_events[c->prof_used++], c->stream);
 }
 
+int traceGridSize(ptap_ctx* c)
+{
+    int occ = c->accel == PTAP_ACCEL_BVH ? traceBvhOccupancy() : traceGridOccupancy();
+    if (c->trace_ctas > 0) occ = std::min(occ, c->trace_ctas);
+    return c->sms * std::max(occ, 1);
+}
+
 int collect(ptap_ctx* ctx)
 {
     if (!ctx->render_pending) return PTAP_OK;
@@ -138,8 +147,63 @@ int collect(ptap_ctx* ctx)
     return PTAP_OK;
 }
 
+// 3x3 inverse in double (host, upload time only)
+bool invert3(const double m[9], double out[9])
+{
+    const double c0 = m[4] * m[8] - m[5] * m[7], c1 = m[5] * m[6] - m[3] * m[8], c2 = m[3] * m[7] - m[4] * m[6];
+    const double det = m[0] * c0 + m[1] * c1 + m[2] * c2;
+    if (!(std::fabs(det) > 1e-300)) return false;
+    const double id = 1.0 / det;
+    out[0] = c0 * id; out[1] = (m[2] * m[7] - m[1] * m[8]) * id; out[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+    out[3] = c1 * id; out[4] = (m[0] * m[8] - m[2] * m[6]) * id; out[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+    out[6] = c2 * id; out[7] = (m[1] * m[6] - m[0] * m[7]) * id; out[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+    return true;
+}
+
+struct TlasItem { float lo[3], hi[3]; int inst; };
+
+float boxArea(const float* lo, const float* hi)
+{
+    const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+    return 2.f * (dx * dy + dy * dz + dz * dx);
+}
+
+// Median-split BVH2 over the instances' world boxes; leaves are single instances (link ~(0x20000000 | model)).
+int buildTlas(std::vector<TlasItem>& items, int b, int e, std::vector<BvhNode>& nodes, int base, float* lo, float* hi, int depth, int& max_depth)
+{
+    max_depth = std::max(max_depth, depth);
+    for (int k = 0; k < 3; ++k) { lo[k] = 3e38f; hi[k] = -3e38f; }
+    for (int i = b; i < e; ++i)
+        for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], items[i].lo[k]); hi[k] = std::max(hi[k], items[i].hi[k]); }
+    if (e - b == 1) return ~(0x20000000 | items[b].inst);
+    int axis = 0; float best = -1.f;
+    for (int k = 0; k < 3; ++k) {
+        float cmin = 3e38f, cmax = -3e38f;
+        for (int i = b; i < e; ++i) { const float c = items[i].lo[k] + items[i].hi[k]; cmin = std::min(cmin, c); cmax = std::max(cmax, c); }
+        if (cmax - cmin > best) { best = cmax - cmin; axis = k; }
+    }
+    const int mid = (b + e) / 2;
+    std::nth_element(items.begin() + b, items.begin() + mid, items.begin() + e,
+                     [axis](const TlasItem& x, const TlasItem& y) { return x.lo[axis] + x.hi[axis] < y.lo[axis] + y.hi[axis]; });
+    const int me = (int)nodes.size();
+    nodes.emplace_back();
+    float l0[3], h0[3], l1[3], h1[3];
+    int c0 = buildTlas(items, b, mid, nodes, base, l0, h0, depth + 1, max_depth);
+    int c1 = buildTlas(items, mid, e, nodes, base, l1, h1, depth + 1, max_depth);
+    if (boxArea(l1, h1) < boxArea(l0, h0)) {          // equal entry distances (origin inside both): visit the smaller box first
+        std::swap(c0, c1);
+        for (int k = 0; k < 3; ++k) { std::swap(l0[k], l1[k]); std::swap(h0[k], h1[k]); }
+    }
+    BvhNode& nd = nodes[me];
+    nd.xy0 = make_float4(l0[0], h0[0], l0[1], h0[1]);
+    nd.xy1 = make_float4(l1[0], h1[0], l1[1], h1[1]);
+    nd.z01 = make_float4(l0[2], h0[2], l1[2], h1[2]);
+    nd.link = make_int4(c0, c1, 0, 0);
+    return base + me;
+}
+
 // Copies a BVH (nodes, leaf order) into the scene arena, gathers the leaf-ordered triangle records, points every model at
-// its mesh's root and derives the world-space cull boxes from the root node's child bounds.
+// its mesh's root, derives the instances' world boxes from the BLAS root bounds and builds the TLAS over them.
 int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id, const int* mesh_root, size_t* bytes)
 {
     const int nt = (int)ctx->h_tris.size(), nm = (int)ctx->h_models.size();
@@ -148,46 +212,103 @@ int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id
         for (int k = 0; k < 2; ++k) {
             const int l = k ? nodes[i].link.y : nodes[i].link.x;
             if (l >= nnodes) return fail(ctx, PTAP_E_INVALID, "BVH node %d: child index out of range", i);
-            if (l < 0) { const int code = ~l, first = code >> 3, cnt = (code & 7) + 1; if (first < 0 || first + cnt > nt) return fail(ctx, PTAP_E_INVALID, "BVH node %d: leaf range out of bounds", i); }
+            if (l < 0) { const int code = ~l, first = code >> 3, cnt = (code & 7) + 1; if (code >= 0x20000000 || first < 0 || first + cnt > nt) return fail(ctx, PTAP_E_INVALID, "BVH node %d: leaf range out of bounds", i); }
         }
     std::vector<TriRec> btris(nt);
     for (int k = 0; k < nt; ++k) {
         if (tri_id[k] < 0 || tri_id[k] >= nt) return fail(ctx, PTAP_E_INVALID, "BVH leaf order entry %d out of range", k);
         btris[k] = ctx->h_tris[tri_id[k]];
     }
-    std::vector<InstanceCull> cull(nm);
+    // depth of every BLAS (the traversal stack is fixed-size)
+    int blas_depth = 0;
+    {
+        std::vector<std::pair<int, int>> todo;
+        std::vector<char> seen(nnodes, 0);
+        for (size_t m = 0; m < ctx->h_meshes.size(); ++m) if (mesh_root[m] >= 0) todo.push_back({mesh_root[m], 1});
+        while (!todo.empty()) {
+            const auto [node, d] = todo.back(); todo.pop_back();
+            if (seen[node]) { if (d > 1) return fail(ctx, PTAP_E_INVALID, "BVH node %d is reachable twice", node); continue; }
+            seen[node] = 1;
+            blas_depth = std::max(blas_depth, d);
+            if (nodes[node].link.x >= 0) todo.push_back({nodes[node].link.x, d + 1});
+            if (nodes[node].link.y >= 0 && nodes[node].link.y != nodes[node].link.x) todo.push_back({nodes[node].link.y, d + 1});
+        }
+    }
+    std::vector<TlasItem> items;
+    double max_scale = 0.0, max_pad = 0.0, max_trans = 1.0;
+    bool consistent = true;
     for (int i = 0; i < nm; ++i) {
         const PtapModel& m = ctx->h_models[i];
         const int root = mesh_root[m.mesh_index];
         if (root >= nnodes) return fail(ctx, PTAP_E_INVALID, "mesh %d: BVH root out of range", m.mesh_index);
         ctx->h_inst[i].grid.z = __builtin_bit_cast(float, root);
-        float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
-        if (root >= 0) {
-            const BvhNode& r = nodes[root];
-            const float blo[2][3] = {{r.xy0.x, r.xy0.z, r.z01.x}, {r.xy1.x, r.xy1.z, r.z01.z}}, bhi[2][3] = {{r.xy0.y, r.xy0.w, r.z01.y}, {r.xy1.y, r.xy1.w, r.z01.w}};
-            float mlo[3], mhi[3];
-            for (int k = 0; k < 3; ++k) { mlo[k] = std::min(blo[0][k], blo[1][k] > bhi[1][k] ? blo[0][k] : blo[1][k]); mhi[k] = std::max(bhi[0][k], blo[1][k] > bhi[1][k] ? bhi[0][k] : bhi[1][k]); }
-            for (int c = 0; c < 8; ++c) {
-                const double p[3] = {(c & 1) ? mhi[0] : mlo[0], (c & 2) ? mhi[1] : mlo[1], (c & 4) ? mhi[2] : mlo[2]};
-                for (int rr = 0; rr < 3; ++rr) {
-                    const float w = (float)(m.model_to_world[0 + rr] * p[0] + m.model_to_world[4 + rr] * p[1] + m.model_to_world[8 + rr] * p[2] + m.model_to_world[12 + rr]);
-                    lo[rr] = std::min(lo[rr], w); hi[rr] = std::max(hi[rr], w);
-                }
+        if (root < 0) continue;
+        // The kernel maps a world ray into model space with world_to_model (Renderer.cpp:381-382), so the world box of an instance is
+        // the image of the BLAS root bounds under the INVERSE of world_to_model (= model_to_world when the two are consistent).
+        const float* W = m.world_to_model; const float* M = m.model_to_world;
+        const double w3[9] = {W[0], W[4], W[8], W[1], W[5], W[9], W[2], W[6], W[10]};     // row-major 3x3
+        double wi[9];
+        if (!invert3(w3, wi)) return fail(ctx, PTAP_E_INVALID, "model %d: world_to_model is singular", i);
+        for (int r = 0; r < 3 && consistent; ++r)
+            for (int c = 0; c < 4; ++c) {          // (M * W)[r][c] against the identity
+                const double scale = c == 3 ? std::max(1.0, std::fabs((double)M[12 + r])) : 1.0;
+                if (c == 3) max_trans = std::max(max_trans, scale);
+                const double v = (double)M[0 + r] * W[4 * c + 0] + (double)M[4 + r] * W[4 * c + 1] + (double)M[8 + r] * W[4 * c + 2] + (c == 3 ? (double)M[12 + r] : 0.0);
+                if (!(std::fabs(v - (r == c ? 1.0 : 0.0)) <= 2e-5 * scale)) { consistent = false; break; }
             }
-            float ext = 0.f;
-            for (int k = 0; k < 3; ++k) ext = std::max(ext, std::max(std::fabs(lo[k]), std::fabs(hi[k])));
-            const float pad = ext * 1e-4f + 1e-3f;
-            for (int k = 0; k < 3; ++k) { lo[k] -= pad; hi[k] += pad; }
+        const BvhNode& r = nodes[root];
+        const bool one = r.link.x == r.link.y;      // single-leaf mesh: the second child is a dummy
+        const float blo[2][3] = {{r.xy0.x, r.xy0.z, r.z01.x}, {r.xy1.x, r.xy1.z, r.z01.z}}, bhi[2][3] = {{r.xy0.y, r.xy0.w, r.z01.y}, {r.xy1.y, r.xy1.w, r.z01.w}};
+        float mlo[3], mhi[3];
+        for (int k = 0; k < 3; ++k) { mlo[k] = one ? blo[0][k] : std::min(blo[0][k], blo[1][k]); mhi[k] = one ? bhi[0][k] : std::max(bhi[0][k], bhi[1][k]); }
+        TlasItem it; it.inst = i;
+        for (int k = 0; k < 3; ++k) { it.lo[k] = 3e38f; it.hi[k] = -3e38f; }
+        double ext = 0.0;
+        for (int c = 0; c < 8; ++c) {
+            const double p[3] = {((c & 1) ? mhi[0] : mlo[0]) - (double)W[12], ((c & 2) ? mhi[1] : mlo[1]) - (double)W[13], ((c & 4) ? mhi[2] : mlo[2]) - (double)W[14]};
+            for (int rr = 0; rr < 3; ++rr) {
+                const double w = wi[3 * rr] * p[0] + wi[3 * rr + 1] * p[1] + wi[3 * rr + 2] * p[2];
+                it.lo[rr] = std::min(it.lo[rr], (float)w); it.hi[rr] = std::max(it.hi[rr], (float)w);
+                ext = std::max(ext, std::fabs(w));
+            }
         }
-        cull[i].lo = make_float4(lo[0], lo[1], lo[2], 0.f); cull[i].hi = make_float4(hi[0], hi[1], hi[2], 0.f);
+        const float pad = (float)(ext * 1e-4 + 1e-3);
+        for (int k = 0; k < 3; ++k) { it.lo[k] -= pad; it.hi[k] += pad; }
+        items.push_back(it);
+        double fro = 0.0;
+        for (double v : wi) fro += v * v;
+        max_scale = std::max(max_scale, std::sqrt(fro));
+        max_pad = std::max(max_pad, (double)pad);
     }
+    std::vector<BvhNode> tlas;
+    int tlas_root = -1, tlas_depth = 0;
+    if (!items.empty()) {
+        float lo[3], hi[3];
+        const int link = buildTlas(items, 0, (int)items.size(), tlas, nnodes, lo, hi, 1, tlas_depth);
+        if (link < 0) {                                   // a single instance: root with a second child that is never entered
+            BvhNode nd;
+            nd.xy0 = make_float4(lo[0], hi[0], lo[1], hi[1]);
+            nd.xy1 = make_float4(1e15f, 1e15f, 1e15f, 1e15f);
+            nd.z01 = make_float4(lo[2], hi[2], 1e15f, 1e15f);
+            nd.link = make_int4(link, link, 0, 0);
+            tlas.push_back(nd);
+            tlas_root = nnodes;
+        } else tlas_root = link;
+    }
+    if (blas_depth + tlas_depth + 4 > kBvhStack) return fail(ctx, PTAP_E_INVALID, "BVH too deep for the traversal stack (%d + %d levels, %d entries)", blas_depth, tlas_depth, kBvhStack);
+    if (nnodes + tlas.size() > ctx->nodes_cap) return fail(ctx, PTAP_E_NOMEM, "BVH node storage exhausted");
     CK(cudaMemcpyAsync(ctx->d_inst, ctx->h_inst.data(), nm * sizeof(InstanceTrace), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_cull, cull.data(), nm * sizeof(InstanceCull), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_nodes, nodes, (size_t)nnodes * sizeof(BvhNode), cudaMemcpyHostToDevice, ctx->stream));
+    if (!tlas.empty()) CK(cudaMemcpyAsync(ctx->d_nodes + nnodes, tlas.data(), tlas.size() * sizeof(BvhNode), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_btris, btris.data(), (size_t)nt * sizeof(TriRec), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_btid, tri_id, (size_t)nt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));      // btris / cull are stack-owned
-    if (bytes) *bytes = nm * (sizeof(InstanceTrace) + sizeof(InstanceCull)) + (size_t)nnodes * sizeof(BvhNode) + (size_t)nt * (sizeof(TriRec) + sizeof(int));
+    CK(cudaStreamSynchronize(ctx->stream));      // btris / tlas are stack-owned
+    if (bytes) *bytes = nm * sizeof(InstanceTrace) + ((size_t)nnodes + tlas.size()) * sizeof(BvhNode) + (size_t)nt * (sizeof(TriRec) + sizeof(int));
+    ctx->sc.tlas_root = tlas_root;
+    ctx->sc.tmin_world = -(float)((kEpsilon + 2e-4) * max_scale * 1.001 + max_pad + 1e-3);
+    ctx->sc.prune = consistent ? 1.0001f : INFINITY;
+    // residual of matrices that passed the check: |(M W - I) [o; 1]| <= 2e-5 * sqrt(3) * (|o|_1 + max |translation|); the kernel adds 1e-4 |o|_1
+    ctx->sc.c_pad = (float)(4e-5 * max_trans + 1e-3);
     ctx->have_bvh = true;
     return PTAP_OK;
 }
@@ -212,6 +333,12 @@ int ptap_create(int device, size_t arena_bytes, ptap_ctx** out)
         delete ctx; return PTAP_E_NO_DEVICE;
     }
     cudaEventCreate(&ctx->ev0); cudaEventCreate(&ctx->ev1);
+    auto envInt = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
+    ctx->sc.vote_tri = std::min(32, std::max(1, envInt("PTAP_VOTE_TRI", kVoteTri)));       // tuning knobs, see tools/tune_trace.py
+    ctx->sc.vote_inst = std::min(32, std::max(1, envInt("PTAP_VOTE_INST", kVoteInst)));
+    ctx->sc.vote_refill = std::min(32, std::max(1, envInt("PTAP_VOTE_REFILL", kVoteRefill)));
+    ctx->sc.batch = std::max(1, envInt("PTAP_BATCH", kTraceBatch));
+    ctx->trace_ctas = std::max(0, envInt("PTAP_TRACE_CTAS", 0));
     if (arena_bytes) {                                          // caller-sized arena: split 1/4 scene, 3/4 frame
         if (ctx->scene_arena.reserve(arena_bytes / 4) != cudaSuccess || ctx->frame_arena.reserve(arena_bytes - arena_bytes / 4) != cudaSuccess) {
             ptap_destroy(ctx); return PTAP_E_NOMEM;
@@ -298,22 +425,22 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
             if (v->refs[i] < 0 || v->refs[i] >= nt) return fail(ctx, PTAP_E_INVALID, "ref %d: triangle index out of range", i);
     }
 
-    // ---- one arena for everything scene-lifetime; BVH storage is reserved up front (2T-1 nodes bound)
-    size_t need = Arena::need(nm, sizeof(InstanceTrace)) + Arena::need(nm, sizeof(InstanceCull)) + Arena::need(nm, sizeof(InstanceShade)) +
-                  Arena::need(nt, sizeof(TriRec)) * 2 + Arena::need(nt, sizeof(int)) + Arena::need((size_t)std::max(nt, 1) * 2, sizeof(BvhNode)) +
+    // ---- one arena for everything scene-lifetime; BVH storage is reserved up front (2T-1 BLAS nodes + 2M TLAS nodes bound)
+    const size_t nodes_cap = (size_t)std::max(nt, 1) * 2 + (size_t)nm * 2 + 2;
+    size_t need = Arena::need(nm, sizeof(InstanceTrace)) + Arena::need(nm, sizeof(InstanceShade)) +
+                  Arena::need(nt, sizeof(TriRec)) * 2 + Arena::need(nt, sizeof(int)) + Arena::need(nodes_cap, sizeof(BvhNode)) +
                   (grid ? Arena::need(v->nvoxels, sizeof(int2)) + Arena::need(v->nrefs, sizeof(int)) : 0) + 4096;
     if (need > ctx->scene_arena.cap) CK(ctx->scene_arena.reserve(need)); else ctx->scene_arena.used = 0;
     Arena& A = ctx->scene_arena;
     InstanceTrace* d_inst = A.alloc<InstanceTrace>(nm);
-    InstanceCull* d_cull = A.alloc<InstanceCull>(nm);
     InstanceShade* d_shade = A.alloc<InstanceShade>(nm);
     TriRec* d_tris = A.alloc<TriRec>(nt);
     TriRec* d_btris = A.alloc<TriRec>(nt);
     int* d_btid = A.alloc<int>(nt);
-    BvhNode* d_nodes = A.alloc<BvhNode>((size_t)std::max(nt, 1) * 2);
+    BvhNode* d_nodes = A.alloc<BvhNode>(nodes_cap);
     int2* d_cells = grid ? A.alloc<int2>(v->nvoxels) : nullptr;
     int* d_refs = grid ? A.alloc<int>(v->nrefs) : nullptr;
-    if (!d_inst || !d_cull || !d_shade || !d_tris || !d_btris || !d_btid || !d_nodes || (grid && (!d_cells || !d_refs))) return fail(ctx, PTAP_E_NOMEM, "scene arena exhausted");
+    if (!d_inst || !d_shade || !d_tris || !d_btris || !d_btid || !d_nodes || (grid && (!d_cells || !d_refs))) return fail(ctx, PTAP_E_NOMEM, "scene arena exhausted");
     CK(cudaMemcpyAsync(d_inst, inst.data(), nm * sizeof(InstanceTrace), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_shade, shade.data(), nm * sizeof(InstanceShade), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_tris, ctx->h_tris.data(), nt * sizeof(TriRec), cudaMemcpyHostToDevice, ctx->stream));
@@ -324,7 +451,7 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
     size_t bytes = nm * (sizeof(InstanceTrace) + sizeof(InstanceShade)) + (size_t)nt * sizeof(TriRec) +
                    (grid ? cells.size() * sizeof(int2) + (size_t)v->nrefs * sizeof(int) : 0);
     ctx->h_inst = inst;
-    ctx->d_inst = d_inst; ctx->d_cull = d_cull; ctx->d_nodes = d_nodes; ctx->d_btris = d_btris; ctx->d_btid = d_btid;
+    ctx->d_inst = d_inst; ctx->d_nodes = d_nodes; ctx->nodes_cap = nodes_cap; ctx->d_btris = d_btris; ctx->d_btid = d_btid;
     ctx->have_bvh = false;
     if (v->bvh_nodes && v->n_bvh_nodes > 0 && v->bvh_tri_id && v->bvh_mesh_root) {
         if (v->n_bvh_tris != nt || v->n_bvh_roots != v->nmeshes) return fail(ctx, PTAP_E_INVALID, "upload_scene: prebuilt BVH does not match the triangle / mesh counts");
@@ -335,7 +462,7 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
     }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stats.scene_bytes = (int64_t)bytes;
-    ctx->sc.inst = d_inst; ctx->sc.cull = d_cull; ctx->sc.shade = d_shade; ctx->sc.tris = d_tris;
+    ctx->sc.inst = d_inst; ctx->sc.cull = nullptr; ctx->sc.shade = d_shade; ctx->sc.tris = d_tris;
     ctx->sc.cells = d_cells; ctx->sc.refs = d_refs; ctx->sc.nodes = d_nodes; ctx->sc.bvh_tris = d_btris; ctx->sc.bvh_tri_id = d_btid;
     ctx->sc.nmodels = nm; ctx->sc.gx = v->grid_dim[0]; ctx->sc.gy = v->grid_dim[1]; ctx->sc.gz = v->grid_dim[2];
     ctx->have_scene = true; ctx->have_grid = grid; ctx->cache_valid = false;
@@ -362,8 +489,7 @@ int ptap_build_accel(ptap_ctx* ctx, int kind)
     } else return fail(ctx, PTAP_E_INVALID, "build_accel: unknown kind %d", kind);
     ctx->accel = kind;
     ctx->cache_valid = false;
-    int occ = kind == PTAP_ACCEL_BVH ? traceBvhOccupancy() : traceGridOccupancy();
-    ctx->grid_trace = ctx->sms * std::max(occ, 1);
+    ctx->grid_trace = traceGridSize(ctx);
     return PTAP_OK;
 }
 
@@ -395,10 +521,7 @@ int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, u
     ctx->flags = flags; ctx->cache_valid = false; ctx->have_frame = true;
     ctx->grid_shade = ctx->sms * std::max(shadeOccupancy(), 1);
     ctx->grid_gen = ctx->sms * 8;
-    if (!ctx->grid_trace) {
-        int occ = ctx->accel == PTAP_ACCEL_BVH ? traceBvhOccupancy() : traceGridOccupancy();
-        ctx->grid_trace = ctx->sms * std::max(occ, 1);
-    }
+    if (!ctx->grid_trace) ctx->grid_trace = traceGridSize(ctx);
     { const int64_t sb = ctx->stats.scene_bytes; ctx->stats = PtapStats{}; ctx->stats.scene_bytes = sb; }
     return PTAP_OK;
 }
@@ -582,10 +705,7 @@ static int traceImpl(ptap_ctx* ctx, const float* rays_od, int32_t n, PtapHit* ou
     CK(cudaMemcpyAsync(O, hO.data(), n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(D, hD.data(), n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(st, 0, sizeof(FrameState), ctx->stream));
-    if (!ctx->grid_trace) {
-        int occ = ctx->accel == PTAP_ACCEL_BVH ? traceBvhOccupancy() : traceGridOccupancy();
-        ctx->grid_trace = ctx->sms * std::max(occ, 1);
-    }
+    if (!ctx->grid_trace) ctx->grid_trace = traceGridSize(ctx);
     launchTrace(ctx, st, O, D, hit, uv, counts ? dcnt : nullptr, 0, n);
     launchResolveHits(ctx->sc, hit, uv, n, dout, ctx->stream);
     CK(cudaMemcpyAsync(out, dout, n * sizeof(PtapHit), cudaMemcpyDeviceToHost, ctx->stream));
@@ -688,9 +808,9 @@ int ptap_bench_trace(ptap_ctx* ctx, const float* rays_od, int32_t n, int32_t rep
     CK(cudaMemcpy(O, hO.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(D, hD.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
     CK(cudaMemset(st, 0, sizeof(FrameState)));
-    for (int w = 0; w < 3; ++w) launchTrace(ctx, st, O, D, hit, nullptr, nullptr, 0, n);
+    for (int w = 0; w < 3; ++w) { CK(cudaMemsetAsync(st, 0, sizeof(FrameState), ctx->stream)); launchTrace(ctx, st, O, D, hit, nullptr, nullptr, 0, n); }
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    for (int r = 0; r < reps; ++r) launchTrace(ctx, st, O, D, hit, nullptr, nullptr, 0, n);
+    for (int r = 0; r < reps; ++r) { CK(cudaMemsetAsync(st, 0, sizeof(FrameState), ctx->stream)); launchTrace(ctx, st, O, D, hit, nullptr, nullptr, 0, n); }   // the memset re-arms the work-stealing cursor
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());

@@ -172,8 +172,9 @@ void buildSceneBvh(const TriRec* tris, int ntris, const PtapMesh* meshes, int nm
             // the whole mesh fits one leaf: give it a root whose second child can never be hit
             BvhNode nd;
             nd.xy0 = make_float4(bounds.lo[0], bounds.hi[0], bounds.lo[1], bounds.hi[1]);
-            nd.xy1 = make_float4(FLT_MAX, -FLT_MAX, FLT_MAX, -FLT_MAX);
-            nd.z01 = make_float4(bounds.lo[2], bounds.hi[2], FLT_MAX, -FLT_MAX);
+            // a far-away point box: (p - o) * inv >= 1e15 - |o| exceeds every ray interval (an inverted box would be un-inverted by the slab's min/max)
+            nd.xy1 = make_float4(1e15f, 1e15f, 1e15f, 1e15f);
+            nd.z01 = make_float4(bounds.lo[2], bounds.hi[2], 1e15f, 1e15f);
             nd.link = make_int4(link, link, 0, 0);
             out.nodes.push_back(nd);
         }

@@ -10,6 +10,7 @@ constexpr float kEpsilon = 0.005f;          // Config.h:4
 constexpr float kFloatMax = 9999999.0f;     // Config.h:5
 constexpr float kFloatMin = -9999990.0f;    // Config.h:6
 constexpr int kMaxDepth = 16;               // rounds per iteration the context reserves state for
+constexpr int kBvhStack = 96;               // traversal stack entries per ray (upload fails for deeper trees)
 
 // Per-model record read by the closest-hit kernels: 9 x float4 = 144 B.
 // Rows 0..2 of the reference's column-major mat4s (the w row is never used by
@@ -50,7 +51,8 @@ struct BvhNode {
     float4 xy0;         // child0: (lo.x, hi.x, lo.y, hi.y)
     float4 xy1;         // child1: (lo.x, hi.x, lo.y, hi.y)
     float4 z01;         // (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
-    int4 link;          // (child0, child1, 0, 0); >= 0: node index, < 0: leaf ~((first << 3) | (count - 1))
+    int4 link;          // (child0, child1, 0, 0); >= 0: node index, < 0: triangle leaf ~((first << 3) | (count - 1)),
+                        // or (TLAS only) instance leaf ~(0x20000000 | model index)
 };
 
 // Device-resident frame state: lets a whole iteration run without a host round trip.
@@ -73,11 +75,17 @@ struct SceneDev {
     const TriRec* tris;         // indexed by GLOBAL triangle id (reference order)
     const int2* cells;          // grid voxels: (start, end) into refs
     const int* refs;            // global triangle ids
-    const BvhNode* nodes;       // all BLAS nodes
+    const BvhNode* nodes;       // all BLAS nodes, then the TLAS nodes
     const TriRec* bvh_tris;     // triangles in BVH leaf order; v0.w..: see bvh_tri_id
     const int* bvh_tri_id;      // leaf-order position -> global triangle id
     int nmodels;
     int gx, gy, gz;
+    int tlas_root;              // node index of the TLAS root, -1 when no instance has triangles
+    float tmin_world;           // lower end of the world-space ray interval: -(EPSILON band mapped to world units + box padding)
+    int batch;                  // rays a warp takes from the work-stealing cursor per atomic (PTAP_BATCH)
+    int vote_tri, vote_inst, vote_refill;   // lanes that must wait in a state before the warp runs that state's step (PTAP_VOTE_*)
+    float c_pad;                // slack of the pruning bound for the residual of model_to_world * world_to_model - I
+    float prune;                // relative slack of cross-instance pruning (1.0001), +inf when some model's matrices are not inverses
 };
 
 struct WaveDev {

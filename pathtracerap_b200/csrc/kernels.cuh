@@ -9,6 +9,8 @@ namespace ptap {
 constexpr int kTraceBlock = 128;
 constexpr int kShadeBlock = 256;     // one look-back tile = one CTA = 256 consecutive slots
 constexpr int kGenBlock = 256;
+constexpr int kTraceBatch = 32;      // rays a warp takes from the work-stealing cursor per atomic
+constexpr int kVoteTri = 8, kVoteInst = 4, kVoteRefill = 4;   // state-machine thresholds of k_trace_bvh (trace_bvh.cu)
 
 // closest hit, grid-compat (trace_grid.cu) and BVH (trace_bvh.cu).  n_fixed < 0: read the count from st->n_active[round].
 void launchTraceGrid(const SceneDev& sc, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, bool count_totals,

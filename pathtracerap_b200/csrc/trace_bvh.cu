@@ -5,8 +5,22 @@
 // every triangle of the model's mesh, nearest model-space t wins (ties: lowest triangle index), converted to a world
 // distance as Renderer.cpp:388-391, nearest world distance wins (ties: lowest model index).  The BVH only decides
 // WHICH triangles get tested: node bounds are conservative for the predicate's tolerance band (bvh_build.cpp), the
-// slab test is evaluated with outward rounding slack, and the triangle arithmetic is the un-contracted exact one,
-// so the winner is bit-identical to brute force.
+// slab test is evaluated with outward rounding slack, pruning bounds carry relative slack, and the triangle
+// arithmetic is the un-contracted exact one, so the winner is bit-identical to brute force.
+//
+// Execution model (DESIGN.md "Closest hit"): a persistent grid of warps, each lane owning one ray at a time, scheduled as a
+// warp-wide state machine.  A lane is in one of five states, encoded in its `node` register: at an inner node, holding
+// a triangle leaf, about to enter an instance, about to leave one, or finished.  Every iteration of the ONE loop
+//  (1) advances all lanes that are at inner nodes by one node (TLAS and BLAS share the 64-byte node format),
+//  (2) counts the lanes waiting in each other state with warp ballots, and
+//  (3) runs a state's step only when enough lanes wait for it (or when it is at least as popular as descending):
+//      one Moller-Trumbore test per lane, the instance entry (the reference's world->model ray set-up), the instance
+//      exit (model t -> world distance, nearest-model bookkeeping), retire + refill from the work-stealing cursor.
+// Lanes never wait for a slower warp-mate's whole descent (the while-while form of this kernel measured 6 active
+// lanes of 32 in its node loop, and the v1 per-model loop 7 of 32): they only wait until their state's queue fills.
+//  * work stealing: each warp takes batches of consecutive rays from a device-side cursor (one atomic per batch).
+//  * cross-instance pruning: once some instance reported a hit at world distance g, TLAS nodes beyond g are skipped and
+//    the next instance is entered with the model-space bound t <= (g + |M o_m - o_w|) / |M3 d_m|.
 //
 // Node = 64 B holding both children's boxes (4 x 16-byte loads); triangles in leaf order, 48 B each.
 #include "kernels.cuh"
@@ -15,39 +29,44 @@ namespace ptap {
 
 namespace {
 
-constexpr int kStack = 64;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kDone = (int)0x80000000u;        // ~0x7fffffff: bottom-of-stack sentinel
+// A negative `node` is ~code with the lane's state in code >> 29:
+//   0: triangle leaf (first << 3 | count - 1), 1: TLAS leaf = enter instance (code & kIndexMask), 2: marker = leave instance, 3: done
+constexpr unsigned kEnterBit = 0x20000000u, kExitBit = 0x40000000u, kIndexMask = 0x1fffffffu;
+#ifndef PTAP_NODE_STEPS
+#define PTAP_NODE_STEPS 2
+#endif
+constexpr int kNodeSteps = PTAP_NODE_STEPS;    // inner nodes a lane may take per scheduling round
 
-struct BvhRay {
-    V3 o, d, inv;
-    float best_t; int best_tri; float best_u, best_v;
-};
-
-// Renderer.cpp:174-215; tie rule of brute force in index order: strictly nearer, or equal t and lower global id
-template <bool COUNT>
-__device__ __forceinline__ void leafTriangle(const SceneDev& sc, BvhRay& r, int k, int4& cnt)
+// Renderer.cpp:174-215; tie rule of brute force in index order: strictly nearer, or equal t and lower global id.
+// `tmax` is the model-space bound of the traversal AND the best t so far (they are the same number once best_tri >= 0).
+template <bool UV, bool COUNT>
+__device__ __forceinline__ void leafTriangle(const SceneDev& sc, const V3& o, const V3& d, float& tmax, int& best_tri, float& best_u, float& best_v,
+                                             int k, int4& cnt)
 {
     const TriRec* __restrict__ tp = &sc.bvh_tris[k];
     const float4 a = ldg4(&tp->v0), b = ldg4(&tp->e1), c = ldg4(&tp->e2);
     if (COUNT) cnt.z++;
     const V3 v0 = v3(a), v0v1 = v3(b), v0v2 = v3(c);
-    const V3 pvec = xcross(r.d, v0v2);
+    const V3 pvec = xcross(d, v0v2);
     const float det = xdot(v0v1, pvec);
     if (xabs(xsub(det, 0.0f)) < kEpsilon) return;
     const float invDet = xdiv(1.0f, det);
-    const V3 tvec = xsub(r.o, v0);
+    const V3 tvec = xsub(o, v0);
     const float u = xmul(xdot(tvec, pvec), invDet);
     if (u < (0.0f - kEpsilon) || u > (1.0f + kEpsilon)) return;
     const V3 qvec = xcross(tvec, v0v1);
-    const float v = xmul(xdot(r.d, qvec), invDet);
+    const float v = xmul(xdot(d, qvec), invDet);
     if (v < (0.0f - kEpsilon) || xadd(u, v) > (1.0f + kEpsilon)) return;
     const float t = xmul(xdot(v0v2, qvec), invDet);
     if (t < (0.0f - kEpsilon)) return;
-    if (t > r.best_t) return;
+    if (t > tmax) return;
     const int id = __ldg(&sc.bvh_tri_id[k]);
-    if (t < r.best_t || (r.best_tri >= 0 && id < r.best_tri)) { r.best_t = t; r.best_tri = id; r.best_u = u; r.best_v = v; }
+    if (t < tmax || (best_tri >= 0 && id < best_tri)) { tmax = t; best_tri = id; if (UV) { best_u = u; best_v = v; } }
 }
 
-// conservative slab test: (plane - o) * inv per plane (no cancellation-prone FMA form), interval test with relative slack
+// conservative slab test: (plane - o) * inv per plane (well conditioned whatever |o| is), interval test with relative slack
 __device__ __forceinline__ bool slab(const V3& o, const V3& inv, float lox, float hix, float loy, float hiy, float loz, float hiz,
                                      float tmin_ray, float tmax_ray, float& tnear)
 {
@@ -60,6 +79,18 @@ __device__ __forceinline__ bool slab(const V3& o, const V3& inv, float lox, floa
     return tn <= tf + (fabsf(tf) * 2e-6f + 1e-6f);
 }
 
+// traversal-only reciprocal: guarded against 0 (the exact predicate never uses it)
+__device__ __forceinline__ float safeInv(float d)
+{
+    const float ooeps = 1e-30f;
+    return __fdividef(1.0f, fabsf(d) > ooeps ? d : copysignf(ooeps, d));     // 1-ulp reciprocal: inside the slab test's 2e-6 slack
+}
+
+__device__ __forceinline__ float worldBound(float g_dist, float prune)
+{
+    return g_dist < kFloatMax ? g_dist * prune + 1e-3f : 3.0e38f;
+}
+
 }  // namespace
 
 template <bool UV, bool COUNT>
@@ -69,89 +100,150 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
 {
     const int n = n_fixed >= 0 ? n_fixed : st->n_active[round];
     if (blockIdx.x == 0 && threadIdx.x == 0 && n_fixed < 0) st->rays_traced += (unsigned long long)n;
-    unsigned long long tot_x = 0, tot_y = 0, tot_z = 0;
-    int stack[kStack];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 o4 = O[i], d4 = D[i];
-        const V3 bo = v3(o4), bd = v3(d4);
-        float g_dist = kFloatMax, g_t = 0.0f, g_u = 0.0f, g_v = 0.0f, last_dist = kFloatMax;
-        int g_model = -1, g_tri = -1;
-        int4 cnt = make_int4(0, 0, 0, 0);
-        BvhRay r;
-        for (int im = 0; im < sc.nmodels; ++im) {
-            const InstanceTrace* __restrict__ inst = &sc.inst[im];
-            const int root = __float_as_int(__ldg(&inst->grid.z));
-            if (root < 0) continue;
-            const float4 w0 = ldg4(&inst->w2m[0]), w1 = ldg4(&inst->w2m[1]), w2 = ldg4(&inst->w2m[2]);
-            r.o = xmat4(w0, w1, w2, bo, 1.0f);                                   // Renderer.cpp:381
-            r.d = xnormalize(xmat4(w0, w1, w2, bd, 0.0f));                       // Renderer.cpp:382
-            // traversal-only reciprocal: guarded against 0 (the exact predicate never uses it)
-            const float ooeps = 1e-30f;
-            r.inv = v3(1.0f / (fabsf(r.d.x) > ooeps ? r.d.x : copysignf(ooeps, r.d.x)),
-                       1.0f / (fabsf(r.d.y) > ooeps ? r.d.y : copysignf(ooeps, r.d.y)),
-                       1.0f / (fabsf(r.d.z) > ooeps ? r.d.z : copysignf(ooeps, r.d.z)));
-            r.best_t = kFloatMax; r.best_tri = -1; r.best_u = 0.0f; r.best_v = 0.0f;
-            last_dist = kFloatMax;
-            const float tmin_ray = -(kEpsilon + 1e-4f);                          // the predicate accepts t >= -EPSILON
+    unsigned int* cursor = &st->fetch[round];
+    const int lane = threadIdx.x & 31;
+    unsigned long long tot_x = 0, tot_z = 0;
+    int4 cnt = make_int4(0, 0, 0, 0);
 
-            int sp = 0;
-            int node = root;
-            for (;;) {
-                // inner node: test both children, descend into the nearer, push the farther
+    if (sc.tlas_root < 0) {                            // no instance has triangles: every ray misses
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+            hit[k] = make_float4(kFloatMax, __int_as_float(-1), __int_as_float(-1), 0.0f);
+            if (UV && uv) uv[k] = make_float2(0.0f, 0.0f);
+            if (COUNT && counts) counts[k] = cnt;
+        }
+        return;
+    }
+
+    int stack[kBvhStack];
+    int sp = 0, node = kDone, i = -1;
+    V3 bo = v3(0, 0, 0), bd = v3(0, 0, 0);          // the ray as stored (Ray::base, Primitive.h:160-164)
+    V3 winv = v3(0, 0, 0);                          // reciprocal of the normalised world direction (TLAS level)
+    V3 ro = v3(0, 0, 0), rd = v3(0, 0, 1), rinv = v3(0, 0, 0);   // the ray of the current level: world, or model space of the entered instance
+    float tmin = 0.0f, tmax = 0.0f;
+    int best_tri = -1; float best_u = 0.0f, best_v = 0.0f;
+    float g_dist = kFloatMax, g_t = 0.0f, g_u = 0.0f, g_v = 0.0f;
+    int g_model = -1, g_tri = -1;
+    int w_next = 0, w_end = 0;
+    bool exhausted = false;
+    const int vote_tri = sc.vote_tri, vote_inst = sc.vote_inst, vote_refill = sc.vote_refill;
+
+    for (;;) {
+        // ---- (1) one inner node for every lane that is at one
+#pragma unroll
+        for (int rep = 0; rep < kNodeSteps; ++rep) {
+            if (node >= 0) {
                 const BvhNode* __restrict__ np = &sc.nodes[node];
                 const float4 xy0 = ldg4(&np->xy0), xy1 = ldg4(&np->xy1), z01 = ldg4(&np->z01);
-                const int4 link = __ldg(&np->link);
+                const int2 link = __ldg(reinterpret_cast<const int2*>(&np->link));
                 if (COUNT) cnt.x++;
                 float tn0, tn1;
-                const bool h0 = slab(r.o, r.inv, xy0.x, xy0.y, xy0.z, xy0.w, z01.x, z01.y, tmin_ray, r.best_t, tn0);
-                const bool h1 = slab(r.o, r.inv, xy1.x, xy1.y, xy1.z, xy1.w, z01.z, z01.w, tmin_ray, r.best_t, tn1);
-                int next = 0; bool have_next = false;
-                if (h0 || h1) {
-                    int c0 = link.x, c1 = link.y;
-                    const bool two = h0 && h1;
-                    if (two ? (tn1 < tn0) : h1) { const int t = c0; c0 = c1; c1 = t; }   // c0 = nearer (or the only) child
-                    if (c0 < 0) {                                                     // leaf: intersect now
-                        const int code = ~c0; const int k0 = code >> 3, kc = (code & 7) + 1;
-                        for (int k = 0; k < kc; ++k) leafTriangle<COUNT>(sc, r, k0 + k, cnt);
-                    } else { next = c0; have_next = true; }
-                    if (two) {
-                        if (c1 < 0) {
-                            const int code = ~c1; const int k0 = code >> 3, kc = (code & 7) + 1;
-                            for (int k = 0; k < kc; ++k) leafTriangle<COUNT>(sc, r, k0 + k, cnt);
-                        } else if (have_next) {
-                            if (sp < kStack) stack[sp++] = c1;
-                        } else { next = c1; have_next = true; }
-                    }
-                }
-                if (have_next) { node = next; continue; }
-                if (sp == 0) break;
-                node = stack[--sp];
-            }
-
-            if (r.best_tri >= 0) {
-                const V3 nd = xnormalize(r.d);                                   // Renderer.cpp:388
-                const V3 pm = xadd(r.o, xscale(nd, r.best_t));                   // Renderer.cpp:389
-                const V3 pw = xmat4(ldg4(&inst->m2w[0]), ldg4(&inst->m2w[1]), ldg4(&inst->m2w[2]), pm, 1.0f);   // :390
-                const float dist = xlength(xsub(pw, bo));                        // Renderer.cpp:391
-                last_dist = dist;
-                if (g_dist > dist) {                                             // Renderer.cpp:393-398
-                    g_dist = dist; g_model = im; g_tri = r.best_tri; g_t = r.best_t; g_u = r.best_u; g_v = r.best_v;
+                const bool h0 = slab(ro, rinv, xy0.x, xy0.y, xy0.z, xy0.w, z01.x, z01.y, tmin, tmax, tn0);
+                const bool h1 = slab(ro, rinv, xy1.x, xy1.y, xy1.z, xy1.w, z01.z, z01.w, tmin, tmax, tn1);
+                if (h0 && h1) {
+                    const bool swap = tn1 < tn0;
+                    stack[sp++] = swap ? link.x : link.y;            // farther child
+                    node = swap ? link.y : link.x;
+                } else if (h0 || h1) {
+                    node = h0 ? link.x : link.y;
+                } else {
+                    node = stack[--sp];
                 }
             }
         }
-        const bool found = g_dist < kFloatMax;
-        hit[i] = make_float4(found ? g_dist : last_dist, __int_as_float(found ? g_tri : -1), __int_as_float(found ? g_model : -1), g_t);
-        if (UV && uv) uv[i] = make_float2(g_u, g_v);
-        if (COUNT) { if (counts) counts[i] = cnt; tot_x += cnt.x; tot_y += cnt.y; tot_z += cnt.z; }
+        // ---- (2) who waits for what: one warp reduction over 6-bit counters, one per state
+        const unsigned code = ~(unsigned)node;
+        const unsigned state = min(code >> 29, 4u);             // 0 tri, 1 enter, 2 exit, 3 done, 4 inner
+        const bool live = state != 3u || i >= 0 || !exhausted;  // a retired lane with nothing left to fetch takes no part
+        const unsigned sum = __reduce_add_sync(kFull, live ? 1u << (6u * state) : 0u);
+        if (sum == 0u) break;                                   // every ray of the launch is retired
+        const int n_tri = sum & 63u, n_enter = (sum >> 6) & 63u, n_exit = (sum >> 12) & 63u, n_done = (sum >> 18) & 63u, n_inner = (sum >> 24) & 63u;
+        const bool s_tri = state == 0u, s_enter = state == 1u, s_exit = state == 2u, s_done = state == 3u;
+
+        // ---- (3a) one triangle of the held leaf (Renderer.cpp:174-215)
+        if (s_tri && n_tri >= min(vote_tri, n_inner)) {
+            leafTriangle<UV, COUNT>(sc, ro, rd, tmax, best_tri, best_u, best_v, (int)(code >> 3), cnt);
+            node = (code & 7u) ? (int)~(code + 7u) : stack[--sp];        // (first + 1, count - 1), or pop when the leaf is finished
+        }
+        // ---- (3b) TLAS leaf: enter instance `im` (Renderer.cpp:381-384)
+        if (s_enter && n_enter >= min(vote_inst, n_inner)) {
+            const int im = (int)(code & kIndexMask);
+            const InstanceTrace* __restrict__ inst = &sc.inst[im];
+            const float4 w0 = ldg4(&inst->w2m[0]), w1 = ldg4(&inst->w2m[1]), w2 = ldg4(&inst->w2m[2]);
+            ro = xmat4(w0, w1, w2, bo, 1.0f);                                   // Renderer.cpp:381
+            const V3 dm = xmat4(w0, w1, w2, bd, 0.0f);
+            const float mlen = xsqrt(xdot(dm, dm));
+            rd = xscale(dm, xdiv(1.0f, mlen));                                  // glm::normalize, Renderer.cpp:382
+            rinv = v3(safeInv(rd.x), safeInv(rd.y), safeInv(rd.z));
+            const float wil = rsqrtf(bd.x * bd.x + bd.y * bd.y + bd.z * bd.z);
+            tmin = -(kEpsilon + 1e-4f);                                         // the predicate accepts t >= -EPSILON
+            tmax = kFloatMax; best_tri = -1;                                    // Renderer.cpp:384
+            if (g_dist < kFloatMax) {
+                // World distance of a model-space t along this ray is t * |d_w| / |W3 d_w| when model_to_world inverts world_to_model
+                // (checked at upload, else sc.prune = inf): a winner needs t <= g * |W3 d_w| / |d_w|, plus slack for the matrices' residual.
+                const float tb = (g_dist * sc.prune + sc.c_pad + 1e-4f * (fabsf(bo.x) + fabsf(bo.y) + fabsf(bo.z))) * (mlen * wil) * 1.0001f;
+                if (tb < kFloatMax) tmax = tb;                                  // false for NaN / inf: no bound
+            }
+            stack[sp++] = (int)~(kExitBit | (unsigned)im);
+            node = __float_as_int(__ldg(&inst->grid.z));                        // BLAS root of the instance's mesh
+        }
+        // ---- (3c) marker popped: leave instance `im` (Renderer.cpp:388-398)
+        if (s_exit && n_exit >= min(vote_inst, n_inner)) {
+            const int im = (int)(code & kIndexMask);
+            if (best_tri >= 0) {
+                const InstanceTrace* __restrict__ inst = &sc.inst[im];
+                const V3 nd = xnormalize(rd);                                    // Renderer.cpp:388
+                const V3 pm = xadd(ro, xscale(nd, tmax));                        // Renderer.cpp:389
+                const V3 pw = xmat4(ldg4(&inst->m2w[0]), ldg4(&inst->m2w[1]), ldg4(&inst->m2w[2]), pm, 1.0f);   // :390
+                const float dist = xlength(xsub(pw, bo));                        // Renderer.cpp:391
+                if (g_dist > dist || (g_dist == dist && im < g_model)) {         // Renderer.cpp:393-398 in model order
+                    g_dist = dist; g_model = im; g_tri = best_tri; g_t = tmax;
+                    if (UV) { g_u = best_u; g_v = best_v; }
+                }
+            }
+            ro = bo; rinv = winv;
+            tmin = sc.tmin_world; tmax = worldBound(g_dist, sc.prune);
+            node = stack[--sp];
+        }
+        // ---- (3d) retire finished rays, refill the lanes from the warp's batch
+        if (n_done > 0 && n_done >= min(vote_refill, n_inner)) {
+            const unsigned m_done = __ballot_sync(kFull, s_done && live);
+            if (s_done && i >= 0) {
+                const bool found = g_dist < kFloatMax;
+                hit[i] = make_float4(found ? g_dist : kFloatMax, __int_as_float(found ? g_tri : -1), __int_as_float(found ? g_model : -1), g_t);
+                if (UV && uv) uv[i] = make_float2(g_u, g_v);
+                if (COUNT) { if (counts) counts[i] = cnt; tot_x += cnt.x; tot_z += cnt.z; }
+                i = -1;
+            }
+            if (w_next >= w_end && !exhausted) {      // the warp's batch is used up: take the next one
+                unsigned b = 0;
+                if (lane == 0) b = atomicAdd(cursor, (unsigned)sc.batch);
+                b = __shfl_sync(kFull, b, 0);
+                if (b >= (unsigned)n) { exhausted = true; w_next = w_end = n; }
+                else { w_next = (int)b; w_end = min((int)b + sc.batch, n); }
+            }
+            const int avail = w_end - w_next;
+            const int rank = __popc(m_done & ((1u << lane) - 1u));
+            if (s_done && live && rank < avail) {
+                i = w_next + rank;
+                const float4 o4 = O[i], d4 = D[i];
+                bo = v3(o4); bd = v3(d4);
+                const float il = rsqrtf(bd.x * bd.x + bd.y * bd.y + bd.z * bd.z);
+                winv = v3(safeInv(bd.x * il), safeInv(bd.y * il), safeInv(bd.z * il));
+                ro = bo; rinv = winv;
+                tmin = sc.tmin_world; tmax = 3.0e38f;
+                g_dist = kFloatMax; g_model = -1; g_tri = -1; g_t = 0.0f; g_u = 0.0f; g_v = 0.0f;
+                best_tri = -1;
+                if (COUNT) cnt = make_int4(0, 0, 0, 0);
+                stack[0] = kDone; sp = 1;
+                node = sc.tlas_root;
+            }
+            w_next += min(__popc(m_done), avail);
+        }
     }
     if (COUNT) {        // counting build: per-warp totals into the frame state (never used for timing)
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            tot_x += __shfl_xor_sync(0xffffffffu, tot_x, d); tot_y += __shfl_xor_sync(0xffffffffu, tot_y, d); tot_z += __shfl_xor_sync(0xffffffffu, tot_z, d);
-        }
-        if ((threadIdx.x & 31) == 0) {
-            atomicAdd(&st->count_nodes, tot_x); atomicAdd(&st->count_refs, tot_y); atomicAdd(&st->count_tris, tot_z);
-        }
+        for (int d = 16; d > 0; d >>= 1) { tot_x += __shfl_xor_sync(kFull, tot_x, d); tot_z += __shfl_xor_sync(kFull, tot_z, d); }
+        if (lane == 0) { atomicAdd(&st->count_nodes, tot_x); atomicAdd(&st->count_tris, tot_z); }
     }
 }
 
