@@ -159,7 +159,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ptap", choices=["ptap", "reference"])
-    ap.add_argument("--workload", default="mesh100k", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="mesh1m", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel of the workload")
     ap.add_argument("--accel", default="bvh", choices=["bvh", "grid"])
     ap.add_argument("--no-cache", action="store_true", help="disable the first-hit cache (Renderer.cpp:594-613)")
@@ -220,7 +220,10 @@ def main():
     r = Renderer(device=dev, width=W, height=H, depth=depth, accel=accel, first_hit_cache=not args.no_cache, profile=True)
     r.allocateOnGPU(scene)
 
-    it0, it1 = rank * spp, (rank + 1) * spp      # sample partition: the union over ranks is one world*spp-sample frame
+    from pathtracerap_b200 import multi_gpu
+    # sample partition, weak scaling: every rank renders `spp` iterations, the union over ranks is one (world * spp)-sample frame
+    it0, it1 = multi_gpu.iteration_range(rank, world, world * spp)
+    lib_stream = torch.cuda.ExternalStream(r.stream_ptr(), device=torch.device("cuda", dev))
 
     def barrier():
         if world > 1:
@@ -231,8 +234,10 @@ def main():
         r.frame_begin()
         r.render(it0, it1)
         if world > 1:
-            r.sync()                             # film complete on the library stream before NCCL touches it
-            dist.reduce(film_t, dst=0, op=dist.ReduceOp.SUM)
+            # the collective is ordered on the LIBRARY's stream (NCCL's stream waits for it and it waits for NCCL), so the device
+            # timer on that stream covers render + reduce and no host synchronisation separates them
+            with torch.cuda.stream(lib_stream):
+                multi_gpu.reduce_film(film_t, 0)
 
     # counting pass (not timed): traversal work per ray of this exact workload, for the algorithmic-bytes figure
     r.set_params(W, H, depth, first_hit_cache=not args.no_cache, count=True)
@@ -240,11 +245,7 @@ def main():
     cst = r.stats()
     avg_nodes, avg_tris, avg_cells, avg_refs = cst["avg_nodes"], cst["avg_tris"], cst["avg_cells"], cst["avg_refs"]
     r.set_params(W, H, depth, first_hit_cache=not args.no_cache, profile=True)
-    film_ptr, film_n = r.film_device_ptr()
-
-    class _Film:          # zero-copy torch view of the library's film buffer for the NCCL reduce
-        __cuda_array_interface__ = {"shape": (film_n,), "typestr": "<f4", "data": (film_ptr, False), "version": 2}
-    film_t = torch.as_tensor(_Film(), device=f"cuda:{dev}") if world > 1 else None
+    film_t = multi_gpu.film_tensor(r) if world > 1 else None      # zero-copy torch view of the library's film buffer
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -259,16 +260,14 @@ def main():
     for _ in range(args.steps):
         r.timer_start()
         step()
-        ms_dev += r.timer_stop()                 # device time on the launching stream (the reduce is ordered after r.sync())
+        ms_dev += r.timer_stop()                 # device time on the launching stream (render + reduce)
         st = r.stats()
         rays += st["rays_traced"]; launches += st["kernel_launches"]; trace_launches += st["trace_launches"]
         ms_trace += st["ms_trace"]; ms_shade += st["ms_shade"]; ms_gen += st["ms_generate"]
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if rank == 0 else None
-    # with N > 1 the reduce runs on torch's stream after the library stream drained: wall time between the barriers is the
-    # honest per-rank time; with N = 1 the device-event time is used.
-    t_rank = t_wall if world > 1 else ms_dev / 1e3
+    t_rank = ms_dev / 1e3                        # CUDA events on the library stream; max over ranks below
     if world > 1:
         tt = torch.tensor([t_rank], dtype=torch.float64, device=f"cuda:{dev}")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -292,7 +291,8 @@ def main():
         r.frame_begin()
         r.render(it0, it1)
         if world > 1:
-            r.sync(); dist.reduce(film_t, dst=0, op=dist.ReduceOp.SUM)
+            with torch.cuda.stream(lib_stream):
+                multi_gpu.reduce_film(film_t, 0)
         N.lib().ptap_read_film(r.h, N.ptr(film_host))
         e2e_rays += r.stats()["rays_traced"]
     barrier()
@@ -320,9 +320,16 @@ def main():
     else:
         bytes_per_ray = 48.0 + 8.0 * avg_cells + 4.0 * avg_refs + 48.0 * avg_tris
     achieved = bytes_per_ray * rays / (ms_trace / 1e3) / 1e9 if ms_trace > 0 else None
+    # measured DRAM bytes of one launch of the same kernel on the same workload, from the committed `ncu --set full` capture
+    traffic, traffic_note = None, "no ncu capture committed for this workload"
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        t = json.load(open(tp)).get(f"{args.workload}:{args.accel}")
+        if t:
+            traffic, traffic_note = t["dram_bytes_per_launch"], t["note"]
     roofline = {"bound": "hbm", "kernel": "k_trace_bvh" if accel == ACCEL_BVH else "k_trace_grid",
                 "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                 "bytes_per_ray": round(bytes_per_ray, 1), "avg_nodes_per_ray": round(avg_nodes, 2), "avg_tris_per_ray": round(avg_tris, 2),
                 "avg_cells_per_ray": round(avg_cells, 2), "avg_refs_per_ray": round(avg_refs, 2),
                 "trace_launches": trace_launches, "avg_launch_ms": round(ms_trace / max(trace_launches, 1), 4),

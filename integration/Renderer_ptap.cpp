@@ -1,0 +1,99 @@
+// Renderer_ptap.cpp - what a maintainer of purvakulkarni15/PathTracerAP adds to switch the render path to libptap.
+//
+// Compile this file INSTEAD OF the reference's Renderer.cpp, inside the reference tree, with the reference's own unmodified
+// headers (Renderer.h, Scene.h, Primitive.h, Config.h, GPUMemoryPool.h, glm).  It defines the four Renderer methods
+// (Renderer.h:46-55) on top of the C ABI of include/ptap.h.  The reference's PODs have the layouts the ABI expects
+// (Primitive.h: Model 160 B, Mesh 40 B, Vertex 32 B, Triangle 12 B, Grid 28 B, Voxel 12 B - checked below), so the
+// seven vectors of Scene are passed through as they are, without conversion or copy on the host.
+//
+//   nvcc -x cu -std=c++17 -I<reference>/PathTracerAP -I<reference>/PathTracerAP/external/include -I<repo>/include \
+//        -c integration/Renderer_ptap.cpp          (g++ works too; nothing in this file is device code)
+//   link:  main.o Scene.o Renderer_ptap.o -L<repo>/pathtracerap_b200 -lptap
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <map>
+#include <vector>
+
+#include "Renderer.h"
+#include "ptap.h"
+
+#ifndef MAX_DEPTH
+#define MAX_DEPTH 5     // the literal of Renderer.cpp:550
+#endif
+
+static_assert(sizeof(Model) == sizeof(PtapModel) && sizeof(Mesh) == sizeof(PtapMesh) && sizeof(Vertex) == sizeof(PtapVertex) &&
+              sizeof(Triangle) == sizeof(PtapTriangle) && sizeof(Grid) == sizeof(PtapGrid) && sizeof(Voxel) == sizeof(PtapVoxel) &&
+              sizeof(Pixel) == 3 * sizeof(float), "libptap's ABI records must match Primitive.h");
+
+namespace {
+
+struct Binding {                      // per-Renderer state the reference keeps in managed memory
+    ptap_ctx* ctx = nullptr;
+    GPUMemoryPool<Pixel> image;       // host view handed out through render_data.dev_image_data
+    std::vector<Pixel> film;
+};
+std::map<const Renderer*, Binding> g_bindings;
+
+void check(const Binding& b, int rc, const char* what)
+{
+    if (rc == PTAP_OK) return;
+    std::fprintf(stderr, "%s failed (%d): %s\n", what, rc, b.ctx ? ptap_last_error(b.ctx) : "no usable CUDA device");
+    std::exit(1);                     // the reference drops CUDA errors silently; failing loudly is deliberate
+}
+
+int envInt(const char* name, int dflt) { const char* v = std::getenv(name); return v && *v ? std::atoi(v) : dflt; }
+
+}  // namespace
+
+void Renderer::allocateOnGPU(Scene& scene)
+{
+    Binding& b = g_bindings[this];
+    check(b, ptap_create(envInt("PTAP_DEVICE", 0), 0, &b.ctx), "ptap_create");
+    PtapSceneView v{};
+    v.models = reinterpret_cast<const PtapModel*>(scene.models.data()); v.nmodels = (int32_t)scene.models.size();
+    v.meshes = reinterpret_cast<const PtapMesh*>(scene.meshes.data()); v.nmeshes = (int32_t)scene.meshes.size();
+    v.vertices = reinterpret_cast<const PtapVertex*>(scene.vertices.data()); v.nvertices = (int32_t)scene.vertices.size();
+    v.triangles = reinterpret_cast<const PtapTriangle*>(scene.triangles.data()); v.ntriangles = (int32_t)scene.triangles.size();
+    v.grids = reinterpret_cast<const PtapGrid*>(scene.grids.data()); v.ngrids = (int32_t)scene.grids.size();
+    v.voxels = reinterpret_cast<const PtapVoxel*>(scene.voxels.data()); v.nvoxels = (int32_t)scene.voxels.size();
+    v.refs = scene.per_voxel_data_pool.data(); v.nrefs = (int32_t)scene.per_voxel_data_pool.size();
+    v.grid_dim[0] = GRID_X; v.grid_dim[1] = GRID_Y; v.grid_dim[2] = GRID_Z;
+    check(b, ptap_upload_scene(b.ctx, &v), "ptap_upload_scene");
+    const char* accel = std::getenv("PTAP_ACCEL");            // default: the reference's own grid walk, bit-compatible hits
+    check(b, ptap_build_accel(b.ctx, accel && std::string(accel) == "bvh" ? PTAP_ACCEL_BVH : PTAP_ACCEL_GRID_COMPAT), "ptap_build_accel");
+    check(b, ptap_set_render_params(b.ctx, RESOLUTION_X, RESOLUTION_Y, MAX_DEPTH, PTAP_FLAG_FIRST_HIT_CACHE), "ptap_set_render_params");
+    render_data = RenderData{};
+}
+
+void Renderer::renderLoop()
+{
+    Binding& b = g_bindings[this];
+    const int iters = envInt("PTAP_ITER", ITER);
+    const auto t0 = std::chrono::high_resolution_clock::now();
+    check(b, ptap_frame_begin(b.ctx), "ptap_frame_begin");
+    check(b, ptap_render(b.ctx, 0, iters), "ptap_render");
+    b.film.resize((size_t)RESOLUTION_X * RESOLUTION_Y);
+    check(b, ptap_read_film(b.ctx, reinterpret_cast<float*>(b.film.data())), "ptap_read_film");
+    b.image.size = (int)b.film.size();
+    b.image.pool = b.film.data();
+    render_data.dev_image_data = &b.image;                    // Renderer.cpp:49 reads the image through this pointer
+    const auto t1 = std::chrono::high_resolution_clock::now();
+    std::cout << "Full run: " << std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count() << " microseconds" << std::endl;   // Renderer.cpp:645-647
+}
+
+void Renderer::renderImage()
+{
+    Binding& b = g_bindings[this];
+    check(b, ptap_write_bmp(b.ctx, "Render.bmp", envInt("PTAP_ITER", ITER)), "ptap_write_bmp");
+}
+
+void Renderer::free()
+{
+    auto it = g_bindings.find(this);
+    if (it == g_bindings.end()) return;
+    if (it->second.ctx) ptap_destroy(it->second.ctx);
+    g_bindings.erase(it);
+    render_data = RenderData{};
+}

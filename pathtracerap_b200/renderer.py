@@ -108,6 +108,10 @@ class Renderer:
         assert rgb.size == self.W * self.H * 3
         self._check(N.lib().ptap_film_add(self.h, N.ptr(rgb)), "film_add")
 
+    def stream_ptr(self) -> int:
+        """cudaStream_t of the context (every kernel and copy of this renderer is ordered on it)."""
+        return int(N.lib().ptap_stream(self.h))
+
     def film_device_ptr(self):
         p = C.c_void_p(); n = C.c_size_t()
         self._check(N.lib().ptap_film_device_ptr(self.h, C.byref(p), C.byref(n)), "film_device_ptr")
