@@ -66,7 +66,7 @@ struct ptap_ctx {
     std::vector<PtapMesh> h_meshes;
     std::vector<PtapModel> h_models;
     std::vector<InstanceTrace> h_inst;
-    InstanceTrace* d_inst = nullptr; BvhNode* d_nodes = nullptr; size_t nodes_cap = 0; TriRec* d_btris = nullptr; int* d_btid = nullptr;
+    InstanceTrace* d_inst = nullptr; TriRec* d_tris = nullptr; BvhNode* d_nodes = nullptr; size_t nodes_cap = 0; TriRec* d_btris = nullptr; int* d_btid = nullptr;
     bool have_scene = false, have_grid = false, have_bvh = false, have_frame = false;
     int accel = PTAP_ACCEL_GRID_COMPAT;
     uint32_t flags = 0;
@@ -214,11 +214,8 @@ int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id
             if (l >= nnodes) return fail(ctx, PTAP_E_INVALID, "BVH node %d: child index out of range", i);
             if (l < 0) { const int code = ~l, first = code >> 3, cnt = (code & 7) + 1; if (code >= 0x20000000 || first < 0 || first + cnt > nt) return fail(ctx, PTAP_E_INVALID, "BVH node %d: leaf range out of bounds", i); }
         }
-    std::vector<TriRec> btris(nt);
-    for (int k = 0; k < nt; ++k) {
+    for (int k = 0; k < nt; ++k)
         if (tri_id[k] < 0 || tri_id[k] >= nt) return fail(ctx, PTAP_E_INVALID, "BVH leaf order entry %d out of range", k);
-        btris[k] = ctx->h_tris[tri_id[k]];
-    }
     // depth of every BLAS (the traversal stack is fixed-size)
     int blas_depth = 0;
     {
@@ -300,10 +297,10 @@ int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id
     CK(cudaMemcpyAsync(ctx->d_inst, ctx->h_inst.data(), nm * sizeof(InstanceTrace), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_nodes, nodes, (size_t)nnodes * sizeof(BvhNode), cudaMemcpyHostToDevice, ctx->stream));
     if (!tlas.empty()) CK(cudaMemcpyAsync(ctx->d_nodes + nnodes, tlas.data(), tlas.size() * sizeof(BvhNode), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_btris, btris.data(), (size_t)nt * sizeof(TriRec), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_btid, tri_id, (size_t)nt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));      // btris / tlas are stack-owned
-    if (bytes) *bytes = nm * sizeof(InstanceTrace) + ((size_t)nnodes + tlas.size()) * sizeof(BvhNode) + (size_t)nt * (sizeof(TriRec) + sizeof(int));
+    launchGatherTris(ctx->d_tris, ctx->d_btid, nt, ctx->d_btris, ctx->stream);     // leaf-order copies are made on the device
+    CK(cudaStreamSynchronize(ctx->stream));      // tlas is stack-owned
+    if (bytes) *bytes = nm * sizeof(InstanceTrace) + ((size_t)nnodes + tlas.size()) * sizeof(BvhNode) + (size_t)nt * sizeof(int);
     ctx->sc.tlas_root = tlas_root;
     ctx->sc.tmin_world = -(float)((kEpsilon + 2e-4) * max_scale * 1.001 + max_pad + 1e-3);
     ctx->sc.prune = consistent ? 1.0001f : INFINITY;
@@ -428,7 +425,7 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
     // ---- one arena for everything scene-lifetime; BVH storage is reserved up front (2T-1 BLAS nodes + 2M TLAS nodes bound)
     const size_t nodes_cap = (size_t)std::max(nt, 1) * 2 + (size_t)nm * 2 + 2;
     size_t need = Arena::need(nm, sizeof(InstanceTrace)) + Arena::need(nm, sizeof(InstanceShade)) +
-                  Arena::need(nt, sizeof(TriRec)) * 2 + Arena::need(nt, sizeof(int)) + Arena::need(nodes_cap, sizeof(BvhNode)) +
+                  Arena::need(nt, sizeof(TriRec)) * 2 + Arena::need(nt, sizeof(float4)) + Arena::need(nt, sizeof(int)) + Arena::need(nodes_cap, sizeof(BvhNode)) +
                   (grid ? Arena::need(v->nvoxels, sizeof(int2)) + Arena::need(v->nrefs, sizeof(int)) : 0) + 4096;
     if (need > ctx->scene_arena.cap) CK(ctx->scene_arena.reserve(need)); else ctx->scene_arena.used = 0;
     Arena& A = ctx->scene_arena;
@@ -436,14 +433,17 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
     InstanceShade* d_shade = A.alloc<InstanceShade>(nm);
     TriRec* d_tris = A.alloc<TriRec>(nt);
     TriRec* d_btris = A.alloc<TriRec>(nt);
+    float4* d_normals = A.alloc<float4>(nt);
     int* d_btid = A.alloc<int>(nt);
     BvhNode* d_nodes = A.alloc<BvhNode>(nodes_cap);
     int2* d_cells = grid ? A.alloc<int2>(v->nvoxels) : nullptr;
     int* d_refs = grid ? A.alloc<int>(v->nrefs) : nullptr;
-    if (!d_inst || !d_shade || !d_tris || !d_btris || !d_btid || !d_nodes || (grid && (!d_cells || !d_refs))) return fail(ctx, PTAP_E_NOMEM, "scene arena exhausted");
+    if (!d_inst || !d_shade || !d_tris || !d_normals || !d_btris || !d_btid || !d_nodes || (grid && (!d_cells || !d_refs))) return fail(ctx, PTAP_E_NOMEM, "scene arena exhausted");
     CK(cudaMemcpyAsync(d_inst, inst.data(), nm * sizeof(InstanceTrace), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_shade, shade.data(), nm * sizeof(InstanceShade), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_tris, ctx->h_tris.data(), nt * sizeof(TriRec), cudaMemcpyHostToDevice, ctx->stream));
+    launchExtractNormals(d_tris, nt, d_normals, ctx->stream);
+    ctx->d_tris = d_tris;
     if (grid) {
         CK(cudaMemcpyAsync(d_cells, cells.data(), cells.size() * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(d_refs, v->refs, v->nrefs * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -462,7 +462,7 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
     }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stats.scene_bytes = (int64_t)bytes;
-    ctx->sc.inst = d_inst; ctx->sc.cull = nullptr; ctx->sc.shade = d_shade; ctx->sc.tris = d_tris;
+    ctx->sc.inst = d_inst; ctx->sc.cull = nullptr; ctx->sc.shade = d_shade; ctx->sc.tris = d_tris; ctx->sc.normals = d_normals;
     ctx->sc.cells = d_cells; ctx->sc.refs = d_refs; ctx->sc.nodes = d_nodes; ctx->sc.bvh_tris = d_btris; ctx->sc.bvh_tri_id = d_btid;
     ctx->sc.nmodels = nm; ctx->sc.gx = v->grid_dim[0]; ctx->sc.gy = v->grid_dim[1]; ctx->sc.gz = v->grid_dim[2];
     ctx->have_scene = true; ctx->have_grid = grid; ctx->cache_valid = false;
@@ -500,7 +500,7 @@ int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, u
     CK(cudaSetDevice(ctx->device));
     if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
     const int N = W * H;
-    const int ntiles = (N + kShadeBlock - 1) / kShadeBlock;
+    const int ntiles = (N + kShadeTile - 1) / kShadeTile;
     size_t need = Arena::need(N, sizeof(float4)) * 8 + Arena::need(N, sizeof(float2)) + Arena::need((size_t)N * 3, sizeof(float)) +
                   Arena::need((size_t)ntiles * kMaxDepth, sizeof(unsigned long long)) + Arena::need(1, sizeof(FrameState)) + 4096;
     if (need > ctx->frame_arena.cap) CK(ctx->frame_arena.reserve(need)); else ctx->frame_arena.used = 0;
@@ -723,7 +723,7 @@ int ptap_shade(ptap_ctx* ctx, const PtapPathIn* paths, int32_t n, int32_t iter, 
     if (!ctx || !ctx->have_scene || !paths || !out || n <= 0 || remaining <= 0) return fail(ctx, PTAP_E_STATE, "shade: scene and buffers required");
     CK(cudaSetDevice(ctx->device));
     if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
-    const int ntiles = (n + kShadeBlock - 1) / kShadeBlock;
+    const int ntiles = (n + kShadeTile - 1) / kShadeTile;
     size_t need = Arena::need(n, sizeof(float4)) * 7 + Arena::need((size_t)n * 3, sizeof(float)) + Arena::need(n, sizeof(int)) +
                   Arena::need(ntiles, sizeof(unsigned long long)) + Arena::need(1, sizeof(FrameState)) + 4096;
     if (need > ctx->scratch.cap) CK(ctx->scratch.reserve(need)); else ctx->scratch.used = 0;

@@ -73,6 +73,7 @@ struct SceneDev {
     const InstanceCull* cull;
     const InstanceShade* shade;
     const TriRec* tris;         // indexed by GLOBAL triangle id (reference order)
+    const float4* normals;      // flat shading normal per GLOBAL triangle id (copy of the TriRec .w lanes, 16-byte gather for k_shade)
     const int2* cells;          // grid voxels: (start, end) into refs
     const int* refs;            // global triangle ids
     const BvhNode* nodes;       // all BLAS nodes, then the TLAS nodes
@@ -96,7 +97,7 @@ struct WaveDev {
     float4* hit_cache;          // round-0 hits (first-hit cache, Renderer.cpp:594-613)
     float2* uv;                 // parity entry only
     float* film;                // W*H*3 running sum (Pixel, Primitive.h:145-148)
-    unsigned long long* tile_status;   // shade look-back words: rounds x tiles
+    unsigned long long* tile_status;   // shade look-back words: rounds x 32-slot tiles
     FrameState* st;
     int W, H, N, depth, ntiles;
     float step_x, step_y;

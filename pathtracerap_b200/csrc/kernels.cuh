@@ -7,7 +7,8 @@
 namespace ptap {
 
 constexpr int kTraceBlock = 128;
-constexpr int kShadeBlock = 256;     // one look-back tile = one CTA = 256 consecutive slots
+constexpr int kShadeBlock = 128;
+constexpr int kShadeTile = 32;       // one look-back tile = one warp = 32 consecutive slots
 constexpr int kGenBlock = 256;
 constexpr int kTraceBatch = 32;      // rays a warp takes from the work-stealing cursor per atomic
 constexpr int kVoteTri = 8, kVoteInst = 4, kVoteRefill = 4;   // state-machine thresholds of k_trace_bvh (trace_bvh.cu)
@@ -28,5 +29,7 @@ int shadeOccupancy();
 void launchResolveHits(const SceneDev& sc, const float4* hit, const float2* uv, int n, PtapHit* out, cudaStream_t stream);
 void launchSetIter(FrameState* st, int iter, cudaStream_t stream);
 void launchFilmAdd(float* film, const float* add, size_t n, cudaStream_t stream);
+void launchExtractNormals(const TriRec* tris, int n, float4* normals, cudaStream_t stream);
+void launchGatherTris(const TriRec* tris, const int* tri_id, int n, TriRec* out, cudaStream_t stream);
 
 }  // namespace ptap

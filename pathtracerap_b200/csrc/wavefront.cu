@@ -95,8 +95,7 @@ __device__ __forceinline__ V3 coat(V3 n, V3 dir, Lcg& rng)
 // (Renderer.cpp:203,397; utility.h:82-88); matrix rows and flat normal are precomputed at upload with the same arithmetic.
 __device__ __forceinline__ V3 worldNormal(const SceneDev& sc, int model, int tri, float4& nm0, float4& nm1, float4& nm2)
 {
-    const TriRec* t = &sc.tris[tri];
-    const V3 n = v3(__ldg(&t->v0.w), __ldg(&t->e1.w), __ldg(&t->e2.w));
+    const V3 n = v3(ldg4(&sc.normals[tri]));
     nm0 = ldg4(&sc.shade[model].nm0); nm1 = ldg4(&sc.shade[model].nm1); nm2 = ldg4(&sc.shade[model].nm2);
     const V3 r = v3(xadd(xadd(xmul(nm0.x, n.x), xmul(nm0.y, n.y)), xmul(nm0.z, n.z)),
                     xadd(xadd(xmul(nm1.x, n.x), xmul(nm1.y, n.y)), xmul(nm1.z, n.z)),
@@ -131,7 +130,7 @@ __global__ void __launch_bounds__(kGenBlock) k_generate(WaveDev wv)
     if (tid >= 1 && tid <= kMaxDepth + 1) st->n_active[tid] = 0;
     if (tid < kMaxDepth + 2) { st->ticket[tid] = 0u; st->fetch[tid] = 0u; }
     const int nwords = wv.ntiles * wv.depth;
-    for (int i = tid; i < nwords; i += stride) wv.tile_status[i] = 0ull;
+    for (int i = tid; i < nwords; i += stride) wv.tile_status[i] = 0ull;      // one look-back word per 32-slot tile and round
     for (int i = tid; i < wv.N; i += stride) {
         const int y = i / wv.W, x = i % wv.W;
         // float world_x = -10.0 + x * step_x  (double add of a float product, Renderer.cpp:541-542)
@@ -145,43 +144,54 @@ __global__ void __launch_bounds__(kGenBlock) k_generate(WaveDev wv)
 
 // shadeRayKernel + stable compaction + film accumulation for one bounce.
 // Slot i of queue `in` holds a path with `remaining` bounces left (every live path of a round has the same count).
+// One warp = one tile of 32 consecutive slots, taken by ticket; no block-level barrier anywhere:
+//   A  load the slot, decide survival (it depends only on hit / material type / remaining), publish the tile's survivor
+//      count in its status word at once (successors can add it without waiting for this tile's shading),
+//   B  shade (normal, RNG, scatter, throughput; film += sqrt(throughput) for terminated paths),
+//   C  decoupled look-back over the predecessors' status words: exclusive offset of the tile, publish the inclusive prefix,
+//   D  write the survivors to queue `in ^ 1` at offset + rank: same order as thrust::stable_partition (Renderer.cpp:628).
 __global__ void __launch_bounds__(kShadeBlock)
 k_shade(SceneDev sc, WaveDev wv, int round, int in, const float4* __restrict__ hit, int remaining, int n_fixed, int iter_fixed,
         int* __restrict__ slot_pos)
 {
-    __shared__ int s_warp_off[kShadeBlock / 32];
-    __shared__ int s_excl;
-    __shared__ unsigned s_tile;
     FrameState* st = wv.st;
     const int n = n_fixed >= 0 ? n_fixed : st->n_active[round];
     const int iter = n_fixed >= 0 ? iter_fixed : st->iter_cur;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const float4* __restrict__ Oi = wv.O[in]; const float4* __restrict__ Di = wv.D[in]; const float4* __restrict__ Ci = wv.C[in];
     float4* __restrict__ Oo = wv.O[in ^ 1]; float4* __restrict__ Do = wv.D[in ^ 1]; float4* __restrict__ Co = wv.C[in ^ 1];
     unsigned long long* status = wv.tile_status + (size_t)round * wv.ntiles;
 
     for (;;) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(&st->ticket[round], 1u);
-        __syncthreads();
-        const int tile = (int)s_tile;
-        const int base = tile * kShadeBlock;
+        unsigned ticket = 0;
+        if (lane == 0) ticket = atomicAdd(&st->ticket[round], 1u);
+        const int tile = (int)__shfl_sync(0xffffffffu, ticket, 0);
+        const int base = tile * kShadeTile;
         if (base >= n) break;
-        const int i = base + threadIdx.x;
-        bool alive = false;
-        float4 o4, d4, c4;
-        if (i < n) {
-            o4 = Oi[i]; d4 = Di[i]; c4 = Ci[i];
-            const float4 h = hit[i];
+        const int i = base + lane;
+        const bool valid = i < n;
+
+        // ---- A: loads, survival, early publication of the tile aggregate
+        float4 o4 = make_float4(0, 0, 0, 0), d4 = o4, c4 = o4, h = make_float4(kFloatMax, 0, 0, 0);
+        if (valid) { h = hit[i]; o4 = Oi[i]; d4 = Di[i]; c4 = Ci[i]; }
+        const bool is_hit = valid && h.x < kFloatMax;                            // Renderer.cpp:426
+        const int tri = __float_as_int(h.y), model = __float_as_int(h.z);
+        const int type = is_hit ? __ldg(&sc.shade[model].mat.x) : -1;
+        // bounces-- leaves > 0 (Renderer.cpp:478, 512); EMISSIVE zeroes the count (Renderer.cpp:459), a miss too (Renderer.cpp:476)
+        const bool alive = is_hit && remaining > 1 && type != PTAP_EMISSIVE;
+        const unsigned ballot = __ballot_sync(0xffffffffu, alive);
+        const int total = __popc(ballot), rank = __popc(ballot & ((1u << lane) - 1u));
+        if (lane == 0) stVolatile(&status[tile], (tile == 0 ? kFlagPrefix : kFlagAgg) | (unsigned long long)total);
+
+        // ---- B: shade
+        if (valid) {
             V3 col = v3(c4);
-            if (h.x < kFloatMax) {                                               // Renderer.cpp:426
-                const int tri = __float_as_int(h.y), model = __float_as_int(h.z);
+            if (is_hit) {
                 float4 nm0, nm1, nm2;
                 const V3 nrm = worldNormal(sc, model, tri, nm0, nm1, nm2);
-                const int type = __ldg(&sc.shade[model].mat.x);
                 const V3 albedo = v3(nm0.w, nm1.w, nm2.w);
                 const V3 dir = xnormalize(v3(d4));                               // Renderer.cpp:428
                 const V3 pt = xadd(v3(o4), xscale(dir, h.x));                    // Renderer.cpp:429
-                alive = remaining > 1;                                           // bounces-- leaves > 0 (Renderer.cpp:478, 512)
                 if (type == PTAP_DIFFUSE || type == PTAP_METAL || type == PTAP_COAT) {   // Renderer.cpp:433-453
                     if (alive) {
                         Lcg rng(iter, i, remaining);
@@ -192,7 +202,6 @@ k_shade(SceneDev sc, WaveDev wv, int round, int in, const float4* __restrict__ h
                     col = xmul(col, albedo);
                 } else if (type == PTAP_EMISSIVE) {                              // Renderer.cpp:454-460
                     col = xmul(col, albedo);
-                    alive = false;
                 } else if (type == PTAP_REFLECTIVE) {                            // Renderer.cpp:461-467
                     col = xmul(col, albedo);
                     const V3 nd = reflectRay(dir, nrm);
@@ -208,57 +217,36 @@ k_shade(SceneDev sc, WaveDev wv, int round, int in, const float4* __restrict__ h
                 px[0] = xadd(px[0], xsqrt(col.x)); px[1] = xadd(px[1], xsqrt(col.y)); px[2] = xadd(px[2], xsqrt(col.z));
             }
         }
-        // ---- order-preserving compaction: ranks inside the tile by ballot, tile offsets by decoupled look-back
-        const unsigned ballot = __ballot_sync(0xffffffffu, alive);
-        const int rank = __popc(ballot & ((1u << lane) - 1u));
-        if (lane == 0) s_warp_off[warp] = __popc(ballot);
-        __syncthreads();
-        if (warp == 0) {
-            const int wt = lane < kShadeBlock / 32 ? s_warp_off[lane] : 0;
-            int incl = wt;
+
+        // ---- C: exclusive offset of the tile by decoupled look-back (the whole warp polls 32 predecessors at a time)
+        int excl = 0;
+        if (tile > 0) {
+            int look = tile - 1;
+            for (;;) {
+                const int idx = look - lane;
+                const unsigned long long w = idx >= 0 ? ldVolatile(&status[idx]) : kFlagPrefix;
+                const unsigned has_prefix = __ballot_sync(0xffffffffu, (w >> 62) == 2ull);
+                const unsigned is_empty = __ballot_sync(0xffffffffu, (w >> 62) == 0ull);
+                const int p = has_prefix ? __ffs(has_prefix) - 1 : 32;           // nearest tile with an inclusive prefix
+                const unsigned need = p >= 31 ? 0xffffffffu : ((2u << p) - 1u);
+                if (is_empty & need) continue;                                   // a needed predecessor has not published yet
+                int v = (lane <= p) ? (int)(w & kValueMask) : 0;
 #pragma unroll
-            for (int d = 1; d < kShadeBlock / 32; d <<= 1) {
-                const int up = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += up;
+                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                excl += v;
+                if (p < 32) break;
+                look -= 32;
             }
-            const int block_total = __shfl_sync(0xffffffffu, incl, kShadeBlock / 32 - 1);
-            if (lane < kShadeBlock / 32) s_warp_off[lane] = incl - wt;
-            int excl = 0;
-            if (tile == 0) {
-                if (lane == 0) stVolatile(&status[0], kFlagPrefix | (unsigned long long)block_total);
-            } else {
-                if (lane == 0) stVolatile(&status[tile], kFlagAgg | (unsigned long long)block_total);
-                int look = tile - 1;
-                for (;;) {
-                    const int idx = look - lane;
-                    unsigned long long w = idx >= 0 ? ldVolatile(&status[idx]) : kFlagPrefix;
-                    const unsigned has_prefix = __ballot_sync(0xffffffffu, (w >> 62) == 2ull);
-                    const unsigned is_empty = __ballot_sync(0xffffffffu, (w >> 62) == 0ull);
-                    const int p = has_prefix ? __ffs(has_prefix) - 1 : 32;       // nearest tile with an inclusive prefix
-                    const unsigned need = p >= 31 ? 0xffffffffu : ((2u << p) - 1u);
-                    if (is_empty & need) continue;                               // a needed predecessor has not published yet
-                    int v = (lane <= p) ? (int)(w & kValueMask) : 0;
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-                    excl += v;
-                    if (p < 32) break;
-                    look -= 32;
-                }
-                if (lane == 0) stVolatile(&status[tile], kFlagPrefix | (unsigned long long)(excl + block_total));
-            }
-            if (lane == 0) {
-                s_excl = excl;
-                if (base + kShadeBlock >= n && n_fixed < 0) st->n_active[round + 1] = excl + block_total;
-                if (base + kShadeBlock >= n && n_fixed >= 0) st->n_active[kMaxDepth + 1] = excl + block_total;
-            }
+            if (lane == 0) stVolatile(&status[tile], kFlagPrefix | (unsigned long long)(excl + total));
         }
-        __syncthreads();
-        if (i < n) {
-            const int pos = alive ? s_excl + s_warp_off[warp] + rank : -1;
+        if (lane == 0 && base + kShadeTile >= n) st->n_active[n_fixed < 0 ? round + 1 : kMaxDepth + 1] = excl + total;
+
+        // ---- D: survivors to their compacted position
+        if (valid) {
+            const int pos = alive ? excl + rank : -1;
             if (alive) { Oo[pos] = o4; Do[pos] = d4; Co[pos] = c4; }
             if (slot_pos) slot_pos[i] = pos;
         }
-        __syncthreads();
     }
 }
 
@@ -284,6 +272,22 @@ __global__ void k_resolve_hits(SceneDev sc, const float4* __restrict__ hit, cons
 }
 
 __global__ void k_set_iter(FrameState* st, int iter) { st->iter_next = iter; }
+
+// normals[t] = flat normal of global triangle t (the .w lanes of its TriRec), one 16-byte record for the shade kernel's gather
+__global__ void k_extract_normals(const TriRec* __restrict__ tris, int n, float4* __restrict__ normals)
+{
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+        normals[t] = make_float4(tris[t].v0.w, tris[t].e1.w, tris[t].e2.w, 0.0f);
+}
+
+// bvh_tris[k] = tris[tri_id[k]]: triangle records in BVH leaf order, gathered on the device (the host uploads each record once)
+__global__ void k_gather_tris(const TriRec* __restrict__ tris, const int* __restrict__ tri_id, int n, TriRec* __restrict__ out)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const TriRec* s = &tris[tri_id[k]];
+        out[k].v0 = s->v0; out[k].e1 = s->e1; out[k].e2 = s->e2;
+    }
+}
 
 __global__ void k_film_add(float* __restrict__ film, const float* __restrict__ add, size_t n)
 {
@@ -311,6 +315,16 @@ void launchResolveHits(const SceneDev& sc, const float4* hit, const float2* uv, 
 }
 
 void launchSetIter(FrameState* st, int iter, cudaStream_t stream) { k_set_iter<<<1, 1, 0, stream>>>(st, iter); }
+
+void launchExtractNormals(const TriRec* tris, int n, float4* normals, cudaStream_t stream)
+{
+    if (n > 0) k_extract_normals<<<148 * 4, 256, 0, stream>>>(tris, n, normals);
+}
+
+void launchGatherTris(const TriRec* tris, const int* tri_id, int n, TriRec* out, cudaStream_t stream)
+{
+    if (n > 0) k_gather_tris<<<148 * 4, 256, 0, stream>>>(tris, tri_id, n, out);
+}
 
 void launchFilmAdd(float* film, const float* add, size_t n, cudaStream_t stream)
 {
