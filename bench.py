@@ -280,7 +280,7 @@ def main():
     value = rays_all / t_max / 1e6
 
     # -------- end to end through the public API with HOST buffers: upload scene (H2D) + render + film read-back (D2H), every step
-    film_host = np.zeros((H, W, 3), np.float32)
+    film_host = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True).numpy()      # page-locked read-back target
     from pathtracerap_b200 import _native as N
     import ctypes as C
     barrier()

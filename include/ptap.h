@@ -69,6 +69,11 @@ typedef struct {
     const PtapBvhNode* bvh_nodes; int32_t n_bvh_nodes;
     const int32_t* bvh_tri_id; int32_t n_bvh_tris;    /* leaf-order position -> global triangle index */
     const int32_t* bvh_mesh_root; int32_t n_bvh_roots;/* per mesh: root node, -1 if empty */
+    int32_t bvh_depth;                                /* deepest BLAS level, 0 = unknown (computed at upload) */
+    /* optional triangle records prepared by ptap_scene_build_bvh (48 B per triangle: v0, v1-v0, v2-v0, flat normal in the .w lanes,
+     * reference arithmetic); NULL/0: ptap_upload_scene derives them from vertices + triangles.  ptap_scene keeps its upload-bound
+     * arrays (these, the BVH nodes, the leaf order) in page-locked host memory when a CUDA device is present. */
+    const void* tri_recs; int32_t n_tri_recs;
 } PtapSceneView;
 
 /* Closest-hit record of the parity entry point.  The reference's IntersectionData (Primitive.h:150-156)

@@ -44,7 +44,8 @@ class SceneView(C.Structure):
                 ("grids", C.c_void_p), ("ngrids", C.c_int32), ("voxels", C.c_void_p), ("nvoxels", C.c_int32),
                 ("refs", C.c_void_p), ("nrefs", C.c_int32), ("grid_dim", C.c_int32 * 3),
                 ("bvh_nodes", C.c_void_p), ("n_bvh_nodes", C.c_int32), ("bvh_tri_id", C.c_void_p), ("n_bvh_tris", C.c_int32),
-                ("bvh_mesh_root", C.c_void_p), ("n_bvh_roots", C.c_int32)]
+                ("bvh_mesh_root", C.c_void_p), ("n_bvh_roots", C.c_int32), ("bvh_depth", C.c_int32),
+                ("tri_recs", C.c_void_p), ("n_tri_recs", C.c_int32)]
 
 
 class Stats(C.Structure):

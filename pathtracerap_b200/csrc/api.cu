@@ -62,7 +62,8 @@ struct ptap_ctx {
     SceneDev sc{};
     WaveDev wv{};
     // host copies kept for the acceleration-structure builds
-    std::vector<TriRec> h_tris;
+    std::vector<TriRec> h_tris;      // kept only when the BVH still has to be built here (no prebuilt one in the view)
+    int ntris = 0;
     std::vector<PtapMesh> h_meshes;
     std::vector<PtapModel> h_models;
     std::vector<InstanceTrace> h_inst;
@@ -204,9 +205,9 @@ int buildTlas(std::vector<TlasItem>& items, int b, int e, std::vector<BvhNode>& 
 
 // Copies a BVH (nodes, leaf order) into the scene arena, gathers the leaf-ordered triangle records, points every model at
 // its mesh's root, derives the instances' world boxes from the BLAS root bounds and builds the TLAS over them.
-int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id, const int* mesh_root, size_t* bytes)
+int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id, const int* mesh_root, int known_depth, size_t* bytes)
 {
-    const int nt = (int)ctx->h_tris.size(), nm = (int)ctx->h_models.size();
+    const int nt = ctx->ntris, nm = (int)ctx->h_models.size();
     if ((size_t)nnodes > (size_t)std::max(nt, 1) * 2) return fail(ctx, PTAP_E_NOMEM, "BVH has more nodes than reserved (2 per triangle)");
     for (int i = 0; i < nnodes; ++i)
         for (int k = 0; k < 2; ++k) {
@@ -217,8 +218,8 @@ int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id
     for (int k = 0; k < nt; ++k)
         if (tri_id[k] < 0 || tri_id[k] >= nt) return fail(ctx, PTAP_E_INVALID, "BVH leaf order entry %d out of range", k);
     // depth of every BLAS (the traversal stack is fixed-size)
-    int blas_depth = 0;
-    {
+    int blas_depth = known_depth;
+    if (known_depth <= 0) {
         std::vector<std::pair<int, int>> todo;
         std::vector<char> seen(nnodes, 0);
         for (size_t m = 0; m < ctx->h_meshes.size(); ++m) if (mesh_root[m] >= 0) todo.push_back({mesh_root[m], 1});
@@ -374,9 +375,11 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
         if (m.mesh_index < 0 || m.mesh_index >= v->nmeshes) return fail(ctx, PTAP_E_INVALID, "model %d: mesh_index %d out of range", i, m.mesh_index);
         if (grid && (m.grid_index < 0 || m.grid_index >= v->ngrids)) return fail(ctx, PTAP_E_INVALID, "model %d: grid_index %d out of range", i, m.grid_index);
     }
-    for (int t = 0; t < nt; ++t)
-        for (int k = 0; k < 3; ++k)
-            if (v->triangles[t].v[k] < 0 || v->triangles[t].v[k] >= v->nvertices) return fail(ctx, PTAP_E_INVALID, "triangle %d: vertex index out of range", t);
+    const bool prepacked = v->tri_recs && v->n_tri_recs == nt && v->bvh_nodes && v->n_bvh_nodes > 0;      // ptap_scene_build_bvh made the records
+    if (!prepacked)
+        for (int t = 0; t < nt; ++t)
+            for (int k = 0; k < 3; ++k)
+                if (v->triangles[t].v[k] < 0 || v->triangles[t].v[k] >= v->nvertices) return fail(ctx, PTAP_E_INVALID, "triangle %d: vertex index out of range", t);
 
     // ---- repack on the host (DESIGN.md "Data layout")
     std::vector<InstanceTrace> inst(nm);
@@ -404,8 +407,13 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
         shade[i].nm2 = make_float4(nmx[6], nmx[7], nmx[8], m.mat.color[2]);
         shade[i].mat = make_int4(m.mat.type, 0, 0, 0);
     }
-    ctx->h_tris.resize(nt);
-    makeTriRecs(v->vertices, v->triangles, nt, ctx->h_tris.data());
+    const TriRec* recs = static_cast<const TriRec*>(v->tri_recs);
+    if (!prepacked) {
+        ctx->h_tris.resize(nt);
+        makeTriRecs(v->vertices, v->triangles, nt, ctx->h_tris.data());
+        recs = ctx->h_tris.data();
+    } else ctx->h_tris.clear();
+    ctx->ntris = nt;
     ctx->h_meshes.assign(v->meshes, v->meshes + v->nmeshes);
     ctx->h_models.assign(v->models, v->models + nm);
 
@@ -441,7 +449,7 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
     if (!d_inst || !d_shade || !d_tris || !d_normals || !d_btris || !d_btid || !d_nodes || (grid && (!d_cells || !d_refs))) return fail(ctx, PTAP_E_NOMEM, "scene arena exhausted");
     CK(cudaMemcpyAsync(d_inst, inst.data(), nm * sizeof(InstanceTrace), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_shade, shade.data(), nm * sizeof(InstanceShade), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_tris, ctx->h_tris.data(), nt * sizeof(TriRec), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_tris, recs, (size_t)nt * sizeof(TriRec), cudaMemcpyHostToDevice, ctx->stream));
     launchExtractNormals(d_tris, nt, d_normals, ctx->stream);
     ctx->d_tris = d_tris;
     if (grid) {
@@ -456,7 +464,7 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
     if (v->bvh_nodes && v->n_bvh_nodes > 0 && v->bvh_tri_id && v->bvh_mesh_root) {
         if (v->n_bvh_tris != nt || v->n_bvh_roots != v->nmeshes) return fail(ctx, PTAP_E_INVALID, "upload_scene: prebuilt BVH does not match the triangle / mesh counts");
         size_t bb = 0;
-        int rc = uploadBvh(ctx, reinterpret_cast<const BvhNode*>(v->bvh_nodes), v->n_bvh_nodes, v->bvh_tri_id, v->bvh_mesh_root, &bb);
+        int rc = uploadBvh(ctx, reinterpret_cast<const BvhNode*>(v->bvh_nodes), v->n_bvh_nodes, v->bvh_tri_id, v->bvh_mesh_root, v->bvh_depth, &bb);
         if (rc) return rc;
         bytes += bb;
     }
@@ -481,8 +489,9 @@ int ptap_build_accel(ptap_ctx* ctx, int kind)
     } else if (kind == PTAP_ACCEL_BVH) {
         if (!ctx->have_bvh) {
             BvhBuildResult res;
+            if ((int)ctx->h_tris.size() != ctx->ntris) return fail(ctx, PTAP_E_STATE, "build_accel: the triangle records were not kept on the host");
             buildSceneBvh(ctx->h_tris.data(), (int)ctx->h_tris.size(), ctx->h_meshes.data(), (int)ctx->h_meshes.size(), res);
-            int rc = uploadBvh(ctx, res.nodes.data(), (int)res.nodes.size(), res.tri_id.data(), res.mesh_root.data(), nullptr);
+            int rc = uploadBvh(ctx, res.nodes.data(), (int)res.nodes.size(), res.tri_id.data(), res.mesh_root.data(), res.max_depth + 1, nullptr);
             if (rc) return rc;
             CK(cudaStreamSynchronize(ctx->stream));
         }
@@ -500,19 +509,20 @@ int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, u
     CK(cudaSetDevice(ctx->device));
     if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
     const int N = W * H;
-    const int ntiles = (N + kShadeTile - 1) / kShadeTile;
+    const int ntiles = (N + kShadeTile - 1) / kShadeTile, nscan = (N + kScanSlots - 1) / kScanSlots;
     size_t need = Arena::need(N, sizeof(float4)) * 8 + Arena::need(N, sizeof(float2)) + Arena::need((size_t)N * 3, sizeof(float)) +
-                  Arena::need((size_t)ntiles * kMaxDepth, sizeof(unsigned long long)) + Arena::need(1, sizeof(FrameState)) + 4096;
+                  Arena::need((size_t)nscan * kMaxDepth, sizeof(unsigned long long)) + Arena::need(ntiles, sizeof(int)) + Arena::need(1, sizeof(FrameState)) + 4096;
     if (need > ctx->frame_arena.cap) CK(ctx->frame_arena.reserve(need)); else ctx->frame_arena.used = 0;
     Arena& A = ctx->frame_arena;
     WaveDev& wv = ctx->wv;
     for (int k = 0; k < 2; ++k) { wv.O[k] = A.alloc<float4>(N); wv.D[k] = A.alloc<float4>(N); wv.C[k] = A.alloc<float4>(N); }
     wv.hit = A.alloc<float4>(N); wv.hit_cache = A.alloc<float4>(N); wv.uv = A.alloc<float2>(N);
     wv.film = A.alloc<float>((size_t)N * 3);
-    wv.tile_status = A.alloc<unsigned long long>((size_t)ntiles * kMaxDepth);
+    wv.tile_status = A.alloc<unsigned long long>((size_t)nscan * kMaxDepth);
+    wv.tile_offset = A.alloc<int>(ntiles);
     wv.st = A.alloc<FrameState>(1);
-    if (!wv.st || !wv.tile_status || !wv.film) return fail(ctx, PTAP_E_NOMEM, "frame arena exhausted");
-    wv.W = W; wv.H = H; wv.N = N; wv.depth = depth; wv.ntiles = ntiles;
+    if (!wv.st || !wv.tile_status || !wv.tile_offset || !wv.film) return fail(ctx, PTAP_E_NOMEM, "frame arena exhausted");
+    wv.W = W; wv.H = H; wv.N = N; wv.depth = depth; wv.ntiles = ntiles; wv.nscan = nscan;
     wv.step_x = (float)(20.0 / (double)W);                       // Renderer.cpp:538-539 (SAMPLESX = SAMPLESY = 1)
     wv.step_y = (float)(16.0 / (double)H);
     CK(cudaMemsetAsync(wv.film, 0, (size_t)N * 3 * sizeof(float), ctx->stream));   // initImageKernel, Renderer.cpp:557-565
@@ -549,6 +559,7 @@ int ptap_render(ptap_ctx* ctx, int32_t iter_begin, int32_t iter_end)
                 launchTrace(ctx, wv.st, wv.O[in], wv.D[in], hitbuf, nullptr, nullptr, round, -1, (ctx->flags & PTAP_FLAG_COUNT) != 0); ++launches; ++trace_launches;
             }
             profMark(ctx, 2);
+            launchScan(ctx->sc, wv, round, hitbuf, wv.depth - round, -1, ctx->stream); ++launches;
             launchShade(ctx->sc, wv, round, in, hitbuf, wv.depth - round, -1, 0, nullptr, ctx->grid_shade, ctx->stream); ++launches;
             in ^= 1;
         }
@@ -723,9 +734,9 @@ int ptap_shade(ptap_ctx* ctx, const PtapPathIn* paths, int32_t n, int32_t iter, 
     if (!ctx || !ctx->have_scene || !paths || !out || n <= 0 || remaining <= 0) return fail(ctx, PTAP_E_STATE, "shade: scene and buffers required");
     CK(cudaSetDevice(ctx->device));
     if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
-    const int ntiles = (n + kShadeTile - 1) / kShadeTile;
+    const int ntiles = (n + kShadeTile - 1) / kShadeTile, nscan = (n + kScanSlots - 1) / kScanSlots;
     size_t need = Arena::need(n, sizeof(float4)) * 7 + Arena::need((size_t)n * 3, sizeof(float)) + Arena::need(n, sizeof(int)) +
-                  Arena::need(ntiles, sizeof(unsigned long long)) + Arena::need(1, sizeof(FrameState)) + 4096;
+                  Arena::need(nscan, sizeof(unsigned long long)) + Arena::need(ntiles, sizeof(int)) + Arena::need(1, sizeof(FrameState)) + 4096;
     if (need > ctx->scratch.cap) CK(ctx->scratch.reserve(need)); else ctx->scratch.used = 0;
     Arena& A = ctx->scratch;
     WaveDev wv{};
@@ -733,9 +744,10 @@ int ptap_shade(ptap_ctx* ctx, const PtapPathIn* paths, int32_t n, int32_t iter, 
     float4* hit = A.alloc<float4>(n);
     wv.film = A.alloc<float>((size_t)n * 3);
     int* slot_pos = A.alloc<int>(n);
-    wv.tile_status = A.alloc<unsigned long long>(ntiles);
+    wv.tile_status = A.alloc<unsigned long long>(nscan);
+    wv.tile_offset = A.alloc<int>(ntiles);
     wv.st = A.alloc<FrameState>(1);
-    wv.N = n; wv.W = n; wv.H = 1; wv.depth = 1; wv.ntiles = ntiles;
+    wv.N = n; wv.W = n; wv.H = 1; wv.depth = 1; wv.ntiles = ntiles; wv.nscan = nscan;
     std::vector<float4> hO(n), hD(n), hC(n), hH(n);
     for (int i = 0; i < n; ++i) {
         const PtapPathIn& p = paths[i];
@@ -743,7 +755,7 @@ int ptap_shade(ptap_ctx* ctx, const PtapPathIn* paths, int32_t n, int32_t iter, 
         hD[i] = make_float4(p.dir[0], p.dir[1], p.dir[2], 0.f);
         hC[i] = make_float4(p.color[0], p.color[1], p.color[2], 0.f);
         const bool miss = p.model < 0 || p.tri < 0;
-        if (!miss && (p.model >= ctx->sc.nmodels || p.tri >= (int)ctx->h_tris.size())) return fail(ctx, PTAP_E_INVALID, "shade: path %d has ids out of range", i);
+        if (!miss && (p.model >= ctx->sc.nmodels || p.tri >= ctx->ntris)) return fail(ctx, PTAP_E_INVALID, "shade: path %d has ids out of range", i);
         hH[i] = make_float4(miss ? kFloatMax : p.dist, __builtin_bit_cast(float, p.tri), __builtin_bit_cast(float, p.model), 0.f);
     }
     CK(cudaMemcpyAsync(wv.O[0], hO.data(), n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
@@ -751,9 +763,10 @@ int ptap_shade(ptap_ctx* ctx, const PtapPathIn* paths, int32_t n, int32_t iter, 
     CK(cudaMemcpyAsync(wv.C[0], hC.data(), n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(hit, hH.data(), n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(wv.film, 0, (size_t)n * 3 * sizeof(float), ctx->stream));
-    CK(cudaMemsetAsync(wv.tile_status, 0, ntiles * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(wv.tile_status, 0, nscan * sizeof(unsigned long long), ctx->stream));
     CK(cudaMemsetAsync(wv.st, 0, sizeof(FrameState), ctx->stream));
     const int grid = ctx->sms * std::max(shadeOccupancy(), 1);
+    launchScan(ctx->sc, wv, 0, hit, remaining, n, ctx->stream);
     launchShade(ctx->sc, wv, 0, 0, hit, remaining, n, iter, slot_pos, grid, ctx->stream);
     std::vector<float4> oO(n), oD(n), oC(n);
     std::vector<float> film((size_t)n * 3);

@@ -97,9 +97,10 @@ struct WaveDev {
     float4* hit_cache;          // round-0 hits (first-hit cache, Renderer.cpp:594-613)
     float2* uv;                 // parity entry only
     float* film;                // W*H*3 running sum (Pixel, Primitive.h:145-148)
-    unsigned long long* tile_status;   // shade look-back words: rounds x 32-slot tiles
+    unsigned long long* tile_status;   // k_scan look-back words: rounds x 2048-slot scan blocks
+    int* tile_offset;           // survivors before each 32-slot tile of the current round (k_scan -> k_shade)
     FrameState* st;
-    int W, H, N, depth, ntiles;
+    int W, H, N, depth, ntiles, nscan;   // ntiles = ceil(N / 32), nscan = ceil(N / 2048)
     float step_x, step_y;
 };
 

@@ -8,7 +8,8 @@ namespace ptap {
 
 constexpr int kTraceBlock = 128;
 constexpr int kShadeBlock = 128;
-constexpr int kShadeTile = 32;       // one look-back tile = one warp = 32 consecutive slots
+constexpr int kShadeTile = 32;       // one compaction tile = one warp = 32 consecutive slots
+constexpr int kScanBlock = 256, kScanSlots = 2048, kScanTiles = kScanSlots / kShadeTile;   // k_scan: slots per CTA, tiles per CTA
 constexpr int kGenBlock = 256;
 constexpr int kTraceBatch = 32;      // rays a warp takes from the work-stealing cursor per atomic
 constexpr int kVoteTri = 8, kVoteInst = 4, kVoteRefill = 4;   // state-machine thresholds of k_trace_bvh (trace_bvh.cu)
@@ -23,6 +24,7 @@ int traceBvhOccupancy();
 
 // wavefront.cu
 void launchGenerate(const WaveDev& wv, int grid, cudaStream_t stream);
+void launchScan(const SceneDev& sc, const WaveDev& wv, int round, const float4* hit, int remaining, int n_fixed, cudaStream_t stream);
 void launchShade(const SceneDev& sc, const WaveDev& wv, int round, int in_buf, const float4* hit, int remaining, int n_fixed,
                  int iter_fixed, int* slot_pos, int grid, cudaStream_t stream);
 int shadeOccupancy();

@@ -42,6 +42,22 @@ struct ptap_scene {
     // optional BVH (ptap_scene_build_bvh); invalidated by any mesh edit
     ptap::BvhBuildResult bvh;
     bool have_bvh = false;
+    int bvh_nnodes = 0;
+    // upload-bound copies of the BVH arrays and the triangle records, page-locked when a CUDA device exists (plain malloc otherwise)
+    struct Staging {
+        void* p = nullptr; size_t bytes = 0; bool pinned = false;
+        void release() { if (p) { if (pinned) cudaFreeHost(p); else free(p); } p = nullptr; bytes = 0; pinned = false; }
+        void* fill(const void* src, size_t n)
+        {
+            release();
+            if (n == 0) return nullptr;
+            if (cudaHostAlloc(&p, n, cudaHostAllocDefault) == cudaSuccess) pinned = true;
+            else { (void)cudaGetLastError(); p = malloc(n); pinned = false; }
+            if (p) { memcpy(p, src, n); bytes = n; }
+            return p;
+        }
+        ~Staging() { release(); }
+    } st_nodes, st_tri_id, st_recs;
     std::string err;
 };
 
@@ -683,6 +699,11 @@ int ptap_scene_build_bvh(ptap_scene* s)
     std::vector<ptap::TriRec> recs(s->triangles.size());
     ptap::makeTriRecs(s->vertices.data(), s->triangles.data(), (int)s->triangles.size(), recs.data());
     ptap::buildSceneBvh(recs.data(), (int)recs.size(), s->meshes.data(), (int)s->meshes.size(), s->bvh);
+    if (!s->st_nodes.fill(s->bvh.nodes.data(), s->bvh.nodes.size() * sizeof(ptap::BvhNode)) ||
+        !s->st_tri_id.fill(s->bvh.tri_id.data(), s->bvh.tri_id.size() * sizeof(int)) ||
+        !s->st_recs.fill(recs.data(), recs.size() * sizeof(ptap::TriRec))) { s->err = "build_bvh: out of host memory"; return PTAP_E_NOMEM; }
+    s->bvh.nodes.clear(); s->bvh.nodes.shrink_to_fit();          // the staging copies are the ones handed out by ptap_scene_view
+    s->bvh_nnodes = (int)(s->st_nodes.bytes / sizeof(ptap::BvhNode));
     s->have_bvh = true;
     return PTAP_OK;
 }
@@ -692,10 +713,13 @@ int ptap_scene_view(const ptap_scene* s, PtapSceneView* out)
     if (!s || !out) return PTAP_E_INVALID;
     static_assert(sizeof(PtapBvhNode) == sizeof(ptap::BvhNode), "public and device BVH node layouts must agree");
     out->bvh_nodes = nullptr; out->n_bvh_nodes = 0; out->bvh_tri_id = nullptr; out->n_bvh_tris = 0; out->bvh_mesh_root = nullptr; out->n_bvh_roots = 0;
+    out->bvh_depth = 0; out->tri_recs = nullptr; out->n_tri_recs = 0;
     if (s->have_bvh) {
-        out->bvh_nodes = reinterpret_cast<const PtapBvhNode*>(s->bvh.nodes.data()); out->n_bvh_nodes = (int)s->bvh.nodes.size();
-        out->bvh_tri_id = s->bvh.tri_id.data(); out->n_bvh_tris = (int)s->bvh.tri_id.size();
+        out->bvh_nodes = static_cast<const PtapBvhNode*>(s->st_nodes.p); out->n_bvh_nodes = s->bvh_nnodes;
+        out->bvh_tri_id = static_cast<const int32_t*>(s->st_tri_id.p); out->n_bvh_tris = (int)s->bvh.tri_id.size();
         out->bvh_mesh_root = s->bvh.mesh_root.data(); out->n_bvh_roots = (int)s->bvh.mesh_root.size();
+        out->bvh_depth = s->bvh.max_depth + 1;
+        out->tri_recs = s->st_recs.p; out->n_tri_recs = (int)(s->st_recs.bytes / sizeof(ptap::TriRec));
     }
     out->models = s->models.data(); out->nmodels = (int)s->models.size();
     out->meshes = s->meshes.data(); out->nmeshes = (int)s->meshes.size();

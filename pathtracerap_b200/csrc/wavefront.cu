@@ -129,8 +129,8 @@ __global__ void __launch_bounds__(kGenBlock) k_generate(WaveDev wv)
     }
     if (tid >= 1 && tid <= kMaxDepth + 1) st->n_active[tid] = 0;
     if (tid < kMaxDepth + 2) { st->ticket[tid] = 0u; st->fetch[tid] = 0u; }
-    const int nwords = wv.ntiles * wv.depth;
-    for (int i = tid; i < nwords; i += stride) wv.tile_status[i] = 0ull;      // one look-back word per 32-slot tile and round
+    const int nwords = wv.nscan * wv.depth;
+    for (int i = tid; i < nwords; i += stride) wv.tile_status[i] = 0ull;      // one look-back word per 2048-slot scan block and round
     for (int i = tid; i < wv.N; i += stride) {
         const int y = i / wv.W, x = i % wv.W;
         // float world_x = -10.0 + x * step_x  (double add of a float product, Renderer.cpp:541-542)
@@ -142,92 +142,64 @@ __global__ void __launch_bounds__(kGenBlock) k_generate(WaveDev wv)
     }
 }
 
-// shadeRayKernel + stable compaction + film accumulation for one bounce.
-// Slot i of queue `in` holds a path with `remaining` bounces left (every live path of a round has the same count).
-// One warp = one tile of 32 consecutive slots, taken by ticket; no block-level barrier anywhere:
-//   A  load the slot, decide survival (it depends only on hit / material type / remaining), publish the tile's survivor
-//      count in its status word at once (successors can add it without waiting for this tile's shading),
-//   B  shade (normal, RNG, scatter, throughput; film += sqrt(throughput) for terminated paths),
-//   C  decoupled look-back over the predecessors' status words: exclusive offset of the tile, publish the inclusive prefix,
-//   D  write the survivors to queue `in ^ 1` at offset + rank: same order as thrust::stable_partition (Renderer.cpp:628).
-__global__ void __launch_bounds__(kShadeBlock)
-k_shade(SceneDev sc, WaveDev wv, int round, int in, const float4* __restrict__ hit, int remaining, int n_fixed, int iter_fixed,
-        int* __restrict__ slot_pos)
+// Survival of slot i after this bounce: bounces-- leaves > 0 (Renderer.cpp:478, 512); EMISSIVE zeroes the count (Renderer.cpp:459),
+// a miss too (Renderer.cpp:476).  It depends only on the hit record, the material type and the round.
+__device__ __forceinline__ bool survives(const SceneDev& sc, const float4& h, int remaining, int& type)
 {
+    const bool is_hit = h.x < kFloatMax;                                         // Renderer.cpp:426
+    type = is_hit ? __ldg(&sc.shade[__float_as_int(h.z)].mat.x) : -1;
+    return is_hit && remaining > 1 && type != PTAP_EMISSIVE;
+}
+
+// compactStencilKernel + the scan half of thrust::stable_partition (Renderer.cpp:506-519, 628-630), as ONE pass over the hit records:
+// for every 32-slot tile of the round's wavefront, the number of surviving paths in all earlier slots (tile_offset), and the new
+// active count.  A CTA takes a 2048-slot block by ticket (8 coalesced slots per thread), scans its 64 tile counts in shared
+// memory, and obtains its own base by decoupled look-back over the earlier CTAs' status words (flag | count in one 64-bit word).
+// k_shade then writes survivors to tile_offset[tile] + rank: the same order-preserving placement, with no dependency between tiles.
+__global__ void __launch_bounds__(kScanBlock)
+k_scan(SceneDev sc, WaveDev wv, int round, const float4* __restrict__ hit, int remaining, int n_fixed)
+{
+    __shared__ int s_cnt[kScanTiles];
+    __shared__ int s_base;
+    __shared__ unsigned s_ticket;
     FrameState* st = wv.st;
     const int n = n_fixed >= 0 ? n_fixed : st->n_active[round];
-    const int iter = n_fixed >= 0 ? iter_fixed : st->iter_cur;
-    const int lane = threadIdx.x & 31;
-    const float4* __restrict__ Oi = wv.O[in]; const float4* __restrict__ Di = wv.D[in]; const float4* __restrict__ Ci = wv.C[in];
-    float4* __restrict__ Oo = wv.O[in ^ 1]; float4* __restrict__ Do = wv.D[in ^ 1]; float4* __restrict__ Co = wv.C[in ^ 1];
-    unsigned long long* status = wv.tile_status + (size_t)round * wv.ntiles;
-
-    for (;;) {
-        unsigned ticket = 0;
-        if (lane == 0) ticket = atomicAdd(&st->ticket[round], 1u);
-        const int tile = (int)__shfl_sync(0xffffffffu, ticket, 0);
-        const int base = tile * kShadeTile;
-        if (base >= n) break;
-        const int i = base + lane;
-        const bool valid = i < n;
-
-        // ---- A: loads, survival, early publication of the tile aggregate
-        float4 o4 = make_float4(0, 0, 0, 0), d4 = o4, c4 = o4, h = make_float4(kFloatMax, 0, 0, 0);
-        if (valid) { h = hit[i]; o4 = Oi[i]; d4 = Di[i]; c4 = Ci[i]; }
-        const bool is_hit = valid && h.x < kFloatMax;                            // Renderer.cpp:426
-        const int tri = __float_as_int(h.y), model = __float_as_int(h.z);
-        const int type = is_hit ? __ldg(&sc.shade[model].mat.x) : -1;
-        // bounces-- leaves > 0 (Renderer.cpp:478, 512); EMISSIVE zeroes the count (Renderer.cpp:459), a miss too (Renderer.cpp:476)
-        const bool alive = is_hit && remaining > 1 && type != PTAP_EMISSIVE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long* status = wv.tile_status + (size_t)round * wv.nscan;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&st->ticket[round], 1u);
+    __syncthreads();
+    const int blk = (int)s_ticket;
+    const int base = blk * kScanSlots;
+    if (base >= n) return;
+#pragma unroll
+    for (int k = 0; k < kScanSlots / kScanBlock; ++k) {
+        const int i = base + k * kScanBlock + threadIdx.x;
+        bool alive = false;
+        if (i < n) { int type; alive = survives(sc, hit[i], remaining, type); }
         const unsigned ballot = __ballot_sync(0xffffffffu, alive);
-        const int total = __popc(ballot), rank = __popc(ballot & ((1u << lane) - 1u));
-        if (lane == 0) stVolatile(&status[tile], (tile == 0 ? kFlagPrefix : kFlagAgg) | (unsigned long long)total);
-
-        // ---- B: shade
-        if (valid) {
-            V3 col = v3(c4);
-            if (is_hit) {
-                float4 nm0, nm1, nm2;
-                const V3 nrm = worldNormal(sc, model, tri, nm0, nm1, nm2);
-                const V3 albedo = v3(nm0.w, nm1.w, nm2.w);
-                const V3 dir = xnormalize(v3(d4));                               // Renderer.cpp:428
-                const V3 pt = xadd(v3(o4), xscale(dir, h.x));                    // Renderer.cpp:429
-                if (type == PTAP_DIFFUSE || type == PTAP_METAL || type == PTAP_COAT) {   // Renderer.cpp:433-453
-                    if (alive) {
-                        Lcg rng(iter, i, remaining);
-                        const V3 nd = type == PTAP_DIFFUSE ? hemisphere(nrm, rng) : type == PTAP_METAL ? metal(nrm, dir, rng) : coat(nrm, dir, rng);
-                        const V3 no = xadd(pt, xscale(nrm, 0.1f));
-                        o4.x = no.x; o4.y = no.y; o4.z = no.z; d4.x = nd.x; d4.y = nd.y; d4.z = nd.z;
-                    }
-                    col = xmul(col, albedo);
-                } else if (type == PTAP_EMISSIVE) {                              // Renderer.cpp:454-460
-                    col = xmul(col, albedo);
-                } else if (type == PTAP_REFLECTIVE) {                            // Renderer.cpp:461-467
-                    col = xmul(col, albedo);
-                    const V3 nd = reflectRay(dir, nrm);
-                    const V3 no = xadd(pt, xscale(nrm, 0.1f));
-                    o4.x = no.x; o4.y = no.y; o4.z = no.z; d4.x = nd.x; d4.y = nd.y; d4.z = nd.z;
-                }                                                                // SPECULAR / REFRACTIVE: no branch, ray unchanged
-            } else {                                                             // Renderer.cpp:471-477
-                col = xmul(col, v3(0.01f, 0.01f, 0.01f));
-            }
-            c4.x = col.x; c4.y = col.y; c4.z = col.z;
-            if (!alive) {                                                        // gatherImageDataKernel, Renderer.cpp:481-496
-                float* px = wv.film + 3 * (size_t)__float_as_int(o4.w);
-                px[0] = xadd(px[0], xsqrt(col.x)); px[1] = xadd(px[1], xsqrt(col.y)); px[2] = xadd(px[2], xsqrt(col.z));
-            }
-        }
-
-        // ---- C: exclusive offset of the tile by decoupled look-back (the whole warp polls 32 predecessors at a time)
+        if (lane == 0) s_cnt[k * (kScanBlock / 32) + warp] = __popc(ballot);     // tile j = k * 8 + warp covers slots base + 32 j ..
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // exclusive scan of the 64 tile counts (two per lane), block total, look-back
+        const int c0 = s_cnt[2 * lane], c1 = s_cnt[2 * lane + 1];
+        int incl = c0 + c1;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int up = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += up; }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        const int ex = incl - (c0 + c1);
         int excl = 0;
-        if (tile > 0) {
-            int look = tile - 1;
+        if (blk == 0) {
+            if (lane == 0) stVolatile(&status[0], kFlagPrefix | (unsigned long long)total);
+        } else {
+            if (lane == 0) stVolatile(&status[blk], kFlagAgg | (unsigned long long)total);
+            int look = blk - 1;
             for (;;) {
                 const int idx = look - lane;
                 const unsigned long long w = idx >= 0 ? ldVolatile(&status[idx]) : kFlagPrefix;
                 const unsigned has_prefix = __ballot_sync(0xffffffffu, (w >> 62) == 2ull);
                 const unsigned is_empty = __ballot_sync(0xffffffffu, (w >> 62) == 0ull);
-                const int p = has_prefix ? __ffs(has_prefix) - 1 : 32;           // nearest tile with an inclusive prefix
+                const int p = has_prefix ? __ffs(has_prefix) - 1 : 32;           // nearest block with an inclusive prefix
                 const unsigned need = p >= 31 ? 0xffffffffu : ((2u << p) - 1u);
                 if (is_empty & need) continue;                                   // a needed predecessor has not published yet
                 int v = (lane <= p) ? (int)(w & kValueMask) : 0;
@@ -237,16 +209,80 @@ k_shade(SceneDev sc, WaveDev wv, int round, int in, const float4* __restrict__ h
                 if (p < 32) break;
                 look -= 32;
             }
-            if (lane == 0) stVolatile(&status[tile], kFlagPrefix | (unsigned long long)(excl + total));
+            if (lane == 0) stVolatile(&status[blk], kFlagPrefix | (unsigned long long)(excl + total));
         }
-        if (lane == 0 && base + kShadeTile >= n) st->n_active[n_fixed < 0 ? round + 1 : kMaxDepth + 1] = excl + total;
+        s_cnt[2 * lane] = excl + ex; s_cnt[2 * lane + 1] = excl + ex + c0;
+        if (lane == 0 && base + kScanSlots >= n) st->n_active[n_fixed < 0 ? round + 1 : kMaxDepth + 1] = excl + total;
+    }
+    __syncthreads();
+    if (threadIdx.x < kScanTiles && base + threadIdx.x * 32 < n) wv.tile_offset[base / 32 + threadIdx.x] = s_cnt[threadIdx.x];
+}
 
-        // ---- D: survivors to their compacted position
-        if (valid) {
-            const int pos = alive ? excl + rank : -1;
-            if (alive) { Oo[pos] = o4; Do[pos] = d4; Co[pos] = c4; }
-            if (slot_pos) slot_pos[i] = pos;
+// shadeRayKernel + the move half of stable_partition + film accumulation for one bounce (Renderer.cpp:411-479, 481-496, 628).
+// Slot i of queue `in` holds a path with `remaining` bounces left (every live path of a round has the same count).
+// One warp per 32-slot tile, tiles independent: load, shade, survivors to tile_offset[tile] + rank in queue `in ^ 1`,
+// terminated paths add sqrt(throughput) to the film (each pixel owns exactly one path per iteration).
+__global__ void __launch_bounds__(kShadeBlock)
+k_shade(SceneDev sc, WaveDev wv, int round, int in, const float4* __restrict__ hit, int remaining, int n_fixed, int iter_fixed,
+        int* __restrict__ slot_pos)
+{
+    const FrameState* st = wv.st;
+    const int n = n_fixed >= 0 ? n_fixed : st->n_active[round];
+    const int iter = n_fixed >= 0 ? iter_fixed : st->iter_cur;
+    const int lane = threadIdx.x & 31;
+    const float4* __restrict__ Oi = wv.O[in]; const float4* __restrict__ Di = wv.D[in]; const float4* __restrict__ Ci = wv.C[in];
+    float4* __restrict__ Oo = wv.O[in ^ 1]; float4* __restrict__ Do = wv.D[in ^ 1]; float4* __restrict__ Co = wv.C[in ^ 1];
+    const int nwarps = gridDim.x * (kShadeBlock / 32);
+    const int ntiles = (n + kShadeTile - 1) / kShadeTile;
+
+    for (int tile = blockIdx.x * (kShadeBlock / 32) + (threadIdx.x >> 5); tile < ntiles; tile += nwarps) {
+        const int i = tile * kShadeTile + lane;
+        const bool valid = i < n;
+        float4 o4 = make_float4(0, 0, 0, 0), d4 = o4, c4 = o4, h = make_float4(kFloatMax, 0, 0, 0);
+        if (valid) { h = hit[i]; o4 = Oi[i]; d4 = Di[i]; c4 = Ci[i]; }
+        const int excl = __ldg(&wv.tile_offset[tile]);
+        int type;
+        const bool alive = survives(sc, h, remaining, type) && valid;
+        const bool is_hit = valid && h.x < kFloatMax;
+        const int tri = __float_as_int(h.y), model = __float_as_int(h.z);
+        const unsigned ballot = __ballot_sync(0xffffffffu, alive);
+        const int rank = __popc(ballot & ((1u << lane) - 1u));
+        if (!valid) continue;
+
+        V3 col = v3(c4);
+        if (is_hit) {
+            float4 nm0, nm1, nm2;
+            const V3 nrm = worldNormal(sc, model, tri, nm0, nm1, nm2);
+            const V3 albedo = v3(nm0.w, nm1.w, nm2.w);
+            const V3 dir = xnormalize(v3(d4));                               // Renderer.cpp:428
+            const V3 pt = xadd(v3(o4), xscale(dir, h.x));                    // Renderer.cpp:429
+            if (type == PTAP_DIFFUSE || type == PTAP_METAL || type == PTAP_COAT) {   // Renderer.cpp:433-453
+                if (alive) {
+                    Lcg rng(iter, i, remaining);
+                    const V3 nd = type == PTAP_DIFFUSE ? hemisphere(nrm, rng) : type == PTAP_METAL ? metal(nrm, dir, rng) : coat(nrm, dir, rng);
+                    const V3 no = xadd(pt, xscale(nrm, 0.1f));
+                    o4.x = no.x; o4.y = no.y; o4.z = no.z; d4.x = nd.x; d4.y = nd.y; d4.z = nd.z;
+                }
+                col = xmul(col, albedo);
+            } else if (type == PTAP_EMISSIVE) {                              // Renderer.cpp:454-460
+                col = xmul(col, albedo);
+            } else if (type == PTAP_REFLECTIVE) {                            // Renderer.cpp:461-467
+                col = xmul(col, albedo);
+                const V3 nd = reflectRay(dir, nrm);
+                const V3 no = xadd(pt, xscale(nrm, 0.1f));
+                o4.x = no.x; o4.y = no.y; o4.z = no.z; d4.x = nd.x; d4.y = nd.y; d4.z = nd.z;
+            }                                                                // SPECULAR / REFRACTIVE: no branch, ray unchanged
+        } else {                                                             // Renderer.cpp:471-477
+            col = xmul(col, v3(0.01f, 0.01f, 0.01f));
         }
+        c4.x = col.x; c4.y = col.y; c4.z = col.z;
+        const int pos = alive ? excl + rank : -1;
+        if (alive) { Oo[pos] = o4; Do[pos] = d4; Co[pos] = c4; }
+        else {                                                               // gatherImageDataKernel, Renderer.cpp:481-496
+            float* px = wv.film + 3 * (size_t)__float_as_int(o4.w);
+            px[0] = xadd(px[0], xsqrt(col.x)); px[1] = xadd(px[1], xsqrt(col.y)); px[2] = xadd(px[2], xsqrt(col.z));
+        }
+        if (slot_pos) slot_pos[i] = pos;
     }
 }
 
@@ -295,6 +331,11 @@ __global__ void k_film_add(float* __restrict__ film, const float* __restrict__ a
 }
 
 void launchGenerate(const WaveDev& wv, int grid, cudaStream_t stream) { k_generate<<<grid, kGenBlock, 0, stream>>>(wv); }
+
+void launchScan(const SceneDev& sc, const WaveDev& wv, int round, const float4* hit, int remaining, int n_fixed, cudaStream_t stream)
+{
+    if (wv.nscan > 0) k_scan<<<wv.nscan, kScanBlock, 0, stream>>>(sc, wv, round, hit, remaining, n_fixed);
+}
 
 void launchShade(const SceneDev& sc, const WaveDev& wv, int round, int in_buf, const float4* hit, int remaining, int n_fixed,
                  int iter_fixed, int* slot_pos, int grid, cudaStream_t stream)
