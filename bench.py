@@ -33,6 +33,7 @@ GOLDEN_SCENE = os.path.join(ROOT, "tests", "golden", "bundled_scene.npz")
 WORKLOADS = {
     "mesh100k": (1920, 1080, 64, 5, "configs[1]: displaced icosphere 81,920 tris (DIFFUSE) in the bundled box with its 4 lights, 1920x1080, 64 spp, depth 5, BVH"),
     "mesh1m": (1920, 1080, 64, 5, "configs[3]: displaced icosphere 1,310,720 tris (DIFFUSE) in the bundled box, 1920x1080, 64 spp, depth 5, BVH"),
+    "mesh5m": (1920, 1080, 64, 5, "configs[3] upper end: displaced icosphere 5,242,880 tris (DIFFUSE) in the bundled box, 1920x1080, 64 spp, depth 5"),
     "bundled": (2800, 2240, 64, 5, "configs[2]: the reference's coded scene (METAL/COAT/REFLECTIVE/DIFFUSE/EMISSIVE, 11 models), 2800x2240, 64 spp, depth 5, BVH"),
     "cornell": (512, 512, 16, 8, "configs[0]: Cornell box from Input data, 512x512, 16 spp, depth 8, diffuse only"),
 }
@@ -57,7 +58,7 @@ def build_scene(workload: str):
         m["mat"]["type"] = np.where(m["mat"]["type"] == EMISSIVE, EMISSIVE, DIFFUSE)
         s = Scene.from_arrays(m, base["meshes"], base["vertices"], base["triangles"])
     else:
-        level = 6 if workload == "mesh100k" else 8
+        level = {"mesh100k": 6, "mesh1m": 8, "mesh5m": 9}[workload]
         keep = [3, 7, 8, 9, 10]                      # box + four lights of Scene.cpp:114-124, 175-221
         s = Scene.from_arrays(base["models"][keep], base["meshes"], base["vertices"], base["triangles"])
         mi = s.add_icosphere(level, radius=1000.0, displacement=0.05, seed=1 if workload == "mesh100k" else 2)
@@ -162,6 +163,7 @@ def main():
     ap.add_argument("--workload", default="mesh1m", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel of the workload")
     ap.add_argument("--accel", default="bvh", choices=["bvh", "grid"])
+    ap.add_argument("--grid-dim", type=int, default=25, help="voxels per axis of the uniform grid (--accel grid); the reference fixes 25 (Config.h:8-10)")
     ap.add_argument("--no-cache", action="store_true", help="disable the first-hit cache (Renderer.cpp:594-613)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -213,7 +215,7 @@ def main():
     if accel == ACCEL_BVH:
         scene.build_bvh()                 # host-side, part of scene construction like the reference's addMeshesToGrid
     else:
-        scene.build_grids(25, 25, 25)
+        scene.build_grids(args.grid_dim, args.grid_dim, args.grid_dim)
     build_s = time.perf_counter() - t0
     ntris = len(arrays["triangles"])
 
@@ -352,7 +354,7 @@ def main():
            "ms_per_step": round(t_max / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
            "config": {"workload": args.workload, "description": desc, "resolution": [W, H], "spp_per_gpu": spp, "depth": depth,
-                      "triangles": ntris, "models": len(arrays["models"]), "accel": args.accel, "first_hit_cache": not args.no_cache,
+                      "triangles": ntris, "models": len(arrays["models"]), "accel": args.accel if args.accel == "bvh" else f"grid {args.grid_dim}^3", "first_hit_cache": not args.no_cache,
                       "parallelism": f"sample-partition x{world}" + (" + 1 NCCL reduce of the film" if world > 1 else ""),
                       "l2": "wavefront state (6 float4 queues + hits, >300 MB at 1080p) exceeds L2 every bounce; the scene is small and L2-resident by design",
                       "host_bvh_build_s": round(build_s, 3)},

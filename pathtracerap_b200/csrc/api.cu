@@ -293,7 +293,7 @@ int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id
             tlas_root = nnodes;
         } else tlas_root = link;
     }
-    if (blas_depth + tlas_depth + 4 > kBvhStack) return fail(ctx, PTAP_E_INVALID, "BVH too deep for the traversal stack (%d + %d levels, %d entries)", blas_depth, tlas_depth, kBvhStack);
+    if (blas_depth + tlas_depth + 6 > kBvhStack) return fail(ctx, PTAP_E_INVALID, "BVH too deep for the traversal stack (%d + %d levels, %d entries)", blas_depth, tlas_depth, kBvhStack);
     if (nnodes + tlas.size() > ctx->nodes_cap) return fail(ctx, PTAP_E_NOMEM, "BVH node storage exhausted");
     CK(cudaMemcpyAsync(ctx->d_inst, ctx->h_inst.data(), nm * sizeof(InstanceTrace), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_nodes, nodes, (size_t)nnodes * sizeof(BvhNode), cudaMemcpyHostToDevice, ctx->stream));
@@ -304,7 +304,8 @@ int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id
     if (bytes) *bytes = nm * sizeof(InstanceTrace) + ((size_t)nnodes + tlas.size()) * sizeof(BvhNode) + (size_t)nt * sizeof(int);
     ctx->sc.tlas_root = tlas_root;
     ctx->sc.tmin_world = -(float)((kEpsilon + 2e-4) * max_scale * 1.001 + max_pad + 1e-3);
-    ctx->sc.prune = consistent ? 1.0001f : INFINITY;
+    ctx->sc.prune = consistent ? 1.0003f : INFINITY;
+    ctx->sc.tie = consistent ? 1.5e-4f : INFINITY;
     // residual of matrices that passed the check: |(M W - I) [o; 1]| <= 2e-5 * sqrt(3) * (|o|_1 + max |translation|); the kernel adds 1e-4 |o|_1
     ctx->sc.c_pad = (float)(4e-5 * max_trans + 1e-3);
     ctx->have_bvh = true;
@@ -718,7 +719,7 @@ static int traceImpl(ptap_ctx* ctx, const float* rays_od, int32_t n, PtapHit* ou
     CK(cudaMemsetAsync(st, 0, sizeof(FrameState), ctx->stream));
     if (!ctx->grid_trace) ctx->grid_trace = traceGridSize(ctx);
     launchTrace(ctx, st, O, D, hit, uv, counts ? dcnt : nullptr, 0, n);
-    launchResolveHits(ctx->sc, hit, uv, n, dout, ctx->stream);
+    launchResolveHits(ctx->sc, O, D, hit, uv, n, dout, ctx->stream);
     CK(cudaMemcpyAsync(out, dout, n * sizeof(PtapHit), cudaMemcpyDeviceToHost, ctx->stream));
     if (counts) CK(cudaMemcpyAsync(counts, dcnt, n * sizeof(int4), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -86,6 +86,7 @@ struct SceneDev {
     int batch;                  // rays a warp takes from the work-stealing cursor per atomic (PTAP_BATCH)
     int vote_tri, vote_inst, vote_refill;   // lanes that must wait in a state before the warp runs that state's step (PTAP_VOTE_*)
     float c_pad;                // slack of the pruning bound for the residual of model_to_world * world_to_model - I
+    float tie;                  // two instances' winners whose approximate world distances differ by less than this relative slack are compared exactly
     float prune;                // relative slack of cross-instance pruning (1.0001), +inf when some model's matrices are not inverses
 };
 
@@ -93,7 +94,7 @@ struct WaveDev {
     float4* O[2];               // (orig.xyz, bits(ipixel)) ping-pong
     float4* D[2];               // (dir.xyz, unused)
     float4* C[2];               // (throughput rgb, unused)
-    float4* hit;                // (dist, bits(tri), bits(model), t_model) per slot
+    float4* hit;                // (dist, bits(tri), bits(model), t_model) per slot; dist < 0: hit whose exact distance the consumer evaluates
     float4* hit_cache;          // round-0 hits (first-hit cache, Renderer.cpp:594-613)
     float2* uv;                 // parity entry only
     float* film;                // W*H*3 running sum (Pixel, Primitive.h:145-148)

@@ -14,6 +14,22 @@ constexpr int kGenBlock = 256;
 constexpr int kTraceBatch = 32;      // rays a warp takes from the work-stealing cursor per atomic
 constexpr int kVoteTri = 8, kVoteInst = 4, kVoteRefill = 4;   // state-machine thresholds of k_trace_bvh (trace_bvh.cu)
 
+// World distance of the hit at model-space parameter t of model `im` along the stored ray (bo, bd), exactly as the reference computes
+// it (Renderer.cpp:381-382 ray set-up, :388-391 conversion).  k_trace_bvh only carries an approximate distance while traversing
+// (it needs the exact one just to break near-ties); the consumers of a hit record (k_shade, k_resolve_hits) evaluate this function,
+// at full SIMT efficiency, instead of the traversal doing it with a handful of active lanes.
+__device__ __forceinline__ float exactHitDistance(const SceneDev& sc, V3 bo, V3 bd, int im, float t)
+{
+    const InstanceTrace* __restrict__ inst = &sc.inst[im];
+    const float4 w0 = ldg4(&inst->w2m[0]), w1 = ldg4(&inst->w2m[1]), w2 = ldg4(&inst->w2m[2]);
+    const V3 ro = xmat4(w0, w1, w2, bo, 1.0f);                                   // Renderer.cpp:381
+    const V3 rd = xnormalize(xmat4(w0, w1, w2, bd, 0.0f));                       // Renderer.cpp:382
+    const V3 nd = xnormalize(rd);                                                // Renderer.cpp:388
+    const V3 pm = xadd(ro, xscale(nd, t));                                       // Renderer.cpp:389
+    const V3 pw = xmat4(ldg4(&inst->m2w[0]), ldg4(&inst->m2w[1]), ldg4(&inst->m2w[2]), pm, 1.0f);   // :390
+    return xlength(xsub(pw, bo));                                                // Renderer.cpp:391
+}
+
 // closest hit, grid-compat (trace_grid.cu) and BVH (trace_bvh.cu).  n_fixed < 0: read the count from st->n_active[round].
 void launchTraceGrid(const SceneDev& sc, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, bool count_totals,
                      FrameState* st, int round, int n_fixed, int grid, cudaStream_t stream);
@@ -28,7 +44,7 @@ void launchScan(const SceneDev& sc, const WaveDev& wv, int round, const float4* 
 void launchShade(const SceneDev& sc, const WaveDev& wv, int round, int in_buf, const float4* hit, int remaining, int n_fixed,
                  int iter_fixed, int* slot_pos, int grid, cudaStream_t stream);
 int shadeOccupancy();
-void launchResolveHits(const SceneDev& sc, const float4* hit, const float2* uv, int n, PtapHit* out, cudaStream_t stream);
+void launchResolveHits(const SceneDev& sc, const float4* O, const float4* D, const float4* hit, const float2* uv, int n, PtapHit* out, cudaStream_t stream);
 void launchSetIter(FrameState* st, int iter, cudaStream_t stream);
 void launchFilmAdd(float* film, const float* add, size_t n, cudaStream_t stream);
 void launchExtractNormals(const TriRec* tris, int n, float4* normals, cudaStream_t stream);

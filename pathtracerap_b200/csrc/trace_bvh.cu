@@ -183,20 +183,34 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
                 const float tb = (g_dist * sc.prune + sc.c_pad + 1e-4f * (fabsf(bo.x) + fabsf(bo.y) + fabsf(bo.z))) * (mlen * wil) * 1.0001f;
                 if (tb < kFloatMax) tmax = tb;                                  // false for NaN / inf: no bound
             }
+            stack[sp++] = __float_as_int(__fdividef(1.0f, mlen * wil));           // world distance per unit of model-space t, for the exit step
             stack[sp++] = (int)~(kExitBit | (unsigned)im);
             node = __float_as_int(__ldg(&inst->grid.z));                        // BLAS root of the instance's mesh
         }
-        // ---- (3c) marker popped: leave instance `im` (Renderer.cpp:388-398)
+        // ---- (3c) marker popped: leave instance `im` (Renderer.cpp:388-398).  The nearest-model decision of the reference compares exact
+        // world distances; here the instance's winner is ranked by t * |d_w| / |W3 d_w| (its world distance up to `tie`), and the
+        // exact distances are evaluated only when two candidates are closer than that slack, or when pruning is off.
         if (s_exit && n_exit >= min(vote_inst, n_inner)) {
             const int im = (int)(code & kIndexMask);
+            const float ascale = __int_as_float(stack[--sp]);                    // pushed under the marker at entry
             if (best_tri >= 0) {
-                const InstanceTrace* __restrict__ inst = &sc.inst[im];
-                const V3 nd = xnormalize(rd);                                    // Renderer.cpp:388
-                const V3 pm = xadd(ro, xscale(nd, tmax));                        // Renderer.cpp:389
-                const V3 pw = xmat4(ldg4(&inst->m2w[0]), ldg4(&inst->m2w[1]), ldg4(&inst->m2w[2]), pm, 1.0f);   // :390
-                const float dist = xlength(xsub(pw, bo));                        // Renderer.cpp:391
-                if (g_dist > dist || (g_dist == dist && im < g_model)) {         // Renderer.cpp:393-398 in model order
-                    g_dist = dist; g_model = im; g_tri = best_tri; g_t = tmax;
+                const float a = tmax * ascale;
+                const float cb = sc.c_pad + 1e-4f * (fabsf(bo.x) + fabsf(bo.y) + fabsf(bo.z));
+                const float a_lo = a - (fabsf(a) * sc.tie + cb), a_hi = a + (fabsf(a) * sc.tie + cb);
+                const float g_lo = g_dist - (g_dist * sc.tie + cb), g_hi = g_dist + (g_dist * sc.tie + cb);
+                bool take;
+                float nd = a;
+                if (a_hi < g_lo && a_hi < 0.99f * kFloatMax) take = true;        // clearly nearer than the current winner (or the first one)
+                else if (g_model >= 0 && a_lo > g_hi) take = false;              // clearly farther
+                else {                                                           // near-tie, or no usable bound: the reference's comparison
+                    const float dn = exactHitDistance(sc, bo, bd, im, tmax);
+                    const float dg = g_model >= 0 ? exactHitDistance(sc, bo, bd, g_model, g_t) : kFloatMax;
+                    take = dg > dn || (dg == dn && g_model >= 0 && im < g_model);   // Renderer.cpp:393 in model order
+                    nd = dn;
+                    if (!take && g_model >= 0) g_dist = dg;
+                }
+                if (take) {
+                    g_dist = nd; g_model = im; g_tri = best_tri; g_t = tmax;
                     if (UV) { g_u = best_u; g_v = best_v; }
                 }
             }
@@ -209,7 +223,8 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
             const unsigned m_done = __ballot_sync(kFull, s_done && live);
             if (s_done && i >= 0) {
                 const bool found = g_dist < kFloatMax;
-                hit[i] = make_float4(found ? g_dist : kFloatMax, __int_as_float(found ? g_tri : -1), __int_as_float(found ? g_model : -1), g_t);
+                // hit.x < 0 tells the consumer to evaluate the exact world distance from (model, t) (kernels.cuh: exactHitDistance)
+                hit[i] = make_float4(found ? -1.0f - g_dist : kFloatMax, __int_as_float(found ? g_tri : -1), __int_as_float(found ? g_model : -1), g_t);
                 if (UV && uv) uv[i] = make_float2(g_u, g_v);
                 if (COUNT) { if (counts) counts[i] = cnt; tot_x += cnt.x; tot_z += cnt.z; }
                 i = -1;

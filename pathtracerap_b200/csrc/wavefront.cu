@@ -255,7 +255,9 @@ k_shade(SceneDev sc, WaveDev wv, int round, int in, const float4* __restrict__ h
             const V3 nrm = worldNormal(sc, model, tri, nm0, nm1, nm2);
             const V3 albedo = v3(nm0.w, nm1.w, nm2.w);
             const V3 dir = xnormalize(v3(d4));                               // Renderer.cpp:428
-            const V3 pt = xadd(v3(o4), xscale(dir, h.x));                    // Renderer.cpp:429
+            // IntersectionData::impact_distance (Renderer.cpp:391): k_trace_bvh leaves it to be evaluated here (hit.x < 0)
+            const float dist = h.x >= 0.0f ? h.x : exactHitDistance(sc, v3(o4), v3(d4), model, h.w);
+            const V3 pt = xadd(v3(o4), xscale(dir, dist));                   // Renderer.cpp:429
             if (type == PTAP_DIFFUSE || type == PTAP_METAL || type == PTAP_COAT) {   // Renderer.cpp:433-453
                 if (alive) {
                     Lcg rng(iter, i, remaining);
@@ -287,7 +289,8 @@ k_shade(SceneDev sc, WaveDev wv, int round, int in, const float4* __restrict__ h
 }
 
 // (dist, tri, model, t) + (u, v) -> PtapHit with the world normal and material the reference would have stored
-__global__ void k_resolve_hits(SceneDev sc, const float4* __restrict__ hit, const float2* __restrict__ uv, int n, PtapHit* __restrict__ out)
+__global__ void k_resolve_hits(SceneDev sc, const float4* __restrict__ O, const float4* __restrict__ D, const float4* __restrict__ hit,
+                               const float2* __restrict__ uv, int n, PtapHit* __restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -300,6 +303,7 @@ __global__ void k_resolve_hits(SceneDev sc, const float4* __restrict__ hit, cons
         const V3 nrm = worldNormal(sc, r.model, r.tri, a, b, c);
         r.normal[0] = nrm.x; r.normal[1] = nrm.y; r.normal[2] = nrm.z;
         r.mat_type = sc.shade[r.model].mat.x;
+        if (h.x < 0.0f) r.dist = exactHitDistance(sc, v3(O[i]), v3(D[i]), r.model, h.w);      // deferred by k_trace_bvh
         if (uv) { r.u = uv[i].x; r.v = uv[i].y; }
     } else {
         r.model = -1; r.tri = -1; r.t_model = 0.0f;
@@ -350,9 +354,9 @@ int shadeOccupancy()
     return nb;
 }
 
-void launchResolveHits(const SceneDev& sc, const float4* hit, const float2* uv, int n, PtapHit* out, cudaStream_t stream)
+void launchResolveHits(const SceneDev& sc, const float4* O, const float4* D, const float4* hit, const float2* uv, int n, PtapHit* out, cudaStream_t stream)
 {
-    if (n > 0) k_resolve_hits<<<(n + 255) / 256, 256, 0, stream>>>(sc, hit, uv, n, out);
+    if (n > 0) k_resolve_hits<<<(n + 255) / 256, 256, 0, stream>>>(sc, O, D, hit, uv, n, out);
 }
 
 void launchSetIter(FrameState* st, int iter, cudaStream_t stream) { k_set_iter<<<1, 1, 0, stream>>>(st, iter); }
