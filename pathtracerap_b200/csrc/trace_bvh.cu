@@ -48,20 +48,20 @@ __device__ __forceinline__ void leafTriangle(const SceneDev& sc, const V3& o, co
     const TriRec* __restrict__ tp = &sc.bvh_tris[k];
     const float4 a = ldg4(&tp->v0), b = ldg4(&tp->e1), c = ldg4(&tp->e2);
     if (COUNT) cnt.z++;
+    // Straight-line evaluation: the reference's early returns (Renderer.cpp:188-201) have no side effects, so testing all of its
+    // rejection conditions at the end gives the same verdict, and the handful of lanes in a triangle step do not diverge further.
     const V3 v0 = v3(a), v0v1 = v3(b), v0v2 = v3(c);
     const V3 pvec = xcross(d, v0v2);
     const float det = xdot(v0v1, pvec);
-    if (xabs(xsub(det, 0.0f)) < kEpsilon) return;
     const float invDet = xdiv(1.0f, det);
     const V3 tvec = xsub(o, v0);
     const float u = xmul(xdot(tvec, pvec), invDet);
-    if (u < (0.0f - kEpsilon) || u > (1.0f + kEpsilon)) return;
     const V3 qvec = xcross(tvec, v0v1);
     const float v = xmul(xdot(d, qvec), invDet);
-    if (v < (0.0f - kEpsilon) || xadd(u, v) > (1.0f + kEpsilon)) return;
     const float t = xmul(xdot(v0v2, qvec), invDet);
-    if (t < (0.0f - kEpsilon)) return;
-    if (t > tmax) return;
+    const bool reject = (xabs(xsub(det, 0.0f)) < kEpsilon) | (u < (0.0f - kEpsilon)) | (u > (1.0f + kEpsilon)) |
+                        (v < (0.0f - kEpsilon)) | (xadd(u, v) > (1.0f + kEpsilon)) | (t < (0.0f - kEpsilon)) | (t > tmax);
+    if (reject || !(t <= tmax)) return;                        // the second test only catches NaN (a degenerate det passes none of the above as true)
     const int id = __ldg(&sc.bvh_tri_id[k]);
     if (t < tmax || (best_tri >= 0 && id < best_tri)) { tmax = t; best_tri = id; if (UV) { best_u = u; best_v = v; } }
 }
