@@ -67,7 +67,7 @@ struct ptap_ctx {
     std::vector<PtapMesh> h_meshes;
     std::vector<PtapModel> h_models;
     std::vector<InstanceTrace> h_inst;
-    InstanceTrace* d_inst = nullptr; TriRec* d_tris = nullptr; BvhNode* d_nodes = nullptr; size_t nodes_cap = 0; TriRec* d_btris = nullptr; int* d_btid = nullptr;
+    InstanceTrace* d_inst = nullptr; TriRec* d_tris = nullptr; BvhNode* d_nodes = nullptr; size_t nodes_cap = 0; LeafTri* d_btris = nullptr; int* d_btid = nullptr;
     bool have_scene = false, have_grid = false, have_bvh = false, have_frame = false;
     int accel = PTAP_ACCEL_GRID_COMPAT;
     uint32_t flags = 0;
@@ -434,14 +434,14 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
     // ---- one arena for everything scene-lifetime; BVH storage is reserved up front (2T-1 BLAS nodes + 2M TLAS nodes bound)
     const size_t nodes_cap = (size_t)std::max(nt, 1) * 2 + (size_t)nm * 2 + 2;
     size_t need = Arena::need(nm, sizeof(InstanceTrace)) + Arena::need(nm, sizeof(InstanceShade)) +
-                  Arena::need(nt, sizeof(TriRec)) * 2 + Arena::need(nt, sizeof(float4)) + Arena::need(nt, sizeof(int)) + Arena::need(nodes_cap, sizeof(BvhNode)) +
+                  Arena::need(nt, sizeof(TriRec)) + Arena::need(nt, sizeof(LeafTri)) + Arena::need(nt, sizeof(float4)) + Arena::need(nt, sizeof(int)) + Arena::need(nodes_cap, sizeof(BvhNode)) +
                   (grid ? Arena::need(v->nvoxels, sizeof(int2)) + Arena::need(v->nrefs, sizeof(int)) : 0) + 4096;
     if (need > ctx->scene_arena.cap) CK(ctx->scene_arena.reserve(need)); else ctx->scene_arena.used = 0;
     Arena& A = ctx->scene_arena;
     InstanceTrace* d_inst = A.alloc<InstanceTrace>(nm);
     InstanceShade* d_shade = A.alloc<InstanceShade>(nm);
     TriRec* d_tris = A.alloc<TriRec>(nt);
-    TriRec* d_btris = A.alloc<TriRec>(nt);
+    LeafTri* d_btris = A.alloc<LeafTri>(nt);
     float4* d_normals = A.alloc<float4>(nt);
     int* d_btid = A.alloc<int>(nt);
     BvhNode* d_nodes = A.alloc<BvhNode>(nodes_cap);

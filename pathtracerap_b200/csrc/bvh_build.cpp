@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -20,7 +21,8 @@ namespace ptap {
 namespace {
 
 constexpr int kBins = 16;
-constexpr int kMaxLeaf = 4;          // SAH may stop earlier; hard cap 8 by the link encoding
+int gMaxLeaf = 4;                    // SAH may stop earlier; hard cap 8 by the link encoding (PTAP_BVH_LEAF, tuning only)
+float gNodeCost = 1.0f;              // cost of one inner node in units of one triangle test (PTAP_BVH_CI, tuning only)
 constexpr double kBandEps = 0.0056;  // > EPSILON (Config.h:4) to absorb rounding of u, v
 
 struct Box {
@@ -84,7 +86,7 @@ struct Builder {
             }
         }
         const float leaf_cost = bounds.area() * n;
-        if (n <= kMaxLeaf && (best_axis < 0 || best_cost + bounds.area() * 1.0f >= leaf_cost)) return makeLeaf();
+        if (n <= gMaxLeaf && (best_axis < 0 || best_cost + bounds.area() * gNodeCost >= leaf_cost)) return makeLeaf();
         int mid;
         if (best_axis < 0) {
             if (n <= 8) return makeLeaf();
@@ -132,6 +134,8 @@ void makeTriRecs(const PtapVertex* vertices, const PtapTriangle* triangles, int 
 void buildSceneBvh(const TriRec* tris, int ntris, const PtapMesh* meshes, int nmeshes, BvhBuildResult& out)
 {
     out.nodes.clear(); out.tri_id.clear();
+    if (const char* e = getenv("PTAP_BVH_LEAF")) gMaxLeaf = std::min(8, std::max(1, atoi(e)));
+    if (const char* e = getenv("PTAP_BVH_CI")) gNodeCost = (float)atof(e);
     out.mesh_root.assign(nmeshes, -1);
     out.max_depth = 0;
     for (int mi = 0; mi < nmeshes; ++mi) {

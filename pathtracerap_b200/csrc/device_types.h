@@ -46,6 +46,14 @@ struct TriRec {
     float4 e2;          // (e2.xyz, n.z)
 };
 
+// Triangle in BVH leaf order, 64 B = two 32-byte vector loads (LDG.E.256 on sm_100): the three edge-form vectors of the TriRec and
+// the GLOBAL triangle id, so that accepting a hit needs no second gather.
+struct __align__(32) LeafTri {
+    float v0[3], e1[3], e2[3];
+    int id;
+    int pad[6];
+};
+
 // BVH2 node, 64 B: both children's bounds and links in one record.
 struct BvhNode {
     float4 xy0;         // child0: (lo.x, hi.x, lo.y, hi.y)
@@ -77,7 +85,7 @@ struct SceneDev {
     const int2* cells;          // grid voxels: (start, end) into refs
     const int* refs;            // global triangle ids
     const BvhNode* nodes;       // all BLAS nodes, then the TLAS nodes
-    const TriRec* bvh_tris;     // triangles in BVH leaf order; v0.w..: see bvh_tri_id
+    const LeafTri* bvh_tris;    // triangles in BVH leaf order
     const int* bvh_tri_id;      // leaf-order position -> global triangle id
     int nmodels;
     int gx, gy, gz;

@@ -46,4 +46,14 @@ __device__ __forceinline__ int f2i_x86(float x) { return (x >= -2147483648.0f &&
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
+// 32-byte read-only vector load (LDG.E.256, sm_100): halves the load instructions and L1 tag look-ups of a 64-byte record
+struct F8 { float v[8]; };
+__device__ __forceinline__ F8 ldg8(const void* p)
+{
+    F8 r;
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7]) : "l"(p));
+    return r;
+}
+
 }  // namespace ptap

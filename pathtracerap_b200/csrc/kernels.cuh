@@ -48,6 +48,6 @@ void launchResolveHits(const SceneDev& sc, const float4* O, const float4* D, con
 void launchSetIter(FrameState* st, int iter, cudaStream_t stream);
 void launchFilmAdd(float* film, const float* add, size_t n, cudaStream_t stream);
 void launchExtractNormals(const TriRec* tris, int n, float4* normals, cudaStream_t stream);
-void launchGatherTris(const TriRec* tris, const int* tri_id, int n, TriRec* out, cudaStream_t stream);
+void launchGatherTris(const TriRec* tris, const int* tri_id, int n, LeafTri* out, cudaStream_t stream);
 
 }  // namespace ptap

@@ -22,7 +22,7 @@
 //  * cross-instance pruning: once some instance reported a hit at world distance g, TLAS nodes beyond g are skipped and
 //    the next instance is entered with the model-space bound t <= (g + |M o_m - o_w|) / |M3 d_m|.
 //
-// Node = 64 B holding both children's boxes (4 x 16-byte loads); triangles in leaf order, 48 B each.
+// Node = 64 B holding both children's boxes, leaf-order triangle = 64 B with its global id: two LDG.E.256 each.
 #include "kernels.cuh"
 
 namespace ptap {
@@ -45,12 +45,11 @@ template <bool UV, bool COUNT>
 __device__ __forceinline__ void leafTriangle(const SceneDev& sc, const V3& o, const V3& d, float& tmax, int& best_tri, float& best_u, float& best_v,
                                              int k, int4& cnt)
 {
-    const TriRec* __restrict__ tp = &sc.bvh_tris[k];
-    const float4 a = ldg4(&tp->v0), b = ldg4(&tp->e1), c = ldg4(&tp->e2);
+    const F8 ta = ldg8(&sc.bvh_tris[k]), tb = ldg8(reinterpret_cast<const char*>(&sc.bvh_tris[k]) + 32);
     if (COUNT) cnt.z++;
     // Straight-line evaluation: the reference's early returns (Renderer.cpp:188-201) have no side effects, so testing all of its
     // rejection conditions at the end gives the same verdict, and the handful of lanes in a triangle step do not diverge further.
-    const V3 v0 = v3(a), v0v1 = v3(b), v0v2 = v3(c);
+    const V3 v0 = v3(ta.v[0], ta.v[1], ta.v[2]), v0v1 = v3(ta.v[3], ta.v[4], ta.v[5]), v0v2 = v3(ta.v[6], ta.v[7], tb.v[0]);
     const V3 pvec = xcross(d, v0v2);
     const float det = xdot(v0v1, pvec);
     const float invDet = xdiv(1.0f, det);
@@ -62,7 +61,7 @@ __device__ __forceinline__ void leafTriangle(const SceneDev& sc, const V3& o, co
     const bool reject = (xabs(xsub(det, 0.0f)) < kEpsilon) | (u < (0.0f - kEpsilon)) | (u > (1.0f + kEpsilon)) |
                         (v < (0.0f - kEpsilon)) | (xadd(u, v) > (1.0f + kEpsilon)) | (t < (0.0f - kEpsilon)) | (t > tmax);
     if (reject || !(t <= tmax)) return;                        // the second test only catches NaN (a degenerate det passes none of the above as true)
-    const int id = __ldg(&sc.bvh_tri_id[k]);
+    const int id = __float_as_int(tb.v[1]);
     if (t < tmax || (best_tri >= 0 && id < best_tri)) { tmax = t; best_tri = id; if (UV) { best_u = u; best_v = v; } }
 }
 
@@ -78,6 +77,11 @@ __device__ __forceinline__ bool slab(const V3& o, const V3& inv, float lox, floa
     tnear = tn;
     return tn <= tf + (fabsf(tf) * 2e-6f + 1e-6f);
 }
+
+#ifndef PTAP_PREFETCH
+#define PTAP_PREFETCH 0
+#endif
+__device__ __forceinline__ void prefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // traversal-only reciprocal: guarded against 0 (the exact predicate never uses it)
 __device__ __forceinline__ float safeInv(float d)
@@ -133,16 +137,22 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
         for (int rep = 0; rep < kNodeSteps; ++rep) {
             if (node >= 0) {
                 const BvhNode* __restrict__ np = &sc.nodes[node];
-                const float4 xy0 = ldg4(&np->xy0), xy1 = ldg4(&np->xy1), z01 = ldg4(&np->z01);
-                const int2 link = __ldg(reinterpret_cast<const int2*>(&np->link));
+                const F8 na = ldg8(np), nb = ldg8(reinterpret_cast<const char*>(np) + 32);      // 64-byte node = 2 x LDG.E.256
+                const float4 xy0 = make_float4(na.v[0], na.v[1], na.v[2], na.v[3]), xy1 = make_float4(na.v[4], na.v[5], na.v[6], na.v[7]);
+                const float4 z01 = make_float4(nb.v[0], nb.v[1], nb.v[2], nb.v[3]);
+                const int2 link = make_int2(__float_as_int(nb.v[4]), __float_as_int(nb.v[5]));
                 if (COUNT) cnt.x++;
                 float tn0, tn1;
                 const bool h0 = slab(ro, rinv, xy0.x, xy0.y, xy0.z, xy0.w, z01.x, z01.y, tmin, tmax, tn0);
                 const bool h1 = slab(ro, rinv, xy1.x, xy1.y, xy1.z, xy1.w, z01.z, z01.w, tmin, tmax, tn1);
                 if (h0 && h1) {
                     const bool swap = tn1 < tn0;
-                    stack[sp++] = swap ? link.x : link.y;            // farther child
+                    const int far = swap ? link.x : link.y;
+                    stack[sp++] = far;                               // farther child
                     node = swap ? link.y : link.x;
+#if PTAP_PREFETCH & 1
+                    if (far >= 0) prefetchL1(&sc.nodes[far]);
+#endif
                 } else if (h0 || h1) {
                     node = h0 ? link.x : link.y;
                 } else {
@@ -152,6 +162,9 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
         }
         // ---- (2) who waits for what: one warp reduction over 6-bit counters, one per state
         const unsigned code = ~(unsigned)node;
+#if PTAP_PREFETCH & 2
+        if (code < kEnterBit) prefetchL1(&sc.bvh_tris[code >> 3]);          // the leaf's first triangle, while the lane waits for the triangle step
+#endif
         const unsigned state = min(code >> 29, 4u);             // 0 tri, 1 enter, 2 exit, 3 done, 4 inner
         const bool live = state != 3u || i >= 0 || !exhausted;  // a retired lane with nothing left to fetch takes no part
         const unsigned sum = __reduce_add_sync(kFull, live ? 1u << (6u * state) : 0u);

@@ -321,11 +321,16 @@ __global__ void k_extract_normals(const TriRec* __restrict__ tris, int n, float4
 }
 
 // bvh_tris[k] = tris[tri_id[k]]: triangle records in BVH leaf order, gathered on the device (the host uploads each record once)
-__global__ void k_gather_tris(const TriRec* __restrict__ tris, const int* __restrict__ tri_id, int n, TriRec* __restrict__ out)
+__global__ void k_gather_tris(const TriRec* __restrict__ tris, const int* __restrict__ tri_id, int n, LeafTri* __restrict__ out)
 {
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        const TriRec* s = &tris[tri_id[k]];
-        out[k].v0 = s->v0; out[k].e1 = s->e1; out[k].e2 = s->e2;
+        const int id = tri_id[k];
+        const float4 a = tris[id].v0, b = tris[id].e1, c = tris[id].e2;
+        float4* o = reinterpret_cast<float4*>(&out[k]);
+        o[0] = make_float4(a.x, a.y, a.z, b.x);
+        o[1] = make_float4(b.y, b.z, c.x, c.y);
+        o[2] = make_float4(c.z, __int_as_float(id), 0.0f, 0.0f);
+        o[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 }
 
@@ -366,7 +371,7 @@ void launchExtractNormals(const TriRec* tris, int n, float4* normals, cudaStream
     if (n > 0) k_extract_normals<<<148 * 4, 256, 0, stream>>>(tris, n, normals);
 }
 
-void launchGatherTris(const TriRec* tris, const int* tri_id, int n, TriRec* out, cudaStream_t stream)
+void launchGatherTris(const TriRec* tris, const int* tri_id, int n, LeafTri* out, cudaStream_t stream)
 {
     if (n > 0) k_gather_tris<<<148 * 4, 256, 0, stream>>>(tris, tri_id, n, out);
 }
