@@ -80,3 +80,30 @@ def test_full_size_properties(big):
     same = (c["model"] == a["model"][sel]) & (c["tri"] == a["tri"][sel])
     assert same.mean() > 0.999                                    # the rest: equal-distance neighbours across a shared edge
     assert np.abs(c["dist"][same] - dist[same] * 0.01).max() <= 1e-3 * np.maximum(dist[same], 1.0).max()
+
+
+def test_full_size_frame_invariants(big):
+    """Whole frames at the bench resolution (1920x1080, depth 5): size-independent properties of the wavefront.
+    Every pixel owns exactly one path per iteration and a path deposits sqrt(throughput) <= 1 once, so after k iterations every film
+    value lies in (0, k]; the active count never grows; rays traced = sum of the active counts; two renders are bit-identical."""
+    name, r, arrays = big
+    from pathtracerap_b200 import ACCEL_BVH
+    W, H, depth, iters = 1920, 1080, 5, 3
+    r.set_params(W, H, depth, first_hit_cache=False)
+    r.render(0, iters)
+    film = r.film()
+    st = r.stats()
+    assert np.isfinite(film).all() and film.min() > 0.0 and film.max() <= iters * (1 + 1e-6)
+    act = st["active_per_round"][:depth]
+    assert act[0] == W * H and all(a >= b for a, b in zip(act, act[1:])) and act[-1] > 0
+    assert st["paths"] == iters * W * H
+    assert iters * act[0] <= st["rays_traced"] <= iters * sum(act) * 1.01 and st["rays_traced"] >= sum(act)
+    r.set_params(W, H, depth, first_hit_cache=False)
+    r.render(0, iters)
+    assert np.array_equal(r.film(), film)                                   # deterministic: no atomics on the film, stable compaction
+    # the first-hit cache changes the launch schedule, not the image (camera rays are identical every iteration, Renderer.cpp:594-613)
+    r.set_params(W, H, depth, first_hit_cache=True)
+    r.render(0, iters)
+    assert np.array_equal(r.film(), film)
+    assert r.stats()["rays_traced"] == st["rays_traced"] - (iters - 1) * W * H
+    r.set_params(64, 32, 5)
