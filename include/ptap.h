@@ -46,13 +46,15 @@ typedef struct { int32_t start, end, entity_type; } PtapVoxel;                  
 
 enum { PTAP_DIFFUSE = 0, PTAP_SPECULAR, PTAP_REFLECTIVE, PTAP_REFRACTIVE, PTAP_EMISSIVE, PTAP_COAT, PTAP_METAL }; /* Primitive.h:70-79 */
 
-/* BVH2 node (new; the reference has no BVH): both children's bounds and links in one 64-byte record.
- * link >= 0: child node index; link < 0: leaf, ~link = (first_leaf_triangle << 3) | (count - 1). */
+/* BVH4 node (new; the reference has no BVH): the boxes of up to four children in SoA form and their links, 128 bytes.
+ * link >= 0: child node index; link < 0: leaf, ~link = (first_leaf_triangle << 3) | (count - 1).
+ * An unused slot holds the point box (1e15, 1e15, 1e15). */
 typedef struct {
-    float xy0[4];   /* child 0: lo.x, hi.x, lo.y, hi.y */
-    float xy1[4];   /* child 1: lo.x, hi.x, lo.y, hi.y */
-    float z01[4];   /* c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z */
-    int32_t link[4];/* child0, child1, 0, 0 */
+    float lox[4], hix[4];
+    float loy[4], hiy[4];
+    float loz[4], hiz[4];
+    int32_t link[4];
+    int32_t pad[4];
 } PtapBvhNode;
 
 /* The seven public vectors of the reference's Scene (Scene.h:26-32) as raw arrays. */

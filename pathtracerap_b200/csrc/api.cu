@@ -169,10 +169,10 @@ float boxArea(const float* lo, const float* hi)
     return 2.f * (dx * dy + dy * dz + dz * dx);
 }
 
-// Median-split BVH2 over the instances' world boxes; leaves are single instances (link ~(0x20000000 | model)).
-int buildTlas(std::vector<TlasItem>& items, int b, int e, std::vector<BvhNode>& nodes, int base, float* lo, float* hi, int depth, int& max_depth)
+// Median-split binary tree over the instances' world boxes (collapsed to 4-wide nodes afterwards); leaves are single instances
+// (link ~(0x20000000 | model)).
+int buildTlas(std::vector<TlasItem>& items, int b, int e, std::vector<Bvh2Node>& nodes, float* lo, float* hi)
 {
-    max_depth = std::max(max_depth, depth);
     for (int k = 0; k < 3; ++k) { lo[k] = 3e38f; hi[k] = -3e38f; }
     for (int i = b; i < e; ++i)
         for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], items[i].lo[k]); hi[k] = std::max(hi[k], items[i].hi[k]); }
@@ -189,18 +189,18 @@ int buildTlas(std::vector<TlasItem>& items, int b, int e, std::vector<BvhNode>& 
     const int me = (int)nodes.size();
     nodes.emplace_back();
     float l0[3], h0[3], l1[3], h1[3];
-    int c0 = buildTlas(items, b, mid, nodes, base, l0, h0, depth + 1, max_depth);
-    int c1 = buildTlas(items, mid, e, nodes, base, l1, h1, depth + 1, max_depth);
+    int c0 = buildTlas(items, b, mid, nodes, l0, h0);
+    int c1 = buildTlas(items, mid, e, nodes, l1, h1);
     if (boxArea(l1, h1) < boxArea(l0, h0)) {          // equal entry distances (origin inside both): visit the smaller box first
         std::swap(c0, c1);
         for (int k = 0; k < 3; ++k) { std::swap(l0[k], l1[k]); std::swap(h0[k], h1[k]); }
     }
-    BvhNode& nd = nodes[me];
+    Bvh2Node& nd = nodes[me];
     nd.xy0 = make_float4(l0[0], h0[0], l0[1], h0[1]);
     nd.xy1 = make_float4(l1[0], h1[0], l1[1], h1[1]);
     nd.z01 = make_float4(l0[2], h0[2], l1[2], h1[2]);
     nd.link = make_int4(c0, c1, 0, 0);
-    return base + me;
+    return me;
 }
 
 // Copies a BVH (nodes, leaf order) into the scene arena, gathers the leaf-ordered triangle records, points every model at
@@ -210,8 +210,8 @@ int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id
     const int nt = ctx->ntris, nm = (int)ctx->h_models.size();
     if ((size_t)nnodes > (size_t)std::max(nt, 1) * 2) return fail(ctx, PTAP_E_NOMEM, "BVH has more nodes than reserved (2 per triangle)");
     for (int i = 0; i < nnodes; ++i)
-        for (int k = 0; k < 2; ++k) {
-            const int l = k ? nodes[i].link.y : nodes[i].link.x;
+        for (int k = 0; k < 4; ++k) {
+            const int l = nodes[i].link[k];
             if (l >= nnodes) return fail(ctx, PTAP_E_INVALID, "BVH node %d: child index out of range", i);
             if (l < 0) { const int code = ~l, first = code >> 3, cnt = (code & 7) + 1; if (code >= 0x20000000 || first < 0 || first + cnt > nt) return fail(ctx, PTAP_E_INVALID, "BVH node %d: leaf range out of bounds", i); }
         }
@@ -228,8 +228,8 @@ int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id
             if (seen[node]) { if (d > 1) return fail(ctx, PTAP_E_INVALID, "BVH node %d is reachable twice", node); continue; }
             seen[node] = 1;
             blas_depth = std::max(blas_depth, d);
-            if (nodes[node].link.x >= 0) todo.push_back({nodes[node].link.x, d + 1});
-            if (nodes[node].link.y >= 0 && nodes[node].link.y != nodes[node].link.x) todo.push_back({nodes[node].link.y, d + 1});
+            for (int k = 0; k < 4; ++k)
+                if (nodes[node].link[k] >= 0 && nodes[node].lox[k] < 1e14f) todo.push_back({nodes[node].link[k], d + 1});
         }
     }
     std::vector<TlasItem> items;
@@ -255,10 +255,12 @@ int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id
                 if (!(std::fabs(v - (r == c ? 1.0 : 0.0)) <= 2e-5 * scale)) { consistent = false; break; }
             }
         const BvhNode& r = nodes[root];
-        const bool one = r.link.x == r.link.y;      // single-leaf mesh: the second child is a dummy
-        const float blo[2][3] = {{r.xy0.x, r.xy0.z, r.z01.x}, {r.xy1.x, r.xy1.z, r.z01.z}}, bhi[2][3] = {{r.xy0.y, r.xy0.w, r.z01.y}, {r.xy1.y, r.xy1.w, r.z01.w}};
-        float mlo[3], mhi[3];
-        for (int k = 0; k < 3; ++k) { mlo[k] = one ? blo[0][k] : std::min(blo[0][k], blo[1][k]); mhi[k] = one ? bhi[0][k] : std::max(bhi[0][k], bhi[1][k]); }
+        float mlo[3] = {3e38f, 3e38f, 3e38f}, mhi[3] = {-3e38f, -3e38f, -3e38f};
+        for (int k = 0; k < 4; ++k) {
+            if (!(r.lox[k] < 1e14f)) continue;      // unused slot
+            mlo[0] = std::min(mlo[0], r.lox[k]); mlo[1] = std::min(mlo[1], r.loy[k]); mlo[2] = std::min(mlo[2], r.loz[k]);
+            mhi[0] = std::max(mhi[0], r.hix[k]); mhi[1] = std::max(mhi[1], r.hiy[k]); mhi[2] = std::max(mhi[2], r.hiz[k]);
+        }
         TlasItem it; it.inst = i;
         for (int k = 0; k < 3; ++k) { it.lo[k] = 3e38f; it.hi[k] = -3e38f; }
         double ext = 0.0;
@@ -282,18 +284,18 @@ int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id
     int tlas_root = -1, tlas_depth = 0;
     if (!items.empty()) {
         float lo[3], hi[3];
-        const int link = buildTlas(items, 0, (int)items.size(), tlas, nnodes, lo, hi, 1, tlas_depth);
-        if (link < 0) {                                   // a single instance: root with a second child that is never entered
-            BvhNode nd;
-            nd.xy0 = make_float4(lo[0], hi[0], lo[1], hi[1]);
-            nd.xy1 = make_float4(1e15f, 1e15f, 1e15f, 1e15f);
-            nd.z01 = make_float4(lo[2], hi[2], 1e15f, 1e15f);
+        std::vector<Bvh2Node> t2;
+        const int link = buildTlas(items, 0, (int)items.size(), t2, lo, hi);
+        if (link < 0) {                                   // a single instance: a root with one child
+            Bvh2Node nd;
+            nd.xy0 = make_float4(lo[0], hi[0], lo[1], hi[1]); nd.xy1 = nd.xy0;
+            nd.z01 = make_float4(lo[2], hi[2], lo[2], hi[2]);
             nd.link = make_int4(link, link, 0, 0);
-            tlas.push_back(nd);
-            tlas_root = nnodes;
-        } else tlas_root = link;
+            t2.push_back(nd);
+        }
+        tlas_root = collapseBvh2(t2.data(), link < 0 ? (int)t2.size() - 1 : link, tlas, nnodes, 1, tlas_depth);
     }
-    if (blas_depth + tlas_depth + 6 > kBvhStack) return fail(ctx, PTAP_E_INVALID, "BVH too deep for the traversal stack (%d + %d levels, %d entries)", blas_depth, tlas_depth, kBvhStack);
+    if (3 * (blas_depth + tlas_depth) + 8 > kBvhStack) return fail(ctx, PTAP_E_INVALID, "BVH too deep for the traversal stack (%d + %d levels, %d entries)", blas_depth, tlas_depth, kBvhStack);
     if (nnodes + tlas.size() > ctx->nodes_cap) return fail(ctx, PTAP_E_NOMEM, "BVH node storage exhausted");
     CK(cudaMemcpyAsync(ctx->d_inst, ctx->h_inst.data(), nm * sizeof(InstanceTrace), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_nodes, nodes, (size_t)nnodes * sizeof(BvhNode), cudaMemcpyHostToDevice, ctx->stream));

@@ -41,7 +41,7 @@ struct Prim { Box box; float c[3]; int id; };
 
 struct Builder {
     std::vector<Prim>& prims;
-    std::vector<BvhNode>& nodes;
+    std::vector<Bvh2Node>& nodes;
     std::vector<int>& order;      // leaf-order list of prim ids (local to the mesh), appended
     int leaf_base;                // leaf-order offset of this mesh in the global arrays
     int max_depth = 0;
@@ -105,7 +105,7 @@ struct Builder {
         Box b0, b1;
         const int l0 = build(begin, mid, b0, depth + 1);
         const int l1 = build(mid, end, b1, depth + 1);
-        BvhNode& nd = nodes[me];
+        Bvh2Node& nd = nodes[me];
         nd.xy0 = make_float4(b0.lo[0], b0.hi[0], b0.lo[1], b0.hi[1]);
         nd.xy1 = make_float4(b1.lo[0], b1.hi[0], b1.lo[1], b1.hi[1]);
         nd.z01 = make_float4(b0.lo[2], b0.hi[2], b1.lo[2], b1.hi[2]);
@@ -115,6 +115,55 @@ struct Builder {
 };
 
 }  // namespace
+
+void setEmptyChild(BvhNode& nd, int slot, int link)
+{
+    // a far-away point box: (p - o) * inv exceeds every ray interval (an inverted box would be un-inverted by the slab's min/max)
+    nd.lox[slot] = nd.hix[slot] = nd.loy[slot] = nd.hiy[slot] = nd.loz[slot] = nd.hiz[slot] = 1e15f;
+    nd.link[slot] = link;
+}
+
+int collapseBvh2(const Bvh2Node* n2, int root2, std::vector<BvhNode>& out, int base, int depth, int& max_depth)
+{
+    struct Child { float lo[3], hi[3]; int link; };
+    auto childrenOf = [&](int n, Child* dst) {
+        const Bvh2Node& nd = n2[n];
+        dst[0] = Child{{nd.xy0.x, nd.xy0.z, nd.z01.x}, {nd.xy0.y, nd.xy0.w, nd.z01.y}, nd.link.x};
+        if (nd.link.x == nd.link.y) return 1;
+        dst[1] = Child{{nd.xy1.x, nd.xy1.z, nd.z01.z}, {nd.xy1.y, nd.xy1.w, nd.z01.w}, nd.link.y};
+        return 2;
+    };
+    max_depth = std::max(max_depth, depth);
+    Child ch[5];
+    int n = childrenOf(root2, ch);
+    while (n < 4) {
+        int best = -1; float best_area = -1.f;
+        for (int i = 0; i < n; ++i) {
+            if (ch[i].link < 0) continue;
+            Box bx; for (int k = 0; k < 3; ++k) { bx.lo[k] = ch[i].lo[k]; bx.hi[k] = ch[i].hi[k]; }
+            const float a = bx.area();
+            if (a > best_area) { best_area = a; best = i; }
+        }
+        if (best < 0) break;
+        Child two[2];
+        const int m = childrenOf(ch[best].link, two);
+        ch[best] = two[0];
+        if (m == 2) ch[n++] = two[1];
+    }
+    const int me = (int)out.size();
+    out.emplace_back();
+    int links[4];
+    for (int i = 0; i < n; ++i) links[i] = ch[i].link >= 0 ? collapseBvh2(n2, ch[i].link, out, base, depth + 1, max_depth) : ch[i].link;
+    BvhNode& nd = out[me];
+    memset(&nd, 0, sizeof nd);
+    for (int i = 0; i < 4; ++i) {
+        if (i < n) {
+            nd.lox[i] = ch[i].lo[0]; nd.hix[i] = ch[i].hi[0]; nd.loy[i] = ch[i].lo[1]; nd.hiy[i] = ch[i].hi[1]; nd.loz[i] = ch[i].lo[2]; nd.hiz[i] = ch[i].hi[2];
+            nd.link[i] = links[i];
+        } else setEmptyChild(nd, i, links[0]);
+    }
+    return base + me;
+}
 
 void makeTriRecs(const PtapVertex* vertices, const PtapTriangle* triangles, int ntris, TriRec* out)
 {
@@ -168,22 +217,23 @@ void buildSceneBvh(const TriRec* tris, int ntris, const PtapMesh* meshes, int nm
             p.c[0] = (float)(cx / 3); p.c[1] = (float)(cy / 3); p.c[2] = (float)(cz / 3);
         }
         std::vector<int> order; order.reserve(prims.size());
-        const int root = (int)out.nodes.size();
-        Builder b{prims, out.nodes, order, (int)out.tri_id.size()};
+        std::vector<Bvh2Node> n2;
+        n2.reserve(prims.size());
+        Builder b{prims, n2, order, (int)out.tri_id.size()};
         Box bounds;
         const int link = b.build(0, (int)prims.size(), bounds, 0);
         if (link < 0) {
-            // the whole mesh fits one leaf: give it a root whose second child can never be hit
-            BvhNode nd;
+            // the whole mesh fits one leaf: a root with a single child
+            Bvh2Node nd;
             nd.xy0 = make_float4(bounds.lo[0], bounds.hi[0], bounds.lo[1], bounds.hi[1]);
-            // a far-away point box: (p - o) * inv >= 1e15 - |o| exceeds every ray interval (an inverted box would be un-inverted by the slab's min/max)
-            nd.xy1 = make_float4(1e15f, 1e15f, 1e15f, 1e15f);
-            nd.z01 = make_float4(bounds.lo[2], bounds.hi[2], 1e15f, 1e15f);
+            nd.xy1 = nd.xy0;
+            nd.z01 = make_float4(bounds.lo[2], bounds.hi[2], bounds.lo[2], bounds.hi[2]);
             nd.link = make_int4(link, link, 0, 0);
-            out.nodes.push_back(nd);
+            n2.push_back(nd);
         }
-        out.mesh_root[mi] = root;
-        out.max_depth = std::max(out.max_depth, b.max_depth);
+        int depth4 = 0;
+        out.mesh_root[mi] = collapseBvh2(n2.data(), link < 0 ? (int)n2.size() - 1 : link, out.nodes, 0, 1, depth4);
+        out.max_depth = std::max(out.max_depth, depth4);
         for (int id : order) out.tri_id.push_back(id);
     }
 }

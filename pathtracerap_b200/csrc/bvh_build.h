@@ -9,11 +9,16 @@
 namespace ptap {
 
 struct BvhBuildResult {
-    std::vector<BvhNode> nodes;      // all BLASes back to back
+    std::vector<BvhNode> nodes;      // all BLASes back to back (4-wide nodes)
     std::vector<int> tri_id;         // leaf-order position -> global triangle id
     std::vector<int> mesh_root;      // per mesh: index of its BLAS root node, -1 if the mesh has no triangles
     int max_depth = 0;
 };
+
+// Collapses the binary subtree rooted at node `root2` of `n2` into 4-wide nodes appended to `out` (absolute index = base + position in
+// `out`): a child is replaced by its own two children, largest box first, until the node has four.  Returns the new root's index.
+int collapseBvh2(const Bvh2Node* n2, int root2, std::vector<BvhNode>& out, int base, int depth, int& max_depth);
+void setEmptyChild(BvhNode& nd, int slot, int link);
 
 // tris: global triangle table (v0, e1, e2 in .xyz).  One BLAS per mesh over [t_start, t_end).
 void buildSceneBvh(const TriRec* tris, int ntris, const PtapMesh* meshes, int nmeshes, BvhBuildResult& out);

@@ -10,7 +10,7 @@ constexpr float kEpsilon = 0.005f;          // Config.h:4
 constexpr float kFloatMax = 9999999.0f;     // Config.h:5
 constexpr float kFloatMin = -9999990.0f;    // Config.h:6
 constexpr int kMaxDepth = 16;               // rounds per iteration the context reserves state for
-constexpr int kBvhStack = 96;               // traversal stack entries per ray (upload fails for deeper trees)
+constexpr int kBvhStack = 160;              // traversal stack entries per ray (upload fails for deeper trees)
 
 // Per-model record read by the closest-hit kernels: 9 x float4 = 144 B.
 // Rows 0..2 of the reference's column-major mat4s (the w row is never used by
@@ -54,13 +54,23 @@ struct __align__(32) LeafTri {
     int pad[6];
 };
 
-// BVH2 node, 64 B: both children's bounds and links in one record.
-struct BvhNode {
+// Binary node of the builder (host only): both children's bounds and links.  The device format is the 4-wide BvhNode below.
+struct Bvh2Node {
     float4 xy0;         // child0: (lo.x, hi.x, lo.y, hi.y)
     float4 xy1;         // child1: (lo.x, hi.x, lo.y, hi.y)
     float4 z01;         // (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
-    int4 link;          // (child0, child1, 0, 0); >= 0: node index, < 0: triangle leaf ~((first << 3) | (count - 1)),
-                        // or (TLAS only) instance leaf ~(0x20000000 | model index)
+    int4 link;          // (child0, child1, 0, 0); >= 0: node index, < 0: leaf; link.x == link.y: only child0 exists
+};
+
+// BVH4 node, 128 B = four 32-byte vector loads (LDG.E.256): the boxes of up to four children in SoA form and their links.
+// link >= 0: node index; link < 0: triangle leaf ~((first << 3) | (count - 1)) or (TLAS only) instance leaf ~(0x20000000 | model index).
+// An unused slot holds a far-away point box that no ray interval reaches.
+struct __align__(32) BvhNode {
+    float lox[4], hix[4];
+    float loy[4], hiy[4];
+    float loz[4], hiz[4];
+    int link[4];
+    int pad[4];
 };
 
 // Device-resident frame state: lets a whole iteration run without a host round trip.

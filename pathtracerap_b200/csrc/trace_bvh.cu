@@ -22,7 +22,7 @@
 //  * cross-instance pruning: once some instance reported a hit at world distance g, TLAS nodes beyond g are skipped and
 //    the next instance is entered with the model-space bound t <= (g + |M o_m - o_w|) / |M3 d_m|.
 //
-// Node = 64 B holding both children's boxes, leaf-order triangle = 64 B with its global id: two LDG.E.256 each.
+// Node = 128 B holding four children's boxes (4 x LDG.E.256), leaf-order triangle = 64 B with its global id (2 x LDG.E.256).
 #include "kernels.cuh"
 
 namespace ptap {
@@ -35,7 +35,7 @@ constexpr int kDone = (int)0x80000000u;        // ~0x7fffffff: bottom-of-stack s
 //   0: triangle leaf (first << 3 | count - 1), 1: TLAS leaf = enter instance (code & kIndexMask), 2: marker = leave instance, 3: done
 constexpr unsigned kEnterBit = 0x20000000u, kExitBit = 0x40000000u, kIndexMask = 0x1fffffffu;
 #ifndef PTAP_NODE_STEPS
-#define PTAP_NODE_STEPS 2
+#define PTAP_NODE_STEPS 1
 #endif
 constexpr int kNodeSteps = PTAP_NODE_STEPS;    // inner nodes a lane may take per scheduling round
 
@@ -132,32 +132,31 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
     const int vote_tri = sc.vote_tri, vote_inst = sc.vote_inst, vote_refill = sc.vote_refill;
 
     for (;;) {
-        // ---- (1) one inner node for every lane that is at one
+        // ---- (1) inner nodes (TLAS and BLAS share the 4-wide format): test the four child boxes, continue with the nearest hit child,
+        // push the other hit children farthest first
 #pragma unroll
         for (int rep = 0; rep < kNodeSteps; ++rep) {
             if (node >= 0) {
-                const BvhNode* __restrict__ np = &sc.nodes[node];
-                const F8 na = ldg8(np), nb = ldg8(reinterpret_cast<const char*>(np) + 32);      // 64-byte node = 2 x LDG.E.256
-                const float4 xy0 = make_float4(na.v[0], na.v[1], na.v[2], na.v[3]), xy1 = make_float4(na.v[4], na.v[5], na.v[6], na.v[7]);
-                const float4 z01 = make_float4(nb.v[0], nb.v[1], nb.v[2], nb.v[3]);
-                const int2 link = make_int2(__float_as_int(nb.v[4]), __float_as_int(nb.v[5]));
+                const char* __restrict__ np = reinterpret_cast<const char*>(&sc.nodes[node]);
+                const F8 nx = ldg8(np), ny = ldg8(np + 32), nz = ldg8(np + 64), nl = ldg8(np + 96);      // 128-byte node = 4 x LDG.E.256
                 if (COUNT) cnt.x++;
-                float tn0, tn1;
-                const bool h0 = slab(ro, rinv, xy0.x, xy0.y, xy0.z, xy0.w, z01.x, z01.y, tmin, tmax, tn0);
-                const bool h1 = slab(ro, rinv, xy1.x, xy1.y, xy1.z, xy1.w, z01.z, z01.w, tmin, tmax, tn1);
-                if (h0 && h1) {
-                    const bool swap = tn1 < tn0;
-                    const int far = swap ? link.x : link.y;
-                    stack[sp++] = far;                               // farther child
-                    node = swap ? link.y : link.x;
-#if PTAP_PREFETCH & 1
-                    if (far >= 0) prefetchL1(&sc.nodes[far]);
-#endif
-                } else if (h0 || h1) {
-                    node = h0 ? link.x : link.y;
-                } else {
-                    node = stack[--sp];
+                int key[4], lnk[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float tn;
+                    const bool h = slab(ro, rinv, nx.v[c], nx.v[4 + c], ny.v[c], ny.v[4 + c], nz.v[c], nz.v[4 + c], tmin, tmax, tn);
+                    // entry distances as order-preserving integers (non-negative floats); a missed child sorts last
+                    key[c] = h ? __float_as_int(fmaxf(tn, 0.0f)) : 0x7f800000;
+                    lnk[c] = __float_as_int(nl.v[c]);
                 }
+#define PTAP_CSWAP(a, b) { const bool sw = key[b] < key[a]; const int ka = sw ? key[b] : key[a], kb = sw ? key[a] : key[b]; \
+                           const int la = sw ? lnk[b] : lnk[a], lb = sw ? lnk[a] : lnk[b]; key[a] = ka; key[b] = kb; lnk[a] = la; lnk[b] = lb; }
+                PTAP_CSWAP(0, 1) PTAP_CSWAP(2, 3) PTAP_CSWAP(0, 2) PTAP_CSWAP(1, 3) PTAP_CSWAP(1, 2)
+#undef PTAP_CSWAP
+                if (key[3] != 0x7f800000) stack[sp++] = lnk[3];
+                if (key[2] != 0x7f800000) stack[sp++] = lnk[2];
+                if (key[1] != 0x7f800000) stack[sp++] = lnk[1];
+                node = key[0] != 0x7f800000 ? lnk[0] : stack[--sp];
             }
         }
         // ---- (2) who waits for what: one warp reduction over 6-bit counters, one per state

@@ -59,15 +59,29 @@ def test_compose_trs_matches_reference_matrices(libptap, golden_scene):
     assert np.allclose(prod, np.eye(4), atol=1e-5)
 
 
+NODE = np.dtype([("lox", "<f4", 4), ("hix", "<f4", 4), ("loy", "<f4", 4), ("hiy", "<f4", 4), ("loz", "<f4", 4), ("hiz", "<f4", 4),
+                 ("link", "<i4", 4), ("pad", "<i4", 4)])          # PtapBvhNode, include/ptap.h
+
+
 def _bvh_of(scene):
-    from pathtracerap_b200 import _native as N
     scene.build_bvh()
     v = scene.view()
-    node_dt = np.dtype([("xy0", "<f4", 4), ("xy1", "<f4", 4), ("z01", "<f4", 4), ("link", "<i4", 4)])
-    nodes = np.frombuffer((C.c_char * (v.n_bvh_nodes * 64)).from_address(v.bvh_nodes), node_dt).copy()
+    assert NODE.itemsize == 128
+    nodes = np.frombuffer((C.c_char * (v.n_bvh_nodes * 128)).from_address(v.bvh_nodes), NODE).copy()
     tri_id = np.frombuffer((C.c_char * (v.n_bvh_tris * 4)).from_address(v.bvh_tri_id), np.int32).copy()
     roots = np.frombuffer((C.c_char * (v.n_bvh_roots * 4)).from_address(v.bvh_mesh_root), np.int32).copy()
+    assert v.bvh_depth >= 1 and v.n_tri_recs == v.n_bvh_tris
     return nodes, tri_id, roots
+
+
+def _slots(nd):
+    """(lo, hi, link) of the used child slots of a 4-wide node (an unused slot holds the far-away point box)."""
+    out = []
+    for k in range(4):
+        if nd["lox"][k] < 1e14:
+            out.append((np.array([nd["lox"][k], nd["loy"][k], nd["loz"][k]], np.float64),
+                        np.array([nd["hix"][k], nd["hiy"][k], nd["hiz"][k]], np.float64), int(nd["link"][k])))
+    return out
 
 
 def _check_bvh(nodes, tri_id, roots, arrays):
@@ -75,6 +89,7 @@ def _check_bvh(nodes, tri_id, roots, arrays):
     assert sorted(tri_id.tolist()) == list(range(len(tris)))            # a permutation: every triangle in exactly one leaf
     e = 0.0056                                                          # the predicate's band (bvh_build.cpp kBandEps)
     max_depth = 0
+    visited = set()
     for mi, root in enumerate(roots):
         if root < 0:
             continue
@@ -82,25 +97,21 @@ def _check_bvh(nodes, tri_id, roots, arrays):
         stack = [(int(root), 1)]
         while stack:
             n, d = stack.pop()
+            assert n not in visited                                     # a tree: no node is reachable twice
+            visited.add(n)
             max_depth = max(max_depth, d)
-            nd = nodes[n]
-            boxes = [((nd["xy0"][0], nd["xy0"][2], nd["z01"][0]), (nd["xy0"][1], nd["xy0"][3], nd["z01"][1])),
-                     ((nd["xy1"][0], nd["xy1"][2], nd["z01"][2]), (nd["xy1"][1], nd["xy1"][3], nd["z01"][3]))]
-            links = [int(nd["link"][0]), int(nd["link"][1])]
-            if links[0] == links[1]:
-                links, boxes = links[:1], boxes[:1]                      # single-leaf mesh: dummy second child
-            for (lo, hi), l in zip(boxes, links):
-                lo, hi = np.array(lo, np.float64), np.array(hi, np.float64)
+            slots = _slots(nodes[n])
+            assert 1 <= len(slots) <= 4
+            for lo, hi, l in slots:
                 if l >= 0:
                     stack.append((l, d + 1))
-                    c = nodes[l]                                         # the child's own boxes nest inside the box its parent holds for it
-                    clo = np.minimum([c["xy0"][0], c["xy0"][2], c["z01"][0]], [c["xy1"][0], c["xy1"][2], c["z01"][2]] if c["link"][0] != c["link"][1] else [np.inf] * 3)
-                    chi = np.maximum([c["xy0"][1], c["xy0"][3], c["z01"][1]], [c["xy1"][1], c["xy1"][3], c["z01"][3]] if c["link"][0] != c["link"][1] else [-np.inf] * 3)
+                    sub = _slots(nodes[l])                               # the child's own boxes nest inside the box its parent holds for it
+                    clo = np.min([s[0] for s in sub], axis=0); chi = np.max([s[1] for s in sub], axis=0)
                     assert (clo >= lo - 1e-3).all() and (chi <= hi + 1e-3).all()
                 else:
                     code = ~l
                     first, cnt = code >> 3, (code & 7) + 1
-                    assert 1 <= cnt <= 8
+                    assert 1 <= cnt <= 8 and code < 0x20000000
                     for k in range(first, first + cnt):
                         t = tris[tri_id[k]]
                         assert meshes[mi]["t_start"] <= tri_id[k] < meshes[mi]["t_end"]
@@ -120,7 +131,7 @@ def test_bvh_builder_invariants_bundled(libptap, golden_scene):
     s = Scene.from_arrays(g["models"], g["meshes"], g["vertices"], g["triangles"])
     nodes, tri_id, roots = _bvh_of(s)
     depth = _check_bvh(nodes, tri_id, roots, g)
-    assert depth + 8 <= 96                                               # kBvhStack (device_types.h)
+    assert 3 * depth + 12 <= 160                                         # kBvhStack (device_types.h): up to 3 pushes per level
 
 
 def test_bvh_builder_invariants_icosphere(libptap):
@@ -132,7 +143,7 @@ def test_bvh_builder_invariants_icosphere(libptap):
     a = s.arrays()
     assert len(a["triangles"]) == 20 * 4 ** 4
     depth = _check_bvh(nodes, tri_id, roots, a)
-    assert depth <= 40
+    assert depth <= 20
     # degenerate input: many identical triangles (identical centroids force the split-by-count path)
     v = np.zeros(3, dtype=a["vertices"].dtype); v["position"] = [[0, 0, 0], [1000, 0, 0], [0, 1000, 0]]; v["normal"] = [[0, 0, 1000]] * 3
     s2 = Scene.empty()
