@@ -666,32 +666,35 @@ int ptap_get_stats(ptap_ctx* ctx, PtapStats* out)
     return PTAP_OK;
 }
 
-// Renderer::renderImage (Renderer.cpp:15-63)
+// Renderer::renderImage (Renderer.cpp:15-63).  The per-pixel conversion runs on the device (k_resolve_bmp), the bytes come back through
+// a page-locked staging buffer, and the host only writes the header and the rows.
 int ptap_write_bmp(ptap_ctx* ctx, const char* path, int32_t iters)
 {
     if (!ctx || !ctx->have_frame || !path || iters <= 0) return fail(ctx, PTAP_E_INVALID, "write_bmp: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    { int rc = collect(ctx); if (rc) return rc; }
     const int W = ctx->wv.W, H = ctx->wv.H;
-    std::vector<float> film((size_t)W * H * 3);
-    int rc = ptap_read_film(ctx, film.data()); if (rc) return rc;
+    const size_t nbytes = (size_t)3 * W * H;
+    if (Arena::need(nbytes, 1) > ctx->scratch.cap) CK(ctx->scratch.reserve(Arena::need(nbytes, 1))); else ctx->scratch.used = 0;
+    unsigned char* d_bytes = ctx->scratch.alloc<unsigned char>(nbytes);
+    unsigned char* h_bytes = nullptr;
+    CK(cudaHostAlloc((void**)&h_bytes, nbytes, cudaHostAllocDefault));
+    const float div = 1 / (float)iters;                                     // Renderer.cpp:42
+    launchResolveBmp(ctx->wv.film, nbytes, div, d_bytes, ctx->stream);
+    cudaError_t e = cudaMemcpyAsync(h_bytes, d_bytes, nbytes, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) { cudaFreeHost(h_bytes); return fail(ctx, (int)e, "write_bmp: %s", cudaGetErrorString(e)); }
     FILE* f = fopen(path, "wb");
-    if (!f) return fail(ctx, PTAP_E_IO, "write_bmp: cannot open %s", path);
+    if (!f) { cudaFreeHost(h_bytes); return fail(ctx, PTAP_E_IO, "write_bmp: cannot open %s", path); }
     unsigned char hdr[54] = {0};
     hdr[0] = 'B'; hdr[1] = 'M'; hdr[10] = 54; hdr[14] = 40; hdr[26] = 1; hdr[28] = 24;
     const int32_t fileSize = 54 + 3 * W * H, imageSize = 3 * W * H;
     memcpy(hdr + 2, &fileSize, 4); memcpy(hdr + 18, &W, 4); memcpy(hdr + 22, &H, 4); memcpy(hdr + 34, &imageSize, 4);
-    fwrite(hdr, 1, 54, f);
-    // rows bottom-up as stored, no padding, bytes written in (x, y, z) order exactly as the reference does (Renderer.cpp:45-53)
-    std::vector<unsigned char> rowbuf((size_t)3 * W);
-    const float div = 1 / (float)iters;
-    for (int y = 0; y < H; ++y) {
-        for (int x = 0; x < W; ++x)
-            for (int k = 0; k < 3; ++k) {
-                const float c = (film[3 * ((size_t)x + (size_t)y * W) + k] * div) * 255.0f;
-                rowbuf[3 * x + k] = (unsigned char)(int)c;
-            }
-        fwrite(rowbuf.data(), 1, rowbuf.size(), f);
-    }
+    // rows bottom-up as stored, no padding, bytes in (x, y, z) order exactly as the reference writes them (Renderer.cpp:45-53)
+    const bool ok = fwrite(hdr, 1, 54, f) == 54 && fwrite(h_bytes, 1, nbytes, f) == nbytes;
     fclose(f);
+    cudaFreeHost(h_bytes);
+    if (!ok) return fail(ctx, PTAP_E_IO, "write_bmp: short write to %s", path);
     return PTAP_OK;
 }
 

@@ -334,6 +334,14 @@ __global__ void k_gather_tris(const TriRec* __restrict__ tris, const int* __rest
     }
 }
 
+// Renderer::renderImage's per-pixel arithmetic on the device (Renderer.cpp:42-53): byte = (char)(image * (1 / ITER) * 255), three bytes per
+// pixel in (x, y, z) order, rows bottom-up as stored.  The host then copies 3 bytes per pixel instead of 12 and only writes the file.
+__global__ void k_resolve_bmp(const float* __restrict__ film, size_t nvalues, float div, unsigned char* __restrict__ out)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvalues; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (unsigned char)(int)xmul(xmul(film[i], div), 255.0f);
+}
+
 __global__ void k_film_add(float* __restrict__ film, const float* __restrict__ add, size_t n)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) film[i] += add[i];
@@ -374,6 +382,11 @@ void launchExtractNormals(const TriRec* tris, int n, float4* normals, cudaStream
 void launchGatherTris(const TriRec* tris, const int* tri_id, int n, LeafTri* out, cudaStream_t stream)
 {
     if (n > 0) k_gather_tris<<<148 * 4, 256, 0, stream>>>(tris, tri_id, n, out);
+}
+
+void launchResolveBmp(const float* film, size_t nvalues, float div, unsigned char* out, cudaStream_t stream)
+{
+    if (nvalues) k_resolve_bmp<<<148 * 8, 256, 0, stream>>>(film, nvalues, div, out);
 }
 
 void launchFilmAdd(float* film, const float* add, size_t n, cudaStream_t stream)
