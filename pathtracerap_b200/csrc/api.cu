@@ -339,6 +339,7 @@ int ptap_create(int device, size_t arena_bytes, ptap_ctx** out)
     ctx->sc.vote_inst = std::min(32, std::max(1, envInt("PTAP_VOTE_INST", kVoteInst)));
     ctx->sc.vote_refill = std::min(32, std::max(1, envInt("PTAP_VOTE_REFILL", kVoteRefill)));
     ctx->sc.batch = std::max(1, envInt("PTAP_BATCH", kTraceBatch));
+    ctx->sc.vote_grid = std::min(32, std::max(1, envInt("PTAP_VOTE_GRID", kVoteGrid)));
     ctx->trace_ctas = std::max(0, envInt("PTAP_TRACE_CTAS", 0));
     if (arena_bytes) {                                          // caller-sized arena: split 1/4 scene, 3/4 frame
         if (ctx->scene_arena.reserve(arena_bytes / 4) != cudaSuccess || ctx->frame_arena.reserve(arena_bytes - arena_bytes / 4) != cudaSuccess) {

@@ -102,6 +102,7 @@ struct SceneDev {
     int tlas_root;              // node index of the TLAS root, -1 when no instance has triangles
     float tmin_world;           // lower end of the world-space ray interval: -(EPSILON band mapped to world units + box padding)
     int batch;                  // rays a warp takes from the work-stealing cursor per atomic (PTAP_BATCH)
+    int vote_grid;              // k_trace_grid: lanes that must wait in a state before its step runs (the most popular state always runs)
     int vote_tri, vote_inst, vote_refill;   // lanes that must wait in a state before the warp runs that state's step (PTAP_VOTE_*)
     float c_pad;                // slack of the pruning bound for the residual of model_to_world * world_to_model - I
     float tie;                  // two instances' winners whose approximate world distances differ by less than this relative slack are compared exactly

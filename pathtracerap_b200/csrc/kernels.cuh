@@ -12,7 +12,8 @@ constexpr int kShadeTile = 32;       // one compaction tile = one warp = 32 cons
 constexpr int kScanBlock = 256, kScanSlots = 2048, kScanTiles = kScanSlots / kShadeTile;   // k_scan: slots per CTA, tiles per CTA
 constexpr int kGenBlock = 256;
 constexpr int kTraceBatch = 32;      // rays a warp takes from the work-stealing cursor per atomic
-constexpr int kVoteTri = 8, kVoteInst = 6, kVoteRefill = 8;   // state-machine thresholds of k_trace_bvh (trace_bvh.cu)
+constexpr int kVoteTri = 8, kVoteInst = 6, kVoteRefill = 8;
+constexpr int kVoteGrid = 5;         // same for k_trace_grid (one threshold for all of its states)   // state-machine thresholds of k_trace_bvh (trace_bvh.cu)
 
 // World distance of the hit at model-space parameter t of model `im` along the stored ray (bo, bd), exactly as the reference computes
 // it (Renderer.cpp:381-382 ray set-up, :388-391 conversion).  k_trace_bvh only carries an approximate distance while traversing

@@ -89,7 +89,7 @@ k_trace_grid(SceneDev sc, const float4* __restrict__ O, const float4* __restrict
     float t_entry = 0.0f;
     int w_next = 0, w_end = 0;
     bool exhausted = false;
-    const int vote = sc.vote_tri;
+    const int vote = sc.vote_grid;
 
     for (;;) {
         // ---- who waits for what
