@@ -162,7 +162,7 @@ def main():
     ap.add_argument("--impl", default="ptap", choices=["ptap", "reference"])
     ap.add_argument("--workload", default="mesh1m", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel of the workload")
-    ap.add_argument("--accel", default="bvh", choices=["bvh", "grid"])
+    ap.add_argument("--accel", default="bvh", choices=["bvh", "lbvh", "grid"], help="bvh: host-built SAH tree (default); lbvh: tree built on the GPU at upload; grid: the reference's uniform grid")
     ap.add_argument("--grid-dim", type=int, default=25, help="voxels per axis of the uniform grid (--accel grid); the reference fixes 25 (Config.h:8-10)")
     ap.add_argument("--no-cache", action="store_true", help="disable the first-hit cache (Renderer.cpp:594-613)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -200,7 +200,7 @@ def main():
     # -------- our arm
     import torch
     import torch.distributed as dist
-    from pathtracerap_b200 import ACCEL_BVH, ACCEL_GRID_COMPAT, Renderer
+    from pathtracerap_b200 import ACCEL_BVH, ACCEL_BVH_DEVICE, ACCEL_GRID_COMPAT, Renderer
 
     if world > 1:
         torch.cuda.set_device(local)
@@ -210,10 +210,12 @@ def main():
     torch.cuda.init()
 
     scene, arrays = build_scene(args.workload)
-    accel = ACCEL_BVH if args.accel == "bvh" else ACCEL_GRID_COMPAT
+    accel = {"bvh": ACCEL_BVH, "lbvh": ACCEL_BVH_DEVICE, "grid": ACCEL_GRID_COMPAT}[args.accel]
     t0 = time.perf_counter()
     if accel == ACCEL_BVH:
         scene.build_bvh()                 # host-side, part of scene construction like the reference's addMeshesToGrid
+    elif accel == ACCEL_BVH_DEVICE:
+        pass                              # built on the GPU inside Renderer.allocateOnGPU / upload
     else:
         scene.build_grids(args.grid_dim, args.grid_dim, args.grid_dim)
     build_s = time.perf_counter() - t0
@@ -317,8 +319,8 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    if accel == ACCEL_BVH:
-        bytes_per_ray = 48.0 + 64.0 * avg_nodes + 48.0 * avg_tris
+    if accel != ACCEL_GRID_COMPAT:
+        bytes_per_ray = 48.0 + 128.0 * avg_nodes + 64.0 * avg_tris
     else:
         bytes_per_ray = 48.0 + 8.0 * avg_cells + 4.0 * avg_refs + 48.0 * avg_tris
     achieved = bytes_per_ray * rays / (ms_trace / 1e3) / 1e9 if ms_trace > 0 else None
@@ -329,7 +331,7 @@ def main():
         t = json.load(open(tp)).get(f"{args.workload}:{args.accel}")
         if t:
             traffic, traffic_note = t["dram_bytes_per_launch"], t["note"]
-    roofline = {"bound": "hbm", "kernel": "k_trace_bvh" if accel == ACCEL_BVH else "k_trace_grid",
+    roofline = {"bound": "hbm", "kernel": "k_trace_bvh" if accel != ACCEL_GRID_COMPAT else "k_trace_grid",
                 "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None,
                 "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                 "bytes_per_ray": round(bytes_per_ray, 1), "avg_nodes_per_ray": round(avg_nodes, 2), "avg_tris_per_ray": round(avg_tris, 2),
@@ -357,7 +359,7 @@ def main():
                       "triangles": ntris, "models": len(arrays["models"]), "accel": args.accel if args.accel == "bvh" else f"grid {args.grid_dim}^3", "first_hit_cache": not args.no_cache,
                       "parallelism": f"sample-partition x{world}" + (" + 1 NCCL reduce of the film" if world > 1 else ""),
                       "l2": "wavefront state (6 float4 queues + hits, >300 MB at 1080p) exceeds L2 every bounce; the scene is small and L2-resident by design",
-                      "host_bvh_build_s": round(build_s, 3)},
+                      "host_accel_build_s": round(build_s, 3), "device_bvh_build_ms": round(r.stats()["ms_build"], 3) if accel == ACCEL_BVH_DEVICE else None},
            "rays_per_step": int(rays_all / args.steps), "ms_per_frame_device": round(ms_dev / args.steps, 3), "wall_s_timed_region": round(t_wall, 3),
            "e2e": {"value": round(e2e_value, 2), "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                    "ms_per_step": round(t_e2e / args.steps * 1e3, 3), "what": "Renderer.upload(scene) from host arrays + renderLoop + film read-back to host, per step"},

@@ -111,6 +111,8 @@ typedef struct {
     float avg_nodes, avg_tris, avg_cells, avg_refs;  /* per traced ray, PTAP_FLAG_COUNT renders only */
     int64_t trace_launches;       /* closest-hit launches inside the last ptap_render call */
     int64_t scene_bytes;          /* bytes copied host->device by the last ptap_upload_scene */
+    float ms_build;               /* device time of the last PTAP_ACCEL_BVH_DEVICE build */
+    int32_t bvh_nodes, bvh_depth; /* 4-wide nodes and levels of that build */
 } PtapStats;
 
 typedef struct ptap_scene ptap_scene;   /* host-side scene: replaces class Scene (Scene.h:21-39) */
@@ -150,7 +152,9 @@ int ptap_scene_config_params(const ptap_scene* s, int32_t out4[4]);
 /* ---- device context: replaces Renderer (Renderer.h:46-55) -------------------------------- */
 
 enum { PTAP_ACCEL_GRID_COMPAT = 0,  /* the reference's per-mesh uniform grid walked exactly as Renderer.cpp:238-360 (oracle tier R0) */
-       PTAP_ACCEL_BVH = 1 };        /* two-level BVH, exact closest hit under the reference's triangle predicate (oracle tier R1) */
+       PTAP_ACCEL_BVH = 1,          /* two-level BVH, exact closest hit under the reference's triangle predicate (oracle tier R1);
+                                       the per-mesh trees are the host's binned-SAH ones (ptap_scene_build_bvh, or built at this call) */
+       PTAP_ACCEL_BVH_DEVICE = 2 }; /* same traversal and results, per-mesh trees built on the GPU (LBVH) in milliseconds */
 
 enum { PTAP_FLAG_FIRST_HIT_CACHE = 1,   /* Renderer.cpp:580,594-613 */
        PTAP_FLAG_PROFILE = 2,           /* per-kernel CUDA-event split in PtapStats (adds event records) */

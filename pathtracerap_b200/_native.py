@@ -34,7 +34,7 @@ assert GRID.itemsize == 28 and VOXEL.itemsize == 12 and HIT.itemsize == 40 and P
 
 FLOAT_MAX = np.float32(9999999.0)
 DIFFUSE, SPECULAR, REFLECTIVE, REFRACTIVE, EMISSIVE, COAT, METAL = range(7)
-ACCEL_GRID_COMPAT, ACCEL_BVH = 0, 1
+ACCEL_GRID_COMPAT, ACCEL_BVH, ACCEL_BVH_DEVICE = 0, 1, 2
 FLAG_FIRST_HIT_CACHE, FLAG_PROFILE, FLAG_COUNT = 1, 2, 4
 
 
@@ -52,7 +52,8 @@ class Stats(C.Structure):
     _fields_ = [("rays_traced", C.c_int64), ("paths", C.c_int64), ("kernel_launches", C.c_int64),
                 ("active_per_round", C.c_int64 * 16), ("ms_render", C.c_float), ("ms_trace", C.c_float),
                 ("ms_shade", C.c_float), ("ms_generate", C.c_float), ("avg_nodes", C.c_float), ("avg_tris", C.c_float),
-                ("avg_cells", C.c_float), ("avg_refs", C.c_float), ("trace_launches", C.c_int64), ("scene_bytes", C.c_int64)]
+                ("avg_cells", C.c_float), ("avg_refs", C.c_float), ("trace_launches", C.c_int64), ("scene_bytes", C.c_int64),
+                ("ms_build", C.c_float), ("bvh_nodes", C.c_int32), ("bvh_depth", C.c_int32)]
 
 
 EXPORTS = [

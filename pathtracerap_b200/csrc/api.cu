@@ -69,6 +69,7 @@ struct ptap_ctx {
     std::vector<InstanceTrace> h_inst;
     InstanceTrace* d_inst = nullptr; TriRec* d_tris = nullptr; BvhNode* d_nodes = nullptr; size_t nodes_cap = 0; LeafTri* d_btris = nullptr; int* d_btid = nullptr;
     bool have_scene = false, have_grid = false, have_bvh = false, have_frame = false;
+    int bvh_kind = -1;               // which builder made the BVH now on the device (PTAP_ACCEL_BVH / PTAP_ACCEL_BVH_DEVICE)
     int accel = PTAP_ACCEL_GRID_COMPAT;
     uint32_t flags = 0;
     bool cache_valid = false;
@@ -100,7 +101,7 @@ float4 row(const float* m, int r) { return make_float4(m[0 + r], m[4 + r], m[8 +
 void launchTrace(ptap_ctx* c, FrameState* st, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, int round, int n_fixed,
                  bool count_totals = false)
 {
-    if (c->accel == PTAP_ACCEL_BVH) launchTraceBvh(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, c->stream);
+    if (c->accel != PTAP_ACCEL_GRID_COMPAT) launchTraceBvh(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, c->stream);
     else launchTraceGrid(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, c->stream);
 }
 
@@ -114,9 +115,17 @@ void profMark(ptap_ctx* c, int kind)
     cudaEventRecord(c->prof_events[c->prof_used++], c->stream);
 }
 
+// zeroes the per-frame counters; what describes the uploaded scene and its acceleration structure stays
+void resetStats(ptap_ctx* c)
+{
+    const PtapStats old = c->stats;
+    c->stats = PtapStats{};
+    c->stats.scene_bytes = old.scene_bytes; c->stats.ms_build = old.ms_build; c->stats.bvh_nodes = old.bvh_nodes; c->stats.bvh_depth = old.bvh_depth;
+}
+
 int traceGridSize(ptap_ctx* c)
 {
-    int occ = c->accel == PTAP_ACCEL_BVH ? traceBvhOccupancy() : traceGridOccupancy();
+    int occ = c->accel != PTAP_ACCEL_GRID_COMPAT ? traceBvhOccupancy() : traceGridOccupancy();
     if (c->trace_ctas > 0) occ = std::min(occ, c->trace_ctas);
     return c->sms * std::max(occ, 1);
 }
@@ -203,42 +212,17 @@ int buildTlas(std::vector<TlasItem>& items, int b, int e, std::vector<Bvh2Node>&
     return me;
 }
 
-// Copies a BVH (nodes, leaf order) into the scene arena, gathers the leaf-ordered triangle records, points every model at
-// its mesh's root, derives the instances' world boxes from the BLAS root bounds and builds the TLAS over them.
-int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id, const int* mesh_root, int known_depth, size_t* bytes)
+// Second half of every BVH build: points every model at its mesh's root, derives the instances' world boxes from the BLAS root bounds
+// (`roots[m]` = host copy of mesh m's root node), builds the TLAS over them behind the `nnodes` BLAS nodes and publishes the scene fields.
+int finishBvh(ptap_ctx* ctx, const BvhNode* roots, const int* mesh_root, int nnodes, int blas_depth, size_t* tlas_bytes)
 {
-    const int nt = ctx->ntris, nm = (int)ctx->h_models.size();
-    if ((size_t)nnodes > (size_t)std::max(nt, 1) * 2) return fail(ctx, PTAP_E_NOMEM, "BVH has more nodes than reserved (2 per triangle)");
-    for (int i = 0; i < nnodes; ++i)
-        for (int k = 0; k < 4; ++k) {
-            const int l = nodes[i].link[k];
-            if (l >= nnodes) return fail(ctx, PTAP_E_INVALID, "BVH node %d: child index out of range", i);
-            if (l < 0) { const int code = ~l, first = code >> 3, cnt = (code & 7) + 1; if (code >= 0x20000000 || first < 0 || first + cnt > nt) return fail(ctx, PTAP_E_INVALID, "BVH node %d: leaf range out of bounds", i); }
-        }
-    for (int k = 0; k < nt; ++k)
-        if (tri_id[k] < 0 || tri_id[k] >= nt) return fail(ctx, PTAP_E_INVALID, "BVH leaf order entry %d out of range", k);
-    // depth of every BLAS (the traversal stack is fixed-size)
-    int blas_depth = known_depth;
-    if (known_depth <= 0) {
-        std::vector<std::pair<int, int>> todo;
-        std::vector<char> seen(nnodes, 0);
-        for (size_t m = 0; m < ctx->h_meshes.size(); ++m) if (mesh_root[m] >= 0) todo.push_back({mesh_root[m], 1});
-        while (!todo.empty()) {
-            const auto [node, d] = todo.back(); todo.pop_back();
-            if (seen[node]) { if (d > 1) return fail(ctx, PTAP_E_INVALID, "BVH node %d is reachable twice", node); continue; }
-            seen[node] = 1;
-            blas_depth = std::max(blas_depth, d);
-            for (int k = 0; k < 4; ++k)
-                if (nodes[node].link[k] >= 0 && nodes[node].lox[k] < 1e14f) todo.push_back({nodes[node].link[k], d + 1});
-        }
-    }
+    const int nm = (int)ctx->h_models.size();
     std::vector<TlasItem> items;
     double max_scale = 0.0, max_pad = 0.0, max_trans = 1.0;
     bool consistent = true;
     for (int i = 0; i < nm; ++i) {
         const PtapModel& m = ctx->h_models[i];
         const int root = mesh_root[m.mesh_index];
-        if (root >= nnodes) return fail(ctx, PTAP_E_INVALID, "mesh %d: BVH root out of range", m.mesh_index);
         ctx->h_inst[i].grid.z = __builtin_bit_cast(float, root);
         if (root < 0) continue;
         // The kernel maps a world ray into model space with world_to_model (Renderer.cpp:381-382), so the world box of an instance is
@@ -254,7 +238,7 @@ int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id
                 const double v = (double)M[0 + r] * W[4 * c + 0] + (double)M[4 + r] * W[4 * c + 1] + (double)M[8 + r] * W[4 * c + 2] + (c == 3 ? (double)M[12 + r] : 0.0);
                 if (!(std::fabs(v - (r == c ? 1.0 : 0.0)) <= 2e-5 * scale)) { consistent = false; break; }
             }
-        const BvhNode& r = nodes[root];
+        const BvhNode& r = roots[m.mesh_index];
         float mlo[3] = {3e38f, 3e38f, 3e38f}, mhi[3] = {-3e38f, -3e38f, -3e38f};
         for (int k = 0; k < 4; ++k) {
             if (!(r.lox[k] < 1e14f)) continue;      // unused slot
@@ -298,12 +282,9 @@ int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id
     if (3 * (blas_depth + tlas_depth) + 8 > kBvhStack) return fail(ctx, PTAP_E_INVALID, "BVH too deep for the traversal stack (%d + %d levels, %d entries)", blas_depth, tlas_depth, kBvhStack);
     if (nnodes + tlas.size() > ctx->nodes_cap) return fail(ctx, PTAP_E_NOMEM, "BVH node storage exhausted");
     CK(cudaMemcpyAsync(ctx->d_inst, ctx->h_inst.data(), nm * sizeof(InstanceTrace), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_nodes, nodes, (size_t)nnodes * sizeof(BvhNode), cudaMemcpyHostToDevice, ctx->stream));
     if (!tlas.empty()) CK(cudaMemcpyAsync(ctx->d_nodes + nnodes, tlas.data(), tlas.size() * sizeof(BvhNode), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->d_btid, tri_id, (size_t)nt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    launchGatherTris(ctx->d_tris, ctx->d_btid, nt, ctx->d_btris, ctx->stream);     // leaf-order copies are made on the device
     CK(cudaStreamSynchronize(ctx->stream));      // tlas is stack-owned
-    if (bytes) *bytes = nm * sizeof(InstanceTrace) + ((size_t)nnodes + tlas.size()) * sizeof(BvhNode) + (size_t)nt * sizeof(int);
+    if (tlas_bytes) *tlas_bytes = nm * sizeof(InstanceTrace) + tlas.size() * sizeof(BvhNode);
     ctx->sc.tlas_root = tlas_root;
     ctx->sc.tmin_world = -(float)((kEpsilon + 2e-4) * max_scale * 1.001 + max_pad + 1e-3);
     ctx->sc.prune = consistent ? 1.0003f : INFINITY;
@@ -311,6 +292,85 @@ int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id
     // residual of matrices that passed the check: |(M W - I) [o; 1]| <= 2e-5 * sqrt(3) * (|o|_1 + max |translation|); the kernel adds 1e-4 |o|_1
     ctx->sc.c_pad = (float)(4e-5 * max_trans + 1e-3);
     ctx->have_bvh = true;
+    return PTAP_OK;
+}
+
+// Copies a BVH (nodes, leaf order) into the scene arena, gathers the leaf-ordered triangle records, points every model at
+// its mesh's root, derives the instances' world boxes from the BLAS root bounds and builds the TLAS over them.
+int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id, const int* mesh_root, int known_depth, size_t* bytes)
+{
+    const int nt = ctx->ntris, nm = (int)ctx->h_models.size();
+    if ((size_t)nnodes > (size_t)std::max(nt, 1) * 2) return fail(ctx, PTAP_E_NOMEM, "BVH has more nodes than reserved (2 per triangle)");
+    for (int i = 0; i < nnodes; ++i)
+        for (int k = 0; k < 4; ++k) {
+            const int l = nodes[i].link[k];
+            if (l >= nnodes) return fail(ctx, PTAP_E_INVALID, "BVH node %d: child index out of range", i);
+            if (l < 0) { const int code = ~l, first = code >> 3, cnt = (code & 7) + 1; if (code >= 0x20000000 || first < 0 || first + cnt > nt) return fail(ctx, PTAP_E_INVALID, "BVH node %d: leaf range out of bounds", i); }
+        }
+    for (int k = 0; k < nt; ++k)
+        if (tri_id[k] < 0 || tri_id[k] >= nt) return fail(ctx, PTAP_E_INVALID, "BVH leaf order entry %d out of range", k);
+    // depth of every BLAS (the traversal stack is fixed-size)
+    int blas_depth = known_depth;
+    if (known_depth <= 0) {
+        std::vector<std::pair<int, int>> todo;
+        std::vector<char> seen(nnodes, 0);
+        for (size_t m = 0; m < ctx->h_meshes.size(); ++m) if (mesh_root[m] >= 0) todo.push_back({mesh_root[m], 1});
+        while (!todo.empty()) {
+            const auto [node, d] = todo.back(); todo.pop_back();
+            if (seen[node]) { if (d > 1) return fail(ctx, PTAP_E_INVALID, "BVH node %d is reachable twice", node); continue; }
+            seen[node] = 1;
+            blas_depth = std::max(blas_depth, d);
+            for (int k = 0; k < 4; ++k)
+                if (nodes[node].link[k] >= 0 && nodes[node].lox[k] < 1e14f) todo.push_back({nodes[node].link[k], d + 1});
+        }
+    }
+    std::vector<BvhNode> roots(ctx->h_meshes.size());
+    for (size_t m = 0; m < roots.size(); ++m) {
+        if (mesh_root[m] >= nnodes) return fail(ctx, PTAP_E_INVALID, "mesh %d: BVH root out of range", (int)m);
+        if (mesh_root[m] >= 0) roots[m] = nodes[mesh_root[m]];
+    }
+    CK(cudaMemcpyAsync(ctx->d_nodes, nodes, (size_t)nnodes * sizeof(BvhNode), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_btid, tri_id, (size_t)nt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    launchGatherTris(ctx->d_tris, ctx->d_btid, nt, ctx->d_btris, ctx->stream);     // leaf-order copies are made on the device
+    size_t tb = 0;
+    const int rc = finishBvh(ctx, roots.data(), mesh_root, nnodes, blas_depth, &tb);
+    if (rc) return rc;
+    if (bytes) *bytes = tb + (size_t)nnodes * sizeof(BvhNode) + (size_t)nt * sizeof(int);
+    ctx->bvh_kind = PTAP_ACCEL_BVH;
+    return PTAP_OK;
+}
+
+// PTAP_ACCEL_BVH_DEVICE: every mesh's BLAS is built on the GPU (bvh_device.cu) straight into the scene arena; only the root nodes come back
+// to the host, for the TLAS.
+int buildBvhOnDevice(ptap_ctx* ctx)
+{
+    const int nt = ctx->ntris, nmesh = (int)ctx->h_meshes.size();
+    int max_tris = 0;
+    for (const PtapMesh& m : ctx->h_meshes) max_tris = std::max(max_tris, m.t_end - m.t_start);
+    const size_t need = deviceBvhScratchBytes(max_tris);
+    if (need > ctx->scratch.cap) CK(ctx->scratch.reserve(need)); else ctx->scratch.used = 0;
+    std::vector<int> mesh_root(nmesh, -1);
+    int nnodes = 0, leaf_base = 0, blas_depth = 0;
+    for (int mi = 0; mi < nmesh; ++mi) {
+        const PtapMesh& m = ctx->h_meshes[mi];
+        const int n = m.t_end - m.t_start;
+        if (n <= 0 || m.t_start < 0 || m.t_end > nt) continue;
+        if ((size_t)nnodes + (size_t)n > ctx->nodes_cap || leaf_base + n > nt) return fail(ctx, PTAP_E_NOMEM, "device BVH build: node / leaf storage exhausted");
+        int made = 0, depth = 0;
+        const int e = buildMeshBvhDevice(ctx->d_tris, m.t_start, m.t_end, m.bb_min, m.bb_max, nnodes, ctx->d_nodes + nnodes, leaf_base, ctx->d_btris, ctx->d_btid,
+                                         ctx->scratch.base, ctx->scratch.cap, ctx->stream, &made, &depth);
+        if (e != 0) return fail(ctx, e, "device BVH build of mesh %d: %s", mi, cudaGetErrorString((cudaError_t)e));
+        mesh_root[mi] = nnodes;
+        nnodes += made; leaf_base += n; blas_depth = std::max(blas_depth, depth);
+    }
+    std::vector<BvhNode> roots(nmesh);
+    for (int mi = 0; mi < nmesh; ++mi)
+        if (mesh_root[mi] >= 0) CK(cudaMemcpyAsync(&roots[mi], ctx->d_nodes + mesh_root[mi], sizeof(BvhNode), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int rc = finishBvh(ctx, roots.data(), mesh_root.data(), nnodes, blas_depth, nullptr);
+    if (rc) return rc;
+    ctx->bvh_kind = PTAP_ACCEL_BVH_DEVICE;
+    ctx->stats.bvh_nodes = nnodes; ctx->stats.bvh_depth = blas_depth;
     return PTAP_OK;
 }
 
@@ -464,7 +524,7 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
                    (grid ? cells.size() * sizeof(int2) + (size_t)v->nrefs * sizeof(int) : 0);
     ctx->h_inst = inst;
     ctx->d_inst = d_inst; ctx->d_nodes = d_nodes; ctx->nodes_cap = nodes_cap; ctx->d_btris = d_btris; ctx->d_btid = d_btid;
-    ctx->have_bvh = false;
+    ctx->have_bvh = false; ctx->bvh_kind = -1;
     if (v->bvh_nodes && v->n_bvh_nodes > 0 && v->bvh_tri_id && v->bvh_mesh_root) {
         if (v->n_bvh_tris != nt || v->n_bvh_roots != v->nmeshes) return fail(ctx, PTAP_E_INVALID, "upload_scene: prebuilt BVH does not match the triangle / mesh counts");
         size_t bb = 0;
@@ -491,13 +551,24 @@ int ptap_build_accel(ptap_ctx* ctx, int kind)
     if (kind == PTAP_ACCEL_GRID_COMPAT) {
         if (!ctx->have_grid) return fail(ctx, PTAP_E_STATE, "build_accel: the uploaded scene carries no grids (call ptap_scene_build_grids first)");
     } else if (kind == PTAP_ACCEL_BVH) {
-        if (!ctx->have_bvh) {
+        if (!ctx->have_bvh || ctx->bvh_kind != PTAP_ACCEL_BVH) {
             BvhBuildResult res;
             if ((int)ctx->h_tris.size() != ctx->ntris) return fail(ctx, PTAP_E_STATE, "build_accel: the triangle records were not kept on the host");
             buildSceneBvh(ctx->h_tris.data(), (int)ctx->h_tris.size(), ctx->h_meshes.data(), (int)ctx->h_meshes.size(), res);
             int rc = uploadBvh(ctx, res.nodes.data(), (int)res.nodes.size(), res.tri_id.data(), res.mesh_root.data(), res.max_depth + 1, nullptr);
             if (rc) return rc;
             CK(cudaStreamSynchronize(ctx->stream));
+        }
+    } else if (kind == PTAP_ACCEL_BVH_DEVICE) {
+        if (ctx->bvh_kind != PTAP_ACCEL_BVH_DEVICE) {
+            cudaEvent_t b0, b1;
+            CK(cudaEventCreate(&b0)); CK(cudaEventCreate(&b1));
+            CK(cudaEventRecord(b0, ctx->stream));
+            const int rc = buildBvhOnDevice(ctx);
+            if (rc) { cudaEventDestroy(b0); cudaEventDestroy(b1); return rc; }
+            CK(cudaEventRecord(b1, ctx->stream)); CK(cudaEventSynchronize(b1));
+            cudaEventElapsedTime(&ctx->stats.ms_build, b0, b1);
+            cudaEventDestroy(b0); cudaEventDestroy(b1);
         }
     } else return fail(ctx, PTAP_E_INVALID, "build_accel: unknown kind %d", kind);
     ctx->accel = kind;
@@ -536,7 +607,7 @@ int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, u
     ctx->grid_shade = ctx->sms * std::max(shadeOccupancy(), 1);
     ctx->grid_gen = ctx->sms * 8;
     if (!ctx->grid_trace) ctx->grid_trace = traceGridSize(ctx);
-    { const int64_t sb = ctx->stats.scene_bytes; ctx->stats = PtapStats{}; ctx->stats.scene_bytes = sb; }
+    resetStats(ctx);
     return PTAP_OK;
 }
 
@@ -595,9 +666,7 @@ int ptap_frame_begin(ptap_ctx* ctx)
     CK(cudaMemsetAsync(ctx->wv.film, 0, (size_t)ctx->wv.N * 3 * sizeof(float), ctx->stream));
     CK(cudaMemsetAsync(ctx->wv.st, 0, sizeof(FrameState), ctx->stream));
     ctx->cache_valid = false;
-    const int64_t sb = ctx->stats.scene_bytes;
-    ctx->stats = PtapStats{};
-    ctx->stats.scene_bytes = sb;
+    resetStats(ctx);
     return PTAP_OK;
 }
 

@@ -1,0 +1,314 @@
+// bvh_device.cu - builds the per-mesh 4-wide BVH on the GPU (PTAP_ACCEL_BVH_DEVICE): an LBVH in milliseconds instead of the host's
+// binned-SAH build in seconds (the reference builds its only structure, the 25^3 grid, on the host: Scene.cpp:318-396).
+//
+//   1  k_lbvh_keys      per triangle: box of the FATTENED triangle (the predicate's tolerance band, as bvh_build.cpp) and the 30-bit Morton
+//                       code of its centroid inside the mesh bounds
+//   2  cub radix sort   (key, triangle id) pairs                                        [library call: not on the render path]
+//   3  k_lbvh_leaves    every sorted triangle (or cluster of kCluster consecutive ones) becomes a leaf: LeafTri records in leaf order, leaf boxes
+//   4  k_lbvh_topology  Karras 2012: every internal node of the binary radix tree over the leaves finds its range and split independently
+//   5  k_lbvh_refit     bottom-up box fit, the second child to arrive at a node continues upwards (one atomic counter per node)
+//   6  k_lbvh_collapse  breadth-first, one launch per level: a binary node and its two children become one 4-wide BvhNode
+//
+// The tree is a different one than the host builder's, so rays visit different boxes; hits are bit-identical all the same, because the
+// boxes are conservative for the reference's predicate and the triangle arithmetic is the exact one (tests/test_gpu_device_bvh.py).
+#include <algorithm>
+#include <cmath>
+#include <utility>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "kernels.cuh"
+
+namespace ptap {
+
+namespace {
+
+constexpr float kBandEpsF = 0.0056f;          // > EPSILON (Config.h:4), as bvh_build.cpp
+#ifndef PTAP_LBVH_CLUSTER
+#define PTAP_LBVH_CLUSTER 1
+#endif
+constexpr int kCluster = PTAP_LBVH_CLUSTER;    // consecutive Morton-sorted triangles per leaf
+
+__device__ __forceinline__ unsigned expandBits(unsigned v)
+{
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+struct Box6 { float lo[3], hi[3]; };
+
+__device__ __forceinline__ Box6 fatBox(const TriRec& r, float slack)
+{
+    // corners of the fattened triangle at (u, v) = (-e, -e), (1 + 2e, -e), (-e, 1 + 2e); the slack dwarfs the rounding of this arithmetic
+    Box6 b;
+    const float uv[3][2] = {{-kBandEpsF, -kBandEpsF}, {1.0f + 2.0f * kBandEpsF, -kBandEpsF}, {-kBandEpsF, 1.0f + 2.0f * kBandEpsF}};
+    const float v0[3] = {r.v0.x, r.v0.y, r.v0.z}, e1[3] = {r.e1.x, r.e1.y, r.e1.z}, e2[3] = {r.e2.x, r.e2.y, r.e2.z};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float lo = 3e38f, hi = -3e38f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float p = v0[k] + uv[c][0] * e1[k] + uv[c][1] * e2[k];
+            lo = fminf(lo, p); hi = fmaxf(hi, p);
+        }
+        const float pad = slack + 2e-6f * fmaxf(fabsf(lo), fabsf(hi));
+        b.lo[k] = lo - pad; b.hi[k] = hi + pad;
+    }
+    return b;
+}
+
+__global__ void k_lbvh_keys(const TriRec* __restrict__ tris, int t0, int n, float3 mlo, float3 minv, unsigned* __restrict__ keys, int* __restrict__ ids)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const TriRec r = tris[t0 + i];
+    const float cx = r.v0.x + (r.e1.x + r.e2.x) * (1.0f / 3.0f), cy = r.v0.y + (r.e1.y + r.e2.y) * (1.0f / 3.0f), cz = r.v0.z + (r.e1.z + r.e2.z) * (1.0f / 3.0f);
+    const unsigned qx = (unsigned)fminf(fmaxf((cx - mlo.x) * minv.x, 0.0f), 1023.0f);
+    const unsigned qy = (unsigned)fminf(fmaxf((cy - mlo.y) * minv.y, 0.0f), 1023.0f);
+    const unsigned qz = (unsigned)fminf(fmaxf((cz - mlo.z) * minv.z, 0.0f), 1023.0f);
+    keys[i] = (expandBits(qx) << 2) | (expandBits(qy) << 1) | expandBits(qz);
+    ids[i] = t0 + i;
+}
+
+// leaf c = sorted triangles [kCluster c, min(kCluster (c + 1), n)): LeafTri records at leaf_base + k, global ids, the cluster's box and its 64-bit key
+__global__ void k_lbvh_leaves(const TriRec* __restrict__ tris, const unsigned* __restrict__ keys, const int* __restrict__ ids, int n, int nleaves,
+                              float slack, int leaf_base, LeafTri* __restrict__ btris, int* __restrict__ btid, Box6* __restrict__ leaf_box,
+                              unsigned long long* __restrict__ leaf_key)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nleaves) return;
+    Box6 box;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { box.lo[k] = 3e38f; box.hi[k] = -3e38f; }
+    const int first = kCluster * c, last = min(first + kCluster, n);
+    for (int s = first; s < last; ++s) {
+        const int id = ids[s];
+        const TriRec r = tris[id];
+        const Box6 b = fatBox(r, slack);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { box.lo[k] = fminf(box.lo[k], b.lo[k]); box.hi[k] = fmaxf(box.hi[k], b.hi[k]); }
+        float4* o = reinterpret_cast<float4*>(&btris[leaf_base + s]);
+        o[0] = make_float4(r.v0.x, r.v0.y, r.v0.z, r.e1.x);
+        o[1] = make_float4(r.e1.y, r.e1.z, r.e2.x, r.e2.y);
+        o[2] = make_float4(r.e2.z, __int_as_float(id), 0.0f, 0.0f);
+        o[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        btid[leaf_base + s] = id;
+    }
+    leaf_box[c] = box;
+    leaf_key[c] = ((unsigned long long)keys[first] << 32) | (unsigned)c;          // the index makes equal Morton codes distinct
+}
+
+__device__ __forceinline__ int delta(const unsigned long long* __restrict__ k, int n, int i, int j)
+{
+    return (j < 0 || j >= n) ? -1 : __clzll(k[i] ^ k[j]);
+}
+
+// Karras, "Maximizing parallelism in the construction of BVHs, octrees and k-d trees" (2012): internal node i of n - 1.
+// child >= 0: internal node; child < 0: leaf ~index.
+__global__ void k_lbvh_topology(const unsigned long long* __restrict__ key, int nleaves, int2* __restrict__ child, int* __restrict__ parent_internal,
+                                int* __restrict__ parent_leaf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nleaves - 1) return;
+    const int d = delta(key, nleaves, i, i + 1) - delta(key, nleaves, i, i - 1) >= 0 ? 1 : -1;
+    const int dmin = delta(key, nleaves, i, i - d);
+    int lmax = 2;
+    while (delta(key, nleaves, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(key, nleaves, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta(key, nleaves, i, j);
+    int s = 0;
+    for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+        if (delta(key, nleaves, i, i + (s + t) * d) > dnode) s += t;
+        if (t <= 1) break;
+    }
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const int left = lo == gamma ? ~gamma : gamma, right = hi == gamma + 1 ? ~(gamma + 1) : gamma + 1;
+    child[i] = make_int2(left, right);
+    if (left >= 0) parent_internal[left] = i; else parent_leaf[~left] = i;
+    if (right >= 0) parent_internal[right] = i; else parent_leaf[~right] = i;
+    if (i == 0) parent_internal[0] = -1;
+}
+
+__device__ __forceinline__ Box6 loadBoxL2(const Box6* p)
+{
+    Box6 b;
+    const float* f = reinterpret_cast<const float*>(p);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { b.lo[k] = __ldcg(f + k); b.hi[k] = __ldcg(f + 3 + k); }
+    return b;
+}
+
+__global__ void k_lbvh_refit(const int2* __restrict__ child, const int* __restrict__ parent_internal, const int* __restrict__ parent_leaf,
+                             const Box6* __restrict__ leaf_box, int nleaves, Box6* __restrict__ node_box, int* __restrict__ arrived)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nleaves) return;
+    int node = parent_leaf[c];
+    while (node >= 0) {
+        if (atomicAdd(&arrived[node], 1) == 0) return;              // the first child to arrive stops; the second one owns the node
+        __threadfence();
+        const int2 ch = child[node];
+        // boxes written by other SMs during this launch: read through L2 (an L1 line may predate the sibling's store)
+        const Box6 a = ch.x >= 0 ? loadBoxL2(&node_box[ch.x]) : leaf_box[~ch.x], b = ch.y >= 0 ? loadBoxL2(&node_box[ch.y]) : leaf_box[~ch.y];
+        Box6 u;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { u.lo[k] = fminf(a.lo[k], b.lo[k]); u.hi[k] = fmaxf(a.hi[k], b.hi[k]); }
+        node_box[node] = u;
+        __threadfence();
+        node = parent_internal[node];
+    }
+}
+
+__device__ __forceinline__ int leafLink(int c, int n, int leaf_base)
+{
+    const int first = kCluster * c, count = min(kCluster, n - first);
+    return ~(((leaf_base + first) << 3) | (count - 1));
+}
+
+// One breadth-first level: frontier item = (binary internal node, index of the 4-wide node that represents it).
+__global__ void k_lbvh_collapse(const int2* __restrict__ child, const Box6* __restrict__ node_box, const Box6* __restrict__ leaf_box, int n, int leaf_base,
+                                const int2* __restrict__ frontier, int nfrontier, int2* __restrict__ next, int* __restrict__ counters /* [0] nodes, [1] next size */,
+                                int node_base, BvhNode* __restrict__ out)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nfrontier) return;
+    const int2 item = frontier[f];
+    int ent[4]; int ne = 0;
+    const int2 ch = child[item.x];
+    const int two[2] = {ch.x, ch.y};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (two[k] >= 0) { const int2 g = child[two[k]]; ent[ne++] = g.x; ent[ne++] = g.y; }
+        else ent[ne++] = two[k];
+    }
+    BvhNode nd;
+    for (int k = 0; k < 4; ++k) {
+        if (k < ne) {
+            const int e = ent[k];
+            const Box6 b = e >= 0 ? node_box[e] : leaf_box[~e];
+            nd.lox[k] = b.lo[0]; nd.hix[k] = b.hi[0]; nd.loy[k] = b.lo[1]; nd.hiy[k] = b.hi[1]; nd.loz[k] = b.lo[2]; nd.hiz[k] = b.hi[2];
+            if (e >= 0) {
+                const int idx = atomicAdd(&counters[0], 1);
+                next[atomicAdd(&counters[1], 1)] = make_int2(e, idx);
+                nd.link[k] = node_base + idx;
+            } else nd.link[k] = leafLink(~e, n, leaf_base);
+        } else {
+            nd.lox[k] = nd.hix[k] = nd.loy[k] = nd.hiy[k] = nd.loz[k] = nd.hiz[k] = 1e15f;      // unused slot: a point box no ray interval reaches
+            nd.link[k] = nd.link[0];
+        }
+        nd.pad[k] = 0;
+    }
+    out[item.y] = nd;
+}
+
+// a mesh whose triangles fit one leaf: a root with a single child
+__global__ void k_lbvh_single(const Box6* __restrict__ leaf_box, int n, int leaf_base, BvhNode* __restrict__ out)
+{
+    BvhNode nd;
+    const Box6 b = leaf_box[0];
+    for (int k = 0; k < 4; ++k) {
+        nd.lox[k] = nd.hix[k] = nd.loy[k] = nd.hiy[k] = nd.loz[k] = nd.hiz[k] = 1e15f;
+        nd.link[k] = leafLink(0, n, leaf_base); nd.pad[k] = 0;
+    }
+    nd.lox[0] = b.lo[0]; nd.hix[0] = b.hi[0]; nd.loy[0] = b.lo[1]; nd.hiy[0] = b.hi[1]; nd.loz[0] = b.lo[2]; nd.hiz[0] = b.hi[2];
+    out[0] = nd;
+}
+
+template <typename T> T* carve(char*& p, size_t count)
+{
+    T* r = reinterpret_cast<T*>(p);
+    p += (count * sizeof(T) + 255) & ~size_t(255);
+    return r;
+}
+
+}  // namespace
+
+size_t deviceBvhScratchBytes(int ntris)
+{
+    const size_t n = (size_t)std::max(ntris, 1), L = (n + kCluster - 1) / kCluster;
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned*)nullptr, (unsigned*)nullptr, (const int*)nullptr, (int*)nullptr, (int)n, 0, 30);
+    return 4 * ((n * 4 + 255) & ~size_t(255)) + cub_bytes + 256 + 2 * ((L * sizeof(Box6) + 255) & ~size_t(255)) + ((L * 8 + 255) & ~size_t(255)) * 4 +
+           ((L * 4 + 255) & ~size_t(255)) * 3 + 4096;
+}
+
+// Builds the BLAS of one mesh (triangles [t0, t1) of the global table) into out_nodes[0 .. *nnodes) with links relative to node_base,
+// leaf-order triangles into btris / btid at [leaf_base, leaf_base + n).  Returns a cudaError_t; *depth = levels of 4-wide nodes.
+int buildMeshBvhDevice(const TriRec* d_tris, int t0, int t1, const float* bb_min, const float* bb_max, int node_base, BvhNode* out_nodes, int leaf_base,
+                       LeafTri* btris, int* btid, char* scratch, size_t scratch_bytes, cudaStream_t stream, int* nnodes, int* depth)
+{
+    const int n = t1 - t0, L = (n + kCluster - 1) / kCluster;
+    *nnodes = 0; *depth = 0;
+    if (n <= 0) return cudaSuccess;
+    if (deviceBvhScratchBytes(n) > scratch_bytes) return cudaErrorMemoryAllocation;
+    char* p = scratch;
+    unsigned* keys = carve<unsigned>(p, n); unsigned* keys2 = carve<unsigned>(p, n);
+    int* ids = carve<int>(p, n); int* ids2 = carve<int>(p, n);
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned*)keys, keys2, (const int*)ids, ids2, n, 0, 30);
+    void* cub_tmp = carve<char>(p, cub_bytes + 1);
+    Box6* leaf_box = carve<Box6>(p, L); Box6* node_box = carve<Box6>(p, L);
+    unsigned long long* leaf_key = carve<unsigned long long>(p, L);
+    int2* child = carve<int2>(p, L); int2* fr_a = carve<int2>(p, L); int2* fr_b = carve<int2>(p, L);
+    int* parent_internal = carve<int>(p, L); int* parent_leaf = carve<int>(p, L); int* arrived = carve<int>(p, L);
+    int* counters = carve<int>(p, 64);
+
+    double ext = 0.0;
+    float3 mlo, minv;
+    {
+        const float lo[3] = {bb_min[0], bb_min[1], bb_min[2]}, hi[3] = {bb_max[0], bb_max[1], bb_max[2]};
+        for (int k = 0; k < 3; ++k) ext = std::max(ext, (double)std::max(std::fabs(lo[k]), std::fabs(hi[k])));
+        mlo = make_float3(lo[0], lo[1], lo[2]);
+        auto inv = [](float a, float b) { return b > a ? 1023.999f / (b - a) : 0.0f; };
+        minv = make_float3(inv(lo[0], hi[0]), inv(lo[1], hi[1]), inv(lo[2], hi[2]));
+    }
+    const float slack = (float)(ext * 4e-6 + 1e-6);
+    const int B = 256;
+    k_lbvh_keys<<<(n + B - 1) / B, B, 0, stream>>>(d_tris, t0, n, mlo, minv, keys, ids);
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, (const unsigned*)keys, keys2, (const int*)ids, ids2, n, 0, 30, stream);
+    if (e != cudaSuccess) return e;
+    k_lbvh_leaves<<<(L + B - 1) / B, B, 0, stream>>>(d_tris, keys2, ids2, n, L, slack, leaf_base, btris, btid, leaf_box, leaf_key);
+    if (L == 1) {
+        k_lbvh_single<<<1, 1, 0, stream>>>(leaf_box, n, leaf_base, out_nodes);
+        *nnodes = 1; *depth = 1;
+        return cudaGetLastError();
+    }
+    k_lbvh_topology<<<(L - 1 + B - 1) / B, B, 0, stream>>>(leaf_key, L, child, parent_internal, parent_leaf);
+    e = cudaMemsetAsync(arrived, 0, (size_t)L * sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+    k_lbvh_refit<<<(L + B - 1) / B, B, 0, stream>>>(child, parent_internal, parent_leaf, leaf_box, L, node_box, arrived);
+    // breadth-first collapse: the root is 4-wide node 0
+    const int2 root = make_int2(0, 0);
+    const int init[2] = {1, 0};
+    e = cudaMemcpyAsync(fr_a, &root, sizeof root, cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(counters, init, sizeof init, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) return e;
+    int nfrontier = 1, levels = 0;
+    int2 *cur = fr_a, *nxt = fr_b;
+    while (nfrontier > 0) {
+        ++levels;
+        k_lbvh_collapse<<<(nfrontier + B - 1) / B, B, 0, stream>>>(child, node_box, leaf_box, n, leaf_base, cur, nfrontier, nxt, counters, node_base, out_nodes);
+        int host_counters[2];
+        e = cudaMemcpyAsync(host_counters, counters, sizeof host_counters, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) return e;
+        nfrontier = host_counters[1];
+        *nnodes = host_counters[0];
+        const int zero = 0;
+        e = cudaMemcpyAsync(counters + 1, &zero, sizeof zero, cudaMemcpyHostToDevice, stream);
+        if (e != cudaSuccess) return e;
+        std::swap(cur, nxt);
+        if (levels > 200) return cudaErrorUnknown;
+    }
+    *depth = levels;
+    return cudaGetLastError();
+}
+
+}  // namespace ptap

@@ -39,6 +39,11 @@ void launchTraceBvh(const SceneDev& sc, const float4* O, const float4* D, float4
                     FrameState* st, int round, int n_fixed, int grid, cudaStream_t stream);
 int traceBvhOccupancy();
 
+// bvh_device.cu
+size_t deviceBvhScratchBytes(int ntris);
+int buildMeshBvhDevice(const TriRec* d_tris, int t0, int t1, const float* bb_min, const float* bb_max, int node_base, BvhNode* out_nodes, int leaf_base,
+                       LeafTri* btris, int* btid, char* scratch, size_t scratch_bytes, cudaStream_t stream, int* nnodes, int* depth);
+
 // wavefront.cu
 void launchGenerate(const WaveDev& wv, int grid, cudaStream_t stream);
 void launchScan(const SceneDev& sc, const WaveDev& wv, int round, const float4* hit, int remaining, int n_fixed, cudaStream_t stream);

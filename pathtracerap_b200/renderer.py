@@ -66,6 +66,11 @@ class Renderer:
         self._check(N.lib().ptap_set_render_params(self.h, width, height, depth, self.flags), "set_render_params")
         self._iters_done = 0
 
+    def build_stats(self) -> dict:
+        """Device time, node count and depth of the last PTAP_ACCEL_BVH_DEVICE build."""
+        st = self.stats()
+        return {"ms_build": st["ms_build"], "bvh_nodes": st["bvh_nodes"], "bvh_depth": st["bvh_depth"]}
+
     def render(self, iter_begin: int, iter_end: int):
         """Enqueue iterations [iter_begin, iter_end) (asynchronous)."""
         self._check(N.lib().ptap_render(self.h, iter_begin, iter_end), "render")
