@@ -8,8 +8,8 @@
 //
 // Resolution, iteration count and depth come from Config.h's macros (the reference's only configuration), overridden by the
 // RESOLUTION / ITER / DEPTH keys of a parsed Config.txt, overridden by the environment (PTAP_WIDTH, PTAP_HEIGHT, PTAP_ITER,
-// PTAP_DEPTH, PTAP_ACCEL=grid|bvh, PTAP_DEVICE).  The acceleration structure defaults to the reference's own 25^3 grid walk
-// (bit-compatible hits); PTAP_ACCEL=bvh selects the BVH.  All errors throw std::runtime_error: there is no CPU fallback.
+// PTAP_DEPTH, PTAP_ACCEL=grid|bvh|lbvh, PTAP_DEVICE).  The acceleration structure defaults to the reference's own 25^3 grid walk
+// (bit-compatible hits); PTAP_ACCEL=bvh selects the BVH (built on the host), lbvh the same built on the GPU.  All errors throw std::runtime_error: there is no CPU fallback.
 #pragma once
 #include <chrono>
 #include <cstdlib>
@@ -37,6 +37,7 @@ public:
         iters = pick("PTAP_ITER", scene.config_iter, ITER);
         depth = pick("PTAP_DEPTH", scene.config_depth, MAX_DEPTH);
         const char* a = std::getenv("PTAP_ACCEL");
+        const bool lbvh = a && std::string(a) == "lbvh";          // tree built on the GPU at this call
         const bool bvh = a && std::string(a) == "bvh";
         check(ptap_create(pick("PTAP_DEVICE", 0, 0), 0, &ctx), "ptap_create");
         PtapSceneView v{};
@@ -49,7 +50,7 @@ public:
         v.refs = scene.per_voxel_data_pool.data(); v.nrefs = (int32_t)scene.per_voxel_data_pool.size();
         v.grid_dim[0] = GRID_X; v.grid_dim[1] = GRID_Y; v.grid_dim[2] = GRID_Z;
         check(ptap_upload_scene(ctx, &v), "ptap_upload_scene");
-        check(ptap_build_accel(ctx, bvh || scene.grids.empty() ? PTAP_ACCEL_BVH : PTAP_ACCEL_GRID_COMPAT), "ptap_build_accel");
+        check(ptap_build_accel(ctx, lbvh ? PTAP_ACCEL_BVH_DEVICE : bvh || scene.grids.empty() ? PTAP_ACCEL_BVH : PTAP_ACCEL_GRID_COMPAT), "ptap_build_accel");
         check(ptap_set_render_params(ctx, width, height, depth, PTAP_FLAG_FIRST_HIT_CACHE), "ptap_set_render_params");
     }
 

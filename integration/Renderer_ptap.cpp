@@ -62,7 +62,8 @@ void Renderer::allocateOnGPU(Scene& scene)
     v.grid_dim[0] = GRID_X; v.grid_dim[1] = GRID_Y; v.grid_dim[2] = GRID_Z;
     check(b, ptap_upload_scene(b.ctx, &v), "ptap_upload_scene");
     const char* accel = std::getenv("PTAP_ACCEL");            // default: the reference's own grid walk, bit-compatible hits
-    check(b, ptap_build_accel(b.ctx, accel && std::string(accel) == "bvh" ? PTAP_ACCEL_BVH : PTAP_ACCEL_GRID_COMPAT), "ptap_build_accel");
+    const int kind = !accel ? PTAP_ACCEL_GRID_COMPAT : std::string(accel) == "bvh" ? PTAP_ACCEL_BVH : std::string(accel) == "lbvh" ? PTAP_ACCEL_BVH_DEVICE : PTAP_ACCEL_GRID_COMPAT;
+    check(b, ptap_build_accel(b.ctx, kind), "ptap_build_accel");
     check(b, ptap_set_render_params(b.ctx, RESOLUTION_X, RESOLUTION_Y, MAX_DEPTH, PTAP_FLAG_FIRST_HIT_CACHE), "ptap_set_render_params");
     render_data = RenderData{};
 }

@@ -534,7 +534,7 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
     }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stats.scene_bytes = (int64_t)bytes;
-    ctx->sc.inst = d_inst; ctx->sc.cull = nullptr; ctx->sc.shade = d_shade; ctx->sc.tris = d_tris; ctx->sc.normals = d_normals;
+    ctx->sc.inst = d_inst; ctx->sc.shade = d_shade; ctx->sc.tris = d_tris; ctx->sc.normals = d_normals;
     ctx->sc.cells = d_cells; ctx->sc.refs = d_refs; ctx->sc.nodes = d_nodes; ctx->sc.bvh_tris = d_btris; ctx->sc.bvh_tri_id = d_btid;
     ctx->sc.nmodels = nm; ctx->sc.gx = v->grid_dim[0]; ctx->sc.gy = v->grid_dim[1]; ctx->sc.gz = v->grid_dim[2];
     ctx->have_scene = true; ctx->have_grid = grid; ctx->cache_valid = false;

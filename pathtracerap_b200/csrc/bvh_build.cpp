@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <thread>
 
 namespace ptap {
@@ -39,12 +40,18 @@ struct Box {
 
 struct Prim { Box box; float c[3]; int id; };
 
+// A subtree the top-level (serial) pass leaves to a worker thread: primitives [begin, end), to be linked at child `slot` of `parent`.
+struct Task { int begin, end, parent, slot, depth; };
+
 struct Builder {
     std::vector<Prim>& prims;
     std::vector<Bvh2Node>& nodes;
     std::vector<int>& order;      // leaf-order list of prim ids (local to the mesh), appended
     int leaf_base;                // leaf-order offset of this mesh in the global arrays
     int max_depth = 0;
+    std::vector<Task>* tasks = nullptr;   // non-null: the top pass; subtrees of at most task_size primitives are deferred
+    int task_size = 0;
+    static constexpr int kDeferred = 0x7fffffff;   // placeholder link of a deferred subtree
 
     static int leafLink(int first, int count) { return ~((first << 3) | (count - 1)); }
 
@@ -56,6 +63,7 @@ struct Builder {
         Box cb; cb.reset();
         for (int i = begin; i < end; ++i) { bounds.grow(prims[i].box); cb.grow(prims[i].c); }
         const int n = end - begin;
+        if (tasks && n <= task_size && depth > 0) return kDeferred;      // bounds are set; the caller records the task
         auto makeLeaf = [&]() {
             int first = leaf_base + (int)order.size();
             for (int i = begin; i < end; ++i) order.push_back(prims[i].id);
@@ -104,7 +112,9 @@ struct Builder {
         nodes.emplace_back();
         Box b0, b1;
         const int l0 = build(begin, mid, b0, depth + 1);
+        if (l0 == kDeferred) tasks->push_back(Task{begin, mid, me, 0, depth + 1});
         const int l1 = build(mid, end, b1, depth + 1);
+        if (l1 == kDeferred) tasks->push_back(Task{mid, end, me, 1, depth + 1});
         Bvh2Node& nd = nodes[me];
         nd.xy0 = make_float4(b0.lo[0], b0.hi[0], b0.lo[1], b0.hi[1]);
         nd.xy1 = make_float4(b1.lo[0], b1.hi[0], b1.lo[1], b1.hi[1]);
@@ -219,9 +229,41 @@ void buildSceneBvh(const TriRec* tris, int ntris, const PtapMesh* meshes, int nm
         std::vector<int> order; order.reserve(prims.size());
         std::vector<Bvh2Node> n2;
         n2.reserve(prims.size());
-        Builder b{prims, n2, order, (int)out.tri_id.size()};
+        const int leaf_base = (int)out.tri_id.size();
+        Builder b{prims, n2, order, leaf_base};
         Box bounds;
+        // Large meshes: the top of the tree is built here, subtrees of <= n/64 primitives on worker threads into private arrays, which are
+        // then appended (node indices and leaf positions shifted).  The tree is the one the serial build produces; only node numbering differs.
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        std::vector<Task> tasks;
+        if (prims.size() >= 65536 && hw > 1) { b.tasks = &tasks; b.task_size = std::max<int>(1024, (int)prims.size() / 64); }
         const int link = b.build(0, (int)prims.size(), bounds, 0);
+        if (!tasks.empty()) {
+            struct Sub { std::vector<Bvh2Node> nodes; std::vector<int> order; int link = 0, depth = 0; };
+            std::vector<Sub> subs(tasks.size());
+            std::atomic<size_t> next{0};
+            auto work = [&]() {
+                for (size_t k; (k = next.fetch_add(1)) < tasks.size();) {
+                    Builder sb{prims, subs[k].nodes, subs[k].order, 0};
+                    Box bb;
+                    subs[k].link = sb.build(tasks[k].begin, tasks[k].end, bb, tasks[k].depth);
+                    subs[k].depth = sb.max_depth;
+                }
+            };
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t + 1 < std::min<unsigned>(hw, (unsigned)tasks.size()); ++t) pool.emplace_back(work);
+            work();
+            for (std::thread& t : pool) t.join();
+            for (size_t k = 0; k < tasks.size(); ++k) {          // tasks were recorded in depth-first order: so is the leaf order
+                const int node_off = (int)n2.size(), leaf_off = leaf_base + (int)order.size();
+                auto shift = [&](int l) { return l >= 0 ? l + node_off : ~(~l + (leaf_off << 3)); };
+                for (Bvh2Node nd : subs[k].nodes) { nd.link.x = shift(nd.link.x); nd.link.y = shift(nd.link.y); n2.push_back(nd); }
+                order.insert(order.end(), subs[k].order.begin(), subs[k].order.end());
+                const int l = shift(subs[k].link);
+                if (tasks[k].slot == 0) n2[tasks[k].parent].link.x = l; else n2[tasks[k].parent].link.y = l;
+                b.max_depth = std::max(b.max_depth, subs[k].depth);
+            }
+        }
         if (link < 0) {
             // the whole mesh fits one leaf: a root with a single child
             Bvh2Node nd;

@@ -23,12 +23,6 @@ struct InstanceTrace {
     float4 grid;        // .x = voxel width z, .y = bits(first voxel of the grid), .z = bits(BLAS root node), .w = bits(first BVH triangle)
 };
 
-// World-space cull box of a model for the BVH path (2 x float4).
-struct InstanceCull {
-    float4 lo;          // .w = bits(mesh t_start)
-    float4 hi;          // .w = bits(mesh t_end)
-};
-
 // Per-model record read by the shade kernel: 4 x float4 = 64 B.
 struct InstanceShade {
     float4 nm0;         // rows of transpose(inverse(mat3(model_to_world))) (utility.h:82-88): nm0 = (r0.x, r0.y, r0.z, color.r)
@@ -88,7 +82,6 @@ struct FrameState {
 
 struct SceneDev {
     const InstanceTrace* inst;
-    const InstanceCull* cull;
     const InstanceShade* shade;
     const TriRec* tris;         // indexed by GLOBAL triangle id (reference order)
     const float4* normals;      // flat shading normal per GLOBAL triangle id (copy of the TriRec .w lanes, 16-byte gather for k_shade)
@@ -96,7 +89,7 @@ struct SceneDev {
     const int* refs;            // global triangle ids
     const BvhNode* nodes;       // all BLAS nodes, then the TLAS nodes
     const LeafTri* bvh_tris;    // triangles in BVH leaf order
-    const int* bvh_tri_id;      // leaf-order position -> global triangle id
+    const int* bvh_tri_id;      // leaf-order position -> global triangle id (build-time input of k_gather_tris; the kernels read LeafTri::id)
     int nmodels;
     int gx, gy, gz;
     int tlas_root;              // node index of the TLAS root, -1 when no instance has triangles

@@ -78,11 +78,6 @@ __device__ __forceinline__ bool slab(const V3& o, const V3& inv, float lox, floa
     return tn <= tf + (fabsf(tf) * 2e-6f + 1e-6f);
 }
 
-#ifndef PTAP_PREFETCH
-#define PTAP_PREFETCH 0
-#endif
-__device__ __forceinline__ void prefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
 // traversal-only reciprocal: guarded against 0 (the exact predicate never uses it)
 __device__ __forceinline__ float safeInv(float d)
 {
@@ -161,9 +156,6 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
         }
         // ---- (2) who waits for what: one warp reduction over 6-bit counters, one per state
         const unsigned code = ~(unsigned)node;
-#if PTAP_PREFETCH & 2
-        if (code < kEnterBit) prefetchL1(&sc.bvh_tris[code >> 3]);          // the leaf's first triangle, while the lane waits for the triangle step
-#endif
         const unsigned state = min(code >> 29, 4u);             // 0 tri, 1 enter, 2 exit, 3 done, 4 inner
         const bool live = state != 3u || i >= 0 || !exhausted;  // a retired lane with nothing left to fetch takes no part
         const unsigned sum = __reduce_add_sync(kFull, live ? 1u << (6u * state) : 0u);

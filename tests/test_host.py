@@ -304,3 +304,14 @@ def test_two_rank_film_reduce_gloo(tmp_path):
                         "--master-port", "29533", str(w)], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stderr[-2000:]
     assert "REDUCE_OK 0 5" in p.stdout
+
+
+def test_bvh_builder_parallel_path(libptap):
+    """Meshes of >= 65,536 triangles build their subtrees on worker threads (bvh_build.cpp); the stitched tree keeps every invariant."""
+    from pathtracerap_b200 import Scene
+    s = Scene.empty()
+    mi = s.add_icosphere(6, radius=1000.0, displacement=0.05, seed=1)     # 81,920 triangles
+    s.add_model(mi)
+    nodes, tri_id, roots = _bvh_of(s)
+    depth = _check_bvh(nodes, tri_id, roots, s.arrays())
+    assert depth <= 16
