@@ -78,6 +78,21 @@ def golden_kat():
 
 
 @pytest.fixture(scope="session")
+def golden_render_bmp():
+    """8x8 box-filtered bytes and channel means of the reference's committed PathTracerAP/Render.bmp (tools/make_render_bmp_fixture.py)."""
+    z = np.load(os.path.join(GOLDEN, "render_bmp_8x8.npz"))
+    return {k: z[k] for k in z.files}
+
+
+def box8_of_film(film_sum, iters):
+    """The bytes Renderer::renderImage would store (Renderer.cpp:45-52: (char)(sum * (1/ITER) * 255)), 8x8 box-filtered."""
+    v = film_sum.astype(np.float32) * np.float32(1.0 / iters) * np.float32(255)
+    by = np.minimum(v, 255).astype(np.uint8)
+    H, W, _ = by.shape
+    return by.astype(np.float64).reshape(H // 8, 8, W // 8, 8, 3).mean(axis=(1, 3)), by.reshape(-1, 3).astype(np.float64).mean(0)
+
+
+@pytest.fixture(scope="session")
 def oracle_scene(port, golden_scene):
     """Bundled scene on the C oracle; its grids come from the oracle's own restatement of addMeshesToGrid."""
     return port.OracleScene(golden_scene)

@@ -85,6 +85,36 @@ def test_frame_vs_reference_film(renderer, golden_films, golden_scene):
     assert rel < 0.01
 
 
+def test_committed_render_bmp(gpu_scene, golden_render_bmp, tmp_path):
+    """The reference's only golden artefact, PathTracerAP/Render.bmp (the author's GPU render of the coded scene at 1000x800, iteration
+    count unrecorded), against the file this library writes for the same scene at 256 iterations: per-channel byte means within 0.1/255
+    and PSNR >= 46 dB after an 8x8 box filter (the committed image still carries its own Monte-Carlo noise).  The grid walk is the
+    reference's algorithm; the BVH (exact closest hit, differs on ~0.4 % of rays) must stay within 0.25/255 of the same means."""
+    from conftest import box8_of_film
+    from pathtracerap_b200 import ACCEL_BVH, ACCEL_GRID_COMPAT, Renderer
+    g = golden_render_bmp
+    H, W = (int(x) for x in g["shape"])
+    iters = 256
+    r = Renderer(width=W, height=H, depth=5, first_hit_cache=True)
+    r.allocateOnGPU(gpu_scene)
+    for accel, mean_tol, min_psnr in ((ACCEL_GRID_COMPAT, 0.1, 46.0), (ACCEL_BVH, 0.25, 44.0)):
+        r.set_accel(accel)
+        r.set_params(W, H, 5, first_hit_cache=True)
+        r.render(0, iters)
+        b8, means = box8_of_film(r.film(), iters)
+        rmse = float(np.sqrt(np.mean((b8 - g["box8"]) ** 2)))
+        psnr = 20 * np.log10(255.0 / rmse)
+        print(f"accel {accel}: channel means {means} vs {g['channel_means']}, box-filtered rmse {rmse:.2f}/255, psnr {psnr:.1f} dB")
+        assert np.abs(means - g["channel_means"]).max() <= mean_tol
+        assert psnr >= min_psnr
+    # the file itself: the bytes ptap_write_bmp stores are the ones compared above
+    r.set_accel(ACCEL_GRID_COMPAT); r.set_params(W, H, 5, first_hit_cache=True); r.render(0, iters)
+    r.renderImage(str(tmp_path / "Render.bmp"))
+    raw = np.frombuffer((tmp_path / "Render.bmp").read_bytes(), np.uint8, W * H * 3, 54).reshape(H, W, 3)
+    assert np.abs(raw.reshape(-1, 3).astype(np.float64).mean(0) - g["channel_means"]).max() <= 0.1
+    r.free()
+
+
 def test_cornell_frame(libptap, golden_scene, golden_films):
     from pathtracerap_b200 import Renderer, Scene
     f = golden_films
