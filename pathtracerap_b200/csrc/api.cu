@@ -400,6 +400,7 @@ int ptap_create(int device, size_t arena_bytes, ptap_ctx** out)
     ctx->sc.vote_refill = std::min(32, std::max(1, envInt("PTAP_VOTE_REFILL", kVoteRefill)));
     ctx->sc.batch = std::max(1, envInt("PTAP_BATCH", kTraceBatch));
     ctx->sc.vote_grid = std::min(32, std::max(1, envInt("PTAP_VOTE_GRID", kVoteGrid)));
+    ctx->sc.shade_sort = envInt("PTAP_SHADE_SORT", 0) != 0;      // measured slower on every workload (profiles/r01/README.md): opt-in
     ctx->trace_ctas = std::max(0, envInt("PTAP_TRACE_CTAS", 0));
     if (arena_bytes) {                                          // caller-sized arena: split 1/4 scene, 3/4 frame
         if (ctx->scene_arena.reserve(arena_bytes / 4) != cudaSuccess || ctx->frame_arena.reserve(arena_bytes - arena_bytes / 4) != cudaSuccess) {
@@ -586,7 +587,8 @@ int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, u
     const int N = W * H;
     const int ntiles = (N + kShadeTile - 1) / kShadeTile, nscan = (N + kScanSlots - 1) / kScanSlots;
     size_t need = Arena::need(N, sizeof(float4)) * 8 + Arena::need(N, sizeof(float2)) + Arena::need((size_t)N * 3, sizeof(float)) +
-                  Arena::need((size_t)nscan * kMaxDepth, sizeof(unsigned long long)) + Arena::need(ntiles, sizeof(int)) + Arena::need(1, sizeof(FrameState)) + 4096;
+                  Arena::need((size_t)nscan * kMaxDepth, sizeof(unsigned long long)) + Arena::need(ntiles, sizeof(int)) * 2 +
+                  Arena::need((size_t)nscan * kScanSlots, 1) + Arena::need(1, sizeof(FrameState)) + 4096;
     if (need > ctx->frame_arena.cap) CK(ctx->frame_arena.reserve(need)); else ctx->frame_arena.used = 0;
     Arena& A = ctx->frame_arena;
     WaveDev& wv = ctx->wv;
@@ -595,8 +597,10 @@ int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, u
     wv.film = A.alloc<float>((size_t)N * 3);
     wv.tile_status = A.alloc<unsigned long long>((size_t)nscan * kMaxDepth);
     wv.tile_offset = A.alloc<int>(ntiles);
+    wv.tile_ballot = A.alloc<unsigned>(ntiles);
+    wv.perm = A.alloc<unsigned char>((size_t)nscan * kScanSlots);
     wv.st = A.alloc<FrameState>(1);
-    if (!wv.st || !wv.tile_status || !wv.tile_offset || !wv.film) return fail(ctx, PTAP_E_NOMEM, "frame arena exhausted");
+    if (!wv.st || !wv.tile_status || !wv.tile_offset || !wv.tile_ballot || !wv.perm || !wv.film) return fail(ctx, PTAP_E_NOMEM, "frame arena exhausted");
     wv.W = W; wv.H = H; wv.N = N; wv.depth = depth; wv.ntiles = ntiles; wv.nscan = nscan;
     wv.step_x = (float)(20.0 / (double)W);                       // Renderer.cpp:538-539 (SAMPLESX = SAMPLESY = 1)
     wv.step_y = (float)(16.0 / (double)H);
@@ -812,7 +816,8 @@ int ptap_shade(ptap_ctx* ctx, const PtapPathIn* paths, int32_t n, int32_t iter, 
     if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
     const int ntiles = (n + kShadeTile - 1) / kShadeTile, nscan = (n + kScanSlots - 1) / kScanSlots;
     size_t need = Arena::need(n, sizeof(float4)) * 7 + Arena::need((size_t)n * 3, sizeof(float)) + Arena::need(n, sizeof(int)) +
-                  Arena::need(nscan, sizeof(unsigned long long)) + Arena::need(ntiles, sizeof(int)) + Arena::need(1, sizeof(FrameState)) + 4096;
+                  Arena::need(nscan, sizeof(unsigned long long)) + Arena::need(ntiles, sizeof(int)) * 2 + Arena::need((size_t)nscan * kScanSlots, 1) +
+                  Arena::need(1, sizeof(FrameState)) + 4096;
     if (need > ctx->scratch.cap) CK(ctx->scratch.reserve(need)); else ctx->scratch.used = 0;
     Arena& A = ctx->scratch;
     WaveDev wv{};
@@ -822,6 +827,8 @@ int ptap_shade(ptap_ctx* ctx, const PtapPathIn* paths, int32_t n, int32_t iter, 
     int* slot_pos = A.alloc<int>(n);
     wv.tile_status = A.alloc<unsigned long long>(nscan);
     wv.tile_offset = A.alloc<int>(ntiles);
+    wv.tile_ballot = A.alloc<unsigned>(ntiles);
+    wv.perm = A.alloc<unsigned char>((size_t)nscan * kScanSlots);
     wv.st = A.alloc<FrameState>(1);
     wv.N = n; wv.W = n; wv.H = 1; wv.depth = 1; wv.ntiles = ntiles; wv.nscan = nscan;
     std::vector<float4> hO(n), hD(n), hC(n), hH(n);

@@ -95,6 +95,7 @@ struct SceneDev {
     int tlas_root;              // node index of the TLAS root, -1 when no instance has triangles
     float tmin_world;           // lower end of the world-space ray interval: -(EPSILON band mapped to world units + box padding)
     int batch;                  // rays a warp takes from the work-stealing cursor per atomic (PTAP_BATCH)
+    int shade_sort;             // k_shade regroups each block's slots by material class before shading (PTAP_SHADE_SORT=1; default off)
     int vote_grid;              // k_trace_grid: lanes that must wait in a state before its step runs (the most popular state always runs)
     int vote_tri, vote_inst, vote_refill;   // lanes that must wait in a state before the warp runs that state's step (PTAP_VOTE_*)
     float c_pad;                // slack of the pruning bound for the residual of model_to_world * world_to_model - I
@@ -112,6 +113,8 @@ struct WaveDev {
     float* film;                // W*H*3 running sum (Pixel, Primitive.h:145-148)
     unsigned long long* tile_status;   // k_scan look-back words: rounds x 2048-slot scan blocks
     int* tile_offset;           // survivors before each 32-slot tile of the current round (k_scan -> k_shade)
+    unsigned* tile_ballot;      // survival bits of each 32-slot tile, in slot order (k_scan -> k_shade<SORT>)
+    unsigned char* perm;        // per 256-slot shade block: regrouped position -> slot within the block (k_scan -> k_shade<SORT>)
     FrameState* st;
     int W, H, N, depth, ntiles, nscan;   // ntiles = ceil(N / 32), nscan = ceil(N / 2048)
     float step_x, step_y;

@@ -160,8 +160,10 @@ __global__ void __launch_bounds__(kScanBlock)
 k_scan(SceneDev sc, WaveDev wv, int round, const float4* __restrict__ hit, int remaining, int n_fixed)
 {
     __shared__ int s_cnt[kScanTiles];
-    __shared__ int s_base;
     __shared__ unsigned s_ticket;
+    constexpr int kSub = kScanSlots / kScanBlock, kWarps = kScanBlock / 32, kClasses = 8;      // 256-slot shade blocks per scan block
+    __shared__ unsigned short s_wcnt[kSub][kWarps][kClasses];       // slots of material class c in tile (k, w) ...
+    __shared__ unsigned short s_wbase[kSub][kWarps][kClasses];      // ... and where they start in the regrouped order of shade block k
     FrameState* st = wv.st;
     const int n = n_fixed >= 0 ? n_fixed : st->n_active[round];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -171,15 +173,43 @@ k_scan(SceneDev sc, WaveDev wv, int round, const float4* __restrict__ hit, int r
     const int blk = (int)s_ticket;
     const int base = blk * kScanSlots;
     if (base >= n) return;
+    const bool sort = sc.shade_sort != 0;
+    unsigned packed[kSub / 4] = {};                                               // (class << 5 | rank in the tile's class) per k, one byte each
 #pragma unroll
     for (int k = 0; k < kScanSlots / kScanBlock; ++k) {
         const int i = base + k * kScanBlock + threadIdx.x;
         bool alive = false;
-        if (i < n) { int type; alive = survives(sc, hit[i], remaining, type); }
+        int type = -1;
+        float hx = kFloatMax;
+        if (i < n) { const float4 h = hit[i]; hx = h.x; alive = survives(sc, h, remaining, type); }
         const unsigned ballot = __ballot_sync(0xffffffffu, alive);
         if (lane == 0) s_cnt[k * (kScanBlock / 32) + warp] = __popc(ballot);     // tile j = k * 8 + warp covers slots base + 32 j ..
+        if (sort) {
+            // material class of the slot: what k_shade will execute for it (survivors by scattering routine, terminated hits, misses)
+            if (lane == 0 && base + k * kScanBlock + warp * 32 < n) wv.tile_ballot[base / 32 + k * kWarps + warp] = ballot;
+            const int cls = i >= n ? 7 : !(hx < kFloatMax) ? 5 : !alive ? 4
+                          : type == PTAP_DIFFUSE ? 0 : type == PTAP_METAL ? 1 : type == PTAP_COAT ? 2 : type == PTAP_REFLECTIVE ? 3 : 6;
+            int r = 0;
+#pragma unroll
+            for (int c = 0; c < kClasses; ++c) {
+                const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+                if (cls == c) r = __popc(m & ((1u << lane) - 1u));
+                if (lane == c) s_wcnt[k][warp][c] = (unsigned short)__popc(m);
+            }
+            packed[k >> 2] |= (unsigned)(cls << 5 | r) << (8 * (k & 3));
+        }
     }
     __syncthreads();
+    if (sort) {
+        // start of (tile w, class c) within shade block k: class-major, tile-minor
+        for (int e = threadIdx.x; e < kSub * kWarps * kClasses; e += kScanBlock) {
+            const int k = e / (kWarps * kClasses), w = (e / kClasses) % kWarps, c = e % kClasses;
+            int acc = 0;
+            for (int cc = 0; cc <= c; ++cc)
+                for (int ww = 0; ww < (cc < c ? kWarps : w); ++ww) acc += s_wcnt[k][ww][cc];
+            s_wbase[k][w][c] = (unsigned short)acc;
+        }
+    }
     if (warp == 0) {
         // exclusive scan of the 64 tile counts (two per lane), block total, look-back
         const int c0 = s_cnt[2 * lane], c1 = s_cnt[2 * lane + 1];
@@ -216,12 +246,26 @@ k_scan(SceneDev sc, WaveDev wv, int round, const float4* __restrict__ hit, int r
     }
     __syncthreads();
     if (threadIdx.x < kScanTiles && base + threadIdx.x * 32 < n) wv.tile_offset[base / 32 + threadIdx.x] = s_cnt[threadIdx.x];
+    if (sort) {
+#pragma unroll
+        for (int k = 0; k < kSub; ++k) {
+            if (base + k * kScanBlock >= n) break;
+            const unsigned pk = (packed[k >> 2] >> (8 * (k & 3))) & 0xffu;
+            wv.perm[base + k * kScanBlock + s_wbase[k][warp][pk >> 5] + (pk & 31u)] = (unsigned char)threadIdx.x;
+        }
+    }
 }
 
 // shadeRayKernel + the move half of stable_partition + film accumulation for one bounce (Renderer.cpp:411-479, 481-496, 628).
 // Slot i of queue `in` holds a path with `remaining` bounces left (every live path of a round has the same count).
-// One warp per 32-slot tile, tiles independent: load, shade, survivors to tile_offset[tile] + rank in queue `in ^ 1`,
-// terminated paths add sqrt(throughput) to the film (each pixel owns exactly one path per iteration).
+// A CTA takes kShadeBlock consecutive slots (kShadeBlock / 32 compaction tiles).  Results are placement-independent: a survivor of slot i
+// goes to tile_offset[tile(i)] + (survivors before i in its tile) in queue `in ^ 1`, its random stream is seeded with i, and a terminated
+// path adds sqrt(throughput) to its own pixel (each pixel owns exactly one path per iteration).  So WHICH thread shades a slot is free,
+// and with SORT the threads of a block take its slots regrouped by material class (DIFFUSE / METAL / COAT / REFLECTIVE survivors,
+// terminated hits, misses: a counting sort per 256-slot block that k_scan makes while it reads the hit records anyway), so that a warp
+// runs one scattering routine instead of up to four in turn.  The reference's per-slot semantics (RNG seed by slot, stable order) are
+// untouched; only the SIMT schedule changes.  No shared memory, no barrier.
+template <bool SORT>
 __global__ void __launch_bounds__(kShadeBlock)
 k_shade(SceneDev sc, WaveDev wv, int round, int in, const float4* __restrict__ hit, int remaining, int n_fixed, int iter_fixed,
         int* __restrict__ slot_pos)
@@ -229,62 +273,68 @@ k_shade(SceneDev sc, WaveDev wv, int round, int in, const float4* __restrict__ h
     const FrameState* st = wv.st;
     const int n = n_fixed >= 0 ? n_fixed : st->n_active[round];
     const int iter = n_fixed >= 0 ? iter_fixed : st->iter_cur;
-    const int lane = threadIdx.x & 31;
     const float4* __restrict__ Oi = wv.O[in]; const float4* __restrict__ Di = wv.D[in]; const float4* __restrict__ Ci = wv.C[in];
     float4* __restrict__ Oo = wv.O[in ^ 1]; float4* __restrict__ Do = wv.D[in ^ 1]; float4* __restrict__ Co = wv.C[in ^ 1];
-    const int nwarps = gridDim.x * (kShadeBlock / 32);
-    const int ntiles = (n + kShadeTile - 1) / kShadeTile;
+    const int nblocks = (n + kShadeBlock - 1) / kShadeBlock;
 
-    for (int tile = blockIdx.x * (kShadeBlock / 32) + (threadIdx.x >> 5); tile < ntiles; tile += nwarps) {
-        const int i = tile * kShadeTile + lane;
-        const bool valid = i < n;
-        float4 o4 = make_float4(0, 0, 0, 0), d4 = o4, c4 = o4, h = make_float4(kFloatMax, 0, 0, 0);
-        if (valid) { h = hit[i]; o4 = Oi[i]; d4 = Di[i]; c4 = Ci[i]; }
-        const int excl = __ldg(&wv.tile_offset[tile]);
+    int s_next = threadIdx.x;
+    if (SORT && (int)blockIdx.x < nblocks) s_next = wv.perm[(size_t)blockIdx.x * kShadeBlock + threadIdx.x];
+    for (int blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const int base = blk * kShadeBlock;
+        const int s = s_next;                                // the slot (within the block) this thread shades: regrouped by material class (k_scan)
+        if (SORT && blk + (int)gridDim.x < nblocks) s_next = wv.perm[(size_t)(blk + gridDim.x) * kShadeBlock + threadIdx.x];   // one block ahead
+        const int i = base + s;
+        const bool in_range = i < n;
+        float4 h = make_float4(kFloatMax, 0, 0, 0);
+        if (in_range) h = hit[i];
         int type;
-        const bool alive = survives(sc, h, remaining, type) && valid;
-        const bool is_hit = valid && h.x < kFloatMax;
-        const int tri = __float_as_int(h.y), model = __float_as_int(h.z);
-        const unsigned ballot = __ballot_sync(0xffffffffu, alive);
-        const int rank = __popc(ballot & ((1u << lane) - 1u));
-        if (!valid) continue;
+        const bool alive = survives(sc, h, remaining, type) && in_range;
+        // survivors of the slot's tile: k_scan's ballot when the slots are regrouped, else this warp holds exactly that tile
+        const unsigned tile_ballot = SORT ? (in_range ? __ldg(&wv.tile_ballot[(base >> 5) + (s >> 5)]) : 0u) : __ballot_sync(0xffffffffu, alive);
+        if (in_range) {
+            float4 o4 = Oi[i], d4 = Di[i], c4 = Ci[i];
+            const int excl = __ldg(&wv.tile_offset[(base >> 5) + (s >> 5)]);
+            const bool is_hit = h.x < kFloatMax;
+            const int tri = __float_as_int(h.y), model = __float_as_int(h.z);
+            const int rank = __popc(tile_ballot & ((1u << (s & 31)) - 1u));
 
-        V3 col = v3(c4);
-        if (is_hit) {
-            float4 nm0, nm1, nm2;
-            const V3 nrm = worldNormal(sc, model, tri, nm0, nm1, nm2);
-            const V3 albedo = v3(nm0.w, nm1.w, nm2.w);
-            const V3 dir = xnormalize(v3(d4));                               // Renderer.cpp:428
-            // IntersectionData::impact_distance (Renderer.cpp:391): k_trace_bvh leaves it to be evaluated here (hit.x < 0)
-            const float dist = h.x >= 0.0f ? h.x : exactHitDistance(sc, v3(o4), v3(d4), model, h.w);
-            const V3 pt = xadd(v3(o4), xscale(dir, dist));                   // Renderer.cpp:429
-            if (type == PTAP_DIFFUSE || type == PTAP_METAL || type == PTAP_COAT) {   // Renderer.cpp:433-453
-                if (alive) {
-                    Lcg rng(iter, i, remaining);
-                    const V3 nd = type == PTAP_DIFFUSE ? hemisphere(nrm, rng) : type == PTAP_METAL ? metal(nrm, dir, rng) : coat(nrm, dir, rng);
+            V3 col = v3(c4);
+            if (is_hit) {
+                float4 nm0, nm1, nm2;
+                const V3 nrm = worldNormal(sc, model, tri, nm0, nm1, nm2);
+                const V3 albedo = v3(nm0.w, nm1.w, nm2.w);
+                const V3 dir = xnormalize(v3(d4));                               // Renderer.cpp:428
+                // IntersectionData::impact_distance (Renderer.cpp:391): k_trace_bvh leaves it to be evaluated here (hit.x < 0)
+                const float dist = h.x >= 0.0f ? h.x : exactHitDistance(sc, v3(o4), v3(d4), model, h.w);
+                const V3 pt = xadd(v3(o4), xscale(dir, dist));                   // Renderer.cpp:429
+                if (type == PTAP_DIFFUSE || type == PTAP_METAL || type == PTAP_COAT) {   // Renderer.cpp:433-453
+                    if (alive) {
+                        Lcg rng(iter, i, remaining);
+                        const V3 nd = type == PTAP_DIFFUSE ? hemisphere(nrm, rng) : type == PTAP_METAL ? metal(nrm, dir, rng) : coat(nrm, dir, rng);
+                        const V3 no = xadd(pt, xscale(nrm, 0.1f));
+                        o4.x = no.x; o4.y = no.y; o4.z = no.z; d4.x = nd.x; d4.y = nd.y; d4.z = nd.z;
+                    }
+                    col = xmul(col, albedo);
+                } else if (type == PTAP_EMISSIVE) {                              // Renderer.cpp:454-460
+                    col = xmul(col, albedo);
+                } else if (type == PTAP_REFLECTIVE) {                            // Renderer.cpp:461-467
+                    col = xmul(col, albedo);
+                    const V3 nd = reflectRay(dir, nrm);
                     const V3 no = xadd(pt, xscale(nrm, 0.1f));
                     o4.x = no.x; o4.y = no.y; o4.z = no.z; d4.x = nd.x; d4.y = nd.y; d4.z = nd.z;
-                }
-                col = xmul(col, albedo);
-            } else if (type == PTAP_EMISSIVE) {                              // Renderer.cpp:454-460
-                col = xmul(col, albedo);
-            } else if (type == PTAP_REFLECTIVE) {                            // Renderer.cpp:461-467
-                col = xmul(col, albedo);
-                const V3 nd = reflectRay(dir, nrm);
-                const V3 no = xadd(pt, xscale(nrm, 0.1f));
-                o4.x = no.x; o4.y = no.y; o4.z = no.z; d4.x = nd.x; d4.y = nd.y; d4.z = nd.z;
-            }                                                                // SPECULAR / REFRACTIVE: no branch, ray unchanged
-        } else {                                                             // Renderer.cpp:471-477
-            col = xmul(col, v3(0.01f, 0.01f, 0.01f));
+                }                                                                // SPECULAR / REFRACTIVE: no branch, ray unchanged
+            } else {                                                             // Renderer.cpp:471-477
+                col = xmul(col, v3(0.01f, 0.01f, 0.01f));
+            }
+            c4.x = col.x; c4.y = col.y; c4.z = col.z;
+            const int pos = alive ? excl + rank : -1;
+            if (alive) { Oo[pos] = o4; Do[pos] = d4; Co[pos] = c4; }
+            else {                                                               // gatherImageDataKernel, Renderer.cpp:481-496
+                float* px = wv.film + 3 * (size_t)__float_as_int(o4.w);
+                px[0] = xadd(px[0], xsqrt(col.x)); px[1] = xadd(px[1], xsqrt(col.y)); px[2] = xadd(px[2], xsqrt(col.z));
+            }
+            if (slot_pos) slot_pos[i] = pos;
         }
-        c4.x = col.x; c4.y = col.y; c4.z = col.z;
-        const int pos = alive ? excl + rank : -1;
-        if (alive) { Oo[pos] = o4; Do[pos] = d4; Co[pos] = c4; }
-        else {                                                               // gatherImageDataKernel, Renderer.cpp:481-496
-            float* px = wv.film + 3 * (size_t)__float_as_int(o4.w);
-            px[0] = xadd(px[0], xsqrt(col.x)); px[1] = xadd(px[1], xsqrt(col.y)); px[2] = xadd(px[2], xsqrt(col.z));
-        }
-        if (slot_pos) slot_pos[i] = pos;
     }
 }
 
@@ -357,13 +407,14 @@ void launchScan(const SceneDev& sc, const WaveDev& wv, int round, const float4* 
 void launchShade(const SceneDev& sc, const WaveDev& wv, int round, int in_buf, const float4* hit, int remaining, int n_fixed,
                  int iter_fixed, int* slot_pos, int grid, cudaStream_t stream)
 {
-    k_shade<<<grid, kShadeBlock, 0, stream>>>(sc, wv, round, in_buf, hit, remaining, n_fixed, iter_fixed, slot_pos);
+    if (sc.shade_sort) k_shade<true><<<grid, kShadeBlock, 0, stream>>>(sc, wv, round, in_buf, hit, remaining, n_fixed, iter_fixed, slot_pos);
+    else k_shade<false><<<grid, kShadeBlock, 0, stream>>>(sc, wv, round, in_buf, hit, remaining, n_fixed, iter_fixed, slot_pos);
 }
 
 int shadeOccupancy()
 {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade, kShadeBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade<true>, kShadeBlock, 0);
     return nb;
 }
 

@@ -1,1 +1,6 @@
-ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:k_trace_bvhILb0ELb0 -c 3 -o gpurun_out/prof_trace_fma python bench.py --spp 2 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_fma.log 2>&1
+python -m pytest tests/test_gpu_wavefront.py tests/test_gpu_scenes.py tests/test_gpu_large.py -m gpu -x -q 2>&1 | tail -15 > gpurun_out/sort_tests.log
+PTAP_SHADE_SORT=0 python -m pytest tests/test_gpu_wavefront.py -m gpu -x -q 2>&1 | tail -5 >> gpurun_out/sort_tests.log
+for w in bundled mesh1m cornell; do
+  PTAP_SHADE_SORT=1 python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/sort1_$w.json 2> gpurun_out/sort1_$w.err
+  PTAP_SHADE_SORT=0 python bench.py --workload $w --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/sort0_$w.json 2> gpurun_out/sort0_$w.err
+done
