@@ -11,6 +11,7 @@
 // PTAP_DEPTH, PTAP_ACCEL=grid|bvh|lbvh, PTAP_DEVICE).  The acceleration structure defaults to the reference's own 25^3 grid walk
 // (bit-compatible hits); PTAP_ACCEL=bvh selects the BVH (built on the host), lbvh the same built on the GPU.  All errors throw std::runtime_error: there is no CPU fallback.
 #pragma once
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <iostream>
@@ -36,6 +37,8 @@ public:
         height = pick("PTAP_HEIGHT", scene.config_height, RESOLUTION_Y);
         iters = pick("PTAP_ITER", scene.config_iter, ITER);
         depth = pick("PTAP_DEPTH", scene.config_depth, MAX_DEPTH);
+        samples_x = std::max(1, pick("PTAP_SAMPLESX", 0, SAMPLESX));   // Config.h:14-15: camera rays per pixel, on one W*SX x H*SY lattice
+        samples_y = std::max(1, pick("PTAP_SAMPLESY", 0, SAMPLESY));
         const char* a = std::getenv("PTAP_ACCEL");
         const bool lbvh = a && std::string(a) == "lbvh";          // tree built on the GPU at this call
         const bool bvh = a && std::string(a) == "bvh";
@@ -51,7 +54,7 @@ public:
         v.grid_dim[0] = GRID_X; v.grid_dim[1] = GRID_Y; v.grid_dim[2] = GRID_Z;
         check(ptap_upload_scene(ctx, &v), "ptap_upload_scene");
         check(ptap_build_accel(ctx, lbvh ? PTAP_ACCEL_BVH_DEVICE : bvh || scene.grids.empty() ? PTAP_ACCEL_BVH : PTAP_ACCEL_GRID_COMPAT), "ptap_build_accel");
-        check(ptap_set_render_params(ctx, width, height, depth, PTAP_FLAG_FIRST_HIT_CACHE), "ptap_set_render_params");
+        check(ptap_set_render_params(ctx, width * samples_x, height * samples_y, depth, PTAP_FLAG_FIRST_HIT_CACHE), "ptap_set_render_params");
     }
 
     void renderLoop()
@@ -63,7 +66,7 @@ public:
         image.size = width * height;
         host_film.resize((size_t)image.size);
         image.pool = host_film.data();
-        check(ptap_read_film(ctx, &host_film[0].color[0]), "ptap_read_film");
+        check(ptap_read_film_resolved(ctx, samples_x, samples_y, &host_film[0].color[0]), "ptap_read_film_resolved");
         render_data.dev_image_data = &image;
         const auto t1 = std::chrono::high_resolution_clock::now();
         PtapStats st{};
@@ -75,7 +78,7 @@ public:
     void renderImage()
     {
         need();
-        check(ptap_write_bmp(ctx, "Render.bmp", iters), "ptap_write_bmp");
+        check(ptap_write_bmp_resolved(ctx, "Render.bmp", iters, samples_x, samples_y), "ptap_write_bmp");
     }
 
     void free()
@@ -87,6 +90,7 @@ public:
 
     RenderData render_data;
     int width = RESOLUTION_X, height = RESOLUTION_Y, iters = ITER, depth = MAX_DEPTH;
+    int samples_x = SAMPLESX, samples_y = SAMPLESY;
 
 private:
     static int pick(const char* env, int from_config, int dflt)

@@ -184,6 +184,15 @@ int ptap_film_device_ptr(ptap_ctx* ctx, void** dev_ptr, size_t* nfloats);   /* f
 int ptap_film_add(ptap_ctx* ctx, const float* rgb);                /* host film += (multi-rank emulation / resume) */
 /* Renderer::renderImage (Renderer.cpp:15-63): 24-bpp BMP, bottom-up, bytes (uint8)(sum/iters*255) */
 int ptap_write_bmp(ptap_ctx* ctx, const char* path, int32_t iters);
+/* Supersampled output: SAMPLESX x SAMPLESY (Config.h:14-15).  generateRaysKernel lays RX*SX x RY*SY camera rays on ONE lattice
+ * (Renderer.cpp:527-542), which is exactly what ptap_set_render_params(RX*SX, RY*SY) renders.  The reference's gather is broken for
+ * SAMPLES > 1: avg = 1 / (SAMPLESX * SAMPLESY) is an integer division (= 0) and ipixel = iray (Renderer.cpp:493, 530-533), so its image
+ * stays black; these two calls implement the evident intent (the commented-out mapping at Renderer.cpp:530-532): pixel (x, y) =
+ * sum of avg * sample over its sx * sy lattice samples, avg = 1.0f / (sx * sy), in row-major sample order.  The film must have been
+ * rendered at (W, H) divisible by (sx, sy); rgb receives (W / sx) * (H / sy) * 3 floats.  sx = sy = 1 equals the plain calls.
+ * Parity unpinned: no reference behaviour exists for this row. */
+int ptap_read_film_resolved(ptap_ctx* ctx, int32_t sx, int32_t sy, float* rgb);
+int ptap_write_bmp_resolved(ptap_ctx* ctx, const char* path, int32_t iters, int32_t sx, int32_t sy);
 int ptap_get_stats(ptap_ctx* ctx, PtapStats* out);
 void* ptap_stream(ptap_ctx* ctx);                                  /* cudaStream_t of the context */
 

@@ -64,7 +64,8 @@ void Renderer::allocateOnGPU(Scene& scene)
     const char* accel = std::getenv("PTAP_ACCEL");            // default: the reference's own grid walk, bit-compatible hits
     const int kind = !accel ? PTAP_ACCEL_GRID_COMPAT : std::string(accel) == "bvh" ? PTAP_ACCEL_BVH : std::string(accel) == "lbvh" ? PTAP_ACCEL_BVH_DEVICE : PTAP_ACCEL_GRID_COMPAT;
     check(b, ptap_build_accel(b.ctx, kind), "ptap_build_accel");
-    check(b, ptap_set_render_params(b.ctx, RESOLUTION_X, RESOLUTION_Y, MAX_DEPTH, PTAP_FLAG_FIRST_HIT_CACHE), "ptap_set_render_params");
+    // nrays = RESOLUTION * SAMPLES camera rays on one lattice (Renderer.cpp:96, 527-542); SAMPLESX = SAMPLESY = 1 in Config.h:14-15
+    check(b, ptap_set_render_params(b.ctx, RESOLUTION_X * SAMPLESX, RESOLUTION_Y * SAMPLESY, MAX_DEPTH, PTAP_FLAG_FIRST_HIT_CACHE), "ptap_set_render_params");
     render_data = RenderData{};
 }
 
@@ -75,7 +76,7 @@ void Renderer::renderLoop()
     const auto t0 = std::chrono::high_resolution_clock::now();
     check(b, ptap_frame_begin(b.ctx), "ptap_frame_begin");
     check(b, ptap_render(b.ctx, 0, iters), "ptap_render");
-    b.film.resize((size_t)RESOLUTION_X * RESOLUTION_Y);
+    b.film.resize((size_t)RESOLUTION_X * SAMPLESX * RESOLUTION_Y * SAMPLESY);
     check(b, ptap_read_film(b.ctx, reinterpret_cast<float*>(b.film.data())), "ptap_read_film");
     b.image.size = (int)b.film.size();
     b.image.pool = b.film.data();
@@ -87,7 +88,8 @@ void Renderer::renderLoop()
 void Renderer::renderImage()
 {
     Binding& b = g_bindings[this];
-    check(b, ptap_write_bmp(b.ctx, "Render.bmp", envInt("PTAP_ITER", ITER)), "ptap_write_bmp");
+    // SAMPLES > 1: each pixel is the mean of its lattice samples (the reference's own gather leaves the image black, Renderer.cpp:493)
+    check(b, ptap_write_bmp_resolved(b.ctx, "Render.bmp", envInt("PTAP_ITER", ITER), SAMPLESX, SAMPLESY), "ptap_write_bmp");
 }
 
 void Renderer::free()

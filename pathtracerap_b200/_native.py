@@ -63,7 +63,7 @@ EXPORTS = [
     "ptap_scene_config_params",
     "ptap_create", "ptap_destroy", "ptap_last_error", "ptap_upload_scene", "ptap_build_accel", "ptap_set_render_params",
     "ptap_render", "ptap_timer_start", "ptap_timer_stop", "ptap_frame_begin", "ptap_film_reset", "ptap_sync", "ptap_read_film", "ptap_film_device_ptr", "ptap_film_add",
-    "ptap_write_bmp", "ptap_get_stats", "ptap_stream", "ptap_trace", "ptap_trace_count", "ptap_shade", "ptap_bench_trace",
+    "ptap_write_bmp", "ptap_read_film_resolved", "ptap_write_bmp_resolved", "ptap_get_stats", "ptap_stream", "ptap_trace", "ptap_trace_count", "ptap_shade", "ptap_bench_trace",
 ]
 
 _lib = None
@@ -114,6 +114,8 @@ def lib():
         L.ptap_film_device_ptr.argtypes = [vp, pp, C.POINTER(C.c_size_t)]
         L.ptap_film_add.argtypes = [vp, vp]
         L.ptap_write_bmp.argtypes = [vp, C.c_char_p, ci]
+        L.ptap_read_film_resolved.argtypes = [vp, ci, ci, vp]
+        L.ptap_write_bmp_resolved.argtypes = [vp, C.c_char_p, ci, ci, ci]
         L.ptap_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.ptap_stream.argtypes = [vp]; L.ptap_stream.restype = vp
         L.ptap_trace.argtypes = [vp, vp, ci, vp]

@@ -742,19 +742,16 @@ int ptap_get_stats(ptap_ctx* ctx, PtapStats* out)
 
 // Renderer::renderImage (Renderer.cpp:15-63).  The per-pixel conversion runs on the device (k_resolve_bmp), the bytes come back through
 // a page-locked staging buffer, and the host only writes the header and the rows.
-int ptap_write_bmp(ptap_ctx* ctx, const char* path, int32_t iters)
+// `film`: W x H x 3 device floats (the context's film, or a resolved copy in the scratch arena after `used_scratch` bytes)
+static int writeBmpFrom(ptap_ctx* ctx, const float* film, int W, int H, const char* path, int32_t iters)
 {
-    if (!ctx || !ctx->have_frame || !path || iters <= 0) return fail(ctx, PTAP_E_INVALID, "write_bmp: bad arguments");
-    CK(cudaSetDevice(ctx->device));
-    { int rc = collect(ctx); if (rc) return rc; }
-    const int W = ctx->wv.W, H = ctx->wv.H;
     const size_t nbytes = (size_t)3 * W * H;
-    if (Arena::need(nbytes, 1) > ctx->scratch.cap) CK(ctx->scratch.reserve(Arena::need(nbytes, 1))); else ctx->scratch.used = 0;
     unsigned char* d_bytes = ctx->scratch.alloc<unsigned char>(nbytes);
+    if (!d_bytes) return fail(ctx, PTAP_E_NOMEM, "write_bmp: scratch arena exhausted");
     unsigned char* h_bytes = nullptr;
     CK(cudaHostAlloc((void**)&h_bytes, nbytes, cudaHostAllocDefault));
     const float div = 1 / (float)iters;                                     // Renderer.cpp:42
-    launchResolveBmp(ctx->wv.film, nbytes, div, d_bytes, ctx->stream);
+    launchResolveBmp(film, nbytes, div, d_bytes, ctx->stream);
     cudaError_t e = cudaMemcpyAsync(h_bytes, d_bytes, nbytes, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) { cudaFreeHost(h_bytes); return fail(ctx, (int)e, "write_bmp: %s", cudaGetErrorString(e)); }
@@ -770,6 +767,51 @@ int ptap_write_bmp(ptap_ctx* ctx, const char* path, int32_t iters)
     cudaFreeHost(h_bytes);
     if (!ok) return fail(ctx, PTAP_E_IO, "write_bmp: short write to %s", path);
     return PTAP_OK;
+}
+
+// scratch arena sized for a resolved film + its bytes; returns the resolved film (device) or nullptr after fail()
+static float* resolveBox(ptap_ctx* ctx, int sx, int sy, const char* who, int* rc)
+{
+    const int W = ctx->wv.W, H = ctx->wv.H;
+    if (sx <= 0 || sy <= 0 || W % sx || H % sy) { *rc = fail(ctx, PTAP_E_INVALID, "%s: %d x %d samples do not divide the %d x %d film", who, sx, sy, W, H); return nullptr; }
+    const size_t nv = (size_t)(W / sx) * (H / sy) * 3;
+    const size_t need = Arena::need(nv, sizeof(float)) + Arena::need(nv, 1) + 4096;
+    if (need > ctx->scratch.cap) { cudaError_t e = ctx->scratch.reserve(need); if (e != cudaSuccess) { *rc = fail(ctx, (int)e, "%s: %s", who, cudaGetErrorString(e)); return nullptr; } }
+    else ctx->scratch.used = 0;
+    float* out = ctx->scratch.alloc<float>(nv);
+    launchResolveBox(ctx->wv.film, W, H, sx, sy, out, ctx->stream);
+    *rc = PTAP_OK;
+    return out;
+}
+
+int ptap_write_bmp_resolved(ptap_ctx* ctx, const char* path, int32_t iters, int32_t sx, int32_t sy)
+{
+    if (!ctx || !ctx->have_frame || !path || iters <= 0) return fail(ctx, PTAP_E_INVALID, "write_bmp: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    { int rc = collect(ctx); if (rc) return rc; }
+    int rc = PTAP_OK;
+    if (sx == 1 && sy == 1) {
+        const size_t nbytes = (size_t)3 * ctx->wv.W * ctx->wv.H;
+        if (Arena::need(nbytes, 1) > ctx->scratch.cap) CK(ctx->scratch.reserve(Arena::need(nbytes, 1))); else ctx->scratch.used = 0;
+        return writeBmpFrom(ctx, ctx->wv.film, ctx->wv.W, ctx->wv.H, path, iters);
+    }
+    const float* film = resolveBox(ctx, sx, sy, "write_bmp_resolved", &rc);
+    if (!film) return rc;
+    return writeBmpFrom(ctx, film, ctx->wv.W / sx, ctx->wv.H / sy, path, iters);
+}
+
+int ptap_write_bmp(ptap_ctx* ctx, const char* path, int32_t iters) { return ptap_write_bmp_resolved(ctx, path, iters, 1, 1); }
+
+int ptap_read_film_resolved(ptap_ctx* ctx, int32_t sx, int32_t sy, float* rgb)
+{
+    if (!ctx || !ctx->have_frame || !rgb) return fail(ctx, PTAP_E_STATE, "read_film_resolved: no render parameters");
+    CK(cudaSetDevice(ctx->device));
+    { int rc = collect(ctx); if (rc) return rc; }
+    int rc = PTAP_OK;
+    const float* film = resolveBox(ctx, sx, sy, "read_film_resolved", &rc);
+    if (!film) return rc;
+    CK(cudaMemcpyAsync(rgb, film, (size_t)(ctx->wv.W / sx) * (ctx->wv.H / sy) * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    return ptap_sync(ctx);
 }
 
 // ---- parity entry points -------------------------------------------------------------------------------------

@@ -54,6 +54,7 @@ void launchResolveHits(const SceneDev& sc, const float4* O, const float4* D, con
 void launchSetIter(FrameState* st, int iter, cudaStream_t stream);
 void launchFilmAdd(float* film, const float* add, size_t n, cudaStream_t stream);
 void launchResolveBmp(const float* film, size_t nvalues, float div, unsigned char* out, cudaStream_t stream);
+void launchResolveBox(const float* film, int W, int H, int sx, int sy, float* out, cudaStream_t stream);
 void launchExtractNormals(const TriRec* tris, int n, float4* normals, cudaStream_t stream);
 void launchGatherTris(const TriRec* tris, const int* tri_id, int n, LeafTri* out, cudaStream_t stream);
 

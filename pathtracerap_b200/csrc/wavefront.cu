@@ -392,6 +392,21 @@ __global__ void k_resolve_bmp(const float* __restrict__ film, size_t nvalues, fl
         out[i] = (unsigned char)(int)xmul(xmul(film[i], div), 255.0f);
 }
 
+// SAMPLESX x SAMPLESY box resolve (ptap.h: ptap_read_film_resolved): out(x, y) = sum over the pixel's lattice samples, row-major, of
+// avg * film(sample), avg = 1.0f / (sx * sy) - the per-sample weight gatherImageDataKernel intends (Renderer.cpp:493).
+__global__ void k_resolve_box(const float* __restrict__ film, int W, int H, int sx, int sy, float* __restrict__ out)
+{
+    const int Wp = W / sx, Hp = H / sy;
+    const float avg = xdiv(1.0f, (float)(sx * sy));
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < (size_t)Wp * Hp * 3; e += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(e % 3), x = (int)((e / 3) % Wp), y = (int)(e / 3 / Wp);
+        float acc = 0.0f;
+        for (int j = 0; j < sy; ++j)
+            for (int i = 0; i < sx; ++i) acc = xadd(acc, xmul(avg, film[((size_t)(y * sy + j) * W + (x * sx + i)) * 3 + c]));
+        out[e] = acc;
+    }
+}
+
 __global__ void k_film_add(float* __restrict__ film, const float* __restrict__ add, size_t n)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) film[i] += add[i];
@@ -433,6 +448,11 @@ void launchExtractNormals(const TriRec* tris, int n, float4* normals, cudaStream
 void launchGatherTris(const TriRec* tris, const int* tri_id, int n, LeafTri* out, cudaStream_t stream)
 {
     if (n > 0) k_gather_tris<<<148 * 4, 256, 0, stream>>>(tris, tri_id, n, out);
+}
+
+void launchResolveBox(const float* film, int W, int H, int sx, int sy, float* out, cudaStream_t stream)
+{
+    k_resolve_box<<<148 * 8, 256, 0, stream>>>(film, W, H, sx, sy, out);
 }
 
 void launchResolveBmp(const float* film, size_t nvalues, float div, unsigned char* out, cudaStream_t stream)

@@ -47,8 +47,9 @@ class Renderer:
         self.render(0, self.iters)
         self.sync()
 
-    def renderImage(self, path: str = "Render.bmp"):
-        self._check(N.lib().ptap_write_bmp(self.h, path.encode(), max(self._iters_done, 1)), "renderImage")
+    def renderImage(self, path: str = "Render.bmp", samples: tuple[int, int] = (1, 1)):
+        """Renderer::renderImage; `samples` = (SAMPLESX, SAMPLESY) of Config.h:14-15 when the film was rendered on the W*SX x H*SY lattice."""
+        self._check(N.lib().ptap_write_bmp_resolved(self.h, path.encode(), max(self._iters_done, 1), samples[0], samples[1]), "renderImage")
 
     def free(self):
         if getattr(self, "h", None):
@@ -106,6 +107,13 @@ class Renderer:
         """Un-normalised running sum, H x W x 3 (render_data.dev_image_data->pool, Renderer.cpp:49)."""
         out = np.zeros((self.H, self.W, 3), np.float32)
         self._check(N.lib().ptap_read_film(self.h, N.ptr(out)), "read_film")
+        return out
+
+    def film_resolved(self, samples: tuple[int, int]) -> np.ndarray:
+        """Box-resolved film for SAMPLESX x SAMPLESY supersampling (ptap.h: ptap_read_film_resolved), (H / sy) x (W / sx) x 3."""
+        sx, sy = samples
+        out = np.zeros((self.H // max(sy, 1), self.W // max(sx, 1), 3), np.float32)
+        self._check(N.lib().ptap_read_film_resolved(self.h, sx, sy, N.ptr(out)), "read_film_resolved")
         return out
 
     def film_add(self, rgb: np.ndarray):

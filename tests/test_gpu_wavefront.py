@@ -168,6 +168,34 @@ def test_bmp_matches_oracle_writer(renderer, port, tmp_path, golden_films):
     assert (tmp_path / "gpu.bmp").read_bytes() == (tmp_path / "cpu.bmp").read_bytes()
 
 
+def test_supersampled_resolve(renderer, port, tmp_path, golden_films):
+    """SURVEY 8f row 4: SAMPLESX x SAMPLESY.  The lattice render is the ordinary path at (W*SX, H*SY) (generateRaysKernel, Renderer.cpp:527-542);
+    the resolve is pixel = sum over its samples (row-major) of avg * sample, avg = 1.0f / (SX*SY) - checked bit for bit against the same
+    fp32 arithmetic in numpy, and the BMP against the oracle's writer on the resolved film.  (The reference's own gather leaves the image
+    black for SAMPLES > 1, Renderer.cpp:493: there is no reference output to match.)"""
+    from pathtracerap_b200 import PtapError
+    f = golden_films
+    W, H, depth, iters = (int(x) for x in f["bundled_params"])
+    renderer.set_params(W, H, depth, first_hit_cache=True)
+    renderer.render(0, iters)
+    hi = renderer.film()
+    for sx, sy in ((2, 2), (4, 1), (1, 3), (1, 1)):
+        got = renderer.film_resolved((sx, sy))
+        avg = np.float32(1.0) / np.float32(sx * sy)
+        want = np.zeros((H // sy, W // sx, 3), np.float32)
+        for j in range(sy):
+            for i in range(sx):
+                want = want + avg * hi[j::sy, i::sx]
+        assert got.shape == want.shape and np.array_equal(got, want), (sx, sy)
+        renderer.renderImage(str(tmp_path / "gpu.bmp"), samples=(sx, sy))
+        port.write_bmp(want, iters, tmp_path / "cpu.bmp")
+        assert (tmp_path / "gpu.bmp").read_bytes() == (tmp_path / "cpu.bmp").read_bytes()
+    with pytest.raises(PtapError):
+        renderer.film_resolved((5, 1))        # 128 is not divisible by 5
+    with pytest.raises(PtapError):
+        renderer.film_resolved((0, 1))
+
+
 def test_errors_are_loud(libptap):
     from pathtracerap_b200 import PtapError, Renderer
     r = Renderer(width=32, height=32, depth=5)
