@@ -116,6 +116,9 @@ def cpu_reference_arm(arrays, depth, sample_w, sample_h, iters, threads=None):
     """The reference's own CPU implementation on a bounded sample: `iters` iterations at sample_w x sample_h of the same
     scene, full bounce loop, 25^3 grid as the reference builds it.  Returns (Mrays/s, rays, seconds, kind, cores, ms_per_iter)."""
     from oracle import ref
+    # every host core this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently run the
+    # reference on one thread and flatter the GPU arm
+    threads = threads or len(os.sched_getaffinity(0))
     if ref.available():
         kind = "reference"
         if threads:
