@@ -61,6 +61,13 @@ struct ptap_ctx {
     Arena scene_arena, frame_arena, scratch;
     SceneDev sc{};
     WaveDev wv{};
+    // Multi-lane rendering (PTAP_LANES, default 4): iterations rotate over `lanes` wavefronts, each on its own stream, so that the drain
+    // of one lane's persistent kernel (its last rays), its latency-bound scan and its ramp-up overlap the other lanes' kernels.
+    // Lane 0 is `wv` on `stream`.  Film adds stay in iteration order (WaveDev::contrib + one ordered add per iteration).
+    int lanes = 1;
+    WaveDev wvx[kMaxLanes]{};            // lanes 1 .. lanes-1 (index 0 unused)
+    cudaStream_t streams[kMaxLanes] = {};
+    cudaEvent_t e_fork = nullptr, e_cache = nullptr, e_join[kMaxLanes] = {}, e_gather[kMaxLanes] = {};
     // host copies kept for the acceleration-structure builds
     std::vector<TriRec> h_tris;      // kept only when the BVH still has to be built here (no prebuilt one in the view)
     int ntris = 0;
@@ -99,10 +106,11 @@ int fail(ptap_ctx* c, int code, const char* fmt, ...)
 float4 row(const float* m, int r) { return make_float4(m[0 + r], m[4 + r], m[8 + r], m[12 + r]); }
 
 void launchTrace(ptap_ctx* c, FrameState* st, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, int round, int n_fixed,
-                 bool count_totals = false)
+                 bool count_totals = false, cudaStream_t stream = nullptr)
 {
-    if (c->accel != PTAP_ACCEL_GRID_COMPAT) launchTraceBvh(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, c->stream);
-    else launchTraceGrid(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, c->stream);
+    if (!stream) stream = c->stream;
+    if (c->accel != PTAP_ACCEL_GRID_COMPAT) launchTraceBvh(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, stream);
+    else launchTraceGrid(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, stream);
 }
 
 void profMark(ptap_ctx* c, int kind)
@@ -138,6 +146,16 @@ int collect(ptap_ctx* ctx)
     CK(cudaEventElapsedTime(&ctx->stats.ms_render, ctx->ev0, ctx->ev1));
     FrameState fs;
     CK(cudaMemcpy(&fs, ctx->wv.st, sizeof fs, cudaMemcpyDeviceToHost));
+    for (int l = 1; l < ctx->lanes; ++l) {             // counters of the other lanes; the rounds reported are those of the latest iteration
+        if (!ctx->wvx[l].st) continue;
+        FrameState f2;
+        CK(cudaMemcpy(&f2, ctx->wvx[l].st, sizeof f2, cudaMemcpyDeviceToHost));
+        const bool later = f2.iter_cur > fs.iter_cur && f2.paths > 0;
+        f2.rays_traced += fs.rays_traced; f2.paths += fs.paths;
+        f2.count_nodes += fs.count_nodes; f2.count_tris += fs.count_tris; f2.count_cells += fs.count_cells; f2.count_refs += fs.count_refs;
+        if (later) fs = f2;
+        else { fs.rays_traced = f2.rays_traced; fs.paths = f2.paths; fs.count_nodes = f2.count_nodes; fs.count_tris = f2.count_tris; fs.count_cells = f2.count_cells; fs.count_refs = f2.count_refs; }
+    }
     ctx->stats.rays_traced = (int64_t)fs.rays_traced;
     ctx->stats.paths = (int64_t)fs.paths;
     for (int i = 0; i < 16; ++i) ctx->stats.active_per_round[i] = i <= kMaxDepth ? fs.n_active[i] : 0;
@@ -400,7 +418,17 @@ int ptap_create(int device, size_t arena_bytes, ptap_ctx** out)
     ctx->sc.vote_refill = std::min(32, std::max(1, envInt("PTAP_VOTE_REFILL", kVoteRefill)));
     ctx->sc.batch = std::max(1, envInt("PTAP_BATCH", kTraceBatch));
     ctx->sc.vote_grid = std::min(32, std::max(1, envInt("PTAP_VOTE_GRID", kVoteGrid)));
-    ctx->sc.shade_sort = envInt("PTAP_SHADE_SORT", 0) != 0;      // measured slower on every workload (profiles/r01/README.md): opt-in
+    ctx->sc.shade_sort = envInt("PTAP_SHADE_SORT", 0) != 0;
+    ctx->lanes = std::min(kMaxLanes, std::max(1, envInt("PTAP_LANES", kDefaultLanes)));
+    ctx->streams[0] = ctx->stream;
+    if (ctx->lanes > 1) {
+        bool ok = cudaEventCreateWithFlags(&ctx->e_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ctx->e_cache, cudaEventDisableTiming) == cudaSuccess;
+        for (int l = 0; l < ctx->lanes; ++l) {
+            if (l > 0) ok = ok && cudaStreamCreateWithFlags(&ctx->streams[l], cudaStreamNonBlocking) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&ctx->e_join[l], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ctx->e_gather[l], cudaEventDisableTiming) == cudaSuccess;
+        }
+        if (!ok) { ptap_destroy(ctx); return PTAP_E_NOMEM; }
+    }      // measured slower on every workload (profiles/r01/README.md): opt-in
     ctx->trace_ctas = std::max(0, envInt("PTAP_TRACE_CTAS", 0));
     if (arena_bytes) {                                          // caller-sized arena: split 1/4 scene, 3/4 frame
         if (ctx->scene_arena.reserve(arena_bytes / 4) != cudaSuccess || ctx->frame_arena.reserve(arena_bytes - arena_bytes / 4) != cudaSuccess) {
@@ -416,6 +444,9 @@ void ptap_destroy(ptap_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int l = 1; l < kMaxLanes; ++l) if (ctx->streams[l]) { cudaStreamSynchronize(ctx->streams[l]); cudaStreamDestroy(ctx->streams[l]); }
+    for (cudaEvent_t e : {ctx->e_fork, ctx->e_cache}) if (e) cudaEventDestroy(e);
+    for (int l = 0; l < kMaxLanes; ++l) { if (ctx->e_join[l]) cudaEventDestroy(ctx->e_join[l]); if (ctx->e_gather[l]) cudaEventDestroy(ctx->e_gather[l]); }
     ctx->scene_arena.release(); ctx->frame_arena.release(); ctx->scratch.release();
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -589,6 +620,10 @@ int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, u
     size_t need = Arena::need(N, sizeof(float4)) * 8 + Arena::need(N, sizeof(float2)) + Arena::need((size_t)N * 3, sizeof(float)) +
                   Arena::need((size_t)nscan * kMaxDepth, sizeof(unsigned long long)) + Arena::need(ntiles, sizeof(int)) * 2 +
                   Arena::need((size_t)nscan * kScanSlots, 1) + Arena::need(1, sizeof(FrameState)) + 4096;
+    if (ctx->lanes > 1)            // every further lane: its own queues, hits, scan state; one contribution buffer per lane (lane 0 too)
+        need += (size_t)(ctx->lanes - 1) * (Arena::need(N, sizeof(float4)) * 7 + Arena::need((size_t)nscan * kMaxDepth, sizeof(unsigned long long)) +
+                                            Arena::need(ntiles, sizeof(int)) * 2 + Arena::need((size_t)nscan * kScanSlots, 1) + Arena::need(1, sizeof(FrameState)) + 4096) +
+                (size_t)ctx->lanes * Arena::need((size_t)N * 3, sizeof(float));
     if (need > ctx->frame_arena.cap) CK(ctx->frame_arena.reserve(need)); else ctx->frame_arena.used = 0;
     Arena& A = ctx->frame_arena;
     WaveDev& wv = ctx->wv;
@@ -604,6 +639,21 @@ int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, u
     wv.W = W; wv.H = H; wv.N = N; wv.depth = depth; wv.ntiles = ntiles; wv.nscan = nscan;
     wv.step_x = (float)(20.0 / (double)W);                       // Renderer.cpp:538-539 (SAMPLESX = SAMPLESY = 1)
     wv.step_y = (float)(16.0 / (double)H);
+    wv.iter_stride = 1; wv.contrib = nullptr;
+    if (ctx->lanes > 1) wv.contrib = A.alloc<float>((size_t)N * 3);
+    for (int l = 1; l < ctx->lanes; ++l) {
+        WaveDev& w2 = ctx->wvx[l];
+        w2 = wv;                                                 // shares film, first-hit cache, uv
+        for (int k = 0; k < 2; ++k) { w2.O[k] = A.alloc<float4>(N); w2.D[k] = A.alloc<float4>(N); w2.C[k] = A.alloc<float4>(N); }
+        w2.hit = A.alloc<float4>(N);
+        w2.tile_status = A.alloc<unsigned long long>((size_t)nscan * kMaxDepth);
+        w2.tile_offset = A.alloc<int>(ntiles); w2.tile_ballot = A.alloc<unsigned>(ntiles);
+        w2.perm = A.alloc<unsigned char>((size_t)nscan * kScanSlots);
+        w2.st = A.alloc<FrameState>(1);
+        w2.contrib = A.alloc<float>((size_t)N * 3);
+        if (!w2.st || !w2.contrib || !wv.contrib || !w2.perm || !w2.hit) return fail(ctx, PTAP_E_NOMEM, "frame arena exhausted (lane %d)", l);
+        CK(cudaMemsetAsync(w2.st, 0, sizeof(FrameState), ctx->stream));
+    }
     CK(cudaMemsetAsync(wv.film, 0, (size_t)N * 3 * sizeof(float), ctx->stream));   // initImageKernel, Renderer.cpp:557-565
     CK(cudaMemsetAsync(wv.st, 0, sizeof(FrameState), ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -622,27 +672,53 @@ int ptap_render(ptap_ctx* ctx, int32_t iter_begin, int32_t iter_end)
     if (iter_end < iter_begin) return fail(ctx, PTAP_E_INVALID, "render: empty iteration range");
     CK(cudaSetDevice(ctx->device));
     if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
-    const WaveDev& wv = ctx->wv;
     const bool cache = ctx->flags & PTAP_FLAG_FIRST_HIT_CACHE;
+    // several lanes only for plain frames (the per-class event timing and the counting build stay on one stream)
+    const int L = (ctx->flags & (PTAP_FLAG_PROFILE | PTAP_FLAG_COUNT)) ? 1 : std::max(1, std::min(ctx->lanes, iter_end - iter_begin));
+    WaveDev lane[kMaxLanes];
+    lane[0] = ctx->wv;
+    for (int l = 1; l < L; ++l) lane[l] = ctx->wvx[l];
+    for (int l = 0; l < L; ++l) { lane[l].iter_stride = L; if (L == 1) lane[l].contrib = nullptr; }
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    launchSetIter(wv.st, iter_begin, ctx->stream);
-    int64_t launches = 1, trace_launches = 0;
+    if (L > 1) CK(cudaEventRecord(ctx->e_fork, ctx->stream));
+    for (int l = 0; l < L; ++l) {
+        if (l > 0) CK(cudaStreamWaitEvent(ctx->streams[l], ctx->e_fork, 0));
+        launchSetIter(lane[l].st, iter_begin + l, ctx->streams[l]);
+    }
+    int64_t launches = L, trace_launches = 0;
+    int cache_lane = -1;                 // lane whose stream produced the first-hit cache in this call; every other lane waits for e_cache once
+    unsigned cache_waited = 0;
     for (int it = iter_begin; it < iter_end; ++it) {
+        const int l = (it - iter_begin) % L;
+        const WaveDev& wv = lane[l];
+        cudaStream_t S = ctx->streams[l];
         profMark(ctx, 0);
-        launchGenerate(wv, ctx->grid_gen, ctx->stream); ++launches;
+        launchGenerate(wv, ctx->grid_gen, S); ++launches;
         int in = 0;
         for (int round = 0; round < wv.depth; ++round) {
             float4* hitbuf = (round == 0 && cache) ? wv.hit_cache : wv.hit;
             if (!(round == 0 && cache && ctx->cache_valid)) {                    // Renderer.cpp:594-620
                 profMark(ctx, 1);
-                launchTrace(ctx, wv.st, wv.O[in], wv.D[in], hitbuf, nullptr, nullptr, round, -1, (ctx->flags & PTAP_FLAG_COUNT) != 0); ++launches; ++trace_launches;
+                launchTrace(ctx, wv.st, wv.O[in], wv.D[in], hitbuf, nullptr, nullptr, round, -1, (ctx->flags & PTAP_FLAG_COUNT) != 0, S); ++launches; ++trace_launches;
+                if (L > 1 && round == 0 && cache) { CK(cudaEventRecord(ctx->e_cache, S)); cache_lane = l; cache_waited = 1u << l; }
+            } else if (L > 1 && cache_lane >= 0 && !(cache_waited >> l & 1u)) {
+                CK(cudaStreamWaitEvent(S, ctx->e_cache, 0)); cache_waited |= 1u << l;
             }
             profMark(ctx, 2);
-            launchScan(ctx->sc, wv, round, hitbuf, wv.depth - round, -1, ctx->stream); ++launches;
-            launchShade(ctx->sc, wv, round, in, hitbuf, wv.depth - round, -1, 0, nullptr, ctx->grid_shade, ctx->stream); ++launches;
+            launchScan(ctx->sc, wv, round, hitbuf, wv.depth - round, -1, S); ++launches;
+            launchShade(ctx->sc, wv, round, in, hitbuf, wv.depth - round, -1, 0, nullptr, ctx->grid_shade, S); ++launches;
             in ^= 1;
         }
+        if (L > 1) {                     // film += this iteration's contributions, in iteration order across the lanes
+            if (it > iter_begin) CK(cudaStreamWaitEvent(S, ctx->e_gather[(l + L - 1) % L], 0));
+            launchFilmAdd(wv.film, wv.contrib, (size_t)wv.N * 3, S); ++launches;
+            CK(cudaEventRecord(ctx->e_gather[l], S));
+        }
         if (cache) ctx->cache_valid = true;
+    }
+    for (int l = 1; l < L; ++l) {
+        CK(cudaEventRecord(ctx->e_join[l], ctx->streams[l]));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->e_join[l], 0));
     }
     profMark(ctx, -1);
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -669,6 +745,7 @@ int ptap_frame_begin(ptap_ctx* ctx)
     if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
     CK(cudaMemsetAsync(ctx->wv.film, 0, (size_t)ctx->wv.N * 3 * sizeof(float), ctx->stream));
     CK(cudaMemsetAsync(ctx->wv.st, 0, sizeof(FrameState), ctx->stream));
+    for (int l = 1; l < ctx->lanes; ++l) if (ctx->wvx[l].st) CK(cudaMemsetAsync(ctx->wvx[l].st, 0, sizeof(FrameState), ctx->stream));
     ctx->cache_valid = false;
     resetStats(ctx);
     return PTAP_OK;

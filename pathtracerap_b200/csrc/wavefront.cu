@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kGenBlock) k_generate(WaveDev wv)
     const int stride = gridDim.x * blockDim.x;
     FrameState* st = wv.st;
     if (tid == 0) {
-        st->iter_cur = st->iter_next; st->iter_next = st->iter_cur + 1;
+        st->iter_cur = st->iter_next; st->iter_next = st->iter_cur + wv.iter_stride;
         st->n_active[0] = wv.N;
         st->paths += (unsigned long long)wv.N;
     }
@@ -329,7 +329,10 @@ k_shade(SceneDev sc, WaveDev wv, int round, int in, const float4* __restrict__ h
             c4.x = col.x; c4.y = col.y; c4.z = col.z;
             const int pos = alive ? excl + rank : -1;
             if (alive) { Oo[pos] = o4; Do[pos] = d4; Co[pos] = c4; }
-            else {                                                               // gatherImageDataKernel, Renderer.cpp:481-496
+            else if (wv.contrib) {                                               // two lanes: the add happens in iteration order (k_film_add)
+                float* px = wv.contrib + 3 * (size_t)__float_as_int(o4.w);
+                px[0] = xsqrt(col.x); px[1] = xsqrt(col.y); px[2] = xsqrt(col.z);
+            } else {                                                             // gatherImageDataKernel, Renderer.cpp:481-496
                 float* px = wv.film + 3 * (size_t)__float_as_int(o4.w);
                 px[0] = xadd(px[0], xsqrt(col.x)); px[1] = xadd(px[1], xsqrt(col.y)); px[2] = xadd(px[2], xsqrt(col.z));
             }
