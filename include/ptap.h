@@ -11,6 +11,17 @@
  * One context per GPU; a context is not thread-safe; no global state; the caller owns all
  * host buffers, the library owns the device arena.  There is no CPU fallback: every compute
  * entry fails with PTAP_E_NO_DEVICE when no sm_100 device is usable.
+ *
+ * Streams: all work of a context is ordered on ONE stream, ptap_stream().  ptap_render pipelines its iterations over several
+ * internal streams ("lanes"), which fork from and join that stream inside the call, so anything the caller orders on
+ * ptap_stream() (an NCCL reduce of the film, a timer event) is ordered with the whole render.
+ *
+ * Environment (read once, in ptap_create; none of them changes a result bit):
+ *   PTAP_LANES=1..8        wavefronts in flight per context (default 4; 130 B of device memory per pixel and lane)
+ *   PTAP_TRACE_CTAS=n      CTAs per SM of the closest-hit kernels (default: occupancy query)
+ *   PTAP_VOTE_TRI / PTAP_VOTE_INST / PTAP_VOTE_REFILL / PTAP_VOTE_GRID, PTAP_BATCH   scheduling thresholds of the closest-hit kernels
+ *   PTAP_SHADE_SORT=1      k_shade takes each 256-slot block regrouped by material class (measured slower; off)
+ *   PTAP_BVH_LEAF, PTAP_BVH_CI   leaf size and node cost of the host SAH builder
  */
 #ifndef PTAP_H
 #define PTAP_H
