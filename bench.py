@@ -261,6 +261,7 @@ def main():
     if rank == 0:
         sampler.start()
     rays = launches = 0
+    lanes = r.stats()["lanes"]
     t_wall0 = time.perf_counter()
     ms_dev = 0.0
     for _ in range(args.steps):
@@ -377,7 +378,7 @@ def main():
            "ms_per_step": round(t_max / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
            "config": {"workload": args.workload, "description": desc, "resolution": [W, H], "spp_per_gpu": spp, "depth": depth,
-                      "triangles": ntris, "models": len(arrays["models"]), "accel": args.accel if args.accel == "bvh" else f"grid {args.grid_dim}^3", "first_hit_cache": not args.no_cache, "lanes": int(os.environ.get("PTAP_LANES", "4")),
+                      "triangles": ntris, "models": len(arrays["models"]), "accel": args.accel if args.accel == "bvh" else f"grid {args.grid_dim}^3", "first_hit_cache": not args.no_cache, "lanes": lanes,
                       "parallelism": f"sample-partition x{world}" + (" + 1 NCCL reduce of the film" if world > 1 else ""),
                       "l2": "wavefront state (6 float4 queues + hits, >300 MB at 1080p) exceeds L2 every bounce; the scene is small and L2-resident by design",
                       "host_accel_build_s": round(build_s, 3), "device_bvh_build_ms": round(r.stats()["ms_build"], 3) if accel == ACCEL_BVH_DEVICE else None},

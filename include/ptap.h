@@ -17,7 +17,8 @@
  * ptap_stream() (an NCCL reduce of the film, a timer event) is ordered with the whole render.
  *
  * Environment (read once, in ptap_create; none of them changes a result bit):
- *   PTAP_LANES=1..8        wavefronts in flight per context (default 4; 130 B of device memory per pixel and lane)
+ *   PTAP_LANES=1..8        wavefronts in flight per context (default: 4, or 8 for frames of at most 2^20 pixels; 130 B of device
+ *                          memory per pixel and lane)
  *   PTAP_TRACE_CTAS=n      CTAs per SM of the closest-hit kernels (default: occupancy query)
  *   PTAP_VOTE_TRI / PTAP_VOTE_INST / PTAP_VOTE_REFILL / PTAP_VOTE_GRID, PTAP_BATCH   scheduling thresholds of the closest-hit kernels
  *   PTAP_SHADE_SORT=1      k_shade takes each 256-slot block regrouped by material class (measured slower; off)
@@ -124,6 +125,7 @@ typedef struct {
     int64_t scene_bytes;          /* bytes copied host->device by the last ptap_upload_scene */
     float ms_build;               /* device time of the last PTAP_ACCEL_BVH_DEVICE build */
     int32_t bvh_nodes, bvh_depth; /* 4-wide nodes and levels of that build */
+    int32_t lanes;                /* wavefronts in flight of the current render parameters (PTAP_LANES, or 4 / 8 by frame size) */
 } PtapStats;
 
 typedef struct ptap_scene ptap_scene;   /* host-side scene: replaces class Scene (Scene.h:21-39) */

@@ -53,7 +53,7 @@ class Stats(C.Structure):
                 ("active_per_round", C.c_int64 * 16), ("ms_render", C.c_float), ("ms_trace", C.c_float),
                 ("ms_shade", C.c_float), ("ms_generate", C.c_float), ("avg_nodes", C.c_float), ("avg_tris", C.c_float),
                 ("avg_cells", C.c_float), ("avg_refs", C.c_float), ("trace_launches", C.c_int64), ("scene_bytes", C.c_int64),
-                ("ms_build", C.c_float), ("bvh_nodes", C.c_int32), ("bvh_depth", C.c_int32)]
+                ("ms_build", C.c_float), ("bvh_nodes", C.c_int32), ("bvh_depth", C.c_int32), ("lanes", C.c_int32)]
 
 
 EXPORTS = [

@@ -11,7 +11,7 @@ constexpr int kShadeBlock = 256;     // slots a CTA of k_shade regroups by mater
 constexpr int kShadeTile = 32;       // one compaction tile = one warp = 32 consecutive slots
 constexpr int kScanBlock = 256, kScanSlots = 2048, kScanTiles = kScanSlots / kShadeTile;   // k_scan: slots per CTA, tiles per CTA
 constexpr int kGenBlock = 256;
-constexpr int kMaxLanes = 8, kDefaultLanes = 4;   // wavefronts in flight per context (api.cu: multi-lane rendering)
+constexpr int kMaxLanes = 8, kDefaultLanes = 4, kSmallFrameLanes = 8;   // wavefronts in flight per context (api.cu: multi-lane rendering)
 constexpr int kTraceBatch = 32;      // rays a warp takes from the work-stealing cursor per atomic
 constexpr int kVoteTri = 8, kVoteInst = 6, kVoteRefill = 8;
 constexpr int kVoteGrid = 5;         // same for k_trace_grid (one threshold for all of its states)   // state-machine thresholds of k_trace_bvh (trace_bvh.cu)
