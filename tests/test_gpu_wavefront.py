@@ -168,6 +168,40 @@ def test_bmp_matches_oracle_writer(renderer, port, tmp_path, golden_films):
     assert (tmp_path / "gpu.bmp").read_bytes() == (tmp_path / "cpu.bmp").read_bytes()
 
 
+def test_lanes_do_not_change_a_bit(gpu_scene, golden_films, monkeypatch):
+    """Multi-lane rendering pipelines iterations over several streams but keeps every film add in iteration order:
+    the film of a 7-iteration frame is bit-identical for 1, 2, 3, 4 and 8 lanes, with and without the first-hit cache, in one call
+    or split over two calls, and the traced-ray count is the same."""
+    from pathtracerap_b200 import ACCEL_BVH, Renderer
+    W, H, depth, _ = (int(x) for x in golden_films["bundled_params"])
+    iters = 7
+    ref_film, ref_rays = {}, {}
+    for lanes in (1, 2, 3, 4, 8):
+        monkeypatch.setenv("PTAP_LANES", str(lanes))
+        r = Renderer(width=W, height=H, depth=depth, accel=ACCEL_BVH, first_hit_cache=True)
+        r.allocateOnGPU(gpu_scene)
+        assert r.stats()["lanes"] == lanes
+        for cache in (True, False):
+            r.set_params(W, H, depth, first_hit_cache=cache)
+            r.render(0, iters)
+            film, rays = r.film(), r.stats()["rays_traced"]
+            if lanes == 1:
+                ref_film[cache], ref_rays[cache] = film, rays
+            assert np.array_equal(film, ref_film[cache]), f"{lanes} lanes, cache={cache}: film differs from the one-lane film"
+            assert rays == ref_rays[cache]
+            r.set_params(W, H, depth, first_hit_cache=cache)
+            r.render(0, 3); r.render(3, iters)
+            assert np.array_equal(r.film(), ref_film[cache]), f"{lanes} lanes, cache={cache}: split render differs"
+        r.free()
+    monkeypatch.delenv("PTAP_LANES")
+    r = Renderer(width=W, height=H, depth=depth)
+    r.allocateOnGPU(gpu_scene)
+    assert r.stats()["lanes"] == 8                      # frames of at most 2^20 pixels default to 8 lanes, larger ones to 4
+    r.set_params(1280, 1024, depth)
+    assert r.stats()["lanes"] == 4
+    r.free()
+
+
 def test_supersampled_resolve(renderer, port, tmp_path, golden_films):
     """SURVEY 8f row 4: SAMPLESX x SAMPLESY.  The lattice render is the ordinary path at (W*SX, H*SY) (generateRaysKernel, Renderer.cpp:527-542);
     the resolve is pixel = sum over its samples (row-major) of avg * sample, avg = 1.0f / (SX*SY) - checked bit for bit against the same
