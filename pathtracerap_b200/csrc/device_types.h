@@ -111,7 +111,7 @@ struct WaveDev {
     float4* hit_cache;          // round-0 hits (first-hit cache, Renderer.cpp:594-613)
     float2* uv;                 // parity entry only
     float* film;                // W*H*3 running sum (Pixel, Primitive.h:145-148)
-    float* contrib;             // two-lane rendering: this iteration's sqrt(throughput) per pixel, added to the film in iteration order; else null
+    float* contrib;             // multi-lane rendering: this iteration's sqrt(throughput) per pixel, added to the film in iteration order; else null
     unsigned long long* tile_status;   // k_scan look-back words: rounds x 2048-slot scan blocks
     int* tile_offset;           // survivors before each 32-slot tile of the current round (k_scan -> k_shade)
     unsigned* tile_ballot;      // survival bits of each 32-slot tile, in slot order (k_scan -> k_shade<SORT>)
@@ -119,7 +119,7 @@ struct WaveDev {
     FrameState* st;
     int W, H, N, depth, ntiles, nscan;   // ntiles = ceil(N / 32), nscan = ceil(N / 2048)
     float step_x, step_y;
-    int iter_stride;            // iterations between two frames of this lane (1, or 2 when two lanes alternate)
+    int iter_stride;            // iterations between two consecutive iterations of this lane (= lanes in use)
 };
 
 }  // namespace ptap

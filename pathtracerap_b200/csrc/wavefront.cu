@@ -3,15 +3,16 @@
 // Replaces generateRaysKernel (Renderer.cpp:521-555), shadeRayKernel (:411-479), compactStencilKernel +
 // thrust::stable_partition (:506-519, :628-630), gatherImageDataKernel (:481-496) and initImageKernel (:557-565).
 //
-// Design (DESIGN.md "Wavefront"): path state is SoA float4 (origin+pixel, direction, throughput) in ping-pong
-// queues.  One kernel per bounce shades a slot, decides whether the path survives, and writes survivors straight
-// to their compacted position in the other queue; terminated paths add sqrt(throughput) to the film on the spot
-// (each pixel owns exactly one path per iteration, so this equals the reference's end-of-iteration gather).
-// The compaction is ORDER-PRESERVING, as thrust::stable_partition is, because the reference seeds its RNG with the
-// slot index after compaction (Renderer.cpp:435, utility.h:57-62): same slots => same random streams => the same
-// image, sample for sample.  It is a single-pass decoupled look-back scan over 256-slot tiles: warp ballots give
-// the in-tile ranks, one 64-bit status word per tile carries (flag, count) between CTAs.  No 80-byte struct is
-// moved twice, no temporary is allocated, no count is read back by the host.
+// Design: path state is SoA float4 (origin+pixel, direction, throughput) in ping-pong queues.
+// Per bounce, k_scan reads the hit records once and produces, for every 32-slot tile, the number of surviving paths in
+// all earlier slots (one pass, decoupled look-back over 2048-slot blocks); k_shade then shades a slot and writes a
+// survivor straight to its compacted position in the other queue, while a terminated path adds sqrt(throughput) to the
+// film on the spot - or, when several lanes are in flight, stores it in the lane's contribution buffer, which one
+// k_film_add per iteration adds to the film in iteration order (each pixel owns exactly one path per iteration, so both
+// equal the reference's end-of-iteration gather).  The compaction is ORDER-PRESERVING, as thrust::stable_partition is,
+// because the reference seeds its RNG with the slot index after compaction (Renderer.cpp:435, utility.h:57-62): same
+// slots => same random streams => the same image, sample for sample.  No 80-byte struct is moved twice, no temporary
+// is allocated, no count is read back by the host.
 #include "kernels.cuh"
 
 namespace ptap {
@@ -329,7 +330,7 @@ k_shade(SceneDev sc, WaveDev wv, int round, int in, const float4* __restrict__ h
             c4.x = col.x; c4.y = col.y; c4.z = col.z;
             const int pos = alive ? excl + rank : -1;
             if (alive) { Oo[pos] = o4; Do[pos] = d4; Co[pos] = c4; }
-            else if (wv.contrib) {                                               // two lanes: the add happens in iteration order (k_film_add)
+            else if (wv.contrib) {                                               // several lanes: the add happens in iteration order (k_film_add)
                 float* px = wv.contrib + 3 * (size_t)__float_as_int(o4.w);
                 px[0] = xsqrt(col.x); px[1] = xsqrt(col.y); px[2] = xsqrt(col.z);
             } else {                                                             // gatherImageDataKernel, Renderer.cpp:481-496
