@@ -35,6 +35,7 @@ WORKLOADS = {
     "mesh1m": (1920, 1080, 64, 5, "configs[3]: displaced icosphere 1,310,720 tris (DIFFUSE) in the bundled box, 1920x1080, 64 spp, depth 5, BVH"),
     "mesh5m": (1920, 1080, 64, 5, "configs[3] upper end: displaced icosphere 5,242,880 tris (DIFFUSE) in the bundled box, 1920x1080, 64 spp, depth 5"),
     "bundled": (2800, 2240, 64, 5, "configs[2]: the reference's coded scene (METAL/COAT/REFLECTIVE/DIFFUSE/EMISSIVE, 11 models), 2800x2240, 64 spp, depth 5, BVH"),
+    "mesh1m4k": (3840, 2160, 128, 5, "configs[4]: the mesh1m scene at 3840x2160, 128 spp per GPU (1024 spp on 8 GPUs), sample-partitioned, one NCCL reduce of the film"),
     "cornell": (512, 512, 16, 8, "configs[0]: Cornell box from Input data, 512x512, 16 spp, depth 8, diffuse only"),
 }
 
@@ -58,7 +59,7 @@ def build_scene(workload: str):
         m["mat"]["type"] = np.where(m["mat"]["type"] == EMISSIVE, EMISSIVE, DIFFUSE)
         s = Scene.from_arrays(m, base["meshes"], base["vertices"], base["triangles"])
     else:
-        level = {"mesh100k": 6, "mesh1m": 8, "mesh5m": 9}[workload]
+        level = {"mesh100k": 6, "mesh1m": 8, "mesh1m4k": 8, "mesh5m": 9}[workload]
         keep = [3, 7, 8, 9, 10]                      # box + four lights of Scene.cpp:114-124, 175-221
         s = Scene.from_arrays(base["models"][keep], base["meshes"], base["vertices"], base["triangles"])
         mi = s.add_icosphere(level, radius=1000.0, displacement=0.05, seed=1 if workload == "mesh100k" else 2)
