@@ -17,5 +17,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:k_trace_bvhILb0ELb0 -c 3 -o $O/prof_trace_bvh_mesh1m python bench.py --spp 2 --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_trace.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'k_shade|k_scan' -s 2 -c 4 -o $O/prof_scan_shade_mesh1m python bench.py --spp 2 --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_shade.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'k_shade|k_scan' -s 2 -c 2 -o $O/prof_scan_shade_bundled python bench.py --workload bundled --spp 2 --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_shade_b.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_trace_grid -s 1 -c 1 -o $O/prof_trace_grid_bundled python bench.py --workload bundled --accel grid --spp 2 --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_grid.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:k_trace_gridILb0ELb0 -s 1 -c 1 -o $O/prof_trace_grid_bundled python bench.py --workload bundled --accel grid --spp 2 --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_grid.log 2>&1
 ls -la $O > $O/ls.txt
