@@ -293,7 +293,9 @@ k_shade(SceneDev sc, WaveDev wv, int round, int in, const float4* __restrict__ h
         // survivors of the slot's tile: k_scan's ballot when the slots are regrouped, else this warp holds exactly that tile
         const unsigned tile_ballot = SORT ? (in_range ? __ldg(&wv.tile_ballot[(base >> 5) + (s >> 5)]) : 0u) : __ballot_sync(0xffffffffu, alive);
         if (in_range) {
-            float4 o4 = Oi[i], d4 = Di[i], c4 = Ci[i];
+            // queue traffic is read once and written once per bounce: streaming (evict-first) loads and stores keep it from displacing
+            // the scene's nodes and triangles in L2 (+0.8 % per frame, profiles/r01/README.md)
+            float4 o4 = __ldcs(&Oi[i]), d4 = __ldcs(&Di[i]), c4 = __ldcs(&Ci[i]);
             const int excl = __ldg(&wv.tile_offset[(base >> 5) + (s >> 5)]);
             const bool is_hit = h.x < kFloatMax;
             const int tri = __float_as_int(h.y), model = __float_as_int(h.z);
@@ -329,7 +331,7 @@ k_shade(SceneDev sc, WaveDev wv, int round, int in, const float4* __restrict__ h
             }
             c4.x = col.x; c4.y = col.y; c4.z = col.z;
             const int pos = alive ? excl + rank : -1;
-            if (alive) { Oo[pos] = o4; Do[pos] = d4; Co[pos] = c4; }
+            if (alive) { __stcs(&Oo[pos], o4); __stcs(&Do[pos], d4); __stcs(&Co[pos], c4); }
             else if (wv.contrib) {                                               // several lanes: the add happens in iteration order (k_film_add)
                 float* px = wv.contrib + 3 * (size_t)__float_as_int(o4.w);
                 px[0] = xsqrt(col.x); px[1] = xsqrt(col.y); px[2] = xsqrt(col.z);
