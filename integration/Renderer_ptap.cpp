@@ -6,7 +6,7 @@
 // (Primitive.h: Model 160 B, Mesh 40 B, Vertex 32 B, Triangle 12 B, Grid 28 B, Voxel 12 B - checked below), so the
 // seven vectors of Scene are passed through as they are, without conversion or copy on the host.
 //
-//   nvcc -x cu -std=c++17 -I<reference>/PathTracerAP -I<reference>/PathTracerAP/external/include -I<repo>/include \
+//   nvcc -x cu -std=c++17 -gencode arch=compute_100a,code=sm_100a -I<reference>/PathTracerAP -I<reference>/PathTracerAP/external/include -I<repo>/include \
 //        -c integration/Renderer_ptap.cpp          (g++ works too; nothing in this file is device code)
 //   link:  main.o Scene.o Renderer_ptap.o -L<repo>/pathtracerap_b200 -lptap
 #include <chrono>

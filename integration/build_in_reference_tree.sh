@@ -9,7 +9,7 @@ REF="${PTAP_REFERENCE:-/root/reference}/PathTracerAP"
 [ -f "$REF/main.cpp" ] || { echo "reference tree not found at $REF" >&2; exit 2; }
 OUT="$HERE/_build"; mkdir -p "$OUT/inc"; ln -sfn "$ROOT/oracle/shim/assimp" "$OUT/inc/assimp"
 INC="-I$REF -I$REF/external/include -I$OUT/inc -I$ROOT/include"
-nvcc -x cu -std=c++17 -w $INC -c "$HERE/Renderer_ptap.cpp" -o "$OUT/Renderer_ptap.o"
+nvcc -x cu -std=c++17 -w -gencode arch=compute_100a,code=sm_100a $INC -c "$HERE/Renderer_ptap.cpp" -o "$OUT/Renderer_ptap.o"
 g++ -std=c++17 -O2 -ffp-contract=off -w $INC -I/usr/local/cuda/include -c "$REF/Scene.cpp" -o "$OUT/Scene.o"
 g++ -std=c++17 -O2 -w $INC -I/usr/local/cuda/include -c "$REF/main.cpp" -o "$OUT/main.o"
 g++ "$OUT/main.o" "$OUT/Scene.o" "$OUT/Renderer_ptap.o" -L"$ROOT/pathtracerap_b200" -lptap -Wl,-rpath,'$ORIGIN/../../pathtracerap_b200' \
