@@ -315,3 +315,19 @@ def test_bvh_builder_parallel_path(libptap):
     nodes, tri_id, roots = _bvh_of(s)
     depth = _check_bvh(nodes, tri_id, roots, s.arrays())
     assert depth <= 16
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/ptap.h is the drop-in boundary: it must compile as C99 (no C++ types, no CUDA headers) and keep the record sizes the
+    reference's PODs have (Model 160, Mesh 40, Vertex 32, Triangle 12, Grid 28, Voxel 12, Material 24 bytes)."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "ptap.h"\n#include <stdio.h>\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(PtapModel), sizeof(PtapMesh), sizeof(PtapVertex), '
+                   'sizeof(PtapTriangle), sizeof(PtapGrid), sizeof(PtapVoxel), sizeof(PtapMaterial), sizeof(PtapBvhNode), sizeof(PtapStats)); return 0; }\n')
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sizes = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    assert sizes[:8] == [160, 40, 32, 12, 28, 12, 24, 128]
+    from pathtracerap_b200 import _native
+    assert sizes[8] == C.sizeof(_native.Stats)
