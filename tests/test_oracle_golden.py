@@ -226,3 +226,33 @@ def test_port_equals_compiled_reference_on_other_scenes(ref, port, golden_scene)
             assert rr.run_iteration(it) == pw.run_iteration(it)
         assert np.array_equal(rr.image(), pw.image())
         rr.close(); pw.close(); rscene.close()
+
+
+def test_port_equals_compiled_reference_on_a_dense_mesh(ref, port, libptap):
+    """Same live comparison on the kind of mesh the throughput workloads use: a displaced icosphere (5120 triangles; the host-side
+    generator of libptap needs no GPU), three instances, so that voxels hold many references and the 3D-DDA early exit matters."""
+    from pathtracerap_b200 import DIFFUSE, Scene
+    s = Scene.empty()
+    mi = s.add_icosphere(4, radius=1000.0, displacement=0.05, seed=2)
+    for k, (tr, sc) in enumerate([((0, 0, 0), 0.2), ((260, 40, -120), 0.12), ((-240, -60, 80), 0.3)]):
+        s.add_model(mi, translate=tr, rotate_y_degrees=25.0 * k, scale=(sc, sc * (1 + 0.3 * k), sc), material=DIFFUSE, color=(0.7, 0.6, 0.5))
+    a = s.arrays()
+    assert len(a["triangles"]) == 5120
+    rscene = ref.RefScene.from_arrays(a["models"], a["meshes"], a["vertices"], a["triangles"])
+    pscene = port.OracleScene({k: a[k] for k in ("models", "meshes", "vertices", "triangles")})
+    ra, pa = rscene.arrays(), pscene.arrays()
+    for k in ("grids", "voxels", "refs"):
+        assert ra[k].tobytes() == pa[k].tobytes(), f"{k} differ"
+    rr = ref.RefRenderer(rscene, 32, 32, 5)
+    rs = np.random.RandomState(4)
+    o = rs.uniform(-600, 600, (6000, 3))
+    d = rs.uniform(-250, 250, (6000, 3)) - o
+    rays = np.concatenate([o, d], 1).astype(np.float32)
+    for mode in (0, 1):
+        x, y = rr.trace_rays(rays, mode), pscene.trace(rays, mode)
+        assert np.array_equal(x["model"], y["model"]) and np.array_equal(x["tri"], y["tri"])
+        hit = x["model"] >= 0
+        assert hit.mean() > 0.3
+        for f in ("dist", "u", "v"):
+            assert np.array_equal(x[f][hit], y[f][hit])
+    rr.close(); rscene.close()
