@@ -202,6 +202,23 @@ def test_lanes_do_not_change_a_bit(gpu_scene, golden_films, monkeypatch):
     r.free()
 
 
+def test_material_class_regrouping_does_not_change_a_bit(gpu_scene, golden_films, monkeypatch):
+    """PTAP_SHADE_SORT=1 (k_scan's counting-sort permutation, k_shade<true>) only changes which thread shades a slot: the
+    film of the five-material scene and the traced-ray count are bit-identical to the default schedule."""
+    from pathtracerap_b200 import ACCEL_BVH, Renderer
+    W, H, depth, _ = (int(x) for x in golden_films["bundled_params"])
+    out = {}
+    for sort in ("0", "1"):
+        monkeypatch.setenv("PTAP_SHADE_SORT", sort)
+        r = Renderer(width=W, height=H, depth=depth, accel=ACCEL_BVH, first_hit_cache=True)
+        r.allocateOnGPU(gpu_scene)
+        r.render(0, 5)
+        out[sort] = (r.film(), r.stats()["rays_traced"])
+        r.free()
+    assert np.array_equal(out["0"][0], out["1"][0]) and out["0"][1] == out["1"][1]
+    assert out["0"][0].mean() > 0.1
+
+
 def test_supersampled_resolve(renderer, port, tmp_path, golden_films):
     """SURVEY 8f row 4: SAMPLESX x SAMPLESY.  The lattice render is the ordinary path at (W*SX, H*SY) (generateRaysKernel, Renderer.cpp:527-542);
     the resolve is pixel = sum over its samples (row-major) of avg * sample, avg = 1.0f / (SX*SY) - checked bit for bit against the same
