@@ -220,6 +220,14 @@ int ptap_trace_count(ptap_ctx* ctx, const float* rays_od, int32_t n, PtapHit* ou
  * order[k] is the slot that the stable compaction moved to position k (k < *n_alive). */
 int ptap_shade(ptap_ctx* ctx, const PtapPathIn* paths, int32_t n, int32_t iter, int32_t remaining, PtapPathOut* out, int32_t* order, int32_t* n_alive);
 
+/* The PRODUCTION closest-hit path under test.  ptap_trace above launches the barycentric-recording instantiations of the closest-hit
+ * kernels; Renderer::renderLoop's replacement (ptap_render) launches the plain ones and defers BVH hit distances to the shade kernel.
+ * This call enqueues iteration `iter` exactly as ptap_render does (one lane) up to and including the closest-hit launch
+ * (computeRaySceneIntersectionKernel, Renderer.cpp:617) of round `round`, and returns that round's wavefront: n_out active rays, their
+ * (origin, direction) as the kernel read them (rays_od, n x 6), their pixels (Ray::meta_data.ipixel), and the hit records the kernel wrote
+ * (u = v = 0).  Buffers hold `cap` entries; any of them may be NULL.  Leaves film and first-hit cache unspecified: ptap_frame_begin next. */
+int ptap_render_probe(ptap_ctx* ctx, int32_t iter, int32_t round, float* rays_od, int32_t* pixels, PtapHit* hits, int32_t cap, int32_t* n_out);
+
 /* device-resident timing helpers for bench.py (inputs already in HBM): trace the active queue of a primed wavefront `reps` times */
 int ptap_bench_trace(ptap_ctx* ctx, const float* rays_od, int32_t n, int32_t reps, float* ms_per_launch);
 

@@ -50,6 +50,7 @@ def lib():
         L.oracle_trace.argtypes = [vp, vp, ci, ci, vp]
         L.oracle_wavefront_create.argtypes = [vp, ci, ci, ci]; L.oracle_wavefront_create.restype = vp
         L.oracle_wavefront_free.argtypes = [vp]
+        L.oracle_wavefront_set_mode.argtypes = [vp, ci]
         for n in ("oracle_init_image", "oracle_generate", "oracle_trace_step", "oracle_gather"):
             getattr(L, n).argtypes = [vp]
         L.oracle_shade_step.argtypes = [vp, ci]
@@ -118,9 +119,11 @@ class OracleScene:
 class OracleWavefront:
     """Renderer::renderLoop restated launch by launch (Renderer.cpp:567-648)."""
 
-    def __init__(self, scene: OracleScene, W: int, H: int, depth: int = 5):
+    def __init__(self, scene: OracleScene, W: int, H: int, depth: int = 5, mode: int = 0):
+        """mode 0: the reference's grid walk (R0); mode 1: brute force over every triangle with the same predicate (R1)."""
         self.scene, self.W, self.H, self.depth, self.N = scene, W, H, depth, W * H
         self.h = lib().oracle_wavefront_create(C.byref(scene.c), W, H, depth)
+        lib().oracle_wavefront_set_mode(self.h, mode)
 
     def init_image(self): lib().oracle_init_image(self.h)
     def generate(self): lib().oracle_generate(self.h)

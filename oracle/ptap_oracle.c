@@ -424,6 +424,7 @@ struct OWavefront {
     const OScene* s; int W, H, depth, N, nrays;
     ORay* rays; ORay* tmp; OHitRecord* hits; OHitRecord* cache; OHit* probe; float* image; int* stencil;
     int cached;
+    int mode;            /* closest-hit tier of oracle_trace_step: 0 = R0 (grid walk, the reference as written), 1 = R1 (every triangle) */
 };
 
 OWavefront* oracle_wavefront_create(const OScene* s, int W, int H, int depth)
@@ -444,6 +445,7 @@ void oracle_wavefront_free(OWavefront* w)
     free(w->rays); free(w->tmp); free(w->hits); free(w->cache); free(w->probe); free(w->image); free(w->stencil); free(w);
 }
 
+void oracle_wavefront_set_mode(OWavefront* w, int mode) { w->mode = mode; }
 int oracle_nrays(const OWavefront* w) { return w->nrays; }
 ORay* oracle_rays(OWavefront* w) { return w->rays; }
 OHitRecord* oracle_hits(OWavefront* w) { return w->hits; }
@@ -492,7 +494,7 @@ void oracle_trace_step(OWavefront* w)                                    /* Rend
     int n = w->nrays < span ? w->nrays : span;
 #pragma omp parallel for schedule(dynamic, 256)
     for (int i = 0; i < n; ++i)
-        trace_one(w->s, ld3(w->rays[i].orig), ld3(w->rays[i].dir), 0, &w->hits[i], &w->probe[i]);
+        trace_one(w->s, ld3(w->rays[i].orig), ld3(w->rays[i].dir), w->mode, &w->hits[i], &w->probe[i]);
 }
 
 void oracle_shade_step(OWavefront* w, int iter)                          /* Renderer.cpp:411-479 */

@@ -80,6 +80,10 @@ void oracle_trace(const OScene* s, const float* rays_od, int n, int mode, OHit* 
 typedef struct OWavefront OWavefront;
 OWavefront* oracle_wavefront_create(const OScene* s, int W, int H, int depth);
 void oracle_wavefront_free(OWavefront* w);
+/* Closest-hit tier of the wavefront's trace step: 0 (default) = R0, the reference's grid walk; 1 = R1, the same per-model ray set-up,
+ * predicate and nearest-model rule applied to EVERY triangle (what an exact acceleration structure must reproduce).  Everything else
+ * of the loop (shade, compaction, gather, seeds) is the reference's. */
+void oracle_wavefront_set_mode(OWavefront* w, int mode);
 void oracle_init_image(OWavefront* w);                          /* Renderer.cpp:557-565 */
 void oracle_generate(OWavefront* w);                            /* Renderer.cpp:521-555 */
 void oracle_trace_step(OWavefront* w);                          /* Renderer.cpp:363-409 */

@@ -62,6 +62,7 @@ def lib():
         for name in ("ref_init_image", "ref_generate", "ref_gather"):
             getattr(L, name).argtypes = [vp]
         L.ref_trace_step.argtypes = [vp, ci]
+        L.ref_trace_step_r1.argtypes = [vp]
         L.ref_shade_step.argtypes = [vp, ci]
         L.ref_compact_step.argtypes = [vp]; L.ref_compact_step.restype = ci
         L.ref_nrays.argtypes = [vp]; L.ref_nrays.restype = ci
@@ -140,6 +141,7 @@ class RefRenderer:
     def init_image(self): lib().ref_init_image(self.h)
     def generate(self): lib().ref_generate(self.h)
     def trace(self, probe: bool = False): lib().ref_trace_step(self.h, int(probe))
+    def trace_r1(self): lib().ref_trace_step_r1(self.h)      # tier R1: every triangle, the reference's predicate (probe always recorded)
     def shade(self, it: int): lib().ref_shade_step(self.h, it)
     def compact(self) -> int: return lib().ref_compact_step(self.h)
     def gather(self): lib().ref_gather(self.h)
@@ -179,14 +181,18 @@ class RefRenderer:
             raise RuntimeError(f"ref_trace failed: {rc}")
         return out
 
-    def run_iteration(self, it: int, probe: bool = False, on_bounce=None):
-        """One iteration of the loop at Renderer.cpp:582-640 without the first-hit cache; returns active rays per bounce."""
+    def run_iteration(self, it: int, probe: bool = False, on_bounce=None, mode: int = 0):
+        """One iteration of the loop at Renderer.cpp:582-640 without the first-hit cache; returns active rays per bounce.
+        mode 1 swaps the closest-hit launch for the R1 tier (brute force with the reference's predicate)."""
         self.generate()
         counts = []
         b = 0
         while self.nrays > 0:
             counts.append(self.nrays)
-            self.trace(probe)
+            if mode == 1:
+                self.trace_r1()
+            else:
+                self.trace(probe)
             if on_bounce is not None:
                 on_bounce(b, self)
             self.shade(it)

@@ -261,6 +261,59 @@ int ref_write_bmp(void* h, const char* dir, int iters)
     return chdir(cwd);
 }
 
+// Oracle tier R1 for one ray slot: the statements of computeRaySceneIntersectionKernel (Renderer.cpp:363-409) with the grid query
+// (Renderer.cpp:386) replaced by computeRayTriangleIntersection (Renderer.cpp:174-215) on EVERY triangle of the model's mesh.
+// Everything that decides the result - per-model ray set-up, predicate, model t -> world distance, nearest-model rule - is the
+// reference's own code; only the culling structure is absent.
+static PtapProbe r1One(RenderData& rd, int iray)
+{
+    const int nmodels = rd.dev_model_data->size;
+    Ray* ray = &rd.dev_ray_data->pool[iray];
+    IntersectionData* hit_info = &rd.dev_intersection_data->pool[iray];
+    float best = hit_info->impact_distance;
+    glm::vec3 best_n(0.f); Material best_mat{}; PtapProbe best_p{-1, -1, 0.f, 0.f, 0.f};
+    for (int imodel = 0; imodel < nmodels; ++imodel) {
+        Model* model = &rd.dev_model_data->pool[imodel];
+        // per-model ray set-up: the statements of Renderer.cpp:381-384
+        ray->transformed.orig = transformPosition(ray->base.orig, model->world_to_model);
+        ray->transformed.dir = glm::normalize(transformDirection(ray->base.dir, model->world_to_model));
+        ray->cache.inv_dir = glm::vec3(1 / ray->transformed.dir.x, 1 / ray->transformed.dir.y, 1 / ray->transformed.dir.z);
+        hit_info->impact_distance = FLOAT_MAX;
+        const Mesh& mesh = rd.dev_mesh_data->pool[model->mesh_index];
+        bool any = false;
+        ptap_probe_tri = -1;
+        for (int t = mesh.triangle_indices.start_index; t < mesh.triangle_indices.end_index; ++t)
+            if (computeRayTriangleIntersection(rd, ray, hit_info, t)) any = true;
+        if (any) {
+            // model t -> world distance: the statements of Renderer.cpp:388-398
+            glm::vec3 nd = glm::normalize(ray->transformed.dir);
+            glm::vec3 pm = ray->transformed.orig + nd * hit_info->impact_distance;
+            glm::vec3 pw = transformPosition(pm, model->model_to_world);
+            hit_info->impact_distance = glm::length(pw - ray->base.orig);
+            if (best > hit_info->impact_distance) {
+                best = hit_info->impact_distance;
+                best_mat = model->mat;
+                best_n = glm::normalize(transformNormal(hit_info->impact_normal, model->model_to_world));
+                best_p = PtapProbe{imodel, ptap_probe_tri, ptap_probe_t, ptap_probe_u, ptap_probe_v};
+            }
+        }
+    }
+    if (best < FLOAT_MAX) {
+        hit_info->impact_distance = best; hit_info->impact_normal = best_n; hit_info->impact_mat = best_mat;
+    }
+    return best_p;
+}
+
+// The wavefront's trace launch at tier R1 (used for BVH film parity: the rest of the loop stays the reference's own kernels).
+void ref_trace_step_r1(void* h)
+{
+    RefRenderer* rr = (RefRenderer*)h;
+    RenderData& rd = rr->r.render_data;
+    const int n = rr->nrays;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int iray = 0; iray < n; ++iray) rr->probe[iray] = r1One(rd, iray);
+}
+
 // ---- closest hit on a caller-supplied ray set ----------------------------------------------
 // rays_od: n x 6 floats (origin, direction; the direction need not be normalised, exactly as
 // Ray::base).  mode 0 = R0 (reference grid walk), mode 1 = R1 (brute force, same predicate).
@@ -285,44 +338,8 @@ int ref_trace(void* h, const float* rays_od, int n, int mode, RefHit* out)
             LAUNCH(computeRaySceneIntersectionKernel, dim3((unsigned)((m + 31) / 32)), dim3(32), m, rd);
             ptap_probe_out = nullptr;
         } else {
-            const int nmodels = rd.dev_model_data->size;
 #pragma omp parallel for schedule(dynamic, 64)
-            for (int iray = 0; iray < m; ++iray) {
-                Ray* ray = &rd.dev_ray_data->pool[iray];
-                IntersectionData* hit_info = &rd.dev_intersection_data->pool[iray];
-                float best = hit_info->impact_distance;
-                glm::vec3 best_n(0.f); Material best_mat{}; PtapProbe best_p{-1, -1, 0.f, 0.f, 0.f};
-                for (int imodel = 0; imodel < nmodels; ++imodel) {
-                    Model* model = &rd.dev_model_data->pool[imodel];
-                    // per-model ray set-up: the statements of Renderer.cpp:381-384
-                    ray->transformed.orig = transformPosition(ray->base.orig, model->world_to_model);
-                    ray->transformed.dir = glm::normalize(transformDirection(ray->base.dir, model->world_to_model));
-                    ray->cache.inv_dir = glm::vec3(1 / ray->transformed.dir.x, 1 / ray->transformed.dir.y, 1 / ray->transformed.dir.z);
-                    hit_info->impact_distance = FLOAT_MAX;
-                    const Mesh& mesh = rd.dev_mesh_data->pool[model->mesh_index];
-                    bool any = false;
-                    ptap_probe_tri = -1;
-                    for (int t = mesh.triangle_indices.start_index; t < mesh.triangle_indices.end_index; ++t)
-                        if (computeRayTriangleIntersection(rd, ray, hit_info, t)) any = true;
-                    if (any) {
-                        // model t -> world distance: the statements of Renderer.cpp:388-398
-                        glm::vec3 nd = glm::normalize(ray->transformed.dir);
-                        glm::vec3 pm = ray->transformed.orig + nd * hit_info->impact_distance;
-                        glm::vec3 pw = transformPosition(pm, model->model_to_world);
-                        hit_info->impact_distance = glm::length(pw - ray->base.orig);
-                        if (best > hit_info->impact_distance) {
-                            best = hit_info->impact_distance;
-                            best_mat = model->mat;
-                            best_n = glm::normalize(transformNormal(hit_info->impact_normal, model->model_to_world));
-                            best_p = PtapProbe{imodel, ptap_probe_tri, ptap_probe_t, ptap_probe_u, ptap_probe_v};
-                        }
-                    }
-                }
-                if (best < FLOAT_MAX) {
-                    hit_info->impact_distance = best; hit_info->impact_normal = best_n; hit_info->impact_mat = best_mat;
-                }
-                rr->probe[iray] = best_p;
-            }
+            for (int iray = 0; iray < m; ++iray) rr->probe[iray] = r1One(rd, iray);
         }
         for (int i = 0; i < m; ++i) {
             const IntersectionData& hd = rd.dev_intersection_data->pool[i];

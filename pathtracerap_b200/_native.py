@@ -63,7 +63,7 @@ EXPORTS = [
     "ptap_scene_config_params",
     "ptap_create", "ptap_destroy", "ptap_last_error", "ptap_upload_scene", "ptap_build_accel", "ptap_set_render_params",
     "ptap_render", "ptap_timer_start", "ptap_timer_stop", "ptap_frame_begin", "ptap_film_reset", "ptap_sync", "ptap_read_film", "ptap_film_device_ptr", "ptap_film_add",
-    "ptap_write_bmp", "ptap_read_film_resolved", "ptap_write_bmp_resolved", "ptap_get_stats", "ptap_stream", "ptap_trace", "ptap_trace_count", "ptap_shade", "ptap_bench_trace",
+    "ptap_write_bmp", "ptap_read_film_resolved", "ptap_write_bmp_resolved", "ptap_get_stats", "ptap_stream", "ptap_trace", "ptap_trace_count", "ptap_shade", "ptap_bench_trace", "ptap_render_probe",
 ]
 
 _lib = None
@@ -122,6 +122,7 @@ def lib():
         L.ptap_trace_count.argtypes = [vp, vp, ci, vp, vp]
         L.ptap_shade.argtypes = [vp, vp, ci, ci, ci, vp, vp, C.POINTER(ci)]
         L.ptap_bench_trace.argtypes = [vp, vp, ci, ci, C.POINTER(C.c_float)]
+        L.ptap_render_probe.argtypes = [vp, ci, ci, vp, vp, vp, ci, C.POINTER(ci)]
         _lib = L
     return _lib
 

@@ -329,26 +329,51 @@ int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id
         }
     for (int k = 0; k < nt; ++k)
         if (tri_id[k] < 0 || tri_id[k] >= nt) return fail(ctx, PTAP_E_INVALID, "BVH leaf order entry %d out of range", k);
-    // depth of every BLAS (the traversal stack is fixed-size)
-    int blas_depth = known_depth;
-    if (known_depth <= 0) {
-        std::vector<std::pair<int, int>> todo;
-        std::vector<char> seen(nnodes, 0);
-        for (size_t m = 0; m < ctx->h_meshes.size(); ++m) if (mesh_root[m] >= 0) todo.push_back({mesh_root[m], 1});
-        while (!todo.empty()) {
-            const auto [node, d] = todo.back(); todo.pop_back();
-            if (seen[node]) { if (d > 1) return fail(ctx, PTAP_E_INVALID, "BVH node %d is reachable twice", node); continue; }
-            seen[node] = 1;
-            blas_depth = std::max(blas_depth, d);
-            for (int k = 0; k < 4; ++k)
-                if (nodes[node].link[k] >= 0 && nodes[node].lox[k] < 1e14f) todo.push_back({nodes[node].link[k], d + 1});
+    // depth of every BLAS (the traversal stack is fixed-size).  Always computed from the nodes: a caller-supplied depth is only a hint
+    // that must not be trusted (an understated one would overflow the per-thread stack); the pass also rejects cycles / shared nodes.
+    for (size_t m = 0; m < ctx->h_meshes.size(); ++m)
+        if (mesh_root[m] >= nnodes) return fail(ctx, PTAP_E_INVALID, "mesh %d: BVH root out of range", (int)m);
+    int blas_depth = 0;
+    (void)known_depth;
+    {
+        // the builders emit parents before children, so one forward sweep gives every node's level; any other order takes the stack walk
+        std::vector<int> level(nnodes, 0);
+        bool ordered = true;
+        for (size_t m = 0; m < ctx->h_meshes.size(); ++m) {
+            if (mesh_root[m] < 0) continue;
+            if (level[mesh_root[m]]) return fail(ctx, PTAP_E_INVALID, "BVH node %d is the root of two meshes", mesh_root[m]);
+            level[mesh_root[m]] = 1;
+        }
+        for (int i = 0; i < nnodes && ordered; ++i) {
+            if (!level[i]) continue;
+            blas_depth = std::max(blas_depth, level[i]);
+            for (int k = 0; k < 4; ++k) {
+                const int l = nodes[i].link[k];
+                if (l < 0 || !(nodes[i].lox[k] < 1e14f)) continue;
+                if (l <= i) { ordered = false; break; }
+                if (level[l]) return fail(ctx, PTAP_E_INVALID, "BVH node %d is reachable twice", l);
+                level[l] = level[i] + 1;
+            }
+        }
+        if (!ordered) {
+            blas_depth = 0;
+            std::vector<std::pair<int, int>> todo;
+            std::vector<char> seen(nnodes, 0);
+            for (size_t m = 0; m < ctx->h_meshes.size(); ++m) if (mesh_root[m] >= 0) todo.push_back({mesh_root[m], 1});
+            while (!todo.empty()) {
+                const auto [node, d] = todo.back(); todo.pop_back();
+                if (seen[node]) return fail(ctx, PTAP_E_INVALID, "BVH node %d is reachable twice", node);
+                if (d > nnodes) return fail(ctx, PTAP_E_INVALID, "BVH has a cycle");
+                seen[node] = 1;
+                blas_depth = std::max(blas_depth, d);
+                for (int k = 0; k < 4; ++k)
+                    if (nodes[node].link[k] >= 0 && nodes[node].lox[k] < 1e14f) todo.push_back({nodes[node].link[k], d + 1});
+            }
         }
     }
     std::vector<BvhNode> roots(ctx->h_meshes.size());
-    for (size_t m = 0; m < roots.size(); ++m) {
-        if (mesh_root[m] >= nnodes) return fail(ctx, PTAP_E_INVALID, "mesh %d: BVH root out of range", (int)m);
+    for (size_t m = 0; m < roots.size(); ++m)
         if (mesh_root[m] >= 0) roots[m] = nodes[mesh_root[m]];
-    }
     CK(cudaMemcpyAsync(ctx->d_nodes, nodes, (size_t)nnodes * sizeof(BvhNode), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_btid, tri_id, (size_t)nt * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     launchGatherTris(ctx->d_tris, ctx->d_btid, nt, ctx->d_btris, ctx->stream);     // leaf-order copies are made on the device
@@ -470,6 +495,9 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
     if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
     const int nm = v->nmodels, nt = v->ntriangles;
     const bool grid = v->grids && v->voxels && v->refs && v->ngrids > 0;
+    // the scene arena is about to be overwritten: whatever was uploaded before is gone even if this call fails half-way
+    ctx->have_scene = false; ctx->have_grid = false; ctx->have_bvh = false; ctx->bvh_kind = -1; ctx->cache_valid = false;
+    ctx->sc.tlas_root = -1; ctx->sc.nmodels = 0;
     for (int i = 0; i < nm; ++i) {
         const PtapModel& m = v->models[i];
         if (m.mesh_index < 0 || m.mesh_index >= v->nmeshes) return fail(ctx, PTAP_E_INVALID, "model %d: mesh_index %d out of range", i, m.mesh_index);
@@ -1038,6 +1066,62 @@ int ptap_bench_trace(ptap_ctx* ctx, const float* rays_od, int32_t n, int32_t rep
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     *ms_per_launch = ms / reps;
+    return PTAP_OK;
+}
+
+// Parity entry for the PRODUCTION closest-hit path.  ptap_trace launches the <UV = true> instantiations of the closest-hit kernels (it
+// returns barycentrics); ptap_render launches <false, false>, a different code object, and leaves BVH hit distances to be evaluated by the
+// consumer.  This call enqueues iteration `iter` exactly as ptap_render does on one lane - same launch wrappers, same arguments, the
+// device-side ray counts - up to and including the closest-hit launch of round `round`, then returns that round's wavefront: the rays the
+// kernel read (n x 6 floats), their pixels, and the hit records it wrote, resolved by the same consumer code k_shade uses for the
+// deferred distance (exactHitDistance).  u, v are 0 (the production instantiation does not record them).  The film and the first-hit cache
+// are left in an unspecified state: call ptap_frame_begin afterwards.
+int ptap_render_probe(ptap_ctx* ctx, int32_t iter, int32_t round, float* rays_od, int32_t* pixels, PtapHit* hits, int32_t cap, int32_t* n_out)
+{
+    if (!ctx || !ctx->have_scene || !ctx->have_frame) return fail(ctx, PTAP_E_STATE, "render_probe: scene and render parameters required");
+    if (ctx->accel == PTAP_ACCEL_GRID_COMPAT && !ctx->have_grid) return fail(ctx, PTAP_E_STATE, "render_probe: no grid in the uploaded scene");
+    if (round < 0 || round >= ctx->wv.depth || !n_out || cap < 0) return fail(ctx, PTAP_E_INVALID, "render_probe: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
+    WaveDev wv = ctx->wv;
+    wv.iter_stride = 1; wv.contrib = nullptr;
+    cudaStream_t S = ctx->stream;
+    ctx->cache_valid = false;
+    launchSetIter(wv.st, iter, S);
+    launchGenerate(wv, ctx->grid_gen, S);
+    int in = 0;
+    for (int r = 0; r <= round; ++r) {
+        launchTrace(ctx, wv.st, wv.O[in], wv.D[in], wv.hit, nullptr, nullptr, r, -1, false, S);       // the instantiation ptap_render launches
+        if (r == round) break;
+        launchScan(ctx->sc, wv, r, wv.hit, wv.depth - r, -1, S);
+        launchShade(ctx->sc, wv, r, in, wv.hit, wv.depth - r, -1, 0, nullptr, ctx->grid_shade, S);
+        in ^= 1;
+    }
+    FrameState fs;
+    CK(cudaMemcpyAsync(&fs, wv.st, sizeof fs, cudaMemcpyDeviceToHost, S));
+    CK(cudaStreamSynchronize(S));
+    CK(cudaGetLastError());
+    const int n = fs.n_active[round];
+    *n_out = n;
+    if (n > cap) return fail(ctx, PTAP_E_INVALID, "render_probe: %d active rays, buffers hold %d", n, cap);
+    if (n == 0) return PTAP_OK;
+    const size_t need = Arena::need(n, sizeof(PtapHit)) + 4096;
+    if (need > ctx->scratch.cap) CK(ctx->scratch.reserve(need)); else ctx->scratch.used = 0;
+    PtapHit* dout = ctx->scratch.alloc<PtapHit>(n);
+    launchResolveHits(ctx->sc, wv.O[in], wv.D[in], wv.hit, nullptr, n, dout, S);
+    std::vector<float4> hO(n), hD(n);
+    CK(cudaMemcpyAsync(hO.data(), wv.O[in], n * sizeof(float4), cudaMemcpyDeviceToHost, S));
+    CK(cudaMemcpyAsync(hD.data(), wv.D[in], n * sizeof(float4), cudaMemcpyDeviceToHost, S));
+    if (hits) CK(cudaMemcpyAsync(hits, dout, n * sizeof(PtapHit), cudaMemcpyDeviceToHost, S));
+    CK(cudaStreamSynchronize(S));
+    CK(cudaGetLastError());
+    for (int i = 0; i < n; ++i) {
+        if (rays_od) {
+            float* p = rays_od + 6 * (size_t)i;
+            p[0] = hO[i].x; p[1] = hO[i].y; p[2] = hO[i].z; p[3] = hD[i].x; p[4] = hD[i].y; p[5] = hD[i].z;
+        }
+        if (pixels) pixels[i] = __builtin_bit_cast(int, hO[i].w);
+    }
     return PTAP_OK;
 }
 

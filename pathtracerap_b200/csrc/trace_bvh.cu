@@ -85,9 +85,11 @@ __device__ __forceinline__ float safeInv(float d)
     return __fdividef(1.0f, fabsf(d) > ooeps ? d : copysignf(ooeps, d));     // 1-ulp reciprocal: inside the slab test's 2e-6 slack
 }
 
-__device__ __forceinline__ float worldBound(float g_dist, float prune)
+// TLAS pruning bound once some instance reported world distance g_dist: g_dist may be the approximation t * |d_w| / |W3 d_w| of the exact
+// distance (off by at most g_dist * tie + cb, tie < prune - 1), so the bound carries the same absolute slack cb as the instance-entry bound
+__device__ __forceinline__ float worldBound(float g_dist, float prune, float cb)
 {
-    return g_dist < kFloatMax ? g_dist * prune + 1e-3f : 3.0e38f;
+    return g_dist < kFloatMax ? g_dist * prune + cb + 1e-3f : 3.0e38f;
 }
 
 }  // namespace
@@ -197,9 +199,11 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
         if (s_exit && n_exit >= min(vote_inst, n_inner)) {
             const int im = (int)(code & kIndexMask);
             const float ascale = __int_as_float(stack[--sp]);                    // pushed under the marker at entry
+            const float cb = sc.c_pad + 1e-4f * (fabsf(bo.x) + fabsf(bo.y) + fabsf(bo.z));
             if (best_tri >= 0) {
-                const float a = tmax * ascale;
-                const float cb = sc.c_pad + 1e-4f * (fabsf(bo.x) + fabsf(bo.y) + fabsf(bo.z));
+                // |t|: the reference ranks instances by length(hit - origin) >= 0 (Renderer.cpp:391-393), and the predicate accepts
+                // t down to -EPSILON, which is up to EPSILON * (world units per model unit) behind the origin
+                const float a = fabsf(tmax * ascale);
                 const float a_lo = a - (fabsf(a) * sc.tie + cb), a_hi = a + (fabsf(a) * sc.tie + cb);
                 const float g_lo = g_dist - (g_dist * sc.tie + cb), g_hi = g_dist + (g_dist * sc.tie + cb);
                 bool take;
@@ -219,7 +223,7 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
                 }
             }
             ro = bo; rinv = winv;
-            tmin = sc.tmin_world; tmax = worldBound(g_dist, sc.prune);
+            tmin = sc.tmin_world; tmax = worldBound(g_dist, sc.prune, cb);
             node = stack[--sp];
         }
         // ---- (3d) retire finished rays, refill the lanes from the warp's batch
@@ -227,8 +231,9 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
             const unsigned m_done = __ballot_sync(kFull, s_done && live);
             if (s_done && i >= 0) {
                 const bool found = g_dist < kFloatMax;
-                // hit.x < 0 tells the consumer to evaluate the exact world distance from (model, t) (kernels.cuh: exactHitDistance)
-                hit[i] = make_float4(found ? -1.0f - g_dist : kFloatMax, __int_as_float(found ? g_tri : -1), __int_as_float(found ? g_model : -1), g_t);
+                // hit.x < 0 (a constant: the consumers only test the sign) tells the consumer to evaluate the exact world distance
+                // from (model, t) (kernels.cuh: exactHitDistance)
+                hit[i] = make_float4(found ? -1.0f : kFloatMax, __int_as_float(found ? g_tri : -1), __int_as_float(found ? g_model : -1), g_t);
                 if (UV && uv) uv[i] = make_float2(g_u, g_v);
                 if (COUNT) { if (counts) counts[i] = cnt; tot_x += cnt.x; tot_z += cnt.z; }
                 i = -1;

@@ -47,4 +47,6 @@ def render_partitioned(renderer, iters: int, rank: int, world: int):
     if world > 1:
         with torch.cuda.stream(torch.cuda.ExternalStream(renderer.stream_ptr())):
             reduce_film(t, 0)
+    # after the reduce rank 0's film holds all `iters` samples: renderImage divides by this count (Renderer.cpp:42)
+    renderer._iters_done = iters if rank == 0 else e - b
     return t

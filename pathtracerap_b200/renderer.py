@@ -154,6 +154,14 @@ class Renderer:
         self._check(N.lib().ptap_shade(self.h, N.ptr(paths), len(paths), it, remaining, N.ptr(out), N.ptr(order), C.byref(n_alive)), "shade")
         return out, order[:n_alive.value]
 
+    def render_probe(self, it: int, round_: int):
+        """The wavefront of round `round_` of iteration `it` as ptap_render enqueues it (production kernel instantiations, one lane):
+        returns (rays n x 6, pixels n, hits n).  Leaves the film unspecified; call frame_begin() before rendering again."""
+        cap = self.W * self.H
+        rays = np.zeros((cap, 6), np.float32); pix = np.zeros(cap, np.int32); hits = np.zeros(cap, N.HIT); n = C.c_int32(0)
+        self._check(N.lib().ptap_render_probe(self.h, it, round_, N.ptr(rays), N.ptr(pix), N.ptr(hits), cap, C.byref(n)), "render_probe")
+        return rays[:n.value], pix[:n.value], hits[:n.value]
+
     def bench_trace(self, rays_od, reps: int = 10) -> float:
         rays_od = np.ascontiguousarray(rays_od, np.float32).reshape(-1, 6)
         ms = C.c_float(0)

@@ -1,4 +1,4 @@
-"""Closest-hit parity beyond the bundled scene: the synthetic 82k- and 1.3M-triangle meshes of bench.py (BASELINE.json configs[1], configs[3]).
+"""Closest-hit parity beyond the bundled scene: the synthetic 82k-, 1.3M- and 5.2M-triangle meshes of bench.py (BASELINE.json configs[1], configs[3]).
 
 The oracle's brute force (tier R1) finishes a few thousand rays on these sizes in seconds; at the full ray counts the checks are
 size-independent properties: a permutation of the ray set permutes the hits (no cross-ray state in the persistent, work-stealing
@@ -31,7 +31,7 @@ def _bounce_rays(n, seed):
     return np.concatenate([o, d], 1).astype(np.float32)
 
 
-@pytest.fixture(scope="module", params=["mesh100k", "mesh1m"])
+@pytest.fixture(scope="module", params=["mesh100k", "mesh1m", "mesh5m"])
 def big(request, libptap):
     import bench
     from pathtracerap_b200 import ACCEL_BVH, Renderer
@@ -45,7 +45,7 @@ def big(request, libptap):
 
 def test_bvh_vs_brute_force_oracle(big, port):
     name, r, arrays = big
-    n = 20000 if name == "mesh100k" else 2000                   # brute force: n x triangles predicate evaluations on the host
+    n = {"mesh100k": 20000, "mesh1m": 20000, "mesh5m": 2000}[name]     # brute force: n x triangles predicate evaluations on the host
     cam = _camera_rays(1920, 1080)
     rays = np.concatenate([cam[np.random.RandomState(3).choice(len(cam), n // 2, replace=False)], _bounce_rays(n - n // 2, 4)])
     oscene = port.OracleScene(arrays)
@@ -57,6 +57,30 @@ def test_bvh_vs_brute_force_oracle(big, port):
     for f in ("t_model", "dist", "u", "v"):
         assert np.array_equal(got[f][hit], want[f][hit]), f
     assert (want["model"][hit] == len(arrays["models"]) - 1).mean() > 0.2      # a good share of the rays ends on the big mesh
+
+
+def test_production_frame_rays_vs_brute_force_oracle(big, port):
+    """The benchmarked configuration itself: a real 1920x1080 iteration through the PRODUCTION kernel instantiation (ptap_render_probe),
+    every round; a seeded subset of each round's rays is re-traced by the brute-force oracle (R1): ids, model t and the world distance
+    the shade kernel derives must be bit-equal."""
+    name, r, arrays = big
+    per_round = {"mesh100k": 4000, "mesh1m": 4000, "mesh5m": 500}[name]
+    W, H, depth = 1920, 1080, 5
+    r.set_params(W, H, depth, first_hit_cache=True)
+    oscene = port.OracleScene(arrays)
+    rs = np.random.RandomState(21)
+    for rnd in range(depth):
+        rays, pix, hits = r.render_probe(0, rnd)
+        assert len(rays) > per_round
+        sel = np.sort(rs.choice(len(rays), per_round, replace=False))
+        want = oscene.trace(rays[sel], 1)
+        got = hits[sel]
+        assert np.array_equal(got["model"], want["model"]) and np.array_equal(got["tri"], want["tri"]), f"round {rnd}"
+        hit = want["model"] >= 0
+        for f in ("t_model", "dist", "normal"):
+            assert np.array_equal(got[f][hit], want[f][hit]), f"round {rnd}: {f}"
+    r.frame_begin()
+    r.set_params(64, 32, 5)
 
 
 def test_full_size_properties(big):

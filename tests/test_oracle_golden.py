@@ -139,6 +139,45 @@ def test_films_golden(port, oracle_scene, golden_scene, golden_films):
     wc.close()
 
 
+def test_films_golden_r1(port, oracle_scene, golden_films):
+    """Tier R1 of the wavefront (every triangle, the reference's predicate and loop): the fixture was produced by the compiled reference's
+    own kernels with only the closest-hit launch swapped (ref_harness.cpp: ref_trace_step_r1).  This is the film an exact BVH must match."""
+    f = golden_films
+    W, H, depth, iters = (int(x) for x in f["bundled_params"])
+    w = port.OracleWavefront(oracle_scene, W, H, depth, mode=1)
+    w.init_image()
+    counts = [w.run_iteration(it) for it in range(iters)]
+    assert np.array_equal(np.array(counts), f["bundled_counts_r1"])
+    assert np.array_equal(w.image(), f["bundled_film_r1"])
+    assert not np.array_equal(f["bundled_film_r1"], f["bundled_film"])      # the tiers do differ (SURVEY 8c: 0.3-0.6 % of rays)
+    w.close()
+    w2 = port.OracleWavefront(oracle_scene, W, H, depth, mode=1)
+    w2.init_image(); w2.render(0, iters, first_hit_cache=True)
+    assert np.array_equal(w2.image(), f["bundled_film_r1"])
+    w2.close()
+
+
+def test_bmp_writer_vs_compiled_reference(ref, port, golden_scene, tmp_path):
+    """Renderer::renderImage (Renderer.cpp:15-63) of the compiled reference, run on its own film, against the port's writer on the same film:
+    the two files must be byte-identical (header, row order, channel order, (char) truncation)."""
+    g = golden_scene
+    rscene = ref.RefScene.from_arrays(g["models"], g["meshes"], g["vertices"], g["triangles"])
+    W, H, iters = 96, 64, 3
+    rr = ref.RefRenderer(rscene, W, H, 5)
+    rr.init_image()
+    for it in range(iters):
+        rr.run_iteration(it)
+    film = rr.image()
+    d = tmp_path / "refout"; d.mkdir()
+    rr.write_bmp(str(d), iters)
+    rr.close(); rscene.close()
+    want = (d / "Render.bmp").read_bytes()
+    port.write_bmp(film, iters, tmp_path / "port.bmp")
+    got = (tmp_path / "port.bmp").read_bytes()
+    assert len(want) == 54 + 3 * W * H
+    assert got == want
+
+
 def test_bmp_writer(port, tmp_path):
     img = np.zeros((4, 8, 3), np.float32)
     img[1, 2] = (2.0, 1.0, 0.5)
@@ -225,7 +264,13 @@ def test_port_equals_compiled_reference_on_other_scenes(ref, port, golden_scene)
         for it in range(2):
             assert rr.run_iteration(it) == pw.run_iteration(it)
         assert np.array_equal(rr.image(), pw.image())
-        rr.close(); pw.close(); rscene.close()
+        # the same two iterations at tier R1 (BVH film parity rests on this mode of the port)
+        pw1 = port.OracleWavefront(pscene, W, H, depth, mode=1)
+        rr.init_image(); pw1.init_image()
+        for it in range(2):
+            assert rr.run_iteration(it, mode=1) == pw1.run_iteration(it)
+        assert np.array_equal(rr.image(), pw1.image())
+        rr.close(); pw.close(); pw1.close(); rscene.close()
 
 
 def test_port_equals_compiled_reference_on_a_dense_mesh(ref, port, libptap):

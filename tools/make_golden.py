@@ -114,6 +114,12 @@ def main():
     r2 = ref.RefRenderer(scene, W, H, depth)
     r2.render_loop(iters)
     assert np.array_equal(r2.image(), film), "step-wise harness differs from Renderer::renderLoop"
+    # the same frame at tier R1 (brute force with the reference's own predicate and loop): what an exact BVH must reproduce
+    r3 = ref.RefRenderer(scene, W, H, depth)
+    r3.init_image()
+    per_iter_r1 = [r3.run_iteration(it, mode=1) for it in range(iters)]
+    film_r1 = r3.image()
+    r3.close()
     r.close(); r2.close()
 
     cm = cornell_models(A["models"])
@@ -125,10 +131,11 @@ def main():
     c_per_iter = [rc.run_iteration(it) for it in range(iters)]
     cfilm = rc.image()
     rc.close()
-    np.savez_compressed(os.path.join(OUT, "films.npz"), bundled_film=film, bundled_counts=np.array(per_iter), bundled_params=np.array([W, H, depth, iters]),
+    np.savez_compressed(os.path.join(OUT, "films.npz"), bundled_film_r1=film_r1, bundled_counts_r1=np.array(per_iter_r1), bundled_film=film, bundled_counts=np.array(per_iter), bundled_params=np.array([W, H, depth, iters]),
                         cornell_film=cfilm, cornell_counts=np.array([c + [0] * (dc - len(c)) for c in c_per_iter]),
                         cornell_params=np.array([Wc, Hc, dc, iters]), cornell_models=CA["models"], cornell_grids=CA["grids"])
     print("bundled 128x96 per-iteration active counts:", per_iter)
+    print("bundled 128x96 per-iteration active counts, tier R1:", per_iter_r1)
     print("cornell 96x96 per-iteration active counts:", c_per_iter)
 
     # Cornell 512x512 iteration-0 checkpoint
