@@ -363,22 +363,61 @@ static int ray_grid(const OScene* s, RayCtx* c, int igrid)
     }
 }
 
-/* One thread of computeRaySceneIntersectionKernel (Renderer.cpp:363-409); `dist_in` is the slot's incoming
+/* Per-ray accumulator of computeRaySceneIntersectionKernel's model loop (Renderer.cpp:372-409). */
+typedef struct { float g_dist; v3 g_normal; OMaterial g_mat; OHit g_probe; float last_dist; } ModelLoop;
+
+static void loop_begin(ModelLoop* L, const OHitRecord* h)
+{
+    L->g_dist = h->dist; L->g_normal = ld3(h->normal); L->g_mat = h->mat; L->last_dist = h->dist;
+    memset(&L->g_probe, 0, sizeof L->g_probe); L->g_probe.model = -1; L->g_probe.tri = -1; L->g_probe.mat_type = -1;
+}
+
+static void model_setup(const OModel* model, v3 bo, v3 bd, RayCtx* c)
+{
+    c->o = mat4_mul(model->w2m, bo, 1.0f);                               /* Renderer.cpp:381 */
+    c->d = normalize(mat4_mul(model->w2m, bd, 0.0f));                    /* Renderer.cpp:382 */
+    c->inv = V(1 / c->d.x, 1 / c->d.y, 1 / c->d.z);                      /* Renderer.cpp:383 */
+    c->dist = O_FLOAT_MAX;                                               /* Renderer.cpp:384 */
+    c->tri = -1;
+}
+
+static void model_finish(ModelLoop* L, const OModel* model, int imodel, v3 bo, RayCtx* c, int hit)
+{
+    if (hit) {
+        v3 nd = normalize(c->d);                                         /* Renderer.cpp:388 */
+        v3 pm = add(c->o, scale(nd, c->dist));                           /* Renderer.cpp:389 */
+        v3 pw = mat4_mul(model->m2w, pm, 1.0f);                          /* Renderer.cpp:390 */
+        c->dist = length3(sub(pw, bo));                                  /* Renderer.cpp:391 */
+        if (L->g_dist > c->dist) {                                       /* Renderer.cpp:393-398 */
+            L->g_dist = c->dist; L->g_mat = model->mat;
+            L->g_normal = normalize(transform_normal(c->normal, model->m2w));
+            L->g_probe.model = imodel; L->g_probe.tri = c->tri; L->g_probe.t_model = c->t; L->g_probe.u = c->u; L->g_probe.v = c->v;
+        }
+    }
+    L->last_dist = c->dist;                                              /* what this model left in the slot */
+}
+
+static void loop_end(ModelLoop* L, OHitRecord* h, OHit* probe)
+{
+    h->dist = L->last_dist;
+    if (L->g_dist < O_FLOAT_MAX) {                                       /* Renderer.cpp:402-408 */
+        h->dist = L->g_dist; st3(h->normal, L->g_normal); h->mat = L->g_mat;
+        L->g_probe.dist = L->g_dist; st3(L->g_probe.normal, L->g_normal); L->g_probe.mat_type = L->g_mat.type;
+    } else {
+        L->g_probe.model = -1; L->g_probe.tri = -1; L->g_probe.dist = h->dist; L->g_probe.t_model = 0; L->g_probe.u = L->g_probe.v = 0;
+    }
+    if (probe) *probe = L->g_probe;
+}
+
+/* One thread of computeRaySceneIntersectionKernel (Renderer.cpp:363-409); h->dist on entry is the slot's incoming
  * hit_info->impact_distance.  Returns the final hit_info fields through *h, ids through *probe. */
 static void trace_one(const OScene* s, v3 bo, v3 bd, int mode, OHitRecord* h, OHit* probe)
 {
-    float g_dist = h->dist;
-    v3 g_normal = ld3(h->normal);
-    OMaterial g_mat = h->mat;
-    OHit g_probe; memset(&g_probe, 0, sizeof g_probe); g_probe.model = -1; g_probe.tri = -1; g_probe.mat_type = -1;
+    ModelLoop L; loop_begin(&L, h);
     RayCtx c; memset(&c, 0, sizeof c);
     for (int imodel = 0; imodel < s->nmodels; ++imodel) {
         const OModel* model = &s->models[imodel];
-        c.o = mat4_mul(model->w2m, bo, 1.0f);                            /* Renderer.cpp:381 */
-        c.d = normalize(mat4_mul(model->w2m, bd, 0.0f));                 /* Renderer.cpp:382 */
-        c.inv = V(1 / c.d.x, 1 / c.d.y, 1 / c.d.z);                      /* Renderer.cpp:383 */
-        c.dist = O_FLOAT_MAX;                                            /* Renderer.cpp:384 */
-        c.tri = -1;
+        model_setup(model, bo, bd, &c);
         int hit;
         if (mode == 0) hit = ray_grid(s, &c, model->grid_index);
         else {
@@ -386,31 +425,47 @@ static void trace_one(const OScene* s, v3 bo, v3 bd, int mode, OHitRecord* h, OH
             hit = 0;
             for (int t = mesh->t_start; t < mesh->t_end; ++t) if (ray_triangle(s, &c, t)) hit = 1;
         }
-        if (hit) {
-            v3 nd = normalize(c.d);                                      /* Renderer.cpp:388 */
-            v3 pm = add(c.o, scale(nd, c.dist));                         /* Renderer.cpp:389 */
-            v3 pw = mat4_mul(model->m2w, pm, 1.0f);                      /* Renderer.cpp:390 */
-            c.dist = length3(sub(pw, bo));                               /* Renderer.cpp:391 */
-            if (g_dist > c.dist) {                                       /* Renderer.cpp:393-398 */
-                g_dist = c.dist; g_mat = model->mat;
-                g_normal = normalize(transform_normal(c.normal, model->m2w));
-                g_probe.model = imodel; g_probe.tri = c.tri; g_probe.t_model = c.t; g_probe.u = c.u; g_probe.v = c.v;
-            }
-        }
+        model_finish(&L, model, imodel, bo, &c, hit);
     }
-    h->dist = c.dist;                                                    /* what the last model left in the slot */
-    if (s->nmodels == 0) h->dist = g_dist;
-    if (g_dist < O_FLOAT_MAX) {                                          /* Renderer.cpp:402-408 */
-        h->dist = g_dist; st3(h->normal, g_normal); h->mat = g_mat;
-        g_probe.dist = g_dist; st3(g_probe.normal, g_normal); g_probe.mat_type = g_mat.type;
-    } else {
-        g_probe.model = -1; g_probe.tri = -1; g_probe.dist = h->dist; g_probe.t_model = 0; g_probe.u = g_probe.v = 0;
+    loop_end(&L, h, probe);
+}
+
+/* Tier R1 for a block of rays: the same statements per (ray, model, triangle) as trace_one(mode 1), with the triangle loop outermost
+ * inside a model so that a large mesh streams through the cache once per block instead of once per ray.  Each ray still sees its
+ * model's triangles in ascending order, so every comparison (and therefore every result bit) is the one trace_one makes. */
+#define O_R1_BLOCK 128
+static void trace_block_r1(const OScene* s, int n, const v3* bo, const v3* bd, OHitRecord** h, OHit** probe)
+{
+    ModelLoop L[O_R1_BLOCK]; RayCtx c[O_R1_BLOCK]; int hit[O_R1_BLOCK];
+    for (int r = 0; r < n; ++r) { loop_begin(&L[r], h[r]); memset(&c[r], 0, sizeof c[r]); }
+    for (int imodel = 0; imodel < s->nmodels; ++imodel) {
+        const OModel* model = &s->models[imodel];
+        const OMesh* mesh = &s->meshes[model->mesh_index];
+        for (int r = 0; r < n; ++r) { model_setup(model, bo[r], bd[r], &c[r]); hit[r] = 0; }
+        for (int t = mesh->t_start; t < mesh->t_end; ++t)
+            for (int r = 0; r < n; ++r) if (ray_triangle(s, &c[r], t)) hit[r] = 1;
+        for (int r = 0; r < n; ++r) model_finish(&L[r], model, imodel, bo[r], &c[r], hit[r]);
     }
-    if (probe) *probe = g_probe;
+    for (int r = 0; r < n; ++r) loop_end(&L[r], h[r], probe ? probe[r] : NULL);
 }
 
 void oracle_trace(const OScene* s, const float* rays_od, int n, int mode, OHit* out)
 {
+    if (mode == 1) {
+        int nblocks = (n + O_R1_BLOCK - 1) / O_R1_BLOCK;
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int b = 0; b < nblocks; ++b) {
+            int i0 = b * O_R1_BLOCK, m = n - i0 < O_R1_BLOCK ? n - i0 : O_R1_BLOCK;
+            v3 bo[O_R1_BLOCK], bd[O_R1_BLOCK]; OHitRecord hr[O_R1_BLOCK]; OHitRecord* hp[O_R1_BLOCK]; OHit* pp[O_R1_BLOCK];
+            for (int r = 0; r < m; ++r) {
+                bo[r] = ld3(rays_od + 6 * (size_t)(i0 + r)); bd[r] = ld3(rays_od + 6 * (size_t)(i0 + r) + 3);
+                memset(&hr[r], 0, sizeof hr[r]); hr[r].dist = O_FLOAT_MAX;   /* Renderer.cpp:553 */
+                hp[r] = &hr[r]; pp[r] = &out[i0 + r];
+            }
+            trace_block_r1(s, m, bo, bd, hp, pp);
+        }
+        return;
+    }
 #pragma omp parallel for schedule(dynamic, 256)
     for (int i = 0; i < n; ++i) {
         OHitRecord h; memset(&h, 0, sizeof h); h.dist = O_FLOAT_MAX;     /* Renderer.cpp:553 */
@@ -492,6 +547,20 @@ void oracle_trace_step(OWavefront* w)                                    /* Rend
 {
     int span = launch_span(w);
     int n = w->nrays < span ? w->nrays : span;
+    if (w->mode == 1) {
+        int nblocks = (n + O_R1_BLOCK - 1) / O_R1_BLOCK;
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int b = 0; b < nblocks; ++b) {
+            int i0 = b * O_R1_BLOCK, m = n - i0 < O_R1_BLOCK ? n - i0 : O_R1_BLOCK;
+            v3 bo[O_R1_BLOCK], bd[O_R1_BLOCK]; OHitRecord* hp[O_R1_BLOCK]; OHit* pp[O_R1_BLOCK];
+            for (int r = 0; r < m; ++r) {
+                bo[r] = ld3(w->rays[i0 + r].orig); bd[r] = ld3(w->rays[i0 + r].dir);
+                hp[r] = &w->hits[i0 + r]; pp[r] = &w->probe[i0 + r];
+            }
+            trace_block_r1(w->s, m, bo, bd, hp, pp);
+        }
+        return;
+    }
 #pragma omp parallel for schedule(dynamic, 256)
     for (int i = 0; i < n; ++i)
         trace_one(w->s, ld3(w->rays[i].orig), ld3(w->rays[i].dir), w->mode, &w->hits[i], &w->probe[i]);
