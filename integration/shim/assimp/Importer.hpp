@@ -1,8 +1,9 @@
-// Minimal stand-in for the part of Assimp the reference calls (Scene.cpp:226-291), used ONLY
-// to build the CPU oracle.  Assimp is not vendored by the reference and is absent here, so
+// Minimal stand-in for the part of Assimp the reference calls (Scene.cpp:226-291), used wherever the reference's own Scene.cpp is
+// compiled in this image: integration/build_in_reference_tree.sh (the drop-in proof) and the oracle builds (oracle/build_ref*.sh include
+// it from here; nothing under integration/ depends on oracle/).  Assimp is not vendored by the reference and is absent here, so
 // its behaviour for the bundled Wavefront files is restated: ReadFile() without
 // aiProcess_JoinIdenticalVertices emits ONE vertex per face corner, in file order, as a
-// single mesh hanging off the root node.  TEST INFRASTRUCTURE - parity unpinned for Assimp
+// single mesh hanging off the root node.  Parity unpinned for Assimp
 // itself (no Assimp build exists to compare with); pinned only by the committed Render.bmp.
 #pragma once
 #include <cstdio>

@@ -65,6 +65,6 @@ mkdir -p "$OUT"
 # arithmetic un-contracted for the same reason.
 g++ -std=c++17 -O2 -ffp-contract=off -fopenmp -fPIC -shared -w \
     -DTHRUST_DEVICE_SYSTEM=THRUST_DEVICE_SYSTEM_OMP \
-    -I"$HERE/shim" -I"$TMP" -I"$REF/external/include" -I/usr/local/cuda/include \
+    -I"$HERE/shim" -I"$HERE/../integration/shim" -I"$TMP" -I"$REF/external/include" -I/usr/local/cuda/include \
     -x c++ "$HERE/ref_harness.cpp" -o "$OUT/libptap_ref.so"
 echo "built $OUT/libptap_ref.so"
