@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PTAP_VERSION 1
+#define PTAP_VERSION 2      /* 2: PtapBvhNode is the 8-wide compressed node; ptap_render_probe */
 
 enum {
     PTAP_OK = 0,
@@ -58,15 +58,19 @@ typedef struct { int32_t start, end, entity_type; } PtapVoxel;                  
 
 enum { PTAP_DIFFUSE = 0, PTAP_SPECULAR, PTAP_REFLECTIVE, PTAP_REFRACTIVE, PTAP_EMISSIVE, PTAP_COAT, PTAP_METAL }; /* Primitive.h:70-79 */
 
-/* BVH4 node (new; the reference has no BVH): the boxes of up to four children in SoA form and their links, 128 bytes.
- * link >= 0: child node index; link < 0: leaf, ~link = (first_leaf_triangle << 3) | (count - 1).
- * An unused slot holds the point box (1e15, 1e15, 1e15). */
+/* 8-wide BVH node (new; the reference has no BVH), 128 bytes.  Child boxes are IEEE-half offsets in a node-local frame:
+ * plane = p + scale * half, lower planes rounded down and upper planes rounded up, so every child box contains the builder's box (which
+ * bounds the reference predicate's tolerance band).  Children occupy octant slots (bit k of the slot: the child lies on the upper side
+ * of the node along axis k).  Inner children are consecutive nodes from child_base in slot order and must come AFTER their parent in
+ * the array; the triangles of the leaf children are consecutive from leaf_base (leaf order) in slot order. */
 typedef struct {
-    float lox[4], hix[4];
-    float loy[4], hiy[4];
-    float loz[4], hiz[4];
-    int32_t link[4];
-    int32_t pad[4];
+    float p[3];               /* node-local origin */
+    float scale;              /* power of two */
+    int32_t child_base;       /* node index of the first inner child */
+    int32_t leaf_base;        /* leaf-order position of the first triangle of the first leaf child */
+    uint32_t leaf_mask;       /* nibble c = (1 << count) - 1 for a leaf of 1..4 triangles in slot c, else 0 */
+    uint32_t inner_mask;      /* bit c: slot c is an inner node */
+    uint16_t lo_x[8], hi_x[8], lo_y[8], hi_y[8], lo_z[8], hi_z[8];
 } PtapBvhNode;
 
 /* The seven public vectors of the reference's Scene (Scene.h:26-32) as raw arrays. */
@@ -83,7 +87,7 @@ typedef struct {
     const PtapBvhNode* bvh_nodes; int32_t n_bvh_nodes;
     const int32_t* bvh_tri_id; int32_t n_bvh_tris;    /* leaf-order position -> global triangle index */
     const int32_t* bvh_mesh_root; int32_t n_bvh_roots;/* per mesh: root node, -1 if empty */
-    int32_t bvh_depth;                                /* deepest BLAS level, 0 = unknown (computed at upload) */
+    int32_t bvh_depth;                                /* deepest BLAS level (a hint: upload always recomputes it from the nodes) */
     /* optional triangle records prepared by ptap_scene_build_bvh (48 B per triangle: v0, v1-v0, v2-v0, flat normal in the .w lanes,
      * reference arithmetic); NULL/0: ptap_upload_scene derives them from vertices + triangles.  ptap_scene keeps its upload-bound
      * arrays (these, the BVH nodes, the leaf order) in page-locked host memory when a CUDA device is present. */
@@ -155,6 +159,9 @@ int ptap_scene_build_grids(ptap_scene* s, int32_t gx, int32_t gy, int32_t gz);
 /* Builds one BVH per mesh on the host (binned SAH); part of scene construction like addMeshesToGrid, so that
  * Renderer::allocateOnGPU only uploads.  Bounds are conservative for the reference's tolerance band. */
 int ptap_scene_build_bvh(ptap_scene* s);
+/* Host-side check of that BVH: the number of triangles whose tolerance band (what the reference's predicate can accept) sticks out of a
+ * compressed child box on its path from the root, plus structural errors; 0 for a correct tree. */
+int ptap_scene_validate_bvh(const ptap_scene* s, int64_t* violations, int32_t* depth);
 int ptap_scene_view(const ptap_scene* s, PtapSceneView* out);     /* pointers stay owned by the scene */
 PtapModel* ptap_scene_models(ptap_scene* s);                      /* mutable, like the public vector */
 void ptap_scene_destroy(ptap_scene* s);

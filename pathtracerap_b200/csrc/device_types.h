@@ -10,7 +10,7 @@ constexpr float kEpsilon = 0.005f;          // Config.h:4
 constexpr float kFloatMax = 9999999.0f;     // Config.h:5
 constexpr float kFloatMin = -9999990.0f;    // Config.h:6
 constexpr int kMaxDepth = 16;               // rounds per iteration the context reserves state for
-constexpr int kBvhStack = 160;              // traversal stack entries per ray (upload fails for deeper trees)
+constexpr int kBvhStack = 64;               // 8-byte traversal stack entries per ray: one per level + 4 per instance entry (upload fails for deeper trees)
 
 // Per-model record read by the closest-hit kernels: 9 x float4 = 144 B.
 // Rows 0..2 of the reference's column-major mat4s (the w row is never used by
@@ -56,16 +56,28 @@ struct Bvh2Node {
     int4 link;          // (child0, child1, 0, 0); >= 0: node index, < 0: leaf; link.x == link.y: only child0 exists
 };
 
-// BVH4 node, 128 B = four 32-byte vector loads (LDG.E.256): the boxes of up to four children in SoA form and their links.
-// link >= 0: node index; link < 0: triangle leaf ~((first << 3) | (count - 1)) or (TLAS only) instance leaf ~(0x20000000 | model index).
-// An unused slot holds a far-away point box that no ray interval reaches.
+// 8-wide BVH node with child boxes compressed to IEEE half offsets in a node-local frame: 128 B = one L1 line.
+//   plane = p + scale * half, every lower plane rounded down and every upper plane rounded up (bvh_build.cpp: quantiseNode), so a child
+//   box always CONTAINS the builder's box, which itself bounds the reference predicate's +-0.005 tolerance band: the structure only
+//   decides which triangles are tested, the exact predicate decides hits.
+// Children sit in slots 0..7 chosen at build time by octant (bit k of the slot = the child lies on the upper side of the node along
+// axis k), so that for a ray whose direction-sign bits are `oct`, visiting slots in ascending (slot ^ oct) is front to back without
+// any sorting at traversal time.  Inner children are consecutive nodes from child_base (in slot order); the triangles of the leaf
+// children are consecutive LeafTri records from leaf_base (in slot order).  TLAS nodes share the format: a leaf child is ONE instance,
+// leaf_base indexes SceneDev::tlas_order.
 struct __align__(32) BvhNode {
-    float lox[4], hix[4];
-    float loy[4], hiy[4];
-    float loz[4], hiz[4];
-    int link[4];
-    int pad[4];
+    float px, py, pz;           // node-local origin (the lower corner of the node)
+    float scale;                // power of two
+    int child_base;             // node index of the first inner child
+    int leaf_base;              // leaf-order position of the first triangle of the first leaf child
+    unsigned leaf_mask;         // nibble c = (1 << count_c) - 1 when slot c is a leaf of 1..4 triangles, else 0
+    unsigned inner_mask;        // bit c set when slot c is an inner node
+    unsigned short lo_x[8], hi_x[8];      // half bits, per slot
+    unsigned short lo_y[8], hi_y[8];
+    unsigned short lo_z[8], hi_z[8];
 };
+static_assert(sizeof(BvhNode) == 128, "BvhNode must be one 128-byte line");
+constexpr int kBvhWidth = 8, kBvhLeafMax = 4;
 
 // Device-resident frame state: lets a whole iteration run without a host round trip.
 struct FrameState {
@@ -87,9 +99,10 @@ struct SceneDev {
     const float4* normals;      // flat shading normal per GLOBAL triangle id (copy of the TriRec .w lanes, 16-byte gather for k_shade)
     const int2* cells;          // grid voxels: (start, end) into refs
     const int* refs;            // global triangle ids
-    const BvhNode* nodes;       // all BLAS nodes, then the TLAS nodes
+    const BvhNode* nodes;       // all BLAS nodes (8-wide), then the TLAS nodes
     const LeafTri* bvh_tris;    // triangles in BVH leaf order
     const int* bvh_tri_id;      // leaf-order position -> global triangle id (build-time input of k_gather_tris; the kernels read LeafTri::id)
+    const int* tlas_order;      // TLAS leaf order -> model index
     int nmodels;
     int gx, gy, gz;
     int tlas_root;              // node index of the TLAS root, -1 when no instance has triangles

@@ -708,6 +708,45 @@ int ptap_scene_build_bvh(ptap_scene* s)
     return PTAP_OK;
 }
 
+// Structural check of the BVH made by ptap_scene_build_bvh, on the host: every triangle's tolerance band - the set of points the reference's
+// predicate can accept, corners at (u, v) = (-e, -e), (1 + 2e, -e), (-e, 1 + 2e), e = 0.0056 > EPSILON - must lie inside EVERY decoded
+// (half-precision, outward-rounded) child box on its path from the root; leaf counts, link ranges and the forest property are checked on
+// the way.  *violations = 0 for a correct tree.
+int ptap_scene_validate_bvh(const ptap_scene* s, int64_t* violations, int32_t* depth)
+{
+    if (!s || !violations || !s->have_bvh) return PTAP_E_STATE;
+    const ptap::BvhNode* nodes = static_cast<const ptap::BvhNode*>(s->st_nodes.p);
+    const ptap::TriRec* recs = static_cast<const ptap::TriRec*>(s->st_recs.p);
+    const int* tri_id = static_cast<const int*>(s->st_tri_id.p);
+    const int nt = (int)s->bvh.tri_id.size();
+    auto band = [&](int pos) {
+        const ptap::TriRec& r = recs[tri_id[pos]];
+        const double e = 0.0056, uv[3][2] = {{-e, -e}, {1 + 2 * e, -e}, {-e, 1 + 2 * e}};
+        ptap::ChildBox b;
+        for (int k = 0; k < 3; ++k) { b.lo[k] = 3e38f; b.hi[k] = -3e38f; }
+        const double v0[3] = {r.v0.x, r.v0.y, r.v0.z}, e1[3] = {r.e1.x, r.e1.y, r.e1.z}, e2[3] = {r.e2.x, r.e2.y, r.e2.z};
+        for (auto& c : uv)
+            for (int k = 0; k < 3; ++k) {
+                const double x = v0[k] + c[0] * e1[k] + c[1] * e2[k];
+                b.lo[k] = std::min(b.lo[k], (float)x); b.hi[k] = std::max(b.hi[k], (float)x);
+            }
+        return b;
+    };
+    long long bad = 0;
+    int maxd = 0;
+    std::vector<char> covered(nt, 0);
+    for (size_t m = 0; m < s->bvh.mesh_root.size(); ++m) {
+        if (s->bvh.mesh_root[m] < 0) continue;
+        int d = 0;
+        bad += ptap::validateBvh(nodes, s->bvh_nnodes, s->bvh.mesh_root[m], nt, [&](int pos) { covered[pos]++; return band(pos); }, &d);
+        maxd = std::max(maxd, d);
+    }
+    for (int k = 0; k < nt; ++k) if (covered[k] != 1) ++bad;          // every leaf-order position belongs to exactly one leaf
+    *violations = bad;
+    if (depth) *depth = maxd;
+    return PTAP_OK;
+}
+
 int ptap_scene_view(const ptap_scene* s, PtapSceneView* out)
 {
     if (!s || !out) return PTAP_E_INVALID;

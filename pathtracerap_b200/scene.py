@@ -115,6 +115,12 @@ class Scene:
         """One BVH per mesh, built on the host as part of scene construction (like addMeshesToGrid for the grid)."""
         self._check(N.lib().ptap_scene_build_bvh(self.h), "build_bvh")
 
+    def validate_bvh(self) -> tuple[int, int]:
+        """(violations, depth) of the host-built BVH: 0 violations = every triangle's tolerance band lies inside every compressed box above it."""
+        bad = C.c_int64(-1); depth = C.c_int32(0)
+        self._check(N.lib().ptap_scene_validate_bvh(self.h, C.byref(bad), C.byref(depth)), "validate_bvh")
+        return bad.value, depth.value
+
     # -- the seven public vectors (Scene.h:26-32) as numpy copies -----------------------------------------------
     def view(self) -> N.SceneView:
         v = N.SceneView()

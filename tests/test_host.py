@@ -59,8 +59,8 @@ def test_compose_trs_matches_reference_matrices(libptap, golden_scene):
     assert np.allclose(prod, np.eye(4), atol=1e-5)
 
 
-NODE = np.dtype([("lox", "<f4", 4), ("hix", "<f4", 4), ("loy", "<f4", 4), ("hiy", "<f4", 4), ("loz", "<f4", 4), ("hiz", "<f4", 4),
-                 ("link", "<i4", 4), ("pad", "<i4", 4)])          # PtapBvhNode, include/ptap.h
+NODE = np.dtype([("p", "<f4", 3), ("scale", "<f4"), ("child_base", "<i4"), ("leaf_base", "<i4"), ("leaf_mask", "<u4"), ("inner_mask", "<u4"),
+                 ("lo_x", "<u2", 8), ("hi_x", "<u2", 8), ("lo_y", "<u2", 8), ("hi_y", "<u2", 8), ("lo_z", "<u2", 8), ("hi_z", "<u2", 8)])   # PtapBvhNode, include/ptap.h
 
 
 def _bvh_of(scene):
@@ -74,13 +74,26 @@ def _bvh_of(scene):
     return nodes, tri_id, roots
 
 
+def _half(bits):
+    return np.array([bits], np.uint16).view(np.float16).astype(np.float64)[0]
+
+
 def _slots(nd):
-    """(lo, hi, link) of the used child slots of a 4-wide node (an unused slot holds the far-away point box)."""
+    """(slot, lo, hi, kind, count) of the used child slots of an 8-wide compressed node, decoded independently of the library:
+    plane = p + scale * half (include/ptap.h)."""
     out = []
-    for k in range(4):
-        if nd["lox"][k] < 1e14:
-            out.append((np.array([nd["lox"][k], nd["loy"][k], nd["loz"][k]], np.float64),
-                        np.array([nd["hix"][k], nd["hiy"][k], nd["hiz"][k]], np.float64), int(nd["link"][k])))
+    p, sc = nd["p"].astype(np.float64), float(nd["scale"])
+    assert sc > 0 and np.log2(sc) == np.round(np.log2(sc))                # a power of two: the decode is exact
+    for c in range(8):
+        inner = (int(nd["inner_mask"]) >> c) & 1
+        nib = (int(nd["leaf_mask"]) >> (4 * c)) & 15
+        assert not (inner and nib)
+        if not (inner or nib):
+            continue
+        lo = p + sc * np.array([_half(nd["lo_x"][c]), _half(nd["lo_y"][c]), _half(nd["lo_z"][c])])
+        hi = p + sc * np.array([_half(nd["hi_x"][c]), _half(nd["hi_y"][c]), _half(nd["hi_z"][c])])
+        assert nib in (0, 1, 3, 7, 15)
+        out.append((c, lo, hi, "inner" if inner else "leaf", bin(nib).count("1")))
     return out
 
 
@@ -94,24 +107,24 @@ def _check_bvh(nodes, tri_id, roots, arrays):
         if root < 0:
             continue
         seen_leaf = []
-        stack = [(int(root), 1)]
+        big = np.full(3, 1e300)
+        stack = [(int(root), 1, -big, big)]
         while stack:
-            n, d = stack.pop()
+            n, d, alo, ahi = stack.pop()                                # (alo, ahi): intersection of every box above this node
             assert n not in visited                                     # a tree: no node is reachable twice
             visited.add(n)
             max_depth = max(max_depth, d)
             slots = _slots(nodes[n])
-            assert 1 <= len(slots) <= 4
-            for lo, hi, l in slots:
-                if l >= 0:
-                    stack.append((l, d + 1))
-                    sub = _slots(nodes[l])                               # the child's own boxes nest inside the box its parent holds for it
-                    clo = np.min([s[0] for s in sub], axis=0); chi = np.max([s[1] for s in sub], axis=0)
-                    assert (clo >= lo - 1e-3).all() and (chi <= hi + 1e-3).all()
+            assert 1 <= len(slots) <= 8
+            ki = kl = 0
+            for c, lo, hi, kind, cnt in slots:
+                lo, hi = np.maximum(lo, alo), np.minimum(hi, ahi)
+                if kind == "inner":
+                    child = int(nodes[n]["child_base"]) + ki; ki += 1
+                    assert child > n                                    # parents precede their children (upload relies on it)
+                    stack.append((child, d + 1, lo, hi))
                 else:
-                    code = ~l
-                    first, cnt = code >> 3, (code & 7) + 1
-                    assert 1 <= cnt <= 8 and code < 0x20000000
+                    first = int(nodes[n]["leaf_base"]) + kl; kl += cnt
                     for k in range(first, first + cnt):
                         t = tris[tri_id[k]]
                         assert meshes[mi]["t_start"] <= tri_id[k] < meshes[mi]["t_end"]
@@ -119,9 +132,9 @@ def _check_bvh(nodes, tri_id, roots, arrays):
                         e1, e2 = p1 - p0, p2 - p0
                         for (u, v) in ((-e, -e), (1 + 2 * e, -e), (-e, 1 + 2 * e)):     # corners of the fattened triangle
                             q = p0 + u * e1 + v * e2
-                            assert (q >= lo).all() and (q <= hi).all(), "leaf box does not bound the predicate's tolerance band"
+                            assert (q >= lo).all() and (q <= hi).all(), "a box above the leaf does not bound the predicate's tolerance band"
                         seen_leaf.append(k)
-        assert len(seen_leaf) == meshes[mi]["t_end"] - meshes[mi]["t_start"]
+        assert len(seen_leaf) == meshes[mi]["t_end"] - meshes[mi]["t_start"] and len(set(seen_leaf)) == len(seen_leaf)
     return max_depth
 
 
@@ -131,7 +144,8 @@ def test_bvh_builder_invariants_bundled(libptap, golden_scene):
     s = Scene.from_arrays(g["models"], g["meshes"], g["vertices"], g["triangles"])
     nodes, tri_id, roots = _bvh_of(s)
     depth = _check_bvh(nodes, tri_id, roots, g)
-    assert 3 * depth + 12 <= 160                                         # kBvhStack (device_types.h): up to 3 pushes per level
+    assert depth + 12 <= 64                                              # kBvhStack (device_types.h): one 8-byte entry per level
+    assert s.validate_bvh() == (0, depth)                                # the library's own checker agrees
 
 
 def test_bvh_builder_invariants_icosphere(libptap):
