@@ -8,7 +8,7 @@
 //
 // Resolution, iteration count and depth come from Config.h's macros (the reference's only configuration), overridden by the
 // RESOLUTION / ITER / DEPTH keys of a parsed Config.txt, overridden by the environment (PTAP_WIDTH, PTAP_HEIGHT, PTAP_ITER,
-// PTAP_DEPTH, PTAP_ACCEL=grid|bvh|lbvh, PTAP_DEVICE).  The acceleration structure defaults to the reference's own 25^3 grid walk
+// PTAP_DEPTH, PTAP_ACCEL=grid|bvh|lbvh, PTAP_DEVICE, PTAP_RANKS = GPUs of this process that share the iterations).  The acceleration structure defaults to the reference's own 25^3 grid walk
 // (bit-compatible hits); PTAP_ACCEL=bvh selects the BVH (built on the host), lbvh the same built on the GPU.  All errors throw std::runtime_error: there is no CPU fallback.
 #pragma once
 #include <algorithm>
@@ -17,6 +17,7 @@
 #include <iostream>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "Config.h"
 #include "GPUMemoryPool.h"
@@ -42,7 +43,6 @@ public:
         const char* a = std::getenv("PTAP_ACCEL");
         const bool lbvh = a && std::string(a) == "lbvh";          // tree built on the GPU at this call
         const bool bvh = a && std::string(a) == "bvh";
-        check(ptap_create(pick("PTAP_DEVICE", 0, 0), 0, &ctx), "ptap_create");
         PtapSceneView v{};
         v.models = scene.models.data(); v.nmodels = (int32_t)scene.models.size();
         v.meshes = scene.meshes.data(); v.nmeshes = (int32_t)scene.meshes.size();
@@ -52,17 +52,32 @@ public:
         v.voxels = scene.voxels.data(); v.nvoxels = (int32_t)scene.voxels.size();
         v.refs = scene.per_voxel_data_pool.data(); v.nrefs = (int32_t)scene.per_voxel_data_pool.size();
         v.grid_dim[0] = GRID_X; v.grid_dim[1] = GRID_Y; v.grid_dim[2] = GRID_Z;
-        check(ptap_upload_scene(ctx, &v), "ptap_upload_scene");
-        check(ptap_build_accel(ctx, lbvh ? PTAP_ACCEL_BVH_DEVICE : bvh || scene.grids.empty() ? PTAP_ACCEL_BVH : PTAP_ACCEL_GRID_COMPAT), "ptap_build_accel");
-        check(ptap_set_render_params(ctx, width * samples_x, height * samples_y, depth, PTAP_FLAG_FIRST_HIT_CACHE), "ptap_set_render_params");
+        // PTAP_RANKS = N: N GPUs of this process (devices PTAP_DEVICE ..), scene replicated, iterations split, films summed onto rank 0
+        const int ranks = std::max(1, pick("PTAP_RANKS", 0, 1)), dev0 = pick("PTAP_DEVICE", 0, 0);
+        all.assign((size_t)ranks, nullptr);
+        for (int r = 0; r < ranks; ++r) {
+            ctx = nullptr;
+            check(ptap_create(dev0 + r, 0, &ctx), "ptap_create");
+            all[(size_t)r] = ctx;
+            check(ptap_upload_scene(ctx, &v), "ptap_upload_scene");
+            check(ptap_build_accel(ctx, lbvh ? PTAP_ACCEL_BVH_DEVICE : bvh || scene.grids.empty() ? PTAP_ACCEL_BVH : PTAP_ACCEL_GRID_COMPAT), "ptap_build_accel");
+            check(ptap_set_render_params(ctx, width * samples_x, height * samples_y, depth, PTAP_FLAG_FIRST_HIT_CACHE | PTAP_FLAG_ITER_TIMES), "ptap_set_render_params");
+        }
+        ctx = all[0];
     }
 
     void renderLoop()
     {
         need();
         const auto t0 = std::chrono::high_resolution_clock::now();
-        check(ptap_frame_begin(ctx), "ptap_frame_begin");
-        check(ptap_render(ctx, 0, iters), "ptap_render");
+        const int ranks = (int)all.size();
+        std::vector<int> first((size_t)ranks + 1, 0);
+        for (int r = 0; r < ranks; ++r) first[(size_t)r + 1] = first[(size_t)r] + iters / ranks + (r < iters % ranks ? 1 : 0);
+        for (int r = 0; r < ranks; ++r) {                     // asynchronous: every GPU starts before any is waited for
+            check(ptap_frame_begin(all[(size_t)r]), "ptap_frame_begin");
+            if (first[(size_t)r + 1] > first[(size_t)r]) check(ptap_render(all[(size_t)r], first[(size_t)r], first[(size_t)r + 1]), "ptap_render");
+        }
+        for (int r = 1; r < ranks; ++r) check(ptap_reduce_peer(all[0], all[(size_t)r]), "ptap_reduce_peer");
         image.size = width * height;
         host_film.resize((size_t)image.size);
         image.pool = host_film.data();
@@ -71,8 +86,14 @@ public:
         const auto t1 = std::chrono::high_resolution_clock::now();
         PtapStats st{};
         ptap_get_stats(ctx, &st);
+        // Renderer.cpp:641-643: one line per iteration (device time between the completions of consecutive iterations of rank 0's share)
+        std::vector<float> ms((size_t)std::max(first[1], 1));
+        int32_t n = 0;
+        check(ptap_get_iteration_times(ctx, ms.data(), (int32_t)ms.size(), &n), "ptap_get_iteration_times");
+        for (int k = 0; k < n && k < (int)ms.size(); ++k)
+            std::cout << "Iteration " << k + 1 << ": " << (long long)((ms[(size_t)k] - (k ? ms[(size_t)k - 1] : 0.0f)) * 1000.0f) << " microseconds" << std::endl;
         std::cout << "Full run: " << std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count() << " microseconds ("
-                  << iters << " iterations, " << st.rays_traced << " rays traced, " << st.ms_render << " ms on the device)" << std::endl;
+                  << iters << " iterations on " << ranks << " GPU(s), " << st.rays_traced << " rays traced on rank 0, " << st.ms_render << " ms on its device)" << std::endl;
     }
 
     void renderImage()
@@ -83,7 +104,8 @@ public:
 
     void free()
     {
-        if (ctx) ptap_destroy(ctx);
+        for (ptap_ctx* c : all) if (c) ptap_destroy(c);
+        all.clear();
         ctx = nullptr;
         render_data.dev_image_data = nullptr;
     }
@@ -105,7 +127,8 @@ private:
         if (rc != PTAP_OK) throw std::runtime_error(std::string(what) + " failed (" + std::to_string(rc) + "): " + (ctx ? ptap_last_error(ctx) : "no usable CUDA device"));
     }
 
-    ptap_ctx* ctx = nullptr;
+    ptap_ctx* ctx = nullptr;             // rank 0: owns the final film
+    std::vector<ptap_ctx*> all;          // PTAP_RANKS contexts, one per GPU (all[0] == ctx)
     GPUMemoryPool<Pixel> image;
     std::vector<Pixel> host_film;
 };

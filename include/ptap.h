@@ -130,6 +130,8 @@ typedef struct {
     float ms_build;               /* device time of the last PTAP_ACCEL_BVH_DEVICE build */
     int32_t bvh_nodes, bvh_depth; /* 4-wide nodes and levels of that build */
     int32_t lanes;                /* wavefronts in flight of the current render parameters (PTAP_LANES, or 4 / 8 by frame size) */
+    float ms_trace_inflight;      /* PTAP_FLAG_STAMP: time of the last ptap_render call during which at least one closest-hit kernel was resident */
+    float ms_trace_sum;           /* PTAP_FLAG_STAMP: summed residency of its closest-hit launches (lanes overlap: may exceed ms_render) */
 } PtapStats;
 
 typedef struct ptap_scene ptap_scene;   /* host-side scene: replaces class Scene (Scene.h:21-39) */
@@ -178,7 +180,11 @@ enum { PTAP_ACCEL_GRID_COMPAT = 0,  /* the reference's per-mesh uniform grid wal
 
 enum { PTAP_FLAG_FIRST_HIT_CACHE = 1,   /* Renderer.cpp:580,594-613 */
        PTAP_FLAG_PROFILE = 2,           /* per-kernel CUDA-event split in PtapStats (adds event records) */
-       PTAP_FLAG_COUNT = 4 };           /* counting build of the closest-hit kernel: avg_* in PtapStats (slower; not for timing) */
+       PTAP_FLAG_COUNT = 4,             /* counting build of the closest-hit kernel: avg_* in PtapStats (slower; not for timing) */
+       PTAP_FLAG_STAMP = 8,
+       PTAP_FLAG_ITER_TIMES = 16 };     /* one event per iteration: ptap_get_iteration_times (the "Iteration k: ..." lines of Renderer.cpp:641-643) */           /* every closest-hit launch records its first start / last end on the device's nanosecond clock
+                                           (two atomics per CTA): ms_trace_inflight / ms_trace_sum in PtapStats, measured inside the real
+                                           multi-lane schedule */
 
 int ptap_create(int device, size_t arena_bytes /* 0 = sized on demand */, ptap_ctx** out);
 void ptap_destroy(ptap_ctx* ctx);                                   /* Renderer::free (Renderer.cpp:132-148) */
@@ -214,6 +220,25 @@ int ptap_write_bmp(ptap_ctx* ctx, const char* path, int32_t iters);
 int ptap_read_film_resolved(ptap_ctx* ctx, int32_t sx, int32_t sy, float* rgb);
 int ptap_write_bmp_resolved(ptap_ctx* ctx, const char* path, int32_t iters, int32_t sx, int32_t sy);
 int ptap_get_stats(ptap_ctx* ctx, PtapStats* out);
+/* PTAP_FLAG_ITER_TIMES: device time from the start of the last ptap_render call to the completion of each of its iterations, in order
+ * (*n = iterations recorded; at most `cap` values are written).  Renderer::renderLoop prints the differences (Renderer.cpp:641-643). */
+int ptap_get_iteration_times(ptap_ctx* ctx, float* ms_since_start, int32_t cap, int32_t* n);
+
+/* ---- multi-GPU: sample partitioning -------------------------------------------------------------------------------
+ * Every GPU renders its own range of iterations [iter_begin, iter_end) of the same frame into its own film (the reference seeds its RNG
+ * with the iteration number, Renderer.cpp:435, so the union is exactly the one-GPU sample set); the films are then summed.
+ * The reference has no multi-GPU path; these calls replace nothing, they extend Renderer::renderLoop. */
+/* One process, several contexts (main.cpp's process-global Renderer on N devices): film(dst) += film(src) over a peer copy (NVLink),
+ * ordered after the renders enqueued on both contexts.  Calling it for src = rank 1, 2, ... gives a fixed order of float additions:
+ * the reduced film is bit-reproducible. */
+int ptap_reduce_peer(ptap_ctx* dst, ptap_ctx* src);
+/* One process per GPU: NCCL (libnccl.so.2 is loaded at run time; PTAP_NCCL_LIB overrides the name).  Rank 0 makes the 128-byte id, the
+ * host side distributes it by whatever means it has (MPI, torch.distributed, a file), every rank joins, and ptap_reduce issues
+ * ncclReduce(sum) of the film onto `root` in place on the context stream - ordered after the render without a host synchronisation. */
+int ptap_nccl_unique_id(void* id128);
+int ptap_nccl_init(ptap_ctx* ctx, const void* id128, int32_t nranks, int32_t rank);
+int ptap_reduce(ptap_ctx* ctx, int32_t root);
+int ptap_nccl_finalize(ptap_ctx* ctx);
 void* ptap_stream(ptap_ctx* ctx);                                  /* cudaStream_t of the context */
 
 /* ---- parity entry points (what BASELINE.json's contract measures) ------------------------- */

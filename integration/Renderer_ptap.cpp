@@ -13,7 +13,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
+#include <algorithm>
 #include <map>
+#include <string>
 #include <vector>
 
 #include "Renderer.h"
@@ -30,7 +32,8 @@ static_assert(sizeof(Model) == sizeof(PtapModel) && sizeof(Mesh) == sizeof(PtapM
 namespace {
 
 struct Binding {                      // per-Renderer state the reference keeps in managed memory
-    ptap_ctx* ctx = nullptr;
+    ptap_ctx* ctx = nullptr;          // rank 0: owns the final film
+    std::vector<ptap_ctx*> all;       // PTAP_RANKS contexts, one per GPU (all[0] == ctx)
     GPUMemoryPool<Pixel> image;       // host view handed out through render_data.dev_image_data
     std::vector<Pixel> film;
 };
@@ -47,10 +50,11 @@ int envInt(const char* name, int dflt) { const char* v = std::getenv(name); retu
 
 }  // namespace
 
+// PTAP_RANKS=N renders on N GPUs of this process (devices PTAP_DEVICE .. PTAP_DEVICE + N - 1): the scene is replicated, every GPU takes
+// a contiguous range of the ITER iterations, and the films are summed onto rank 0 in rank order over peer copies (ptap_reduce_peer).
 void Renderer::allocateOnGPU(Scene& scene)
 {
     Binding& b = g_bindings[this];
-    check(b, ptap_create(envInt("PTAP_DEVICE", 0), 0, &b.ctx), "ptap_create");
     PtapSceneView v{};
     v.models = reinterpret_cast<const PtapModel*>(scene.models.data()); v.nmodels = (int32_t)scene.models.size();
     v.meshes = reinterpret_cast<const PtapMesh*>(scene.meshes.data()); v.nmeshes = (int32_t)scene.meshes.size();
@@ -60,28 +64,48 @@ void Renderer::allocateOnGPU(Scene& scene)
     v.voxels = reinterpret_cast<const PtapVoxel*>(scene.voxels.data()); v.nvoxels = (int32_t)scene.voxels.size();
     v.refs = scene.per_voxel_data_pool.data(); v.nrefs = (int32_t)scene.per_voxel_data_pool.size();
     v.grid_dim[0] = GRID_X; v.grid_dim[1] = GRID_Y; v.grid_dim[2] = GRID_Z;
-    check(b, ptap_upload_scene(b.ctx, &v), "ptap_upload_scene");
     const char* accel = std::getenv("PTAP_ACCEL");            // default: the reference's own grid walk, bit-compatible hits
     const int kind = !accel ? PTAP_ACCEL_GRID_COMPAT : std::string(accel) == "bvh" ? PTAP_ACCEL_BVH : std::string(accel) == "lbvh" ? PTAP_ACCEL_BVH_DEVICE : PTAP_ACCEL_GRID_COMPAT;
-    check(b, ptap_build_accel(b.ctx, kind), "ptap_build_accel");
-    // nrays = RESOLUTION * SAMPLES camera rays on one lattice (Renderer.cpp:96, 527-542); SAMPLESX = SAMPLESY = 1 in Config.h:14-15
-    check(b, ptap_set_render_params(b.ctx, RESOLUTION_X * SAMPLESX, RESOLUTION_Y * SAMPLESY, MAX_DEPTH, PTAP_FLAG_FIRST_HIT_CACHE), "ptap_set_render_params");
+    const int ranks = std::max(1, envInt("PTAP_RANKS", 1)), dev0 = envInt("PTAP_DEVICE", 0);
+    b.all.assign(ranks, nullptr);
+    for (int r = 0; r < ranks; ++r) {
+        b.ctx = nullptr;
+        check(b, ptap_create(dev0 + r, 0, &b.ctx), "ptap_create");
+        b.all[r] = b.ctx;
+        check(b, ptap_upload_scene(b.ctx, &v), "ptap_upload_scene");
+        check(b, ptap_build_accel(b.ctx, kind), "ptap_build_accel");
+        // nrays = RESOLUTION * SAMPLES camera rays on one lattice (Renderer.cpp:96, 527-542); SAMPLESX = SAMPLESY = 1 in Config.h:14-15
+        check(b, ptap_set_render_params(b.ctx, RESOLUTION_X * SAMPLESX, RESOLUTION_Y * SAMPLESY, MAX_DEPTH, PTAP_FLAG_FIRST_HIT_CACHE | PTAP_FLAG_ITER_TIMES), "ptap_set_render_params");
+    }
+    b.ctx = b.all[0];
     render_data = RenderData{};
 }
 
 void Renderer::renderLoop()
 {
     Binding& b = g_bindings[this];
-    const int iters = envInt("PTAP_ITER", ITER);
+    const int iters = envInt("PTAP_ITER", ITER), ranks = (int)b.all.size();
     const auto t0 = std::chrono::high_resolution_clock::now();
-    check(b, ptap_frame_begin(b.ctx), "ptap_frame_begin");
-    check(b, ptap_render(b.ctx, 0, iters), "ptap_render");
+    std::vector<int> first(ranks + 1, 0);
+    for (int r = 0; r < ranks; ++r) first[r + 1] = first[r] + iters / ranks + (r < iters % ranks ? 1 : 0);
+    for (int r = 0; r < ranks; ++r) {                         // asynchronous: every GPU starts before any is waited for
+        check(b, ptap_frame_begin(b.all[r]), "ptap_frame_begin");
+        if (first[r + 1] > first[r]) check(b, ptap_render(b.all[r], first[r], first[r + 1]), "ptap_render");
+    }
+    for (int r = 1; r < ranks; ++r) check(b, ptap_reduce_peer(b.all[0], b.all[r]), "ptap_reduce_peer");
     b.film.resize((size_t)RESOLUTION_X * SAMPLESX * RESOLUTION_Y * SAMPLESY);
     check(b, ptap_read_film(b.ctx, reinterpret_cast<float*>(b.film.data())), "ptap_read_film");
     b.image.size = (int)b.film.size();
     b.image.pool = b.film.data();
     render_data.dev_image_data = &b.image;                    // Renderer.cpp:49 reads the image through this pointer
     const auto t1 = std::chrono::high_resolution_clock::now();
+    // Renderer.cpp:641-643 prints one line per iteration.  Iterations are enqueued without host round trips and overlap on the device, so
+    // the figure is the device time between the completions of consecutive iterations (rank 0's share when several GPUs render).
+    std::vector<float> ms((size_t)std::max(first[1], 1));
+    int32_t n = 0;
+    check(b, ptap_get_iteration_times(b.ctx, ms.data(), (int32_t)ms.size(), &n), "ptap_get_iteration_times");
+    for (int k = 0; k < n && k < (int)ms.size(); ++k)
+        std::cout << "Iteration " << k + 1 << ": " << (long long)((ms[k] - (k ? ms[k - 1] : 0.0f)) * 1000.0f) << " microseconds" << std::endl;
     std::cout << "Full run: " << std::chrono::duration_cast<std::chrono::microseconds>(t1 - t0).count() << " microseconds" << std::endl;   // Renderer.cpp:645-647
 }
 
@@ -96,7 +120,7 @@ void Renderer::free()
 {
     auto it = g_bindings.find(this);
     if (it == g_bindings.end()) return;
-    if (it->second.ctx) ptap_destroy(it->second.ctx);
+    for (ptap_ctx* c : it->second.all) if (c) ptap_destroy(c);
     g_bindings.erase(it);
     render_data = RenderData{};
 }

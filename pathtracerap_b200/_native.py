@@ -35,7 +35,7 @@ assert GRID.itemsize == 28 and VOXEL.itemsize == 12 and HIT.itemsize == 40 and P
 FLOAT_MAX = np.float32(9999999.0)
 DIFFUSE, SPECULAR, REFLECTIVE, REFRACTIVE, EMISSIVE, COAT, METAL = range(7)
 ACCEL_GRID_COMPAT, ACCEL_BVH, ACCEL_BVH_DEVICE = 0, 1, 2
-FLAG_FIRST_HIT_CACHE, FLAG_PROFILE, FLAG_COUNT = 1, 2, 4
+FLAG_FIRST_HIT_CACHE, FLAG_PROFILE, FLAG_COUNT, FLAG_STAMP, FLAG_ITER_TIMES = 1, 2, 4, 8, 16
 
 
 class SceneView(C.Structure):
@@ -53,7 +53,8 @@ class Stats(C.Structure):
                 ("active_per_round", C.c_int64 * 16), ("ms_render", C.c_float), ("ms_trace", C.c_float),
                 ("ms_shade", C.c_float), ("ms_generate", C.c_float), ("avg_nodes", C.c_float), ("avg_tris", C.c_float),
                 ("avg_cells", C.c_float), ("avg_refs", C.c_float), ("trace_launches", C.c_int64), ("scene_bytes", C.c_int64),
-                ("ms_build", C.c_float), ("bvh_nodes", C.c_int32), ("bvh_depth", C.c_int32), ("lanes", C.c_int32)]
+                ("ms_build", C.c_float), ("bvh_nodes", C.c_int32), ("bvh_depth", C.c_int32), ("lanes", C.c_int32),
+                ("ms_trace_inflight", C.c_float), ("ms_trace_sum", C.c_float)]
 
 
 EXPORTS = [
@@ -63,7 +64,8 @@ EXPORTS = [
     "ptap_scene_config_params",
     "ptap_create", "ptap_destroy", "ptap_last_error", "ptap_upload_scene", "ptap_build_accel", "ptap_set_render_params",
     "ptap_render", "ptap_timer_start", "ptap_timer_stop", "ptap_frame_begin", "ptap_film_reset", "ptap_sync", "ptap_read_film", "ptap_film_device_ptr", "ptap_film_add",
-    "ptap_write_bmp", "ptap_read_film_resolved", "ptap_write_bmp_resolved", "ptap_get_stats", "ptap_stream", "ptap_trace", "ptap_trace_count", "ptap_shade", "ptap_bench_trace", "ptap_render_probe",
+    "ptap_write_bmp", "ptap_read_film_resolved", "ptap_write_bmp_resolved", "ptap_get_stats", "ptap_stream", "ptap_trace", "ptap_trace_count", "ptap_shade", "ptap_bench_trace", "ptap_render_probe", "ptap_get_iteration_times",
+    "ptap_reduce_peer", "ptap_nccl_unique_id", "ptap_nccl_init", "ptap_reduce", "ptap_nccl_finalize",
 ]
 
 _lib = None
@@ -124,6 +126,12 @@ def lib():
         L.ptap_shade.argtypes = [vp, vp, ci, ci, ci, vp, vp, C.POINTER(ci)]
         L.ptap_bench_trace.argtypes = [vp, vp, ci, ci, C.POINTER(C.c_float)]
         L.ptap_render_probe.argtypes = [vp, ci, ci, vp, vp, vp, ci, C.POINTER(ci)]
+        L.ptap_get_iteration_times.argtypes = [vp, vp, ci, C.POINTER(ci)]
+        L.ptap_reduce_peer.argtypes = [vp, vp]
+        L.ptap_nccl_unique_id.argtypes = [vp]
+        L.ptap_nccl_init.argtypes = [vp, vp, ci, ci]
+        L.ptap_reduce.argtypes = [vp, ci]
+        L.ptap_nccl_finalize.argtypes = [vp]
         _lib = L
     return _lib
 

@@ -6,6 +6,8 @@
 // arena per lifetime class (scene, frame), bump-allocated at 256 B alignment, and passes raw pointers by value.
 // A whole iteration is enqueued without a host round trip: the active-ray count of every bounce lives in device
 // memory (FrameState) and all kernels are persistent grids sized from the SM count.
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
@@ -84,6 +86,13 @@ struct ptap_ctx {
     int grid_trace = 0, grid_shade = 0, grid_gen = 0;
     int trace_ctas = 0;              // PTAP_TRACE_CTAS: CTAs per SM of the closest-hit kernels (0 = occupancy query)
     PtapStats stats{};
+    std::vector<cudaEvent_t> iter_events;      // completion of every iteration of the last render call (PTAP_FLAG_ITER_TIMES)
+    int iter_events_used = 0;
+    std::vector<float> iter_ms;
+    void* nccl_comm = nullptr;                 // ptap_nccl_init
+    cudaEvent_t e_peer = nullptr;
+    unsigned long long* d_stamps = nullptr;   // PTAP_FLAG_STAMP: (start, end) %globaltimer words of the closest-hit launches of the last render call
+    int stamps_used = 0;
     bool render_pending = false;
     std::string err;
 };
@@ -106,12 +115,14 @@ int fail(ptap_ctx* c, int code, const char* fmt, ...)
 
 float4 row(const float* m, int r) { return make_float4(m[0 + r], m[4 + r], m[8 + r], m[12 + r]); }
 
+constexpr int kMaxStamps = 8192;     // closest-hit launches of one render call that can be stamped (PTAP_FLAG_STAMP)
+
 void launchTrace(ptap_ctx* c, FrameState* st, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, int round, int n_fixed,
-                 bool count_totals = false, cudaStream_t stream = nullptr)
+                 bool count_totals = false, cudaStream_t stream = nullptr, unsigned long long* stamp = nullptr)
 {
     if (!stream) stream = c->stream;
-    if (c->accel != PTAP_ACCEL_GRID_COMPAT) launchTraceBvh(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, stream);
-    else launchTraceGrid(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, stream);
+    if (c->accel != PTAP_ACCEL_GRID_COMPAT) launchTraceBvh(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, stream, stamp);
+    else launchTraceGrid(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, stream, stamp);
 }
 
 void profMark(ptap_ctx* c, int kind)
@@ -174,6 +185,31 @@ int collect(ptap_ctx* ctx)
         else ctx->stats.ms_shade += ms;
     }
     ctx->prof_used = 0;
+    ctx->iter_ms.assign(ctx->iter_events_used, 0.f);
+    for (int k = 0; k < ctx->iter_events_used; ++k) cudaEventElapsedTime(&ctx->iter_ms[k], ctx->ev0, ctx->iter_events[k]);
+    ctx->iter_events_used = 0;
+    ctx->stats.ms_trace_inflight = ctx->stats.ms_trace_sum = 0.f;
+    if (ctx->stamps_used > 0 && ctx->d_stamps) {
+        // closest-hit launches of the call as [start, end] intervals on the device's nanosecond clock: their summed lengths, and the length
+        // of their union (time during which at least one closest-hit kernel was resident - lanes overlap, so the union is what a rate may
+        // be divided by)
+        std::vector<unsigned long long> h((size_t)ctx->stamps_used * 2);
+        CK(cudaMemcpy(h.data(), ctx->d_stamps, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        std::vector<std::pair<unsigned long long, unsigned long long>> iv;
+        double sum = 0.0;
+        for (int k = 0; k < ctx->stamps_used; ++k)
+            if (h[2 * k + 1] >= h[2 * k]) { iv.push_back({h[2 * k], h[2 * k + 1]}); sum += (double)(h[2 * k + 1] - h[2 * k]); }
+        std::sort(iv.begin(), iv.end());
+        double uni = 0.0; unsigned long long cur_b = 0, cur_e = 0; bool open = false;
+        for (auto& x : iv) {
+            if (!open) { cur_b = x.first; cur_e = x.second; open = true; }
+            else if (x.first <= cur_e) cur_e = std::max(cur_e, x.second);
+            else { uni += (double)(cur_e - cur_b); cur_b = x.first; cur_e = x.second; }
+        }
+        if (open) uni += (double)(cur_e - cur_b);
+        ctx->stats.ms_trace_inflight = (float)(uni * 1e-6); ctx->stats.ms_trace_sum = (float)(sum * 1e-6);
+        ctx->stamps_used = 0;
+    }
     return PTAP_OK;
 }
 
@@ -471,6 +507,9 @@ void ptap_destroy(ptap_ctx* ctx)
     for (int l = 0; l < kMaxLanes; ++l) { if (ctx->e_join[l]) cudaEventDestroy(ctx->e_join[l]); if (ctx->e_gather[l]) cudaEventDestroy(ctx->e_gather[l]); }
     ctx->scene_arena.release(); ctx->frame_arena.release(); ctx->scratch.release();
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : ctx->iter_events) cudaEventDestroy(e);
+    if (ctx->e_peer) cudaEventDestroy(ctx->e_peer);
+    if (ctx->nccl_comm) ptap_nccl_finalize(ctx);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->tm0) { cudaEventDestroy(ctx->tm0); cudaEventDestroy(ctx->tm1); }
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -647,7 +686,7 @@ int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, u
     const int ntiles = (N + kShadeTile - 1) / kShadeTile, nscan = (N + kScanSlots - 1) / kScanSlots;
     size_t need = Arena::need(N, sizeof(float4)) * 8 + Arena::need(N, sizeof(float2)) + Arena::need((size_t)N * 3, sizeof(float)) +
                   Arena::need((size_t)nscan * kMaxDepth, sizeof(unsigned long long)) + Arena::need(ntiles, sizeof(int)) * 2 +
-                  Arena::need((size_t)nscan * kScanSlots, 1) + Arena::need(1, sizeof(FrameState)) + 4096;
+                  Arena::need((size_t)nscan * kScanSlots, 1) + Arena::need(1, sizeof(FrameState)) + Arena::need(2 * kMaxStamps, sizeof(unsigned long long)) + 4096;
     if (ctx->lanes > 1)            // every further lane: its own queues, hits, scan state; one contribution buffer per lane (lane 0 too)
         need += (size_t)(ctx->lanes - 1) * (Arena::need(N, sizeof(float4)) * 7 + Arena::need((size_t)nscan * kMaxDepth, sizeof(unsigned long long)) +
                                             Arena::need(ntiles, sizeof(int)) * 2 + Arena::need((size_t)nscan * kScanSlots, 1) + Arena::need(1, sizeof(FrameState)) + 4096) +
@@ -663,7 +702,8 @@ int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, u
     wv.tile_ballot = A.alloc<unsigned>(ntiles);
     wv.perm = A.alloc<unsigned char>((size_t)nscan * kScanSlots);
     wv.st = A.alloc<FrameState>(1);
-    if (!wv.st || !wv.tile_status || !wv.tile_offset || !wv.tile_ballot || !wv.perm || !wv.film) return fail(ctx, PTAP_E_NOMEM, "frame arena exhausted");
+    ctx->d_stamps = A.alloc<unsigned long long>(2 * kMaxStamps); ctx->stamps_used = 0;
+    if (!ctx->d_stamps || !wv.st || !wv.tile_status || !wv.tile_offset || !wv.tile_ballot || !wv.perm || !wv.film) return fail(ctx, PTAP_E_NOMEM, "frame arena exhausted");
     wv.W = W; wv.H = H; wv.N = N; wv.depth = depth; wv.ntiles = ntiles; wv.nscan = nscan;
     wv.step_x = (float)(20.0 / (double)W);                       // Renderer.cpp:538-539 (SAMPLESX = SAMPLESY = 1)
     wv.step_y = (float)(16.0 / (double)H);
@@ -707,6 +747,13 @@ int ptap_render(ptap_ctx* ctx, int32_t iter_begin, int32_t iter_end)
     lane[0] = ctx->wv;
     for (int l = 1; l < L; ++l) lane[l] = ctx->wvx[l];
     for (int l = 0; l < L; ++l) { lane[l].iter_stride = L; if (L == 1) lane[l].contrib = nullptr; }
+    const bool stamping = (ctx->flags & PTAP_FLAG_STAMP) != 0;
+    if (stamping) {
+        // start words to all-ones (atomicMin), end words to zero (atomicMax): one interleaved pattern written by two strided memsets
+        CK(cudaMemset2DAsync(ctx->d_stamps, 16, 0xff, 8, kMaxStamps, ctx->stream));
+        CK(cudaMemset2DAsync(ctx->d_stamps + 1, 16, 0x00, 8, kMaxStamps, ctx->stream));
+    }
+    ctx->stamps_used = 0; ctx->iter_events_used = 0;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
     if (L > 1) CK(cudaEventRecord(ctx->e_fork, ctx->stream));
     for (int l = 0; l < L; ++l) {
@@ -727,7 +774,8 @@ int ptap_render(ptap_ctx* ctx, int32_t iter_begin, int32_t iter_end)
             float4* hitbuf = (round == 0 && cache) ? wv.hit_cache : wv.hit;
             if (!(round == 0 && cache && ctx->cache_valid)) {                    // Renderer.cpp:594-620
                 profMark(ctx, 1);
-                launchTrace(ctx, wv.st, wv.O[in], wv.D[in], hitbuf, nullptr, nullptr, round, -1, (ctx->flags & PTAP_FLAG_COUNT) != 0, S); ++launches; ++trace_launches;
+                unsigned long long* stamp = stamping && ctx->stamps_used < kMaxStamps ? ctx->d_stamps + 2 * (size_t)ctx->stamps_used++ : nullptr;
+                launchTrace(ctx, wv.st, wv.O[in], wv.D[in], hitbuf, nullptr, nullptr, round, -1, (ctx->flags & PTAP_FLAG_COUNT) != 0, S, stamp); ++launches; ++trace_launches;
                 if (L > 1 && round == 0 && cache) { CK(cudaEventRecord(ctx->e_cache, S)); cache_lane = l; cache_waited = 1u << l; }
             } else if (L > 1 && cache_lane >= 0 && !(cache_waited >> l & 1u)) {
                 CK(cudaStreamWaitEvent(S, ctx->e_cache, 0)); cache_waited |= 1u << l;
@@ -743,6 +791,10 @@ int ptap_render(ptap_ctx* ctx, int32_t iter_begin, int32_t iter_end)
             CK(cudaEventRecord(ctx->e_gather[l], S));
         }
         if (cache) ctx->cache_valid = true;
+        if (ctx->flags & PTAP_FLAG_ITER_TIMES) {
+            if (ctx->iter_events_used == (int)ctx->iter_events.size()) { cudaEvent_t e; CK(cudaEventCreate(&e)); ctx->iter_events.push_back(e); }
+            CK(cudaEventRecord(ctx->iter_events[ctx->iter_events_used++], S));
+        }
     }
     for (int l = 1; l < L; ++l) {
         CK(cudaEventRecord(ctx->e_join[l], ctx->streams[l]));
@@ -1116,6 +1168,130 @@ int ptap_render_probe(ptap_ctx* ctx, int32_t iter, int32_t round, float* rays_od
         }
         if (pixels) pixels[i] = __builtin_bit_cast(int, hO[i].w);
     }
+    return PTAP_OK;
+}
+
+int ptap_get_iteration_times(ptap_ctx* ctx, float* ms_since_start, int32_t cap, int32_t* n)
+{
+    if (!ctx || !n) return PTAP_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    int rc = collect(ctx); if (rc) return rc;
+    *n = (int32_t)ctx->iter_ms.size();
+    for (int k = 0; k < *n && k < cap && ms_since_start; ++k) ms_since_start[k] = ctx->iter_ms[k];
+    return PTAP_OK;
+}
+
+// ---- multi-GPU: combining the per-GPU films ------------------------------------------------------------------------
+
+// film(dst) += film(src), both contexts in this process (any two devices, or the same one).  The copy crosses NVLink as a peer copy
+// ordered after everything enqueued on src so far; the add runs on dst's stream.  Calling this for src = rank 1, 2, ... in turn gives a
+// FIXED order of float additions, so the reduced film is bit-reproducible (a tree or ring reduction is not).
+int ptap_reduce_peer(ptap_ctx* dst, ptap_ctx* src)
+{
+    ptap_ctx* ctx = dst;
+    if (!dst || !src || dst == src || !dst->have_frame || !src->have_frame) return fail(ctx, PTAP_E_STATE, "reduce_peer: two contexts with render parameters required");
+    if (dst->wv.N != src->wv.N || dst->wv.W != src->wv.W) return fail(ctx, PTAP_E_INVALID, "reduce_peer: the films differ in size");
+    const size_t n = (size_t)dst->wv.N * 3;
+    CK(cudaSetDevice(src->device));
+    if (!src->e_peer) CK(cudaEventCreateWithFlags(&src->e_peer, cudaEventDisableTiming));
+    CK(cudaEventRecord(src->e_peer, src->stream));
+    CK(cudaSetDevice(dst->device));
+    if (!dst->e_peer) CK(cudaEventCreateWithFlags(&dst->e_peer, cudaEventDisableTiming));
+    if (dst->device != src->device) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, dst->device, src->device) == cudaSuccess && can) {
+            const cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctx, (int)e, "reduce_peer: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    }
+    if (Arena::need(n, sizeof(float)) > dst->scratch.cap) CK(dst->scratch.reserve(Arena::need(n, sizeof(float)))); else dst->scratch.used = 0;
+    float* tmp = dst->scratch.alloc<float>(n);
+    CK(cudaStreamWaitEvent(dst->stream, src->e_peer, 0));
+    if (dst->device == src->device) CK(cudaMemcpyAsync(tmp, src->wv.film, n * sizeof(float), cudaMemcpyDeviceToDevice, dst->stream));
+    else CK(cudaMemcpyPeerAsync(tmp, dst->device, src->wv.film, src->device, n * sizeof(float), dst->stream));
+    CK(cudaEventRecord(dst->e_peer, dst->stream));
+    launchFilmAdd(dst->wv.film, tmp, n, dst->stream);
+    CK(cudaSetDevice(src->device));
+    CK(cudaStreamWaitEvent(src->stream, dst->e_peer, 0));       // src may not reuse its film before the copy has read it
+    CK(cudaSetDevice(dst->device));
+    return PTAP_OK;
+}
+
+// One process per GPU: NCCL, resolved at run time (dlopen) so that libptap.so itself has no link-time dependency on it.
+namespace {
+
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+
+NcclApi& nccl()
+{
+    static NcclApi a;
+    if (a.lib || a.ok) return a;
+    const char* names[] = {getenv("PTAP_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) { if (nm && *nm && (a.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break; }
+    if (!a.lib) return a;
+    a.GetUniqueId = reinterpret_cast<int (*)(NcclId*)>(dlsym(a.lib, "ncclGetUniqueId"));
+    a.CommInitRank = reinterpret_cast<int (*)(void**, int, NcclId, int)>(dlsym(a.lib, "ncclCommInitRank"));
+    a.Reduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, int, void*, cudaStream_t)>(dlsym(a.lib, "ncclReduce"));
+    a.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(a.lib, "ncclCommDestroy"));
+    a.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(a.lib, "ncclGetErrorString"));
+    a.ok = a.GetUniqueId && a.CommInitRank && a.Reduce && a.CommDestroy;
+    return a;
+}
+
+}  // namespace
+
+int ptap_nccl_unique_id(void* id128)
+{
+    if (!id128) return PTAP_E_INVALID;
+    NcclApi& a = nccl();
+    if (!a.ok) return PTAP_E_STATE;
+    NcclId id; memset(&id, 0, sizeof id);
+    const int rc = a.GetUniqueId(&id);
+    memcpy(id128, &id, sizeof id);
+    return rc == 0 ? PTAP_OK : PTAP_E_STATE;
+}
+
+int ptap_nccl_init(ptap_ctx* ctx, const void* id128, int32_t nranks, int32_t rank)
+{
+    if (!ctx || !id128 || nranks <= 0 || rank < 0 || rank >= nranks) return fail(ctx, PTAP_E_INVALID, "nccl_init: bad arguments");
+    NcclApi& a = nccl();
+    if (!a.ok) return fail(ctx, PTAP_E_STATE, "nccl_init: libnccl.so.2 could not be loaded (%s); set PTAP_NCCL_LIB", dlerror() ? dlerror() : "symbols missing");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->nccl_comm) ptap_nccl_finalize(ctx);
+    NcclId id; memcpy(&id, id128, sizeof id);
+    const int rc = a.CommInitRank(&ctx->nccl_comm, nranks, id, rank);
+    if (rc != 0) { ctx->nccl_comm = nullptr; return fail(ctx, PTAP_E_STATE, "ncclCommInitRank: %s", a.GetErrorString ? a.GetErrorString(rc) : "error"); }
+    return PTAP_OK;
+}
+
+int ptap_nccl_finalize(ptap_ctx* ctx)
+{
+    if (!ctx || !ctx->nccl_comm) return PTAP_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    nccl().CommDestroy(ctx->nccl_comm);
+    ctx->nccl_comm = nullptr;
+    return PTAP_OK;
+}
+
+// ncclReduce(sum) of the film onto `root`, in place, ordered on the context stream after the render (no host synchronisation).
+int ptap_reduce(ptap_ctx* ctx, int32_t root)
+{
+    if (!ctx || !ctx->have_frame) return fail(ctx, PTAP_E_STATE, "reduce: no render parameters");
+    if (!ctx->nccl_comm) return fail(ctx, PTAP_E_STATE, "reduce: ptap_nccl_init has not been called");
+    CK(cudaSetDevice(ctx->device));
+    const int rc = nccl().Reduce(ctx->wv.film, ctx->wv.film, (size_t)ctx->wv.N * 3, /* ncclFloat32 */ 7, /* ncclSum */ 0, root, ctx->nccl_comm, ctx->stream);
+    if (rc != 0) return fail(ctx, PTAP_E_STATE, "ncclReduce: %s", nccl().GetErrorString ? nccl().GetErrorString(rc) : "error");
     return PTAP_OK;
 }
 

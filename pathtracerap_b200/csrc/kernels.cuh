@@ -20,6 +20,13 @@ constexpr int kVoteGrid = 5;         // same for k_trace_grid (one threshold for
 // it (Renderer.cpp:381-382 ray set-up, :388-391 conversion).  k_trace_bvh only carries an approximate distance while traversing
 // (it needs the exact one just to break near-ties); the consumers of a hit record (k_shade, k_resolve_hits) evaluate this function,
 // at full SIMT efficiency, instead of the traversal doing it with a handful of active lanes.
+__device__ __forceinline__ unsigned long long globalTimerNs()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __device__ __forceinline__ float exactHitDistance(const SceneDev& sc, V3 bo, V3 bd, int im, float t)
 {
     const InstanceTrace* __restrict__ inst = &sc.inst[im];
@@ -33,11 +40,13 @@ __device__ __forceinline__ float exactHitDistance(const SceneDev& sc, V3 bo, V3 
 }
 
 // closest hit, grid-compat (trace_grid.cu) and BVH (trace_bvh.cu).  n_fixed < 0: read the count from st->n_active[round].
+// stamp (may be null): two 64-bit words that receive the earliest start and the latest end of the launch in %globaltimer nanoseconds
+// (atomicMin / atomicMax by every CTA), so that bench.py can time the closest-hit kernel inside the real multi-lane schedule.
 void launchTraceGrid(const SceneDev& sc, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, bool count_totals,
-                     FrameState* st, int round, int n_fixed, int grid, cudaStream_t stream);
+                     FrameState* st, int round, int n_fixed, int grid, cudaStream_t stream, unsigned long long* stamp = nullptr);
 int traceGridOccupancy();
 void launchTraceBvh(const SceneDev& sc, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, bool count_totals,
-                    FrameState* st, int round, int n_fixed, int grid, cudaStream_t stream);
+                    FrameState* st, int round, int n_fixed, int grid, cudaStream_t stream, unsigned long long* stamp = nullptr);
 int traceBvhOccupancy();
 
 // bvh_device.cu

@@ -126,10 +126,11 @@ __device__ __forceinline__ unsigned permuteByOctant(unsigned h, unsigned oct)
 template <bool UV, bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock)
 k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict__ D, float4* __restrict__ hit,
-            float2* __restrict__ uv, int4* __restrict__ counts, FrameState* st, int round, int n_fixed)
+            float2* __restrict__ uv, int4* __restrict__ counts, FrameState* st, int round, int n_fixed, unsigned long long* __restrict__ stamp)
 {
     const int n = n_fixed >= 0 ? n_fixed : st->n_active[round];
     if (blockIdx.x == 0 && threadIdx.x == 0 && n_fixed < 0) st->rays_traced += (unsigned long long)n;
+    if (stamp && threadIdx.x == 0) atomicMin(stamp, globalTimerNs());
     unsigned int* cursor = &st->fetch[round];
     const int lane = threadIdx.x & 31;
     unsigned long long tot_x = 0, tot_z = 0;
@@ -328,6 +329,7 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
             w_next += min(__popc(m_done), avail);
         }
     }
+    if (stamp && (threadIdx.x & 31) == 0) atomicMax(stamp + 1, globalTimerNs());
     if (COUNT) {        // counting build: per-warp totals into the frame state (never used for timing)
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) { tot_x += __shfl_xor_sync(kFull, tot_x, d); tot_z += __shfl_xor_sync(kFull, tot_z, d); }
@@ -336,11 +338,11 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
 }
 
 void launchTraceBvh(const SceneDev& sc, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, bool count_totals,
-                     FrameState* st, int round, int n_fixed, int grid, cudaStream_t stream)
+                     FrameState* st, int round, int n_fixed, int grid, cudaStream_t stream, unsigned long long* stamp)
 {
-    if (counts || count_totals) k_trace_bvh<true, true><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed);
-    else if (uv) k_trace_bvh<true, false><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed);
-    else k_trace_bvh<false, false><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed);
+    if (counts || count_totals) k_trace_bvh<true, true><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, stamp);
+    else if (uv) k_trace_bvh<true, false><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, stamp);
+    else k_trace_bvh<false, false><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, stamp);
 }
 
 int traceBvhOccupancy()

@@ -67,11 +67,12 @@ enum : unsigned { F_INTERSECT = 1u, F_ANY = 2u, F_POST = 4u, F_MODEL_HIT = 8u };
 template <bool UV, bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock)
 k_trace_grid(SceneDev sc, const float4* __restrict__ O, const float4* __restrict__ D, float4* __restrict__ hit,
-             float2* __restrict__ uv, int4* __restrict__ counts, FrameState* st, int round, int n_fixed)
+             float2* __restrict__ uv, int4* __restrict__ counts, FrameState* st, int round, int n_fixed, unsigned long long* __restrict__ stamp)
 {
     constexpr unsigned kFull = 0xffffffffu;
     const int n = n_fixed >= 0 ? n_fixed : st->n_active[round];
     if (blockIdx.x == 0 && threadIdx.x == 0 && n_fixed < 0) st->rays_traced += (unsigned long long)n;
+    if (stamp && threadIdx.x == 0) atomicMin(stamp, globalTimerNs());
     unsigned int* cursor = &st->fetch[round];
     const int lane = threadIdx.x & 31;
     const int GX = sc.gx, GY = sc.gy, GZ = sc.gz;
@@ -239,6 +240,7 @@ k_trace_grid(SceneDev sc, const float4* __restrict__ O, const float4* __restrict
             w_next += min(__popc(m_done), avail);
         }
     }
+    if (stamp && (threadIdx.x & 31) == 0) atomicMax(stamp + 1, globalTimerNs());
     if (COUNT) {        // counting build: per-warp totals into the frame state (never used for timing)
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
@@ -249,11 +251,11 @@ k_trace_grid(SceneDev sc, const float4* __restrict__ O, const float4* __restrict
 }
 
 void launchTraceGrid(const SceneDev& sc, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, bool count_totals,
-                     FrameState* st, int round, int n_fixed, int grid, cudaStream_t stream)
+                     FrameState* st, int round, int n_fixed, int grid, cudaStream_t stream, unsigned long long* stamp)
 {
-    if (counts || count_totals) k_trace_grid<true, true><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed);
-    else if (uv) k_trace_grid<true, false><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed);
-    else k_trace_grid<false, false><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed);
+    if (counts || count_totals) k_trace_grid<true, true><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, stamp);
+    else if (uv) k_trace_grid<true, false><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, stamp);
+    else k_trace_grid<false, false><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, stamp);
 }
 
 int traceGridOccupancy()

@@ -61,9 +61,9 @@ class Renderer:
         self.accel = accel
         self._check(N.lib().ptap_build_accel(self.h, accel), "build_accel")
 
-    def set_params(self, width, height, depth, first_hit_cache=True, profile=False, count=False):
+    def set_params(self, width, height, depth, first_hit_cache=True, profile=False, count=False, stamp=False):
         self.W, self.H, self.depth = width, height, depth
-        self.flags = (N.FLAG_FIRST_HIT_CACHE if first_hit_cache else 0) | (N.FLAG_PROFILE if profile else 0) | (N.FLAG_COUNT if count else 0)
+        self.flags = (N.FLAG_FIRST_HIT_CACHE if first_hit_cache else 0) | (N.FLAG_PROFILE if profile else 0) | (N.FLAG_COUNT if count else 0) | (N.FLAG_STAMP if stamp else 0)
         self._check(N.lib().ptap_set_render_params(self.h, width, height, depth, self.flags), "set_render_params")
         self._iters_done = 0
 
