@@ -296,7 +296,7 @@ int finishBvh(ptap_ctx* ctx, const BvhNode* roots, const int* mesh_root, int nno
             }
         const BvhNode& r = roots[m.mesh_index];
         float mlo[3] = {3e38f, 3e38f, 3e38f}, mhi[3] = {-3e38f, -3e38f, -3e38f};
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < kBvhWidth; ++k) {
             if (!((r.inner_mask >> k & 1u) || (r.leaf_mask >> (4 * k) & 15u))) continue;      // unused slot
             double lo[3], hi[3];
             decodeChild(r, k, lo, hi);
@@ -336,7 +336,7 @@ int finishBvh(ptap_ctx* ctx, const BvhNode* roots, const int* mesh_root, int nno
             t2.push_back(nd);
         }
         auto emit = [](int l, std::vector<int>& dst) { dst.push_back(~l & 0x1fffffff); return 1; };      // one instance per TLAS leaf
-        tlas_root = collapseBvh8(t2.data(), link < 0 ? (int)t2.size() - 1 : link, tlas, nnodes, tlas_order, emit, tlas_depth);
+        tlas_root = collapseBvhWide(t2.data(), link < 0 ? (int)t2.size() - 1 : link, tlas, nnodes, tlas_order, emit, tlas_depth);
     }
     // stack entries: one per level below the node in hand, four per instance entry, the bottom sentinel
     if (blas_depth + tlas_depth + 8 > kBvhStack) return fail(ctx, PTAP_E_INVALID, "BVH too deep for the traversal stack (%d + %d levels, %d entries)", blas_depth, tlas_depth, kBvhStack);
@@ -384,9 +384,9 @@ int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id
             if (!level[i]) continue;
             blas_depth = std::max(blas_depth, level[i]);
             const BvhNode& nd = nodes[i];
-            if (nd.inner_mask > 0xffu) return fail(ctx, PTAP_E_INVALID, "BVH node %d: bad inner mask", i);
+            if ((nd.inner_mask >> kBvhWidth) || (kBvhWidth < 8 && (nd.leaf_mask >> (4 * kBvhWidth)))) return fail(ctx, PTAP_E_INVALID, "BVH node %d: mask bits beyond the node width", i);
             int ninner = 0, nleaf = 0;
-            for (int c = 0; c < 8; ++c) {
+            for (int c = 0; c < kBvhWidth; ++c) {
                 const unsigned nib = nd.leaf_mask >> (4 * c) & 15u;
                 if (nd.inner_mask >> c & 1u) { if (nib) return fail(ctx, PTAP_E_INVALID, "BVH node %d: slot %d is both inner and leaf", i, c); ++ninner; }
                 else if (nib) { if (nib != 1u && nib != 3u && nib != 7u && nib != 15u) return fail(ctx, PTAP_E_INVALID, "BVH node %d: bad leaf count in slot %d", i, c); nleaf += __builtin_popcount(nib); }

@@ -159,7 +159,7 @@ float halfToFloat(unsigned short h)
 void quantiseNode(BvhNode& nd, const ChildBox boxes[8], unsigned used)
 {
     double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX}, mag = 0.0;
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < kBvhWidth; ++c) {
         if (!(used >> c & 1)) continue;
         for (int k = 0; k < 3; ++k) {
             lo[k] = std::min(lo[k], (double)boxes[c].lo[k]); hi[k] = std::max(hi[k], (double)boxes[c].hi[k]);
@@ -171,33 +171,44 @@ void quantiseNode(BvhNode& nd, const ChildBox boxes[8], unsigned used)
     // a few 2^-24 of the coordinates involved; 2^-20 of the largest coordinate of the node plus one float ulp of p covers it many times.
     const double margin = std::ldexp(mag, -20) + 1e-30;
     const float p[3] = {std::nextafter((float)(lo[0] - margin), -FLT_MAX), std::nextafter((float)(lo[1] - margin), -FLT_MAX), std::nextafter((float)(lo[2] - margin), -FLT_MAX)};
-    double ext = 0.0;
-    for (int k = 0; k < 3; ++k) ext = std::max(ext, hi[k] + margin - (double)p[k]);
-    // scale = 2^e with ext / scale in (8192, 16384]: the offsets use the top of the half range whatever the size of the node
-    int e = 0;
-    if (ext > 0.0) { std::frexp(ext, &e); e -= 14; }           // ext = m * 2^(e+14), m in [0.5, 1)  =>  ext / 2^e in [8192, 16384)
-    const double scale = std::ldexp(1.0, e);
-    nd.px = p[0]; nd.py = p[1]; nd.pz = p[2]; nd.scale = (float)scale;
-    unsigned short* lox[3] = {nd.lo_x, nd.lo_y, nd.lo_z};
-    unsigned short* hix[3] = {nd.hi_x, nd.hi_y, nd.hi_z};
-    for (int c = 0; c < 8; ++c)
-        for (int k = 0; k < 3; ++k) {
-            if (used >> c & 1) {
-                lox[k][c] = halfRoundDown((float)(((double)boxes[c].lo[k] - margin - (double)p[k]) / scale - 1e-3));
-                hix[k][c] = halfRoundUp((float)(((double)boxes[c].hi[k] + margin - (double)p[k]) / scale + 1e-3));
-            } else { lox[k][c] = 0x7bff; hix[k][c] = 0; }       // inverted: never entered (its mask bits are clear anyway)
-        }
+    nd.px = p[0]; nd.py = p[1]; nd.pz = p[2];
+    if (kBvhWidth == 8) {
+        double ext = 0.0;
+        for (int k = 0; k < 3; ++k) ext = std::max(ext, hi[k] + margin - (double)p[k]);
+        // scale = 2^e with ext / scale in (8192, 16384]: the offsets use the top of the half range whatever the size of the node
+        int e = 0;
+        if (ext > 0.0) { std::frexp(ext, &e); e -= 14; }           // ext = m * 2^(e+14), m in [0.5, 1)  =>  ext / 2^e in [8192, 16384)
+        const double scale = std::ldexp(1.0, e);
+        nd.scale = (float)scale;
+        for (int c = 0; c < 8; ++c)
+            for (int k = 0; k < 3; ++k) {
+                if (used >> c & 1) {
+                    nd.planes.h[k][0][c] = halfRoundDown((float)(((double)boxes[c].lo[k] - margin - (double)p[k]) / scale - 1e-3));
+                    nd.planes.h[k][1][c] = halfRoundUp((float)(((double)boxes[c].hi[k] + margin - (double)p[k]) / scale + 1e-3));
+                } else { nd.planes.h[k][0][c] = 0x7bff; nd.planes.h[k][1][c] = 0; }       // inverted: never entered (its mask bits are clear anyway)
+            }
+    } else {
+        for (int c = 0; c < 4; ++c)
+            for (int k = 0; k < 3; ++k) {
+                if (used >> c & 1) {
+                    // binary32 offsets, rounded outward: p + offset (in real arithmetic) lies beyond the builder's plane by at least the margin
+                    nd.planes.f[k][0][c] = std::nextafter((float)((double)boxes[c].lo[k] - margin - (double)p[k]), -FLT_MAX);
+                    nd.planes.f[k][1][c] = std::nextafter((float)((double)boxes[c].hi[k] + margin - (double)p[k]), FLT_MAX);
+                } else { nd.planes.f[k][0][c] = 3e38f; nd.planes.f[k][1][c] = -3e38f; }
+            }
+    }
 }
 
 void decodeChild(const BvhNode& nd, int c, double lo[3], double hi[3])
 {
-    const unsigned short* lox[3] = {nd.lo_x, nd.lo_y, nd.lo_z};
-    const unsigned short* hix[3] = {nd.hi_x, nd.hi_y, nd.hi_z};
     const double p[3] = {nd.px, nd.py, nd.pz};
-    for (int k = 0; k < 3; ++k) { lo[k] = p[k] + (double)nd.scale * halfToFloat(lox[k][c]); hi[k] = p[k] + (double)nd.scale * halfToFloat(hix[k][c]); }
+    for (int k = 0; k < 3; ++k) {
+        if (kBvhWidth == 8) { lo[k] = p[k] + (double)nd.scale * halfToFloat(nd.planes.h[k][0][c]); hi[k] = p[k] + (double)nd.scale * halfToFloat(nd.planes.h[k][1][c]); }
+        else { lo[k] = p[k] + (double)nd.planes.f[k][0][c]; hi[k] = p[k] + (double)nd.planes.f[k][1][c]; }
+    }
 }
 
-int collapseBvh8(const Bvh2Node* n2, int root2, std::vector<BvhNode>& out, int base, std::vector<int>& order,
+int collapseBvhWide(const Bvh2Node* n2, int root2, std::vector<BvhNode>& out, int base, std::vector<int>& order,
                  const std::function<int(int, std::vector<int>&)>& emit_leaf, int& max_depth)
 {
     struct Child { float lo[3], hi[3]; int link; };
@@ -232,17 +243,34 @@ int collapseBvh8(const Bvh2Node* n2, int root2, std::vector<BvhNode>& out, int b
             ch[best] = two[0];
             if (m == 2) ch[n++] = two[1];
         }
-        // slot assignment by octant: child c should sit in the slot whose corner direction its centre points to (greedy on the largest
-        // remaining dot product of (centre - node centre) with the slot's (+-1, +-1, +-1))
+        // slot assignment: child c should sit in the slot whose corner direction its centre points to (greedy on the largest remaining dot
+        // product of (centre - node centre) with the slot's (+-1, ...)).  Width 8: three sign bits per slot.  Width 4: the two axes along
+        // which the children's centres are most spread carry the two slot bits.
         float nlo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, nhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
         for (int i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) { nlo[k] = std::min(nlo[k], ch[i].lo[k]); nhi[k] = std::max(nhi[k], ch[i].hi[k]); }
+        int axis_of_bit[3] = {0, 1, 2};
+        if (kBvhWidth == 4) {
+            float spread[3];
+            for (int k = 0; k < 3; ++k) {
+                float cmin = FLT_MAX, cmax = -FLT_MAX;
+                for (int i = 0; i < n; ++i) { const float c = 0.5f * (ch[i].lo[k] + ch[i].hi[k]); cmin = std::min(cmin, c); cmax = std::max(cmax, c); }
+                spread[k] = cmax - cmin;
+            }
+            int a = 0;
+            for (int k = 1; k < 3; ++k) if (spread[k] > spread[a]) a = k;
+            int b2 = a == 0 ? 1 : 0;
+            for (int k = 0; k < 3; ++k) if (k != a && spread[k] > spread[b2]) b2 = k;
+            axis_of_bit[0] = a; axis_of_bit[1] = b2;
+        }
+        const int nbits = kBvhWidth == 8 ? 3 : 2;
         float cost[8][8];
         for (int i = 0; i < n; ++i)
-            for (int s = 0; s < 8; ++s) {
+            for (int s = 0; s < kBvhWidth; ++s) {
                 float acc = 0.f;
-                for (int k = 0; k < 3; ++k) {
+                for (int bit = 0; bit < nbits; ++bit) {
+                    const int k = axis_of_bit[bit];
                     const float d = 0.5f * (ch[i].lo[k] + ch[i].hi[k]) - 0.5f * (nlo[k] + nhi[k]);
-                    acc += (s >> k & 1) ? d : -d;
+                    acc += (s >> bit & 1) ? d : -d;
                 }
                 cost[i][s] = acc;
             }
@@ -251,7 +279,7 @@ int collapseBvh8(const Bvh2Node* n2, int root2, std::vector<BvhNode>& out, int b
             int bi = -1, bs = -1; float bc = -FLT_MAX;
             for (int i = 0; i < n; ++i) {
                 if (child_done[i]) continue;
-                for (int s = 0; s < 8; ++s) if (!slot_used[s] && cost[i][s] > bc) { bc = cost[i][s]; bi = i; bs = s; }
+                for (int s = 0; s < kBvhWidth; ++s) if (!slot_used[s] && cost[i][s] > bc) { bc = cost[i][s]; bi = i; bs = s; }
             }
             slot_of[bi] = bs; child_done[bi] = true; slot_used[bs] = true;
         }
@@ -263,13 +291,13 @@ int collapseBvh8(const Bvh2Node* n2, int root2, std::vector<BvhNode>& out, int b
         ChildBox boxes[8];
         unsigned used = 0;
         int ninner = 0;
-        for (int s = 0; s < 8; ++s) if (child_in_slot[s] >= 0 && ch[child_in_slot[s]].link >= 0) ++ninner;
+        for (int s = 0; s < kBvhWidth; ++s) if (child_in_slot[s] >= 0 && ch[child_in_slot[s]].link >= 0) ++ninner;
         nd.child_base = base + (int)out.size();
         nd.leaf_base = (int)order.size();
         const int first_child = (int)out.size();
         out.resize(out.size() + ninner);
         int next_inner = 0;
-        for (int s = 0; s < 8; ++s) {
+        for (int s = 0; s < kBvhWidth; ++s) {
             const int i = child_in_slot[s];
             if (i < 0) continue;
             used |= 1u << s;
@@ -284,6 +312,11 @@ int collapseBvh8(const Bvh2Node* n2, int root2, std::vector<BvhNode>& out, int b
             }
         }
         quantiseNode(nd, boxes, used);
+        if (kBvhWidth == 4) {            // slot key per sign octant: bit 0 / 1 = the ray runs downwards along axis a / b
+            unsigned order = 0u;
+            for (unsigned oct = 0; oct < 8; ++oct) order |= (((oct >> axis_of_bit[0]) & 1u) | (((oct >> axis_of_bit[1]) & 1u) << 1)) << (2 * oct);
+            nd.order = order;
+        }
         out[w.index] = nd;
     }
     return base + root_index;
@@ -308,7 +341,8 @@ long long validateBvh(const BvhNode* nodes, int nnodes, int root, int nleafprims
         maxd = std::max(maxd, it.depth);
         const BvhNode& nd = nodes[it.node];
         int inner_rank = 0, leaf_rank = 0;
-        for (int c = 0; c < 8; ++c) {
+        if ((nd.inner_mask >> kBvhWidth) || (kBvhWidth < 8 && (nd.leaf_mask >> (4 * kBvhWidth)))) ++bad;
+        for (int c = 0; c < kBvhWidth; ++c) {
             const bool inner = nd.inner_mask >> c & 1;
             const unsigned nib = nd.leaf_mask >> (4 * c) & 15u;
             if (inner && nib) { ++bad; continue; }
@@ -441,7 +475,7 @@ void buildSceneBvh(const TriRec* tris, int ntris, const PtapMesh* meshes, int nm
             return cnt;
         };
         int depth8 = 0;
-        out.mesh_root[mi] = collapseBvh8(n2.data(), link < 0 ? (int)n2.size() - 1 : link, out.nodes, 0, out.tri_id, emit, depth8);
+        out.mesh_root[mi] = collapseBvhWide(n2.data(), link < 0 ? (int)n2.size() - 1 : link, out.nodes, 0, out.tri_id, emit, depth8);
         out.max_depth = std::max(out.max_depth, depth8);
     }
 }

@@ -32,7 +32,7 @@ void decodeChild(const BvhNode& nd, int c, double lo[3], double hi[3]);
 // `out`): a child is replaced by its own two children, largest box first, until the node has eight; children are then assigned to
 // slots by octant (device_types.h: BvhNode) and their boxes compressed.  Every binary leaf link is handed to `emit_leaf(link, order)`,
 // which appends the leaf's primitives to `order` (the new leaf order) and returns how many it appended (1..4).  Returns the root's index.
-int collapseBvh8(const Bvh2Node* n2, int root2, std::vector<BvhNode>& out, int base, std::vector<int>& order,
+int collapseBvhWide(const Bvh2Node* n2, int root2, std::vector<BvhNode>& out, int base, std::vector<int>& order,
                  const std::function<int(int, std::vector<int>&)>& emit_leaf, int& max_depth);
 
 // tris: global triangle table (v0, e1, e2 in .xyz).  One BLAS per mesh over [t_start, t_end).

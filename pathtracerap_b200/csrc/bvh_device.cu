@@ -165,13 +165,13 @@ __device__ __forceinline__ void writeLeafTri(const TriRec* __restrict__ tris, in
     o[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
-// Compresses up to eight child boxes into `nd` exactly as bvh_build.cpp: quantiseNode does on the host: local origin just below the
-// node's lower corner, power-of-two scale that puts the largest offset in (8192, 16384], lower planes rounded DOWN and upper planes
-// rounded UP to IEEE half after an outward margin of 2^-20 of the largest coordinate.
+// Encodes up to kBvhWidth child boxes into `nd` as bvh_build.cpp: quantiseNode does on the host: local origin just below the node's lower
+// corner, offsets rounded outward after a margin of 2^-20 of the largest coordinate (width 8: IEEE half times a power-of-two scale that
+// puts the largest offset in (8192, 16384]; width 4: binary32).
 __device__ void quantiseNodeDevice(BvhNode& nd, const Box6* boxes, const int* slot_entry)
 {
     float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f}, mag = 0.0f;
-    for (int c = 0; c < 8; ++c) {
+    for (int c = 0; c < kBvhWidth; ++c) {
         if (slot_entry[c] < 0) continue;
         const Box6& b = boxes[slot_entry[c]];
         for (int k = 0; k < 3; ++k) {
@@ -182,22 +182,32 @@ __device__ void quantiseNodeDevice(BvhNode& nd, const Box6* boxes, const int* sl
     const float margin = __fmul_ru(mag, 9.5367431640625e-7f) + 1e-30f;       // 2^-20
     float p[3], ext = 0.0f;
     for (int k = 0; k < 3; ++k) { p[k] = nextafterf(__fsub_rd(lo[k], margin), -3e38f); ext = fmaxf(ext, __fsub_ru(__fadd_ru(hi[k], margin), p[k])); }
-    int e = 0;
-    if (ext > 0.0f) { frexpf(ext, &e); e -= 14; }
-    const float scale = ldexpf(1.0f, e), inv_scale = ldexpf(1.0f, -e);        // exact powers of two
-    nd.px = p[0]; nd.py = p[1]; nd.pz = p[2]; nd.scale = scale;
-    unsigned short* lox[3] = {nd.lo_x, nd.lo_y, nd.lo_z};
-    unsigned short* hix[3] = {nd.hi_x, nd.hi_y, nd.hi_z};
-    for (int c = 0; c < 8; ++c)
-        for (int k = 0; k < 3; ++k) {
-            if (slot_entry[c] >= 0) {
-                const Box6& b = boxes[slot_entry[c]];
-                const float l = __fsub_rd(__fmul_rd(__fsub_rd(__fsub_rd(b.lo[k], margin), p[k]), inv_scale), 1e-3f);
-                const float h = __fadd_ru(__fmul_ru(__fsub_ru(__fadd_ru(b.hi[k], margin), p[k]), inv_scale), 1e-3f);
-                lox[k][c] = __half_as_ushort(__float2half_rd(l));
-                hix[k][c] = __half_as_ushort(__float2half_ru(h));
-            } else { lox[k][c] = 0x7bff; hix[k][c] = 0; }
-        }
+    nd.px = p[0]; nd.py = p[1]; nd.pz = p[2];
+    if (kBvhWidth == 8) {
+        int e = 0;
+        if (ext > 0.0f) { frexpf(ext, &e); e -= 14; }
+        const float scale = ldexpf(1.0f, e), inv_scale = ldexpf(1.0f, -e);    // exact powers of two
+        nd.scale = scale;
+        for (int c = 0; c < 8; ++c)
+            for (int k = 0; k < 3; ++k) {
+                if (slot_entry[c] >= 0) {
+                    const Box6& b = boxes[slot_entry[c]];
+                    const float l = __fsub_rd(__fmul_rd(__fsub_rd(__fsub_rd(b.lo[k], margin), p[k]), inv_scale), 1e-3f);
+                    const float h = __fadd_ru(__fmul_ru(__fsub_ru(__fadd_ru(b.hi[k], margin), p[k]), inv_scale), 1e-3f);
+                    nd.planes.h[k][0][c] = __half_as_ushort(__float2half_rd(l));
+                    nd.planes.h[k][1][c] = __half_as_ushort(__float2half_ru(h));
+                } else { nd.planes.h[k][0][c] = 0x7bff; nd.planes.h[k][1][c] = 0; }
+            }
+    } else {
+        for (int c = 0; c < 4; ++c)
+            for (int k = 0; k < 3; ++k) {
+                if (slot_entry[c] >= 0) {
+                    const Box6& b = boxes[slot_entry[c]];
+                    nd.planes.f[k][0][c] = nextafterf(__fsub_rd(__fsub_rd(b.lo[k], margin), p[k]), -3e38f);
+                    nd.planes.f[k][1][c] = nextafterf(__fsub_ru(__fadd_ru(b.hi[k], margin), p[k]), 3e38f);
+                } else { nd.planes.f[k][0][c] = 3e38f; nd.planes.f[k][1][c] = -3e38f; }
+            }
+    }
 }
 
 // One breadth-first level: frontier item = (binary internal node, index of the 8-wide node that represents it).
@@ -212,10 +222,10 @@ __global__ void k_lbvh_collapse(const TriRec* __restrict__ tris, const int* __re
     const int2 item = frontier[f];
     // entries: >= 0 internal binary node, < 0 leaf ~position.  An internal node over at most kBvhLeafMax sorted triangles is kept closed:
     // it becomes one leaf child.
-    int ent[8]; Box6 box[8]; int ne = 0;
+    int ent[kBvhWidth]; Box6 box[kBvhWidth]; int ne = 0;
     auto put = [&](int e, int at) { ent[at] = e; box[at] = e >= 0 ? node_box[e] : leaf_box[~e]; };
     { const int2 ch = child[item.x]; put(ch.x, 0); put(ch.y, 1); ne = 2; }
-    while (ne < 8) {
+    while (ne < kBvhWidth) {
         int best = -1; float best_area = -1.0f;
         for (int i = 0; i < ne; ++i) {
             if (ent[i] < 0) continue;
@@ -228,9 +238,22 @@ __global__ void k_lbvh_collapse(const TriRec* __restrict__ tris, const int* __re
         const int2 ch = child[ent[best]];
         put(ch.x, best); put(ch.y, ne); ++ne;
     }
-    // octant slots: greedy on the largest remaining (centre - node centre) . (+-1, +-1, +-1), as the host builder
+    // ordered slots: greedy on the largest remaining (centre - node centre) . (+-1, ...), as the host builder (width 8: three axes;
+    // width 4: the two axes along which the children's centres are most spread)
     float nlo[3] = {3e38f, 3e38f, 3e38f}, nhi[3] = {-3e38f, -3e38f, -3e38f};
     for (int i = 0; i < ne; ++i) for (int k = 0; k < 3; ++k) { nlo[k] = fminf(nlo[k], box[i].lo[k]); nhi[k] = fmaxf(nhi[k], box[i].hi[k]); }
+    int ax0 = 0, ax1 = 1;
+    if (kBvhWidth == 4) {
+        float spread[3];
+        for (int k = 0; k < 3; ++k) {
+            float cmin = 3e38f, cmax = -3e38f;
+            for (int i = 0; i < ne; ++i) { const float c = 0.5f * (box[i].lo[k] + box[i].hi[k]); cmin = fminf(cmin, c); cmax = fmaxf(cmax, c); }
+            spread[k] = cmax - cmin;
+        }
+        ax0 = spread[1] > spread[0] ? 1 : 0; if (spread[2] > spread[ax0]) ax0 = 2;
+        ax1 = ax0 == 0 ? 1 : 0;
+        for (int k = 0; k < 3; ++k) if (k != ax0 && spread[k] > spread[ax1]) ax1 = k;
+    }
     int slot_entry[8];
     for (int s = 0; s < 8; ++s) slot_entry[s] = -1;
     unsigned done = 0u, used = 0u;
@@ -238,12 +261,13 @@ __global__ void k_lbvh_collapse(const TriRec* __restrict__ tris, const int* __re
         int bi = -1, bs = -1; float bc = -3e38f;
         for (int i = 0; i < ne; ++i) {
             if (done >> i & 1u) continue;
-            const float d0 = 0.5f * (box[i].lo[0] + box[i].hi[0]) - 0.5f * (nlo[0] + nhi[0]);
-            const float d1 = 0.5f * (box[i].lo[1] + box[i].hi[1]) - 0.5f * (nlo[1] + nhi[1]);
-            const float d2 = 0.5f * (box[i].lo[2] + box[i].hi[2]) - 0.5f * (nlo[2] + nhi[2]);
-            for (int s = 0; s < 8; ++s) {
+            float d[3];
+            for (int k = 0; k < 3; ++k) d[k] = 0.5f * (box[i].lo[k] + box[i].hi[k]) - 0.5f * (nlo[k] + nhi[k]);
+            for (int s = 0; s < kBvhWidth; ++s) {
                 if (used >> s & 1u) continue;
-                const float c = ((s & 1) ? d0 : -d0) + ((s & 2) ? d1 : -d1) + ((s & 4) ? d2 : -d2);
+                float c;
+                if (kBvhWidth == 8) c = ((s & 1) ? d[0] : -d[0]) + ((s & 2) ? d[1] : -d[1]) + ((s & 4) ? d[2] : -d[2]);
+                else { const float da = ax0 == 0 ? d[0] : ax0 == 1 ? d[1] : d[2], db = ax1 == 0 ? d[0] : ax1 == 1 ? d[1] : d[2]; c = ((s & 1) ? da : -da) + ((s & 2) ? db : -db); }
                 if (c > bc) { bc = c; bi = i; bs = s; }
             }
         }
@@ -252,7 +276,7 @@ __global__ void k_lbvh_collapse(const TriRec* __restrict__ tris, const int* __re
     BvhNode nd;
     nd.inner_mask = 0u; nd.leaf_mask = 0u;
     int ninner = 0, nleaf = 0;
-    for (int s = 0; s < 8; ++s) {
+    for (int s = 0; s < kBvhWidth; ++s) {
         const int i = slot_entry[s];
         if (i < 0) continue;
         const int e = ent[i];
@@ -265,7 +289,7 @@ __global__ void k_lbvh_collapse(const TriRec* __restrict__ tris, const int* __re
     const int lbase = leaf_base + (nleaf ? atomicAdd(&counters[2], nleaf) : 0);
     nd.child_base = node_base + cbase; nd.leaf_base = lbase;
     int ki = 0, kl = 0;
-    for (int s = 0; s < 8; ++s) {
+    for (int s = 0; s < kBvhWidth; ++s) {
         const int i = slot_entry[s];
         if (i < 0) continue;
         const int e = ent[i];
@@ -281,6 +305,11 @@ __global__ void k_lbvh_collapse(const TriRec* __restrict__ tris, const int* __re
         }
     }
     quantiseNodeDevice(nd, box, slot_entry);
+    if (kBvhWidth == 4) {            // slot key per sign octant, as the host builder
+        unsigned order = 0u;
+        for (unsigned oct = 0; oct < 8; ++oct) order |= (((oct >> ax0) & 1u) | (((oct >> ax1) & 1u) << 1)) << (2 * oct);
+        nd.order = order;
+    }
     out[item.y] = nd;
 }
 
@@ -294,6 +323,7 @@ __global__ void k_lbvh_single(const TriRec* __restrict__ tris, const int* __rest
     BvhNode nd;
     nd.inner_mask = 0u; nd.leaf_mask = (1u << n) - 1u; nd.child_base = 0; nd.leaf_base = leaf_base;
     quantiseNodeDevice(nd, &b, slot_entry);
+    if (kBvhWidth == 4) nd.order = 0u;
     for (int j = 0; j < n; ++j) { writeLeafTri(tris, ids[j], &btris[leaf_base + j]); btid[leaf_base + j] = ids[j]; }
     out[0] = nd;
 }

@@ -56,28 +56,37 @@ struct Bvh2Node {
     int4 link;          // (child0, child1, 0, 0); >= 0: node index, < 0: leaf; link.x == link.y: only child0 exists
 };
 
-// 8-wide BVH node with child boxes compressed to IEEE half offsets in a node-local frame: 128 B = one L1 line.
-//   plane = p + scale * half, every lower plane rounded down and every upper plane rounded up (bvh_build.cpp: quantiseNode), so a child
-//   box always CONTAINS the builder's box, which itself bounds the reference predicate's +-0.005 tolerance band: the structure only
-//   decides which triangles are tested, the exact predicate decides hits.
-// Children sit in slots 0..7 chosen at build time by octant (bit k of the slot = the child lies on the upper side of the node along
-// axis k), so that for a ray whose direction-sign bits are `oct`, visiting slots in ascending (slot ^ oct) is front to back without
-// any sorting at traversal time.  Inner children are consecutive nodes from child_base (in slot order); the triangles of the leaf
+// Wide BVH node, 128 B = one L1 line, child boxes as OFFSETS in a node-local frame: plane = p + offset, every lower plane rounded
+// down and every upper plane rounded up (bvh_build.cpp: encodeNode), so a child box always CONTAINS the builder's box, which itself
+// bounds the reference predicate's +-0.005 tolerance band: the structure only decides which triangles are tested, the exact predicate
+// decides hits.  The local frame is what makes a one-FMA slab test safe (trace_bvh.cu).
+//   PTAP_BVH_WIDTH 4 (default): four children, offsets in binary32.
+//   PTAP_BVH_WIDTH 8: eight children, offsets as IEEE half times a power-of-two scale (measured slower on B200: profiles/r02).
+// Children sit in slots chosen at build time so that visiting the hit children in ascending (slot ^ key) is front to back for a ray
+// whose direction signs select `key` - no sorting at traversal time.  Width 8: bit k of the slot = upper side of the node along axis
+// k, key = the ray's three sign bits.  Width 4: the node picks its two most spread axes (a, b), bit 0 / 1 of the slot = upper side
+// along a / b, and `order` holds the 2-bit key for each of the 8 sign combinations.
+// Inner children are consecutive nodes from child_base (in slot order) and come after their parent; the triangles of the leaf
 // children are consecutive LeafTri records from leaf_base (in slot order).  TLAS nodes share the format: a leaf child is ONE instance,
 // leaf_base indexes SceneDev::tlas_order.
+#ifndef PTAP_BVH_WIDTH
+#define PTAP_BVH_WIDTH 4
+#endif
+constexpr int kBvhWidth = PTAP_BVH_WIDTH, kBvhLeafMax = 4;
+static_assert(kBvhWidth == 4 || kBvhWidth == 8, "PTAP_BVH_WIDTH must be 4 or 8");
 struct __align__(32) BvhNode {
-    float px, py, pz;           // node-local origin (the lower corner of the node)
-    float scale;                // power of two
+    float px, py, pz;           // node-local origin (just below the lower corner of the node)
+    union { float scale; unsigned order; };   // width 8: power-of-two scale of the half offsets; width 4: 2-bit slot key per sign octant (bits 2 oct .. 2 oct + 1)
     int child_base;             // node index of the first inner child
     int leaf_base;              // leaf-order position of the first triangle of the first leaf child
     unsigned leaf_mask;         // nibble c = (1 << count_c) - 1 when slot c is a leaf of 1..4 triangles, else 0
     unsigned inner_mask;        // bit c set when slot c is an inner node
-    unsigned short lo_x[8], hi_x[8];      // half bits, per slot
-    unsigned short lo_y[8], hi_y[8];
-    unsigned short lo_z[8], hi_z[8];
+    union {                     // planes[axis][0 = lower, 1 = upper][slot]
+        unsigned short h[3][2][8];      // width 8: half bits
+        float f[3][2][4];               // width 4
+    } planes;
 };
 static_assert(sizeof(BvhNode) == 128, "BvhNode must be one 128-byte line");
-constexpr int kBvhWidth = 8, kBvhLeafMax = 4;
 
 // Device-resident frame state: lets a whole iteration run without a host round trip.
 struct FrameState {

@@ -1,4 +1,4 @@
-// trace_bvh.cu - closest hit through a two-level, 8-wide, compressed BVH (PTAP_ACCEL_BVH / PTAP_ACCEL_BVH_DEVICE).
+// trace_bvh.cu - closest hit through a two-level wide BVH with node-local child boxes (PTAP_ACCEL_BVH / PTAP_ACCEL_BVH_DEVICE).
 //
 // New design; the reference has no BVH.  Semantics = oracle tier R1: for every model, the reference's own per-model
 // ray set-up (Renderer.cpp:381-384) and its tolerant Moller-Trumbore predicate (Renderer.cpp:174-215) applied to
@@ -8,16 +8,16 @@
 // compressed (bvh_build.cpp), the slab test carries relative slack, pruning bounds carry slack, and the triangle
 // arithmetic is the un-contracted exact one, so the winner is bit-identical to brute force.
 //
-// Node = 128 B = one L1 line (device_types.h: BvhNode): eight child boxes as IEEE-half offsets in a node-local frame, children in
-// octant slots.  What that buys, per node visit:
-//  * one FMA per plane.  t = half * (scale * inv) + (p - o) * inv: the (p - o) term is evaluated once per node RELATIVE TO THE NODE,
-//    so the cancellation error of the FMA form is bounded by the node's own extent (the global o * inv form of the textbook kernels is
-//    unbounded for axis-parallel rays, which is why the previous 4-wide kernel used a subtract and a multiply per plane);
-//  * no sorting: a ray with direction-sign bits `oct` visits the hit children in ascending (slot ^ oct), front to back by construction
-//    of the slots, so the hit mask is permuted by three conditional bit swaps instead of a comparator network on entry distances;
-//  * near / far planes are chosen by ADDRESS (the lo / hi halves of an axis are 16 bytes apart), not by min / max per child;
-//  * one 8-byte stack entry per node (child base, pending-children mask) instead of one entry per hit child;
-//  * half the node visits of the 4-wide tree and half the scheduling rounds.
+// Node = 128 B = one L1 line (device_types.h: BvhNode): child boxes as offsets in a node-local frame, children in ordered slots.
+// Default: four children, binary32 offsets (PTAP_BVH_WIDTH=8 builds the eight-children / IEEE-half variant, measured slower on B200).
+// What the format buys, per node visit:
+//  * one FMA per plane.  t = offset * inv + (p - o) * inv: the (p - o) term is evaluated once per node RELATIVE TO THE NODE, so the
+//    cancellation error of the FMA form is bounded by the node's own extent (the global o * inv form of the textbook kernels is
+//    unbounded for axis-parallel rays, which is why round 1's kernel spent a subtract and a multiply per plane);
+//  * no sorting: the hit children are visited in ascending (slot ^ key), front to back by construction of the slots, so the hit mask
+//    is permuted by conditional bit swaps instead of a comparator network on entry distances;
+//  * near / far planes are chosen by ADDRESS (the lower / upper planes of an axis are 16 bytes apart), not by min / max per child;
+//  * one 8-byte stack entry per node (child base, pending-children mask) instead of one entry per hit child.
 //
 // Execution model (DESIGN.md "Closest hit"): a persistent grid of warps, each lane owning one ray at a time, scheduled as a warp-wide
 // state machine.  A lane holds a NODE GROUP (child base + mask of hit inner children still to visit) and a TRIANGLE GROUP (leaf base +
@@ -82,6 +82,12 @@ __device__ __forceinline__ unsigned octOf(const V3& d)
     return (__float_as_uint(d.x) >> 31) | ((__float_as_uint(d.y) >> 31) << 1) | ((__float_as_uint(d.z) >> 31) << 2);
 }
 
+// byte offsets (x | y << 8 | z << 16) of the near planes of the three axes inside a node: lower planes at 32 / 64 / 96, upper planes 16 further
+__device__ __forceinline__ unsigned nearOffsets(unsigned oct)
+{
+    return (32u + ((oct & 1u) << 4)) | ((64u + ((oct & 2u) << 3)) << 8) | ((96u + ((oct & 4u) << 2)) << 16);
+}
+
 // TLAS pruning bound once some instance reported world distance g_dist: g_dist may be the approximation t * |d_w| / |W3 d_w| of the exact
 // distance (off by at most g_dist * tie + cb, tie < prune - 1), so the bound carries the same absolute slack cb as the instance-entry bound
 __device__ __forceinline__ float worldBound(float g_dist, float prune, float cb)
@@ -110,15 +116,32 @@ __device__ __forceinline__ bool childHit(float nx, float ny, float nz, float fx,
     return tn <= tf + __fmaf_rn(fabsf(tf), 2e-6f, 1e-6f);
 }
 
-// new position k holds old position k ^ oct (8-bit mask)
-__device__ __forceinline__ unsigned permuteByOctant(unsigned h, unsigned oct)
+// new position k holds old position k ^ key (mask of kBvhWidth bits)
+__device__ __forceinline__ unsigned permuteByKey(unsigned h, unsigned key)
 {
     const unsigned a = ((h & 0x55u) << 1) | ((h >> 1) & 0x55u);
-    h = (oct & 1u) ? a : h;
+    h = (key & 1u) ? a : h;
     const unsigned b = ((h & 0x33u) << 2) | ((h >> 2) & 0x33u);
-    h = (oct & 2u) ? b : h;
-    const unsigned c = ((h & 0x0fu) << 4) | ((h >> 4) & 0x0fu);
-    return (oct & 4u) ? c : h;
+    h = (key & 2u) ? b : h;
+    if (kBvhWidth == 8) {
+        const unsigned c = ((h & 0x0fu) << 4) | ((h >> 4) & 0x0fu);
+        h = (key & 4u) ? c : h;
+    }
+    return h;
+}
+
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)          // FFMA2 (sm_100): two binary32 FMAs per issue slot
+{
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+
+__device__ __forceinline__ bool intervalHit(float nx, float ny, float nz, float fx, float fy, float fz, float tmin, float tmax)
+{
+    const float tn = fmaxf(fmaxf(fmaxf(nx, ny), nz), tmin);
+    const float tf = fminf(fminf(fminf(fx, fy), fz), tmax);
+    return tn <= tf + __fmaf_rn(fabsf(tf), 2e-6f, 1e-6f);
 }
 
 }  // namespace
@@ -148,6 +171,7 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
     uint2 stack[kBvhStack];
     int sp = 0, i = -1;
     unsigned flags = kDone;                         // octant of the current level | kInBlas | kExit | kDone
+    unsigned near_off = 0u;                         // byte offsets of the near planes within a node, one byte per axis (from the octant)
     int g_base = 0; unsigned g_bits = 0u;           // node group: child base, pending hit inner children (bits 0-7, traversal order) | inner mask << 8
     int t_base = 0; unsigned t_mask = 0u, t_lm = 0u;   // triangle group: leaf base, pending triangles, the node's leaf mask
     int exit_im = 0;
@@ -170,34 +194,55 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
         }
         // ---- (1b) inner step: the nearest pending child of the node group
         if (!(flags & (kExit | kDone)) && t_mask == 0u && (g_bits & 0xffu) != 0u) {
-            const unsigned oct = flags & kOctMask;
             unsigned h = g_bits & 0xffu;
-            const unsigned k = (unsigned)__ffs((int)h) - 1u, c = k ^ oct;
+            const unsigned k = (unsigned)__ffs((int)h) - 1u, c = k ^ ((g_bits >> 16) & 7u);
             const int node = g_base + __popc((g_bits >> 8) & ((1u << c) - 1u));
             h &= h - 1u;
-            if (h) stack[sp++] = make_uint2((unsigned)g_base, (g_bits & 0xff00u) | h);
+            if (h) stack[sp++] = make_uint2((unsigned)g_base, (g_bits & 0xffff00u) | h);
             const char* __restrict__ np = reinterpret_cast<const char*>(&sc.nodes[node]);
-            const F8 hd = ldg8(np);                                              // origin, scale, bases, masks
-            const int nox = (int)(oct & 1u) << 4, noy = (int)(oct & 2u) << 3, noz = (int)(oct & 4u) << 2;
-            const uint4 NX = ldg4u(np + 32 + nox), FX = ldg4u(np + 48 - nox);    // near / far planes by address
-            const uint4 NY = ldg4u(np + 64 + noy), FY = ldg4u(np + 80 - noy);
-            const uint4 NZ = ldg4u(np + 96 + noz), FZ = ldg4u(np + 112 - noz);
+            const F8 hd = ldg8(np);                                              // origin, scale / order, bases, masks
+            // near / far planes by address: the lower and upper planes of an axis are 16 bytes apart, `near_off` holds the three byte
+            // offsets of the near ones (set when the level's ray is set up), the far ones are at offset ^ 16
+            const unsigned nox = near_off & 0xffu, noy = (near_off >> 8) & 0xffu, noz = near_off >> 16;
+            const uint4 NX = ldg4u(np + nox), FX = ldg4u(np + (nox ^ 16u));
+            const uint4 NY = ldg4u(np + noy), FY = ldg4u(np + (noy ^ 16u));
+            const uint4 NZ = ldg4u(np + noz), FZ = ldg4u(np + (noz ^ 16u));
             if (COUNT) cnt.x++;
-            const float sx = hd.v[3] * rinv.x, sy = hd.v[3] * rinv.y, sz = hd.v[3] * rinv.z;
             const float cx = (hd.v[0] - ro.x) * rinv.x, cy = (hd.v[1] - ro.y) * rinv.y, cz = (hd.v[2] - ro.z) * rinv.z;
             const unsigned lm = __float_as_uint(hd.v[6]), im = __float_as_uint(hd.v[7]);
             const unsigned nxw[4] = {NX.x, NX.y, NX.z, NX.w}, fxw[4] = {FX.x, FX.y, FX.z, FX.w};
             const unsigned nyw[4] = {NY.x, NY.y, NY.z, NY.w}, fyw[4] = {FY.x, FY.y, FY.z, FY.w};
             const unsigned nzw[4] = {NZ.x, NZ.y, NZ.z, NZ.w}, fzw[4] = {FZ.x, FZ.y, FZ.z, FZ.w};
-            unsigned hits = 0u, tm = 0u;
+            unsigned hits = 0u, tm = 0u, key;
+            if (kBvhWidth == 8) {
+                const float sx = hd.v[3] * rinv.x, sy = hd.v[3] * rinv.y, sz = hd.v[3] * rinv.z;
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                const float2 ax = halves(nxw[w]), bx = halves(fxw[w]), ay = halves(nyw[w]), by = halves(fyw[w]), az = halves(nzw[w]), bz = halves(fzw[w]);
-                if (childHit(ax.x, ay.x, az.x, bx.x, by.x, bz.x, sx, sy, sz, cx, cy, cz, tmin, tmax)) { hits |= 1u << (2 * w); tm |= lm & (0xfu << (8 * w)); }
-                if (childHit(ax.y, ay.y, az.y, bx.y, by.y, bz.y, sx, sy, sz, cx, cy, cz, tmin, tmax)) { hits |= 2u << (2 * w); tm |= lm & (0xf0u << (8 * w)); }
+                for (int w = 0; w < 4; ++w) {
+                    const float2 ax = halves(nxw[w]), bx = halves(fxw[w]), ay = halves(nyw[w]), by = halves(fyw[w]), az = halves(nzw[w]), bz = halves(fzw[w]);
+                    if (childHit(ax.x, ay.x, az.x, bx.x, by.x, bz.x, sx, sy, sz, cx, cy, cz, tmin, tmax)) { hits |= 1u << (2 * w); tm |= lm & (0xfu << (8 * w)); }
+                    if (childHit(ax.y, ay.y, az.y, bx.y, by.y, bz.y, sx, sy, sz, cx, cy, cz, tmin, tmax)) { hits |= 2u << (2 * w); tm |= lm & (0xf0u << (8 * w)); }
+                }
+                key = flags & kOctMask;
+            } else {
+                // four children, two per FFMA2: t = offset * inv + (p - o) * inv
+                const float2 ix = make_float2(rinv.x, rinv.x), iy = make_float2(rinv.y, rinv.y), iz = make_float2(rinv.z, rinv.z);
+                const float2 ccx = make_float2(cx, cx), ccy = make_float2(cy, cy), ccz = make_float2(cz, cz);
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                    const float2 tnx = fma2(make_float2(__uint_as_float(nxw[2 * w]), __uint_as_float(nxw[2 * w + 1])), ix, ccx);
+                    const float2 tny = fma2(make_float2(__uint_as_float(nyw[2 * w]), __uint_as_float(nyw[2 * w + 1])), iy, ccy);
+                    const float2 tnz = fma2(make_float2(__uint_as_float(nzw[2 * w]), __uint_as_float(nzw[2 * w + 1])), iz, ccz);
+                    const float2 tfx = fma2(make_float2(__uint_as_float(fxw[2 * w]), __uint_as_float(fxw[2 * w + 1])), ix, ccx);
+                    const float2 tfy = fma2(make_float2(__uint_as_float(fyw[2 * w]), __uint_as_float(fyw[2 * w + 1])), iy, ccy);
+                    const float2 tfz = fma2(make_float2(__uint_as_float(fzw[2 * w]), __uint_as_float(fzw[2 * w + 1])), iz, ccz);
+                    if (intervalHit(tnx.x, tny.x, tnz.x, tfx.x, tfy.x, tfz.x, tmin, tmax)) hits |= 1u << (2 * w);
+                    if (intervalHit(tnx.y, tny.y, tnz.y, tfx.y, tfy.y, tfz.y, tmin, tmax)) hits |= 2u << (2 * w);
+                }
+                tm = lm & (((hits * 0x249u) & 0x1111u) * 15u);                   // hit bit c -> nibble c: the triangles of the hit leaf children
+                key = (__float_as_uint(hd.v[3]) >> (2u * (flags & kOctMask))) & 3u;   // the node's slot key for this sign octant
             }
             g_base = __float_as_int(hd.v[4]);
-            g_bits = permuteByOctant(hits & im, oct) | (im << 8);
+            g_bits = permuteByKey(hits & im, key) | (im << 8) | (key << 16);
             t_base = __float_as_int(hd.v[5]); t_mask = tm; t_lm = lm;
         }
         // ---- (2) who waits for what: one warp reduction over 6-bit counters, one per state
@@ -245,9 +290,9 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
                 if (tb < kFloatMax) tmax = tb;                                  // false for NaN / inf: no bound
             }
             const unsigned oct = octOf(rd);
-            flags = oct | kInBlas;
+            flags = oct | kInBlas; near_off = nearOffsets(oct);
             g_base = __float_as_int(__ldg(&inst->grid.z));                      // BLAS root of the instance's mesh, as a one-child group
-            g_bits = (1u << oct) | (1u << 8);
+            g_bits = 1u | (1u << 8);                                             // hit bit 0, inner bit 0, key 0
             t_mask = 0u;
         }
         // ---- (3c) marker popped: leave instance `exit_im` (Renderer.cpp:388-398).  The nearest-model decision of the reference compares exact
@@ -285,7 +330,7 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
             const float il = rsqrtf(bd.x * bd.x + bd.y * bd.y + bd.z * bd.z);
             const V3 wd = v3(bd.x * il, bd.y * il, bd.z * il);
             ro = bo; rinv = v3(safeInv(wd.x), safeInv(wd.y), safeInv(wd.z));
-            flags = octOf(wd);
+            flags = octOf(wd); near_off = nearOffsets(flags);
             tmin = sc.tmin_world; tmax = worldBound(g_dist, sc.prune, cb);
         }
         // ---- (3d) retire finished rays, refill the lanes from the warp's batch
@@ -321,9 +366,8 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
                 best_tri = -1;
                 if (COUNT) cnt = make_int4(0, 0, 0, 0);
                 stack[0] = make_uint2(0u, kDoneMark); sp = 1;
-                const unsigned oct = octOf(wd);
-                flags = oct;
-                g_base = sc.tlas_root; g_bits = (1u << oct) | (1u << 8);         // the TLAS root as a one-child group
+                flags = octOf(wd); near_off = nearOffsets(flags);
+                g_base = sc.tlas_root; g_bits = 1u | (1u << 8);                  // the TLAS root as a one-child group (key 0)
                 t_mask = 0u;
             }
             w_next += min(__popc(m_done), avail);

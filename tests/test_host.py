@@ -59,13 +59,17 @@ def test_compose_trs_matches_reference_matrices(libptap, golden_scene):
     assert np.allclose(prod, np.eye(4), atol=1e-5)
 
 
-NODE = np.dtype([("p", "<f4", 3), ("scale", "<f4"), ("child_base", "<i4"), ("leaf_base", "<i4"), ("leaf_mask", "<u4"), ("inner_mask", "<u4"),
-                 ("lo_x", "<u2", 8), ("hi_x", "<u2", 8), ("lo_y", "<u2", 8), ("hi_y", "<u2", 8), ("lo_z", "<u2", 8), ("hi_z", "<u2", 8)])   # PtapBvhNode, include/ptap.h
+NODE8 = np.dtype([("p", "<f4", 3), ("scale", "<f4"), ("child_base", "<i4"), ("leaf_base", "<i4"), ("leaf_mask", "<u4"), ("inner_mask", "<u4"),
+                  ("planes", "<u2", (3, 2, 8))])                                      # PtapBvhNode, width 8 (include/ptap.h)
+NODE4 = np.dtype([("p", "<f4", 3), ("order", "<u4"), ("child_base", "<i4"), ("leaf_base", "<i4"), ("leaf_mask", "<u4"), ("inner_mask", "<u4"),
+                  ("planes", "<f4", (3, 2, 4))])                                      # PtapBvhNode, width 4
 
 
 def _bvh_of(scene):
     scene.build_bvh()
     v = scene.view()
+    from pathtracerap_b200 import _native as N
+    NODE = NODE4 if N.lib().ptap_bvh_node_width() == 4 else NODE8
     assert NODE.itemsize == 128
     nodes = np.frombuffer((C.c_char * (v.n_bvh_nodes * 128)).from_address(v.bvh_nodes), NODE).copy()
     tri_id = np.frombuffer((C.c_char * (v.n_bvh_tris * 4)).from_address(v.bvh_tri_id), np.int32).copy()
@@ -74,27 +78,42 @@ def _bvh_of(scene):
     return nodes, tri_id, roots
 
 
-def _half(bits):
-    return np.array([bits], np.uint16).view(np.float16).astype(np.float64)[0]
-
-
 def _slots(nd):
-    """(slot, lo, hi, kind, count) of the used child slots of an 8-wide compressed node, decoded independently of the library:
-    plane = p + scale * half (include/ptap.h)."""
+    """(slot, lo, hi, kind, count) of the used child slots of a wide node, decoded independently of the library: plane = p + offset,
+    offset = binary32 (width 4) or scale * half (width 8), include/ptap.h."""
     out = []
-    p, sc = nd["p"].astype(np.float64), float(nd["scale"])
-    assert sc > 0 and np.log2(sc) == np.round(np.log2(sc))                # a power of two: the decode is exact
-    for c in range(8):
+    p = nd["p"].astype(np.float64)
+    width = nd["planes"].shape[-1]
+    if width == 8:
+        sc = float(nd["scale"])
+        assert sc > 0 and np.log2(sc) == np.round(np.log2(sc))                # a power of two: the decode is exact
+        planes = nd["planes"].view(np.float16).astype(np.float64) * sc
+    else:
+        planes = nd["planes"].astype(np.float64)
+        assert int(nd["order"]) < (1 << 16)
+    assert int(nd["inner_mask"]) >> width == 0 and (width == 8 or int(nd["leaf_mask"]) >> (4 * width) == 0)
+    for c in range(width):
         inner = (int(nd["inner_mask"]) >> c) & 1
         nib = (int(nd["leaf_mask"]) >> (4 * c)) & 15
         assert not (inner and nib)
         if not (inner or nib):
             continue
-        lo = p + sc * np.array([_half(nd["lo_x"][c]), _half(nd["lo_y"][c]), _half(nd["lo_z"][c])])
-        hi = p + sc * np.array([_half(nd["hi_x"][c]), _half(nd["hi_y"][c]), _half(nd["hi_z"][c])])
+        lo, hi = p + planes[:, 0, c], p + planes[:, 1, c]
         assert nib in (0, 1, 3, 7, 15)
         out.append((c, lo, hi, "inner" if inner else "leaf", bin(nib).count("1")))
     return out
+
+
+def _check_order(nd, slots):
+    """Width 4: for every sign octant the node's key must be the two sign bits of its two ordering axes - i.e. (slot ^ key) ascending is a
+    consistent front-to-back order: two octants that agree on the axes' signs share a key, and the keys take all four values."""
+    keys = [(int(nd["order"]) >> (2 * o)) & 3 for o in range(8)]
+    assert sorted(set(keys)) == [0, 1, 2, 3]
+    axes = [k for k in range(3) if any(keys[o] != keys[o ^ (1 << k)] for o in range(8))]
+    assert len(axes) == 2
+    free = [k for k in range(3) if k not in axes][0]
+    assert all(keys[o] == keys[o ^ (1 << free)] for o in range(8))
+    assert keys[0] == 0 and keys[7] == 3
 
 
 def _check_bvh(nodes, tri_id, roots, arrays):
@@ -116,6 +135,8 @@ def _check_bvh(nodes, tri_id, roots, arrays):
             max_depth = max(max_depth, d)
             slots = _slots(nodes[n])
             assert 1 <= len(slots) <= 8
+            if len(slots) > 1 and 'order' in nodes.dtype.names:
+                _check_order(nodes[n], slots)
             ki = kl = 0
             for c, lo, hi, kind, cnt in slots:
                 lo, hi = np.maximum(lo, alo), np.minimum(hi, ahi)
