@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define PTAP_VERSION 2      /* 2: PtapBvhNode is the 8-wide compressed node; ptap_render_probe */
+#define PTAP_VERSION 2      /* 2: PtapBvhNode carries node-local offsets; ptap_render_probe, ptap_reduce*, stamps */
 
 enum {
     PTAP_OK = 0,
@@ -58,24 +58,17 @@ typedef struct { int32_t start, end, entity_type; } PtapVoxel;                  
 
 enum { PTAP_DIFFUSE = 0, PTAP_SPECULAR, PTAP_REFLECTIVE, PTAP_REFRACTIVE, PTAP_EMISSIVE, PTAP_COAT, PTAP_METAL }; /* Primitive.h:70-79 */
 
-/* Wide BVH node (new; the reference has no BVH), 128 bytes.  Child boxes are OFFSETS in a node-local frame: plane = p + offset,
- * lower planes rounded down and upper planes rounded up, so every child box contains the builder's box (which bounds the reference
- * predicate's tolerance band).  ptap_bvh_node_width() tells which of the two layouts the library was built with:
- *   4 (default): planes.f[axis][0 lower | 1 upper][slot] in binary32; `order` holds, for each of the 8 combinations of ray-direction
- *      signs (bit k = direction negative along axis k), the 2-bit key such that ascending (slot ^ key) is front to back;
- *   8: planes.h[axis][lower | upper][slot] as IEEE half, to be multiplied by the power-of-two `scale`; key = the three sign bits.
- * Inner children are consecutive nodes from child_base in slot order and must come AFTER their parent in the array; the triangles of
- * the leaf children are consecutive from leaf_base (leaf order) in slot order. */
+/* BVH4 node (new; the reference has no BVH), 128 bytes: a node-local origin, the links of up to four children, and their boxes as
+ * binary32 OFFSETS from that origin: plane = p + planes[axis][0 lower | 1 upper][slot], lower planes rounded down and upper planes rounded
+ * up, so every child box contains the builder's box (which bounds the reference predicate's tolerance band).
+ * link >= 0: child node index; link < 0: leaf, ~link = (first_leaf_triangle << 3) | (count - 1).
+ * An unused slot holds an inverted box (lower offsets 1e15, upper offsets -1e15). */
 typedef struct {
-    float p[3];               /* node-local origin */
-    union { float scale; uint32_t order; } u;
-    int32_t child_base;       /* node index of the first inner child */
-    int32_t leaf_base;        /* leaf-order position of the first triangle of the first leaf child */
-    uint32_t leaf_mask;       /* nibble c = (1 << count) - 1 for a leaf of 1..4 triangles in slot c, else 0 */
-    uint32_t inner_mask;      /* bit c: slot c is an inner node */
-    union { uint16_t h[3][2][8]; float f[3][2][4]; } planes;
+    float p[3];
+    int32_t pad;
+    int32_t link[4];
+    float planes[3][2][4];
 } PtapBvhNode;
-int ptap_bvh_node_width(void);
 
 /* The seven public vectors of the reference's Scene (Scene.h:26-32) as raw arrays. */
 typedef struct {

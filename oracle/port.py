@@ -29,7 +29,7 @@ _lib = None
 
 
 def build(force: bool = False) -> str:
-    src = [os.path.join(HERE, f) for f in ("ptap_oracle.c", "ptap_oracle.h")]
+    src = [os.path.join(HERE, f) for f in ("ptap_oracle.c", "synth.c", "ptap_oracle.h")]
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in src):
         subprocess.check_call(["make", "-s", "-C", HERE, "libptap_oracle.so"])
     return LIB_PATH
@@ -61,6 +61,9 @@ def lib():
         L.oracle_render.argtypes = [vp, ci, ci, ci, vp]
         L.oracle_write_bmp.argtypes = [vp, ci, ci, ci, C.c_char_p]; L.oracle_write_bmp.restype = ci
         L.oracle_set_threads.argtypes = [ci]
+        L.oracle_compose_trs.argtypes = [vp, C.c_float, vp, vp, vp]
+        L.oracle_icosphere_triangles.argtypes = [ci]; L.oracle_icosphere_triangles.restype = ci
+        L.oracle_icosphere.argtypes = [ci, C.c_float, C.c_float, C.c_uint, vp, vp, vp]; L.oracle_icosphere.restype = ci
         L.oracle_max_threads.restype = ci
         _lib = L
     return _lib
@@ -168,6 +171,40 @@ class OracleWavefront:
         if self.h:
             lib().oracle_wavefront_free(self.h)
             self.h = None
+
+
+def compose_trs(translate, rotate_y_degrees, scale):
+    """(model_to_world, world_to_model) as Scene.cpp:34-39 composes them: glm::translate * rotate(Y) * scale, glm::inverse."""
+    t = np.ascontiguousarray(translate, np.float32); s = np.ascontiguousarray(scale, np.float32)
+    m2w = np.zeros(16, np.float32); w2m = np.zeros(16, np.float32)
+    lib().oracle_compose_trs(_ptr(t), float(rotate_y_degrees), _ptr(s), _ptr(m2w), _ptr(w2m))
+    return m2w, w2m
+
+
+def icosphere(level, radius=1000.0, displacement=0.05, seed=1):
+    """(vertices, triangles, bb_min, bb_max) of the synthetic displaced icosphere: 20 * 4^level triangles, un-joined vertices."""
+    n = lib().oracle_icosphere_triangles(level)
+    v = np.zeros(3 * n, VERTEX); lo = np.zeros(3, np.float32); hi = np.zeros(3, np.float32)
+    got = lib().oracle_icosphere(level, radius, displacement, seed, _ptr(v), _ptr(lo), _ptr(hi))
+    assert got == n
+    t = np.zeros(n, TRIANGLE); t["v"] = np.arange(3 * n, dtype=np.int32).reshape(n, 3)
+    return v, t, lo, hi
+
+
+def scene_with_mesh(base, keep_models, mesh_vertices, mesh_triangles, bb_min, bb_max, model):
+    """The four reference-layout arrays of `base` restricted to `keep_models`, plus one more mesh and one model using it."""
+    models = np.concatenate([np.ascontiguousarray(base["models"], MODEL)[keep_models], np.zeros(1, MODEL)])
+    meshes = np.concatenate([np.ascontiguousarray(base["meshes"], MESH), np.zeros(1, MESH)])
+    nv, nt = len(base["vertices"]), len(base["triangles"])
+    m = meshes[-1]
+    m["v_start"], m["v_end"], m["t_start"], m["t_end"], m["bb_min"], m["bb_max"] = nv, nv + len(mesh_vertices), nt, nt + len(mesh_triangles), bb_min, bb_max
+    tri = mesh_triangles.copy(); tri["v"] += nv
+    mm = models[-1]
+    mm["mesh_index"] = len(meshes) - 1
+    mm["model_to_world"], mm["world_to_model"] = model["m2w"], model["w2m"]
+    mm["mat"]["type"] = model["type"]; mm["mat"]["color"] = model["color"]
+    return {"models": models, "meshes": meshes, "vertices": np.concatenate([np.ascontiguousarray(base["vertices"], VERTEX), mesh_vertices]),
+            "triangles": np.concatenate([np.ascontiguousarray(base["triangles"], TRIANGLE), tri])}
 
 
 def write_bmp(image_sum, iters, path):

@@ -100,6 +100,12 @@ void oracle_render(OWavefront* w, int iter_begin, int iter_end, int first_hit_ca
 /* Renderer.cpp:15-63 */
 int oracle_write_bmp(const float* image_sum, int W, int H, int iters, const char* path);
 
+/* synth.c: scene inputs without the product library.  glm::translate * rotate(Y) * scale and its inverse (Scene.cpp:34-39); the displaced
+ * icosphere of the synthetic workloads (3 vertices per triangle, triangle t = vertices 3t .. 3t+2; returns the triangle count). */
+void oracle_compose_trs(const float translate[3], float rotate_y_degrees, const float scale[3], float model_to_world[16], float world_to_model[16]);
+int oracle_icosphere_triangles(int level);
+int oracle_icosphere(int level, float radius, float displacement, unsigned seed, OVertex* vertices, float bb_min[3], float bb_max[3]);
+
 void oracle_set_threads(int n);
 int oracle_max_threads(void);
 

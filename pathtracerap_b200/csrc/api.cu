@@ -77,7 +77,7 @@ struct ptap_ctx {
     std::vector<PtapMesh> h_meshes;
     std::vector<PtapModel> h_models;
     std::vector<InstanceTrace> h_inst;
-    InstanceTrace* d_inst = nullptr; TriRec* d_tris = nullptr; BvhNode* d_nodes = nullptr; size_t nodes_cap = 0; LeafTri* d_btris = nullptr; int* d_btid = nullptr; int* d_tlas_order = nullptr;
+    InstanceTrace* d_inst = nullptr; TriRec* d_tris = nullptr; BvhNode* d_nodes = nullptr; size_t nodes_cap = 0; LeafTri* d_btris = nullptr; int* d_btid = nullptr;
     bool have_scene = false, have_grid = false, have_bvh = false, have_frame = false;
     int bvh_kind = -1;               // which builder made the BVH now on the device (PTAP_ACCEL_BVH / PTAP_ACCEL_BVH_DEVICE)
     int accel = PTAP_ACCEL_GRID_COMPAT;
@@ -296,8 +296,8 @@ int finishBvh(ptap_ctx* ctx, const BvhNode* roots, const int* mesh_root, int nno
             }
         const BvhNode& r = roots[m.mesh_index];
         float mlo[3] = {3e38f, 3e38f, 3e38f}, mhi[3] = {-3e38f, -3e38f, -3e38f};
-        for (int k = 0; k < kBvhWidth; ++k) {
-            if (!((r.inner_mask >> k & 1u) || (r.leaf_mask >> (4 * k) & 15u))) continue;      // unused slot
+        for (int k = 0; k < 4; ++k) {
+            if (!slotUsed(r, k)) continue;
             double lo[3], hi[3];
             decodeChild(r, k, lo, hi);
             for (int a = 0; a < 3; ++a) { mlo[a] = std::min(mlo[a], std::nextafter((float)lo[a], -3e38f)); mhi[a] = std::max(mhi[a], std::nextafter((float)hi[a], 3e38f)); }
@@ -322,7 +322,6 @@ int finishBvh(ptap_ctx* ctx, const BvhNode* roots, const int* mesh_root, int nno
         max_pad = std::max(max_pad, (double)pad);
     }
     std::vector<BvhNode> tlas;
-    std::vector<int> tlas_order;
     int tlas_root = -1, tlas_depth = 0;
     if (!items.empty()) {
         float lo[3], hi[3];
@@ -335,17 +334,12 @@ int finishBvh(ptap_ctx* ctx, const BvhNode* roots, const int* mesh_root, int nno
             nd.link = make_int4(link, link, 0, 0);
             t2.push_back(nd);
         }
-        auto emit = [](int l, std::vector<int>& dst) { dst.push_back(~l & 0x1fffffff); return 1; };      // one instance per TLAS leaf
-        tlas_root = collapseBvhWide(t2.data(), link < 0 ? (int)t2.size() - 1 : link, tlas, nnodes, tlas_order, emit, tlas_depth);
+        tlas_root = collapseBvh2(t2.data(), link < 0 ? (int)t2.size() - 1 : link, tlas, nnodes, 1, tlas_depth);
     }
-    // stack entries: one per level below the node in hand, four per instance entry, the bottom sentinel
-    if (blas_depth + tlas_depth + 8 > kBvhStack) return fail(ctx, PTAP_E_INVALID, "BVH too deep for the traversal stack (%d + %d levels, %d entries)", blas_depth, tlas_depth, kBvhStack);
+    if (3 * (blas_depth + tlas_depth) + 8 > kBvhStack) return fail(ctx, PTAP_E_INVALID, "BVH too deep for the traversal stack (%d + %d levels, %d entries)", blas_depth, tlas_depth, kBvhStack);
     if (nnodes + tlas.size() > ctx->nodes_cap) return fail(ctx, PTAP_E_NOMEM, "BVH node storage exhausted");
     CK(cudaMemcpyAsync(ctx->d_inst, ctx->h_inst.data(), nm * sizeof(InstanceTrace), cudaMemcpyHostToDevice, ctx->stream));
-    if (!tlas.empty()) {
-        CK(cudaMemcpyAsync(ctx->d_nodes + nnodes, tlas.data(), tlas.size() * sizeof(BvhNode), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->d_tlas_order, tlas_order.data(), tlas_order.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    }
+    if (!tlas.empty()) CK(cudaMemcpyAsync(ctx->d_nodes + nnodes, tlas.data(), tlas.size() * sizeof(BvhNode), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));      // tlas is stack-owned
     if (tlas_bytes) *tlas_bytes = nm * sizeof(InstanceTrace) + tlas.size() * sizeof(BvhNode);
     ctx->sc.tlas_root = tlas_root;
@@ -363,40 +357,53 @@ int finishBvh(ptap_ctx* ctx, const BvhNode* roots, const int* mesh_root, int nno
 int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id, const int* mesh_root, int known_depth, size_t* bytes)
 {
     const int nt = ctx->ntris, nm = (int)ctx->h_models.size();
-    if ((size_t)nnodes > ctx->nodes_cap) return fail(ctx, PTAP_E_NOMEM, "BVH has more nodes than reserved (one per triangle)");
+    if ((size_t)nnodes > ctx->nodes_cap) return fail(ctx, PTAP_E_NOMEM, "BVH has more nodes than reserved (2 per triangle)");
+    for (int i = 0; i < nnodes; ++i)
+        for (int k = 0; k < 4; ++k) {
+            const int l = nodes[i].link[k];
+            if (l >= nnodes) return fail(ctx, PTAP_E_INVALID, "BVH node %d: child index out of range", i);
+            if (l < 0) { const int code = ~l, first = code >> 3, cnt = (code & 7) + 1; if (code >= 0x20000000 || first < 0 || first + cnt > nt) return fail(ctx, PTAP_E_INVALID, "BVH node %d: leaf range out of bounds", i); }
+        }
     for (int k = 0; k < nt; ++k)
         if (tri_id[k] < 0 || tri_id[k] >= nt) return fail(ctx, PTAP_E_INVALID, "BVH leaf order entry %d out of range", k);
     for (size_t m = 0; m < ctx->h_meshes.size(); ++m)
         if (mesh_root[m] >= nnodes) return fail(ctx, PTAP_E_INVALID, "mesh %d: BVH root out of range", (int)m);
-    // Structure check and depth of every BLAS (the traversal stack is fixed-size).  Always computed from the nodes: a caller-supplied depth
-    // is only a hint that must not be trusted (an understated one would overflow the per-thread stack).  The builders emit parents before
-    // children, so ONE forward sweep gives every node's level and proves the links form a forest (each node has one parent, no cycles).
+    // Depth of every BLAS (the traversal stack is fixed-size).  Always computed from the nodes: a caller-supplied depth is only a hint that
+    // must not be trusted (an understated one would overflow the per-thread stack); the pass also rejects cycles and shared nodes.
     int blas_depth = 0;
     (void)known_depth;
     {
+        // the builders emit parents before children, so one forward sweep gives every node's level; any other order takes the stack walk
         std::vector<int> level(nnodes, 0);
+        bool ordered = true;
         for (size_t m = 0; m < ctx->h_meshes.size(); ++m) {
             if (mesh_root[m] < 0) continue;
             if (level[mesh_root[m]]) return fail(ctx, PTAP_E_INVALID, "BVH node %d is the root of two meshes", mesh_root[m]);
             level[mesh_root[m]] = 1;
         }
-        for (int i = 0; i < nnodes; ++i) {
+        for (int i = 0; i < nnodes && ordered; ++i) {
             if (!level[i]) continue;
             blas_depth = std::max(blas_depth, level[i]);
-            const BvhNode& nd = nodes[i];
-            if ((nd.inner_mask >> kBvhWidth) || (kBvhWidth < 8 && (nd.leaf_mask >> (4 * kBvhWidth)))) return fail(ctx, PTAP_E_INVALID, "BVH node %d: mask bits beyond the node width", i);
-            int ninner = 0, nleaf = 0;
-            for (int c = 0; c < kBvhWidth; ++c) {
-                const unsigned nib = nd.leaf_mask >> (4 * c) & 15u;
-                if (nd.inner_mask >> c & 1u) { if (nib) return fail(ctx, PTAP_E_INVALID, "BVH node %d: slot %d is both inner and leaf", i, c); ++ninner; }
-                else if (nib) { if (nib != 1u && nib != 3u && nib != 7u && nib != 15u) return fail(ctx, PTAP_E_INVALID, "BVH node %d: bad leaf count in slot %d", i, c); nleaf += __builtin_popcount(nib); }
-            }
-            if (nleaf && (nd.leaf_base < 0 || nd.leaf_base + nleaf > nt)) return fail(ctx, PTAP_E_INVALID, "BVH node %d: leaf range out of bounds", i);
-            for (int k = 0; k < ninner; ++k) {
-                const int l = nd.child_base + k;
-                if (l <= i || l >= nnodes) return fail(ctx, PTAP_E_INVALID, "BVH node %d: child index out of range or not after its parent", i);
+            for (int k = 0; k < 4; ++k) {
+                const int l = nodes[i].link[k];
+                if (l < 0 || !slotUsed(nodes[i], k)) continue;
+                if (l <= i) { ordered = false; break; }
                 if (level[l]) return fail(ctx, PTAP_E_INVALID, "BVH node %d is reachable twice", l);
                 level[l] = level[i] + 1;
+            }
+        }
+        if (!ordered) {
+            blas_depth = 0;
+            std::vector<std::pair<int, int>> todo;
+            std::vector<char> seen(nnodes, 0);
+            for (size_t m = 0; m < ctx->h_meshes.size(); ++m) if (mesh_root[m] >= 0) todo.push_back({mesh_root[m], 1});
+            while (!todo.empty()) {
+                const auto [node, d] = todo.back(); todo.pop_back();
+                if (seen[node]) return fail(ctx, PTAP_E_INVALID, "BVH node %d is reachable twice", node);
+                seen[node] = 1;
+                blas_depth = std::max(blas_depth, d);
+                for (int k = 0; k < 4; ++k)
+                    if (nodes[node].link[k] >= 0 && slotUsed(nodes[node], k)) todo.push_back({nodes[node].link[k], d + 1});
             }
         }
     }
@@ -590,10 +597,10 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
             if (v->refs[i] < 0 || v->refs[i] >= nt) return fail(ctx, PTAP_E_INVALID, "ref %d: triangle index out of range", i);
     }
 
-    // ---- one arena for everything scene-lifetime; BVH storage is reserved up front (T BLAS nodes + 2M TLAS nodes bound)
-    const size_t nodes_cap = (size_t)std::max(nt, 1) + (size_t)nm * 2 + 16;       // an 8-wide node has >= 2 children (a lone root: 1)
+    // ---- one arena for everything scene-lifetime; BVH storage is reserved up front (2T-1 BLAS nodes + 2M TLAS nodes bound)
+    const size_t nodes_cap = (size_t)std::max(nt, 1) * 2 + (size_t)nm * 2 + 2;
     size_t need = Arena::need(nm, sizeof(InstanceTrace)) + Arena::need(nm, sizeof(InstanceShade)) +
-                  Arena::need(nt, sizeof(TriRec)) + Arena::need(nt, sizeof(LeafTri)) + Arena::need(nt, sizeof(float4)) + Arena::need(nt, sizeof(int)) + Arena::need(nodes_cap, sizeof(BvhNode)) + Arena::need(nm, sizeof(int)) +
+                  Arena::need(nt, sizeof(TriRec)) + Arena::need(nt, sizeof(LeafTri)) + Arena::need(nt, sizeof(float4)) + Arena::need(nt, sizeof(int)) + Arena::need(nodes_cap, sizeof(BvhNode)) +
                   (grid ? Arena::need(v->nvoxels, sizeof(int2)) + Arena::need(v->nrefs, sizeof(int)) : 0) + 4096;
     if (need > ctx->scene_arena.cap) CK(ctx->scene_arena.reserve(need)); else ctx->scene_arena.used = 0;
     Arena& A = ctx->scene_arena;
@@ -604,10 +611,9 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
     float4* d_normals = A.alloc<float4>(nt);
     int* d_btid = A.alloc<int>(nt);
     BvhNode* d_nodes = A.alloc<BvhNode>(nodes_cap);
-    int* d_tlas_order = A.alloc<int>(nm);
     int2* d_cells = grid ? A.alloc<int2>(v->nvoxels) : nullptr;
     int* d_refs = grid ? A.alloc<int>(v->nrefs) : nullptr;
-    if (!d_inst || !d_shade || !d_tris || !d_normals || !d_btris || !d_btid || !d_nodes || !d_tlas_order || (grid && (!d_cells || !d_refs))) return fail(ctx, PTAP_E_NOMEM, "scene arena exhausted");
+    if (!d_inst || !d_shade || !d_tris || !d_normals || !d_btris || !d_btid || !d_nodes || (grid && (!d_cells || !d_refs))) return fail(ctx, PTAP_E_NOMEM, "scene arena exhausted");
     CK(cudaMemcpyAsync(d_inst, inst.data(), nm * sizeof(InstanceTrace), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_shade, shade.data(), nm * sizeof(InstanceShade), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_tris, recs, (size_t)nt * sizeof(TriRec), cudaMemcpyHostToDevice, ctx->stream));
@@ -620,7 +626,7 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
     size_t bytes = nm * (sizeof(InstanceTrace) + sizeof(InstanceShade)) + (size_t)nt * sizeof(TriRec) +
                    (grid ? cells.size() * sizeof(int2) + (size_t)v->nrefs * sizeof(int) : 0);
     ctx->h_inst = inst;
-    ctx->d_inst = d_inst; ctx->d_nodes = d_nodes; ctx->nodes_cap = nodes_cap; ctx->d_btris = d_btris; ctx->d_btid = d_btid; ctx->d_tlas_order = d_tlas_order;
+    ctx->d_inst = d_inst; ctx->d_nodes = d_nodes; ctx->nodes_cap = nodes_cap; ctx->d_btris = d_btris; ctx->d_btid = d_btid;
     ctx->have_bvh = false; ctx->bvh_kind = -1;
     if (v->bvh_nodes && v->n_bvh_nodes > 0 && v->bvh_tri_id && v->bvh_mesh_root) {
         if (v->n_bvh_tris != nt || v->n_bvh_roots != v->nmeshes) return fail(ctx, PTAP_E_INVALID, "upload_scene: prebuilt BVH does not match the triangle / mesh counts");
@@ -632,7 +638,7 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stats.scene_bytes = (int64_t)bytes;
     ctx->sc.inst = d_inst; ctx->sc.shade = d_shade; ctx->sc.tris = d_tris; ctx->sc.normals = d_normals;
-    ctx->sc.cells = d_cells; ctx->sc.refs = d_refs; ctx->sc.nodes = d_nodes; ctx->sc.bvh_tris = d_btris; ctx->sc.bvh_tri_id = d_btid; ctx->sc.tlas_order = d_tlas_order;
+    ctx->sc.cells = d_cells; ctx->sc.refs = d_refs; ctx->sc.nodes = d_nodes; ctx->sc.bvh_tris = d_btris; ctx->sc.bvh_tri_id = d_btid;
     ctx->sc.nmodels = nm; ctx->sc.gx = v->grid_dim[0]; ctx->sc.gy = v->grid_dim[1]; ctx->sc.gz = v->grid_dim[2];
     ctx->have_scene = true; ctx->have_grid = grid; ctx->cache_valid = false;
     ctx->accel = grid ? PTAP_ACCEL_GRID_COMPAT : PTAP_ACCEL_BVH;

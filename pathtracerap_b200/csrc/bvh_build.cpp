@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <functional>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -22,7 +23,7 @@ namespace ptap {
 namespace {
 
 constexpr int kBins = 16;
-int gMaxLeaf = 4;                    // SAH may stop earlier; hard cap 4 = one nibble of BvhNode::leaf_mask (PTAP_BVH_LEAF, tuning only)
+int gMaxLeaf = 4;                    // SAH may stop earlier; hard cap 8 by the link encoding (PTAP_BVH_LEAF, tuning only)
 float gNodeCost = 1.0f;              // cost of one inner node in units of one triangle test (PTAP_BVH_CI, tuning only)
 constexpr double kBandEps = 0.0056;  // > EPSILON (Config.h:4) to absorb rounding of u, v
 
@@ -97,7 +98,7 @@ struct Builder {
         if (n <= gMaxLeaf && (best_axis < 0 || best_cost + bounds.area() * gNodeCost >= leaf_cost)) return makeLeaf();
         int mid;
         if (best_axis < 0) {
-            if (n <= kBvhLeafMax) return makeLeaf();
+            if (n <= 8) return makeLeaf();
             mid = begin + n / 2;         // identical centroids: split by count
         } else {
             const float lo = cb.lo[best_axis], scale = kBins / (cb.hi[best_axis] - cb.lo[best_axis]);
@@ -126,200 +127,36 @@ struct Builder {
 
 }  // namespace
 
-// ---- IEEE binary16 with directed rounding ----------------------------------------------------------------------------------------------
-
-static unsigned short halfMagnitude(double a, bool up)      // a >= 0
+void encodeNode(BvhNode& nd, const ChildBox boxes[4], unsigned used)
 {
-    if (a == 0.0) return 0;
-    if (a >= 65504.0) return 0x7bff;                          // callers keep |x| far below this (quantiseNode picks the scale)
-    int e; std::frexp(a, &e); e -= 1;                         // a = m * 2^e, m in [1, 2)
-    if (e < -14) {                                            // subnormal half: multiples of 2^-24
-        const double q = std::ldexp(a, 24);
-        double m = std::floor(q);
-        if (up && m != q) m += 1.0;
-        return (unsigned short)m;                             // 0x400 (the smallest normal) falls out naturally
-    }
-    const double q = std::ldexp(a, 10 - e);                   // in [1024, 2048)
-    double m = std::floor(q);
-    if (up && m != q) m += 1.0;
-    if (m >= 2048.0) { m = 1024.0; e += 1; }
-    return (unsigned short)(((e + 15) << 10) | ((int)m - 1024));
-}
-
-unsigned short halfRoundDown(float x) { return x >= 0.f ? halfMagnitude(x, false) : (unsigned short)(0x8000 | halfMagnitude(-(double)x, true)); }
-unsigned short halfRoundUp(float x) { return x >= 0.f ? halfMagnitude(x, true) : (unsigned short)(0x8000 | halfMagnitude(-(double)x, false)); }
-
-float halfToFloat(unsigned short h)
-{
-    const int e = (h >> 10) & 31, m = h & 1023;
-    const double v = e == 0 ? std::ldexp((double)m, -24) : std::ldexp((double)(m + 1024), e - 25);
-    return (float)((h & 0x8000) ? -v : v);
-}
-
-void quantiseNode(BvhNode& nd, const ChildBox boxes[8], unsigned used)
-{
-    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX}, mag = 0.0;
-    for (int c = 0; c < kBvhWidth; ++c) {
+    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mag = 0.0;
+    for (int c = 0; c < 4; ++c) {
         if (!(used >> c & 1)) continue;
         for (int k = 0; k < 3; ++k) {
-            lo[k] = std::min(lo[k], (double)boxes[c].lo[k]); hi[k] = std::max(hi[k], (double)boxes[c].hi[k]);
+            lo[k] = std::min(lo[k], (double)boxes[c].lo[k]);
             mag = std::max(mag, std::max(std::fabs((double)boxes[c].lo[k]), std::fabs((double)boxes[c].hi[k])));
         }
     }
-    if (!used) { for (int k = 0; k < 3; ++k) lo[k] = hi[k] = 0.0; }
+    if (!used) { for (int k = 0; k < 3; ++k) lo[k] = 0.0; }
     // Margin for the traversal's own arithmetic: it evaluates (p - o) * inv and one FMA per plane in binary32, which perturbs a plane by
-    // a few 2^-24 of the coordinates involved; 2^-20 of the largest coordinate of the node plus one float ulp of p covers it many times.
+    // a few 2^-24 of the coordinates involved; 2^-20 of the largest coordinate of the node covers it many times over.
     const double margin = std::ldexp(mag, -20) + 1e-30;
     const float p[3] = {std::nextafter((float)(lo[0] - margin), -FLT_MAX), std::nextafter((float)(lo[1] - margin), -FLT_MAX), std::nextafter((float)(lo[2] - margin), -FLT_MAX)};
-    nd.px = p[0]; nd.py = p[1]; nd.pz = p[2];
-    if (kBvhWidth == 8) {
-        double ext = 0.0;
-        for (int k = 0; k < 3; ++k) ext = std::max(ext, hi[k] + margin - (double)p[k]);
-        // scale = 2^e with ext / scale in (8192, 16384]: the offsets use the top of the half range whatever the size of the node
-        int e = 0;
-        if (ext > 0.0) { std::frexp(ext, &e); e -= 14; }           // ext = m * 2^(e+14), m in [0.5, 1)  =>  ext / 2^e in [8192, 16384)
-        const double scale = std::ldexp(1.0, e);
-        nd.scale = (float)scale;
-        for (int c = 0; c < 8; ++c)
-            for (int k = 0; k < 3; ++k) {
-                if (used >> c & 1) {
-                    nd.planes.h[k][0][c] = halfRoundDown((float)(((double)boxes[c].lo[k] - margin - (double)p[k]) / scale - 1e-3));
-                    nd.planes.h[k][1][c] = halfRoundUp((float)(((double)boxes[c].hi[k] + margin - (double)p[k]) / scale + 1e-3));
-                } else { nd.planes.h[k][0][c] = 0x7bff; nd.planes.h[k][1][c] = 0; }       // inverted: never entered (its mask bits are clear anyway)
-            }
-    } else {
-        for (int c = 0; c < 4; ++c)
-            for (int k = 0; k < 3; ++k) {
-                if (used >> c & 1) {
-                    // binary32 offsets, rounded outward: p + offset (in real arithmetic) lies beyond the builder's plane by at least the margin
-                    nd.planes.f[k][0][c] = std::nextafter((float)((double)boxes[c].lo[k] - margin - (double)p[k]), -FLT_MAX);
-                    nd.planes.f[k][1][c] = std::nextafter((float)((double)boxes[c].hi[k] + margin - (double)p[k]), FLT_MAX);
-                } else { nd.planes.f[k][0][c] = 3e38f; nd.planes.f[k][1][c] = -3e38f; }
-            }
-    }
+    nd.px = p[0]; nd.py = p[1]; nd.pz = p[2]; nd.pad = 0;
+    for (int c = 0; c < 4; ++c)
+        for (int k = 0; k < 3; ++k) {
+            if (used >> c & 1) {
+                // rounded outward: p + offset (in real arithmetic) lies beyond the builder's plane by at least the margin
+                nd.planes[k][0][c] = std::nextafter((float)((double)boxes[c].lo[k] - margin - (double)p[k]), -FLT_MAX);
+                nd.planes[k][1][c] = std::nextafter((float)((double)boxes[c].hi[k] + margin - (double)p[k]), FLT_MAX);
+            } else { nd.planes[k][0][c] = 1e15f; nd.planes[k][1][c] = -1e15f; }       // inverted: near > far on every axis, never entered
+        }
 }
 
 void decodeChild(const BvhNode& nd, int c, double lo[3], double hi[3])
 {
     const double p[3] = {nd.px, nd.py, nd.pz};
-    for (int k = 0; k < 3; ++k) {
-        if (kBvhWidth == 8) { lo[k] = p[k] + (double)nd.scale * halfToFloat(nd.planes.h[k][0][c]); hi[k] = p[k] + (double)nd.scale * halfToFloat(nd.planes.h[k][1][c]); }
-        else { lo[k] = p[k] + (double)nd.planes.f[k][0][c]; hi[k] = p[k] + (double)nd.planes.f[k][1][c]; }
-    }
-}
-
-int collapseBvhWide(const Bvh2Node* n2, int root2, std::vector<BvhNode>& out, int base, std::vector<int>& order,
-                 const std::function<int(int, std::vector<int>&)>& emit_leaf, int& max_depth)
-{
-    struct Child { float lo[3], hi[3]; int link; };
-    auto childrenOf = [&](int n, Child* dst) {
-        const Bvh2Node& nd = n2[n];
-        dst[0] = Child{{nd.xy0.x, nd.xy0.z, nd.z01.x}, {nd.xy0.y, nd.xy0.w, nd.z01.y}, nd.link.x};
-        if (nd.link.x == nd.link.y) return 1;
-        dst[1] = Child{{nd.xy1.x, nd.xy1.z, nd.z01.z}, {nd.xy1.y, nd.xy1.w, nd.z01.w}, nd.link.y};
-        return 2;
-    };
-    struct Work { int node2, index, depth; };
-    std::vector<Work> todo;
-    const int root_index = (int)out.size();
-    out.emplace_back();
-    todo.push_back(Work{root2, root_index, 1});
-    while (!todo.empty()) {
-        const Work w = todo.back(); todo.pop_back();
-        max_depth = std::max(max_depth, w.depth);
-        Child ch[9];
-        int n = childrenOf(w.node2, ch);
-        while (n < kBvhWidth) {                      // open the inner child with the largest box
-            int best = -1; float best_area = -1.f;
-            for (int i = 0; i < n; ++i) {
-                if (ch[i].link < 0) continue;
-                Box bx; for (int k = 0; k < 3; ++k) { bx.lo[k] = ch[i].lo[k]; bx.hi[k] = ch[i].hi[k]; }
-                const float a = bx.area();
-                if (a > best_area) { best_area = a; best = i; }
-            }
-            if (best < 0) break;
-            Child two[2];
-            const int m = childrenOf(ch[best].link, two);
-            ch[best] = two[0];
-            if (m == 2) ch[n++] = two[1];
-        }
-        // slot assignment: child c should sit in the slot whose corner direction its centre points to (greedy on the largest remaining dot
-        // product of (centre - node centre) with the slot's (+-1, ...)).  Width 8: three sign bits per slot.  Width 4: the two axes along
-        // which the children's centres are most spread carry the two slot bits.
-        float nlo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, nhi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-        for (int i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) { nlo[k] = std::min(nlo[k], ch[i].lo[k]); nhi[k] = std::max(nhi[k], ch[i].hi[k]); }
-        int axis_of_bit[3] = {0, 1, 2};
-        if (kBvhWidth == 4) {
-            float spread[3];
-            for (int k = 0; k < 3; ++k) {
-                float cmin = FLT_MAX, cmax = -FLT_MAX;
-                for (int i = 0; i < n; ++i) { const float c = 0.5f * (ch[i].lo[k] + ch[i].hi[k]); cmin = std::min(cmin, c); cmax = std::max(cmax, c); }
-                spread[k] = cmax - cmin;
-            }
-            int a = 0;
-            for (int k = 1; k < 3; ++k) if (spread[k] > spread[a]) a = k;
-            int b2 = a == 0 ? 1 : 0;
-            for (int k = 0; k < 3; ++k) if (k != a && spread[k] > spread[b2]) b2 = k;
-            axis_of_bit[0] = a; axis_of_bit[1] = b2;
-        }
-        const int nbits = kBvhWidth == 8 ? 3 : 2;
-        float cost[8][8];
-        for (int i = 0; i < n; ++i)
-            for (int s = 0; s < kBvhWidth; ++s) {
-                float acc = 0.f;
-                for (int bit = 0; bit < nbits; ++bit) {
-                    const int k = axis_of_bit[bit];
-                    const float d = 0.5f * (ch[i].lo[k] + ch[i].hi[k]) - 0.5f * (nlo[k] + nhi[k]);
-                    acc += (s >> bit & 1) ? d : -d;
-                }
-                cost[i][s] = acc;
-            }
-        int slot_of[8]; bool child_done[8] = {}, slot_used[8] = {};
-        for (int round = 0; round < n; ++round) {
-            int bi = -1, bs = -1; float bc = -FLT_MAX;
-            for (int i = 0; i < n; ++i) {
-                if (child_done[i]) continue;
-                for (int s = 0; s < kBvhWidth; ++s) if (!slot_used[s] && cost[i][s] > bc) { bc = cost[i][s]; bi = i; bs = s; }
-            }
-            slot_of[bi] = bs; child_done[bi] = true; slot_used[bs] = true;
-        }
-        int child_in_slot[8];
-        for (int s = 0; s < 8; ++s) child_in_slot[s] = -1;
-        for (int i = 0; i < n; ++i) child_in_slot[slot_of[i]] = i;
-        BvhNode nd;
-        memset(&nd, 0, sizeof nd);
-        ChildBox boxes[8];
-        unsigned used = 0;
-        int ninner = 0;
-        for (int s = 0; s < kBvhWidth; ++s) if (child_in_slot[s] >= 0 && ch[child_in_slot[s]].link >= 0) ++ninner;
-        nd.child_base = base + (int)out.size();
-        nd.leaf_base = (int)order.size();
-        const int first_child = (int)out.size();
-        out.resize(out.size() + ninner);
-        int next_inner = 0;
-        for (int s = 0; s < kBvhWidth; ++s) {
-            const int i = child_in_slot[s];
-            if (i < 0) continue;
-            used |= 1u << s;
-            for (int k = 0; k < 3; ++k) { boxes[s].lo[k] = ch[i].lo[k]; boxes[s].hi[k] = ch[i].hi[k]; }
-            if (ch[i].link >= 0) {
-                nd.inner_mask |= 1u << s;
-                todo.push_back(Work{ch[i].link, first_child + next_inner, w.depth + 1});
-                ++next_inner;
-            } else {
-                const int cnt = emit_leaf(ch[i].link, order);
-                nd.leaf_mask |= ((1u << cnt) - 1u) << (4 * s);
-            }
-        }
-        quantiseNode(nd, boxes, used);
-        if (kBvhWidth == 4) {            // slot key per sign octant: bit 0 / 1 = the ray runs downwards along axis a / b
-            unsigned order = 0u;
-            for (unsigned oct = 0; oct < 8; ++oct) order |= (((oct >> axis_of_bit[0]) & 1u) | (((oct >> axis_of_bit[1]) & 1u) << 1)) << (2 * oct);
-            nd.order = order;
-        }
-        out[w.index] = nd;
-    }
-    return base + root_index;
+    for (int k = 0; k < 3; ++k) { lo[k] = p[k] + (double)nd.planes[k][0][c]; hi[k] = p[k] + (double)nd.planes[k][1][c]; }
 }
 
 long long validateBvh(const BvhNode* nodes, int nnodes, int root, int nleafprims, const std::function<ChildBox(int)>& prim_box, int* depth)
@@ -340,35 +177,76 @@ long long validateBvh(const BvhNode* nodes, int nnodes, int root, int nleafprims
         seen[it.node] = 1;
         maxd = std::max(maxd, it.depth);
         const BvhNode& nd = nodes[it.node];
-        int inner_rank = 0, leaf_rank = 0;
-        if ((nd.inner_mask >> kBvhWidth) || (kBvhWidth < 8 && (nd.leaf_mask >> (4 * kBvhWidth)))) ++bad;
-        for (int c = 0; c < kBvhWidth; ++c) {
-            const bool inner = nd.inner_mask >> c & 1;
-            const unsigned nib = nd.leaf_mask >> (4 * c) & 15u;
-            if (inner && nib) { ++bad; continue; }
-            if (!inner && !nib) continue;
+        for (int c = 0; c < 4; ++c) {
+            if (!slotUsed(nd, c)) continue;
             double lo[3], hi[3];
             decodeChild(nd, c, lo, hi);
             for (int k = 0; k < 3; ++k) { lo[k] = std::max(lo[k], it.lo[k]); hi[k] = std::min(hi[k], it.hi[k]); }
-            if (inner) {
-                Item ch{}; ch.node = nd.child_base + inner_rank++; ch.depth = it.depth + 1;
+            const int l = nd.link[c];
+            if (l >= 0) {
+                Item ch{}; ch.node = l; ch.depth = it.depth + 1;
                 for (int k = 0; k < 3; ++k) { ch.lo[k] = lo[k]; ch.hi[k] = hi[k]; }
                 todo.push_back(ch);
             } else {
-                const int cnt = nib == 1 ? 1 : nib == 3 ? 2 : nib == 7 ? 3 : nib == 15 ? 4 : -1;
-                if (cnt < 0) { ++bad; continue; }
+                const int code = ~l, first = code >> 3, cnt = (code & 7) + 1;
+                if (code >= 0x20000000) { ++bad; continue; }
                 for (int j = 0; j < cnt; ++j) {
-                    const int pos = nd.leaf_base + leaf_rank + j;
+                    const int pos = first + j;
                     if (pos < 0 || pos >= nleafprims) { ++bad; continue; }
                     const ChildBox pb = prim_box(pos);
                     for (int k = 0; k < 3; ++k) if (!(lo[k] <= (double)pb.lo[k] && hi[k] >= (double)pb.hi[k])) ++bad;
                 }
-                leaf_rank += cnt;
             }
         }
     }
     if (depth) *depth = maxd;
     return bad;
+}
+
+int collapseBvh2(const Bvh2Node* n2, int root2, std::vector<BvhNode>& out, int base, int depth, int& max_depth)
+{
+    struct Child { float lo[3], hi[3]; int link; };
+    auto childrenOf = [&](int n, Child* dst) {
+        const Bvh2Node& nd = n2[n];
+        dst[0] = Child{{nd.xy0.x, nd.xy0.z, nd.z01.x}, {nd.xy0.y, nd.xy0.w, nd.z01.y}, nd.link.x};
+        if (nd.link.x == nd.link.y) return 1;
+        dst[1] = Child{{nd.xy1.x, nd.xy1.z, nd.z01.z}, {nd.xy1.y, nd.xy1.w, nd.z01.w}, nd.link.y};
+        return 2;
+    };
+    max_depth = std::max(max_depth, depth);
+    Child ch[5];
+    int n = childrenOf(root2, ch);
+    while (n < 4) {
+        int best = -1; float best_area = -1.f;
+        for (int i = 0; i < n; ++i) {
+            if (ch[i].link < 0) continue;
+            Box bx; for (int k = 0; k < 3; ++k) { bx.lo[k] = ch[i].lo[k]; bx.hi[k] = ch[i].hi[k]; }
+            const float a = bx.area();
+            if (a > best_area) { best_area = a; best = i; }
+        }
+        if (best < 0) break;
+        Child two[2];
+        const int m = childrenOf(ch[best].link, two);
+        ch[best] = two[0];
+        if (m == 2) ch[n++] = two[1];
+    }
+    const int me = (int)out.size();
+    out.emplace_back();
+    int links[4];
+    for (int i = 0; i < n; ++i) links[i] = ch[i].link >= 0 ? collapseBvh2(n2, ch[i].link, out, base, depth + 1, max_depth) : ch[i].link;
+    BvhNode& nd = out[me];
+    memset(&nd, 0, sizeof nd);
+    ChildBox boxes[4];
+    unsigned used = 0u;
+    for (int i = 0; i < 4; ++i) {
+        if (i < n) {
+            for (int k = 0; k < 3; ++k) { boxes[i].lo[k] = ch[i].lo[k]; boxes[i].hi[k] = ch[i].hi[k]; }
+            used |= 1u << i;
+            nd.link[i] = links[i];
+        } else nd.link[i] = links[0];
+    }
+    encodeNode(nd, boxes, used);
+    return base + me;
 }
 
 void makeTriRecs(const PtapVertex* vertices, const PtapTriangle* triangles, int ntris, TriRec* out)
@@ -389,7 +267,7 @@ void makeTriRecs(const PtapVertex* vertices, const PtapTriangle* triangles, int 
 void buildSceneBvh(const TriRec* tris, int ntris, const PtapMesh* meshes, int nmeshes, BvhBuildResult& out)
 {
     out.nodes.clear(); out.tri_id.clear();
-    if (const char* e = getenv("PTAP_BVH_LEAF")) gMaxLeaf = std::min(kBvhLeafMax, std::max(1, atoi(e)));
+    if (const char* e = getenv("PTAP_BVH_LEAF")) gMaxLeaf = std::min(8, std::max(1, atoi(e)));
     if (const char* e = getenv("PTAP_BVH_CI")) gNodeCost = (float)atof(e);
     out.mesh_root.assign(nmeshes, -1);
     out.max_depth = 0;
@@ -422,10 +300,11 @@ void buildSceneBvh(const TriRec* tris, int ntris, const PtapMesh* meshes, int nm
             }
             p.c[0] = (float)(cx / 3); p.c[1] = (float)(cy / 3); p.c[2] = (float)(cz / 3);
         }
-        std::vector<int> order; order.reserve(prims.size());      // binary-tree leaf order: positions -> global triangle ids
+        std::vector<int> order; order.reserve(prims.size());
         std::vector<Bvh2Node> n2;
         n2.reserve(prims.size());
-        Builder b{prims, n2, order, 0};
+        const int leaf_base = (int)out.tri_id.size();
+        Builder b{prims, n2, order, leaf_base};
         Box bounds;
         // Large meshes: the top of the tree is built here, subtrees of <= n/64 primitives on worker threads into private arrays, which are
         // then appended (node indices and leaf positions shifted).  The tree is the one the serial build produces; only node numbering differs.
@@ -450,7 +329,7 @@ void buildSceneBvh(const TriRec* tris, int ntris, const PtapMesh* meshes, int nm
             work();
             for (std::thread& t : pool) t.join();
             for (size_t k = 0; k < tasks.size(); ++k) {          // tasks were recorded in depth-first order: so is the leaf order
-                const int node_off = (int)n2.size(), leaf_off = (int)order.size();
+                const int node_off = (int)n2.size(), leaf_off = leaf_base + (int)order.size();
                 auto shift = [&](int l) { return l >= 0 ? l + node_off : ~(~l + (leaf_off << 3)); };
                 for (Bvh2Node nd : subs[k].nodes) { nd.link.x = shift(nd.link.x); nd.link.y = shift(nd.link.y); n2.push_back(nd); }
                 order.insert(order.end(), subs[k].order.begin(), subs[k].order.end());
@@ -468,15 +347,10 @@ void buildSceneBvh(const TriRec* tris, int ntris, const PtapMesh* meshes, int nm
             nd.link = make_int4(link, link, 0, 0);
             n2.push_back(nd);
         }
-        // binary leaf link ~((first << 3) | (count - 1)) over `order` -> the leaf's triangles appended to the scene-wide leaf order
-        auto emit = [&](int l, std::vector<int>& dst) {
-            const int code = ~l, first = code >> 3, cnt = (code & 7) + 1;
-            for (int j = 0; j < cnt; ++j) dst.push_back(order[first + j]);
-            return cnt;
-        };
-        int depth8 = 0;
-        out.mesh_root[mi] = collapseBvhWide(n2.data(), link < 0 ? (int)n2.size() - 1 : link, out.nodes, 0, out.tri_id, emit, depth8);
-        out.max_depth = std::max(out.max_depth, depth8);
+        int depth4 = 0;
+        out.mesh_root[mi] = collapseBvh2(n2.data(), link < 0 ? (int)n2.size() - 1 : link, out.nodes, 0, 1, depth4);
+        out.max_depth = std::max(out.max_depth, depth4);
+        for (int id : order) out.tri_id.push_back(id);
     }
 }
 

@@ -1,16 +1,14 @@
-// bvh_device.cu - builds the per-mesh 8-wide compressed BVH on the GPU (PTAP_ACCEL_BVH_DEVICE): an LBVH in milliseconds instead of the host's
+// bvh_device.cu - builds the per-mesh 4-wide BVH on the GPU (PTAP_ACCEL_BVH_DEVICE): an LBVH in milliseconds instead of the host's
 // binned-SAH build in seconds (the reference builds its only structure, the 25^3 grid, on the host: Scene.cpp:318-396).
 //
 //   1  k_lbvh_keys      per triangle: box of the FATTENED triangle (the predicate's tolerance band, as bvh_build.cpp) and the 30-bit Morton
 //                       code of its centroid inside the mesh bounds
 //   2  cub radix sort   (key, triangle id) pairs                                        [library call: not on the render path]
-//   3  k_lbvh_leaves    every sorted triangle becomes a leaf of the binary radix tree: its box and 64-bit key
+//   3  k_lbvh_leaves    every sorted triangle (or cluster of kCluster consecutive ones) becomes a leaf: LeafTri records in leaf order, leaf boxes
 //   4  k_lbvh_topology  Karras 2012: every internal node of the binary radix tree over the leaves finds its range and split independently
 //   5  k_lbvh_refit     bottom-up box fit, the second child to arrive at a node continues upwards (one atomic counter per node)
-//   6  k_lbvh_collapse  breadth-first, one launch per level: a binary node becomes one 8-wide BvhNode (device_types.h) - the child with the
-//                       largest box is opened until eight remain, a subtree of at most four triangles becomes ONE leaf child, children
-//                       go to octant slots, boxes are compressed with outward rounding (the same node the host builder emits), and the
-//                       node's leaf triangles are written as consecutive LeafTri records
+//   6  k_lbvh_collapse  breadth-first, one launch per level: a binary node and its two children become one 4-wide BvhNode, its child boxes
+//                       encoded as outward-rounded offsets from a node-local origin exactly as the host builder does (bvh_build.cpp: encodeNode)
 //
 // The tree is a different one than the host builder's, so rays visit different boxes; hits are bit-identical all the same, because the
 // boxes are conservative for the reference's predicate and the triangle arithmetic is the exact one (tests/test_gpu_device_bvh.py).
@@ -19,7 +17,6 @@
 #include <utility>
 
 #include <cub/device/device_radix_sort.cuh>
-#include <cuda_fp16.h>
 
 #include "kernels.cuh"
 
@@ -28,6 +25,10 @@ namespace ptap {
 namespace {
 
 constexpr float kBandEpsF = 0.0056f;          // > EPSILON (Config.h:4), as bvh_build.cpp
+#ifndef PTAP_LBVH_CLUSTER
+#define PTAP_LBVH_CLUSTER 1
+#endif
+constexpr int kCluster = PTAP_LBVH_CLUSTER;    // consecutive Morton-sorted triangles per leaf
 
 __device__ __forceinline__ unsigned expandBits(unsigned v)
 {
@@ -73,14 +74,32 @@ __global__ void k_lbvh_keys(const TriRec* __restrict__ tris, int t0, int n, floa
     ids[i] = t0 + i;
 }
 
-// leaf c = sorted triangle c: its box (bounding the predicate's tolerance band) and its 64-bit key
-__global__ void k_lbvh_leaves(const TriRec* __restrict__ tris, const unsigned* __restrict__ keys, const int* __restrict__ ids, int n,
-                              float slack, Box6* __restrict__ leaf_box, unsigned long long* __restrict__ leaf_key)
+// leaf c = sorted triangles [kCluster c, min(kCluster (c + 1), n)): LeafTri records at leaf_base + k, global ids, the cluster's box and its 64-bit key
+__global__ void k_lbvh_leaves(const TriRec* __restrict__ tris, const unsigned* __restrict__ keys, const int* __restrict__ ids, int n, int nleaves,
+                              float slack, int leaf_base, LeafTri* __restrict__ btris, int* __restrict__ btid, Box6* __restrict__ leaf_box,
+                              unsigned long long* __restrict__ leaf_key)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
-    leaf_box[c] = fatBox(tris[ids[c]], slack);
-    leaf_key[c] = ((unsigned long long)keys[c] << 32) | (unsigned)c;          // the index makes equal Morton codes distinct
+    if (c >= nleaves) return;
+    Box6 box;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { box.lo[k] = 3e38f; box.hi[k] = -3e38f; }
+    const int first = kCluster * c, last = min(first + kCluster, n);
+    for (int s = first; s < last; ++s) {
+        const int id = ids[s];
+        const TriRec r = tris[id];
+        const Box6 b = fatBox(r, slack);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { box.lo[k] = fminf(box.lo[k], b.lo[k]); box.hi[k] = fmaxf(box.hi[k], b.hi[k]); }
+        float4* o = reinterpret_cast<float4*>(&btris[leaf_base + s]);
+        o[0] = make_float4(r.v0.x, r.v0.y, r.v0.z, r.e1.x);
+        o[1] = make_float4(r.e1.y, r.e1.z, r.e2.x, r.e2.y);
+        o[2] = make_float4(r.e2.z, __int_as_float(id), 0.0f, 0.0f);
+        o[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        btid[leaf_base + s] = id;
+    }
+    leaf_box[c] = box;
+    leaf_key[c] = ((unsigned long long)keys[first] << 32) | (unsigned)c;          // the index makes equal Morton codes distinct
 }
 
 __device__ __forceinline__ int delta(const unsigned long long* __restrict__ k, int n, int i, int j)
@@ -90,8 +109,8 @@ __device__ __forceinline__ int delta(const unsigned long long* __restrict__ k, i
 
 // Karras, "Maximizing parallelism in the construction of BVHs, octrees and k-d trees" (2012): internal node i of n - 1.
 // child >= 0: internal node; child < 0: leaf ~index.
-__global__ void k_lbvh_topology(const unsigned long long* __restrict__ key, int nleaves, int2* __restrict__ child, int2* __restrict__ range,
-                                int* __restrict__ parent_internal, int* __restrict__ parent_leaf)
+__global__ void k_lbvh_topology(const unsigned long long* __restrict__ key, int nleaves, int2* __restrict__ child, int* __restrict__ parent_internal,
+                                int* __restrict__ parent_leaf)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nleaves - 1) return;
@@ -113,7 +132,6 @@ __global__ void k_lbvh_topology(const unsigned long long* __restrict__ key, int 
     const int lo = min(i, j), hi = max(i, j);
     const int left = lo == gamma ? ~gamma : gamma, right = hi == gamma + 1 ? ~(gamma + 1) : gamma + 1;
     child[i] = make_int2(left, right);
-    range[i] = make_int2(lo, hi);
     if (left >= 0) parent_internal[left] = i; else parent_leaf[~left] = i;
     if (right >= 0) parent_internal[right] = i; else parent_leaf[~right] = i;
     if (i == 0) parent_internal[0] = -1;
@@ -149,182 +167,76 @@ __global__ void k_lbvh_refit(const int2* __restrict__ child, const int* __restri
     }
 }
 
-__device__ __forceinline__ float boxArea(const Box6& b)
+__device__ __forceinline__ int leafLink(int c, int n, int leaf_base)
 {
-    const float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
-    return dx * dy + dy * dz + dz * dx;
+    const int first = kCluster * c, count = min(kCluster, n - first);
+    return ~(((leaf_base + first) << 3) | (count - 1));
 }
 
-__device__ __forceinline__ void writeLeafTri(const TriRec* __restrict__ tris, int id, LeafTri* __restrict__ dst)
+// Child boxes of `nd` from up to four boxes (`ne` of them, slots 0 .. ne - 1), as bvh_build.cpp: encodeNode does on the host: local origin
+// just below the node's lower corner, binary32 offsets rounded outward after a margin of 2^-20 of the largest coordinate; unused slots
+// get an inverted box.
+__device__ void encodeNodeDevice(BvhNode& nd, const Box6* boxes, int ne)
 {
-    const TriRec r = tris[id];
-    float4* o = reinterpret_cast<float4*>(dst);
-    o[0] = make_float4(r.v0.x, r.v0.y, r.v0.z, r.e1.x);
-    o[1] = make_float4(r.e1.y, r.e1.z, r.e2.x, r.e2.y);
-    o[2] = make_float4(r.e2.z, __int_as_float(id), 0.0f, 0.0f);
-    o[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-}
-
-// Encodes up to kBvhWidth child boxes into `nd` as bvh_build.cpp: quantiseNode does on the host: local origin just below the node's lower
-// corner, offsets rounded outward after a margin of 2^-20 of the largest coordinate (width 8: IEEE half times a power-of-two scale that
-// puts the largest offset in (8192, 16384]; width 4: binary32).
-__device__ void quantiseNodeDevice(BvhNode& nd, const Box6* boxes, const int* slot_entry)
-{
-    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f}, mag = 0.0f;
-    for (int c = 0; c < kBvhWidth; ++c) {
-        if (slot_entry[c] < 0) continue;
-        const Box6& b = boxes[slot_entry[c]];
+    float lo[3] = {3e38f, 3e38f, 3e38f}, mag = 0.0f;
+    for (int c = 0; c < ne; ++c)
         for (int k = 0; k < 3; ++k) {
-            lo[k] = fminf(lo[k], b.lo[k]); hi[k] = fmaxf(hi[k], b.hi[k]);
-            mag = fmaxf(mag, fmaxf(fabsf(b.lo[k]), fabsf(b.hi[k])));
+            lo[k] = fminf(lo[k], boxes[c].lo[k]);
+            mag = fmaxf(mag, fmaxf(fabsf(boxes[c].lo[k]), fabsf(boxes[c].hi[k])));
         }
-    }
     const float margin = __fmul_ru(mag, 9.5367431640625e-7f) + 1e-30f;       // 2^-20
-    float p[3], ext = 0.0f;
-    for (int k = 0; k < 3; ++k) { p[k] = nextafterf(__fsub_rd(lo[k], margin), -3e38f); ext = fmaxf(ext, __fsub_ru(__fadd_ru(hi[k], margin), p[k])); }
-    nd.px = p[0]; nd.py = p[1]; nd.pz = p[2];
-    if (kBvhWidth == 8) {
-        int e = 0;
-        if (ext > 0.0f) { frexpf(ext, &e); e -= 14; }
-        const float scale = ldexpf(1.0f, e), inv_scale = ldexpf(1.0f, -e);    // exact powers of two
-        nd.scale = scale;
-        for (int c = 0; c < 8; ++c)
-            for (int k = 0; k < 3; ++k) {
-                if (slot_entry[c] >= 0) {
-                    const Box6& b = boxes[slot_entry[c]];
-                    const float l = __fsub_rd(__fmul_rd(__fsub_rd(__fsub_rd(b.lo[k], margin), p[k]), inv_scale), 1e-3f);
-                    const float h = __fadd_ru(__fmul_ru(__fsub_ru(__fadd_ru(b.hi[k], margin), p[k]), inv_scale), 1e-3f);
-                    nd.planes.h[k][0][c] = __half_as_ushort(__float2half_rd(l));
-                    nd.planes.h[k][1][c] = __half_as_ushort(__float2half_ru(h));
-                } else { nd.planes.h[k][0][c] = 0x7bff; nd.planes.h[k][1][c] = 0; }
-            }
-    } else {
-        for (int c = 0; c < 4; ++c)
-            for (int k = 0; k < 3; ++k) {
-                if (slot_entry[c] >= 0) {
-                    const Box6& b = boxes[slot_entry[c]];
-                    nd.planes.f[k][0][c] = nextafterf(__fsub_rd(__fsub_rd(b.lo[k], margin), p[k]), -3e38f);
-                    nd.planes.f[k][1][c] = nextafterf(__fsub_ru(__fadd_ru(b.hi[k], margin), p[k]), 3e38f);
-                } else { nd.planes.f[k][0][c] = 3e38f; nd.planes.f[k][1][c] = -3e38f; }
-            }
-    }
+    float p[3];
+    for (int k = 0; k < 3; ++k) p[k] = nextafterf(__fsub_rd(lo[k], margin), -3e38f);
+    nd.px = p[0]; nd.py = p[1]; nd.pz = p[2]; nd.pad = 0;
+    for (int c = 0; c < 4; ++c)
+        for (int k = 0; k < 3; ++k) {
+            if (c < ne) {
+                nd.planes[k][0][c] = nextafterf(__fsub_rd(__fsub_rd(boxes[c].lo[k], margin), p[k]), -3e38f);
+                nd.planes[k][1][c] = nextafterf(__fsub_ru(__fadd_ru(boxes[c].hi[k], margin), p[k]), 3e38f);
+            } else { nd.planes[k][0][c] = 1e15f; nd.planes[k][1][c] = -1e15f; }
+        }
 }
 
-// One breadth-first level: frontier item = (binary internal node, index of the 8-wide node that represents it).
-// counters: [0] nodes allocated, [1] size of the next frontier, [2] leaf triangles written.
-__global__ void k_lbvh_collapse(const TriRec* __restrict__ tris, const int* __restrict__ ids, const int2* __restrict__ child, const int2* __restrict__ range,
-                                const Box6* __restrict__ node_box, const Box6* __restrict__ leaf_box, int leaf_base,
-                                const int2* __restrict__ frontier, int nfrontier, int2* __restrict__ next, int* __restrict__ counters,
-                                int node_base, BvhNode* __restrict__ out, LeafTri* __restrict__ btris, int* __restrict__ btid)
+// One breadth-first level: frontier item = (binary internal node, index of the 4-wide node that represents it).
+__global__ void k_lbvh_collapse(const int2* __restrict__ child, const Box6* __restrict__ node_box, const Box6* __restrict__ leaf_box, int n, int leaf_base,
+                                const int2* __restrict__ frontier, int nfrontier, int2* __restrict__ next, int* __restrict__ counters /* [0] nodes, [1] next size */,
+                                int node_base, BvhNode* __restrict__ out)
 {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nfrontier) return;
     const int2 item = frontier[f];
-    // entries: >= 0 internal binary node, < 0 leaf ~position.  An internal node over at most kBvhLeafMax sorted triangles is kept closed:
-    // it becomes one leaf child.
-    int ent[kBvhWidth]; Box6 box[kBvhWidth]; int ne = 0;
-    auto put = [&](int e, int at) { ent[at] = e; box[at] = e >= 0 ? node_box[e] : leaf_box[~e]; };
-    { const int2 ch = child[item.x]; put(ch.x, 0); put(ch.y, 1); ne = 2; }
-    while (ne < kBvhWidth) {
-        int best = -1; float best_area = -1.0f;
-        for (int i = 0; i < ne; ++i) {
-            if (ent[i] < 0) continue;
-            const int2 r = range[ent[i]];
-            if (r.y - r.x + 1 <= kBvhLeafMax) continue;
-            const float a = boxArea(box[i]);
-            if (a > best_area) { best_area = a; best = i; }
-        }
-        if (best < 0) break;
-        const int2 ch = child[ent[best]];
-        put(ch.x, best); put(ch.y, ne); ++ne;
-    }
-    // ordered slots: greedy on the largest remaining (centre - node centre) . (+-1, ...), as the host builder (width 8: three axes;
-    // width 4: the two axes along which the children's centres are most spread)
-    float nlo[3] = {3e38f, 3e38f, 3e38f}, nhi[3] = {-3e38f, -3e38f, -3e38f};
-    for (int i = 0; i < ne; ++i) for (int k = 0; k < 3; ++k) { nlo[k] = fminf(nlo[k], box[i].lo[k]); nhi[k] = fmaxf(nhi[k], box[i].hi[k]); }
-    int ax0 = 0, ax1 = 1;
-    if (kBvhWidth == 4) {
-        float spread[3];
-        for (int k = 0; k < 3; ++k) {
-            float cmin = 3e38f, cmax = -3e38f;
-            for (int i = 0; i < ne; ++i) { const float c = 0.5f * (box[i].lo[k] + box[i].hi[k]); cmin = fminf(cmin, c); cmax = fmaxf(cmax, c); }
-            spread[k] = cmax - cmin;
-        }
-        ax0 = spread[1] > spread[0] ? 1 : 0; if (spread[2] > spread[ax0]) ax0 = 2;
-        ax1 = ax0 == 0 ? 1 : 0;
-        for (int k = 0; k < 3; ++k) if (k != ax0 && spread[k] > spread[ax1]) ax1 = k;
-    }
-    int slot_entry[8];
-    for (int s = 0; s < 8; ++s) slot_entry[s] = -1;
-    unsigned done = 0u, used = 0u;
-    for (int round = 0; round < ne; ++round) {
-        int bi = -1, bs = -1; float bc = -3e38f;
-        for (int i = 0; i < ne; ++i) {
-            if (done >> i & 1u) continue;
-            float d[3];
-            for (int k = 0; k < 3; ++k) d[k] = 0.5f * (box[i].lo[k] + box[i].hi[k]) - 0.5f * (nlo[k] + nhi[k]);
-            for (int s = 0; s < kBvhWidth; ++s) {
-                if (used >> s & 1u) continue;
-                float c;
-                if (kBvhWidth == 8) c = ((s & 1) ? d[0] : -d[0]) + ((s & 2) ? d[1] : -d[1]) + ((s & 4) ? d[2] : -d[2]);
-                else { const float da = ax0 == 0 ? d[0] : ax0 == 1 ? d[1] : d[2], db = ax1 == 0 ? d[0] : ax1 == 1 ? d[1] : d[2]; c = ((s & 1) ? da : -da) + ((s & 2) ? db : -db); }
-                if (c > bc) { bc = c; bi = i; bs = s; }
-            }
-        }
-        slot_entry[bs] = bi; done |= 1u << bi; used |= 1u << bs;
+    int ent[4]; int ne = 0;
+    const int2 ch = child[item.x];
+    const int two[2] = {ch.x, ch.y};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (two[k] >= 0) { const int2 g = child[two[k]]; ent[ne++] = g.x; ent[ne++] = g.y; }
+        else ent[ne++] = two[k];
     }
     BvhNode nd;
-    nd.inner_mask = 0u; nd.leaf_mask = 0u;
-    int ninner = 0, nleaf = 0;
-    for (int s = 0; s < kBvhWidth; ++s) {
-        const int i = slot_entry[s];
-        if (i < 0) continue;
-        const int e = ent[i];
-        const int cnt = e < 0 ? 1 : range[e].y - range[e].x + 1;
-        if (e >= 0 && cnt > kBvhLeafMax) { nd.inner_mask |= 1u << s; ++ninner; }
-        else { nd.leaf_mask |= ((1u << cnt) - 1u) << (4 * s); nleaf += cnt; }
+    Box6 boxes[4];
+    for (int k = 0; k < 4; ++k) {
+        if (k < ne) {
+            const int e = ent[k];
+            boxes[k] = e >= 0 ? node_box[e] : leaf_box[~e];
+            if (e >= 0) {
+                const int idx = atomicAdd(&counters[0], 1);
+                next[atomicAdd(&counters[1], 1)] = make_int2(e, idx);
+                nd.link[k] = node_base + idx;
+            } else nd.link[k] = leafLink(~e, n, leaf_base);
+        } else nd.link[k] = nd.link[0];
     }
-    const int cbase = ninner ? atomicAdd(&counters[0], ninner) : 0;
-    const int fbase = ninner ? atomicAdd(&counters[1], ninner) : 0;
-    const int lbase = leaf_base + (nleaf ? atomicAdd(&counters[2], nleaf) : 0);
-    nd.child_base = node_base + cbase; nd.leaf_base = lbase;
-    int ki = 0, kl = 0;
-    for (int s = 0; s < kBvhWidth; ++s) {
-        const int i = slot_entry[s];
-        if (i < 0) continue;
-        const int e = ent[i];
-        if (nd.inner_mask >> s & 1u) { next[fbase + ki] = make_int2(e, cbase + ki); ++ki; }
-        else {
-            const int first = e < 0 ? ~e : range[e].x, cnt = e < 0 ? 1 : range[e].y - range[e].x + 1;
-            for (int j = 0; j < cnt; ++j) {
-                const int id = ids[first + j];
-                writeLeafTri(tris, id, &btris[lbase + kl]);
-                btid[lbase + kl] = id;
-                ++kl;
-            }
-        }
-    }
-    quantiseNodeDevice(nd, box, slot_entry);
-    if (kBvhWidth == 4) {            // slot key per sign octant, as the host builder
-        unsigned order = 0u;
-        for (unsigned oct = 0; oct < 8; ++oct) order |= (((oct >> ax0) & 1u) | (((oct >> ax1) & 1u) << 1)) << (2 * oct);
-        nd.order = order;
-    }
+    encodeNodeDevice(nd, boxes, ne);
     out[item.y] = nd;
 }
 
-// a mesh of at most kBvhLeafMax triangles: a root with a single leaf child
-__global__ void k_lbvh_single(const TriRec* __restrict__ tris, const int* __restrict__ ids, const Box6* __restrict__ leaf_box, int n, int leaf_base,
-                              BvhNode* __restrict__ out, LeafTri* __restrict__ btris, int* __restrict__ btid)
+// a mesh whose triangles fit one leaf: a root with a single child
+__global__ void k_lbvh_single(const Box6* __restrict__ leaf_box, int n, int leaf_base, BvhNode* __restrict__ out)
 {
-    Box6 b = leaf_box[0];
-    for (int c = 1; c < n; ++c) for (int k = 0; k < 3; ++k) { b.lo[k] = fminf(b.lo[k], leaf_box[c].lo[k]); b.hi[k] = fmaxf(b.hi[k], leaf_box[c].hi[k]); }
-    int slot_entry[8] = {0, -1, -1, -1, -1, -1, -1, -1};
     BvhNode nd;
-    nd.inner_mask = 0u; nd.leaf_mask = (1u << n) - 1u; nd.child_base = 0; nd.leaf_base = leaf_base;
-    quantiseNodeDevice(nd, &b, slot_entry);
-    if (kBvhWidth == 4) nd.order = 0u;
-    for (int j = 0; j < n; ++j) { writeLeafTri(tris, ids[j], &btris[leaf_base + j]); btid[leaf_base + j] = ids[j]; }
+    const Box6 b = leaf_box[0];
+    for (int k = 0; k < 4; ++k) nd.link[k] = leafLink(0, n, leaf_base);
+    encodeNodeDevice(nd, &b, 1);
     out[0] = nd;
 }
 
@@ -339,19 +251,19 @@ template <typename T> T* carve(char*& p, size_t count)
 
 size_t deviceBvhScratchBytes(int ntris)
 {
-    const size_t n = (size_t)std::max(ntris, 1), L = n;
+    const size_t n = (size_t)std::max(ntris, 1), L = (n + kCluster - 1) / kCluster;
     size_t cub_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned*)nullptr, (unsigned*)nullptr, (const int*)nullptr, (int*)nullptr, (int)n, 0, 30);
-    return 4 * ((n * 4 + 255) & ~size_t(255)) + cub_bytes + 256 + 2 * ((L * sizeof(Box6) + 255) & ~size_t(255)) + ((L * 8 + 255) & ~size_t(255)) * 5 +
+    return 4 * ((n * 4 + 255) & ~size_t(255)) + cub_bytes + 256 + 2 * ((L * sizeof(Box6) + 255) & ~size_t(255)) + ((L * 8 + 255) & ~size_t(255)) * 4 +
            ((L * 4 + 255) & ~size_t(255)) * 3 + 4096;
 }
 
-// Builds the BLAS of one mesh (triangles [t0, t1) of the global table) into out_nodes[0 .. *nnodes) with child links relative to node_base,
-// leaf-order triangles into btris / btid at [leaf_base, leaf_base + n).  Returns a cudaError_t; *depth = levels of 8-wide nodes.
+// Builds the BLAS of one mesh (triangles [t0, t1) of the global table) into out_nodes[0 .. *nnodes) with links relative to node_base,
+// leaf-order triangles into btris / btid at [leaf_base, leaf_base + n).  Returns a cudaError_t; *depth = levels of 4-wide nodes.
 int buildMeshBvhDevice(const TriRec* d_tris, int t0, int t1, const float* bb_min, const float* bb_max, int node_base, BvhNode* out_nodes, int leaf_base,
                        LeafTri* btris, int* btid, char* scratch, size_t scratch_bytes, cudaStream_t stream, int* nnodes, int* depth)
 {
-    const int n = t1 - t0, L = n;
+    const int n = t1 - t0, L = (n + kCluster - 1) / kCluster;
     *nnodes = 0; *depth = 0;
     if (n <= 0) return cudaSuccess;
     if (deviceBvhScratchBytes(n) > scratch_bytes) return cudaErrorMemoryAllocation;
@@ -363,7 +275,7 @@ int buildMeshBvhDevice(const TriRec* d_tris, int t0, int t1, const float* bb_min
     void* cub_tmp = carve<char>(p, cub_bytes + 1);
     Box6* leaf_box = carve<Box6>(p, L); Box6* node_box = carve<Box6>(p, L);
     unsigned long long* leaf_key = carve<unsigned long long>(p, L);
-    int2* child = carve<int2>(p, L); int2* range = carve<int2>(p, L); int2* fr_a = carve<int2>(p, L); int2* fr_b = carve<int2>(p, L);
+    int2* child = carve<int2>(p, L); int2* fr_a = carve<int2>(p, L); int2* fr_b = carve<int2>(p, L);
     int* parent_internal = carve<int>(p, L); int* parent_leaf = carve<int>(p, L); int* arrived = carve<int>(p, L);
     int* counters = carve<int>(p, 64);
 
@@ -381,19 +293,19 @@ int buildMeshBvhDevice(const TriRec* d_tris, int t0, int t1, const float* bb_min
     k_lbvh_keys<<<(n + B - 1) / B, B, 0, stream>>>(d_tris, t0, n, mlo, minv, keys, ids);
     cudaError_t e = cub::DeviceRadixSort::SortPairs(cub_tmp, cub_bytes, (const unsigned*)keys, keys2, (const int*)ids, ids2, n, 0, 30, stream);
     if (e != cudaSuccess) return e;
-    k_lbvh_leaves<<<(L + B - 1) / B, B, 0, stream>>>(d_tris, keys2, ids2, n, slack, leaf_box, leaf_key);
-    if (n <= kBvhLeafMax) {
-        k_lbvh_single<<<1, 1, 0, stream>>>(d_tris, ids2, leaf_box, n, leaf_base, out_nodes, btris, btid);
+    k_lbvh_leaves<<<(L + B - 1) / B, B, 0, stream>>>(d_tris, keys2, ids2, n, L, slack, leaf_base, btris, btid, leaf_box, leaf_key);
+    if (L == 1) {
+        k_lbvh_single<<<1, 1, 0, stream>>>(leaf_box, n, leaf_base, out_nodes);
         *nnodes = 1; *depth = 1;
         return cudaGetLastError();
     }
-    k_lbvh_topology<<<(L - 1 + B - 1) / B, B, 0, stream>>>(leaf_key, L, child, range, parent_internal, parent_leaf);
+    k_lbvh_topology<<<(L - 1 + B - 1) / B, B, 0, stream>>>(leaf_key, L, child, parent_internal, parent_leaf);
     e = cudaMemsetAsync(arrived, 0, (size_t)L * sizeof(int), stream);
     if (e != cudaSuccess) return e;
     k_lbvh_refit<<<(L + B - 1) / B, B, 0, stream>>>(child, parent_internal, parent_leaf, leaf_box, L, node_box, arrived);
-    // breadth-first collapse: the root is 8-wide node 0
+    // breadth-first collapse: the root is 4-wide node 0
     const int2 root = make_int2(0, 0);
-    const int init[3] = {1, 0, 0};
+    const int init[2] = {1, 0};
     e = cudaMemcpyAsync(fr_a, &root, sizeof root, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(counters, init, sizeof init, cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) return e;
@@ -401,9 +313,8 @@ int buildMeshBvhDevice(const TriRec* d_tris, int t0, int t1, const float* bb_min
     int2 *cur = fr_a, *nxt = fr_b;
     while (nfrontier > 0) {
         ++levels;
-        k_lbvh_collapse<<<(nfrontier + 63) / 64, 64, 0, stream>>>(d_tris, ids2, child, range, node_box, leaf_box, leaf_base, cur, nfrontier, nxt, counters,
-                                                                    node_base, out_nodes, btris, btid);
-        int host_counters[3];
+        k_lbvh_collapse<<<(nfrontier + B - 1) / B, B, 0, stream>>>(child, node_box, leaf_box, n, leaf_base, cur, nfrontier, nxt, counters, node_base, out_nodes);
+        int host_counters[2];
         e = cudaMemcpyAsync(host_counters, counters, sizeof host_counters, cudaMemcpyDeviceToHost, stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess) return e;

@@ -10,7 +10,7 @@ constexpr float kEpsilon = 0.005f;          // Config.h:4
 constexpr float kFloatMax = 9999999.0f;     // Config.h:5
 constexpr float kFloatMin = -9999990.0f;    // Config.h:6
 constexpr int kMaxDepth = 16;               // rounds per iteration the context reserves state for
-constexpr int kBvhStack = 64;               // 8-byte traversal stack entries per ray: one per level + 4 per instance entry (upload fails for deeper trees)
+constexpr int kBvhStack = 160;              // traversal stack entries per ray (upload fails for deeper trees)
 
 // Per-model record read by the closest-hit kernels: 9 x float4 = 144 B.
 // Rows 0..2 of the reference's column-major mat4s (the w row is never used by
@@ -56,35 +56,19 @@ struct Bvh2Node {
     int4 link;          // (child0, child1, 0, 0); >= 0: node index, < 0: leaf; link.x == link.y: only child0 exists
 };
 
-// Wide BVH node, 128 B = one L1 line, child boxes as OFFSETS in a node-local frame: plane = p + offset, every lower plane rounded
-// down and every upper plane rounded up (bvh_build.cpp: encodeNode), so a child box always CONTAINS the builder's box, which itself
-// bounds the reference predicate's +-0.005 tolerance band: the structure only decides which triangles are tested, the exact predicate
-// decides hits.  The local frame is what makes a one-FMA slab test safe (trace_bvh.cu).
-//   PTAP_BVH_WIDTH 4 (default): four children, offsets in binary32.
-//   PTAP_BVH_WIDTH 8: eight children, offsets as IEEE half times a power-of-two scale (measured slower on B200: profiles/r02).
-// Children sit in slots chosen at build time so that visiting the hit children in ascending (slot ^ key) is front to back for a ray
-// whose direction signs select `key` - no sorting at traversal time.  Width 8: bit k of the slot = upper side of the node along axis
-// k, key = the ray's three sign bits.  Width 4: the node picks its two most spread axes (a, b), bit 0 / 1 of the slot = upper side
-// along a / b, and `order` holds the 2-bit key for each of the 8 sign combinations.
-// Inner children are consecutive nodes from child_base (in slot order) and come after their parent; the triangles of the leaf
-// children are consecutive LeafTri records from leaf_base (in slot order).  TLAS nodes share the format: a leaf child is ONE instance,
-// leaf_base indexes SceneDev::tlas_order.
-#ifndef PTAP_BVH_WIDTH
-#define PTAP_BVH_WIDTH 4
-#endif
-constexpr int kBvhWidth = PTAP_BVH_WIDTH, kBvhLeafMax = 4;
-static_assert(kBvhWidth == 4 || kBvhWidth == 8, "PTAP_BVH_WIDTH must be 4 or 8");
+// BVH4 node, 128 B = one L1 line: up to four children, their boxes as binary32 OFFSETS in a node-local frame, and their links.
+//   plane = p + offset, every lower plane rounded down and every upper plane rounded up after an outward margin (bvh_build.cpp:
+//   encodeNode), so a child box always CONTAINS the builder's box, which itself bounds the reference predicate's +-0.005 tolerance band:
+//   the structure only decides which triangles are tested, the exact predicate decides hits.  The node-local frame is what makes a
+//   one-FMA-per-plane slab test safe (trace_bvh.cu); the lower and upper planes of an axis sit 16 bytes apart so that the traversal
+//   picks the near / far ones by address from the ray's direction signs.
+// link >= 0: node index; link < 0: triangle leaf ~((first << 3) | (count - 1)) or (TLAS only) instance leaf ~(0x20000000 | model index).
+// An unused slot holds an inverted box (lower offsets +1e15, upper offsets -1e15) that no ray interval enters.
 struct __align__(32) BvhNode {
     float px, py, pz;           // node-local origin (just below the lower corner of the node)
-    union { float scale; unsigned order; };   // width 8: power-of-two scale of the half offsets; width 4: 2-bit slot key per sign octant (bits 2 oct .. 2 oct + 1)
-    int child_base;             // node index of the first inner child
-    int leaf_base;              // leaf-order position of the first triangle of the first leaf child
-    unsigned leaf_mask;         // nibble c = (1 << count_c) - 1 when slot c is a leaf of 1..4 triangles, else 0
-    unsigned inner_mask;        // bit c set when slot c is an inner node
-    union {                     // planes[axis][0 = lower, 1 = upper][slot]
-        unsigned short h[3][2][8];      // width 8: half bits
-        float f[3][2][4];               // width 4
-    } planes;
+    int pad;
+    int link[4];
+    float planes[3][2][4];      // [axis][0 = lower, 1 = upper][slot]
 };
 static_assert(sizeof(BvhNode) == 128, "BvhNode must be one 128-byte line");
 
@@ -108,10 +92,9 @@ struct SceneDev {
     const float4* normals;      // flat shading normal per GLOBAL triangle id (copy of the TriRec .w lanes, 16-byte gather for k_shade)
     const int2* cells;          // grid voxels: (start, end) into refs
     const int* refs;            // global triangle ids
-    const BvhNode* nodes;       // all BLAS nodes (8-wide), then the TLAS nodes
+    const BvhNode* nodes;       // all BLAS nodes, then the TLAS nodes
     const LeafTri* bvh_tris;    // triangles in BVH leaf order
     const int* bvh_tri_id;      // leaf-order position -> global triangle id (build-time input of k_gather_tris; the kernels read LeafTri::id)
-    const int* tlas_order;      // TLAS leaf order -> model index
     int nmodels;
     int gx, gy, gz;
     int tlas_root;              // node index of the TLAS root, -1 when no instance has triangles

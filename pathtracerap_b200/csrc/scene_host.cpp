@@ -747,8 +747,6 @@ int ptap_scene_validate_bvh(const ptap_scene* s, int64_t* violations, int32_t* d
     return PTAP_OK;
 }
 
-int ptap_bvh_node_width(void) { return ptap::kBvhWidth; }
-
 int ptap_scene_view(const ptap_scene* s, PtapSceneView* out)
 {
     if (!s || !out) return PTAP_E_INVALID;

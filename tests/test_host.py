@@ -59,17 +59,12 @@ def test_compose_trs_matches_reference_matrices(libptap, golden_scene):
     assert np.allclose(prod, np.eye(4), atol=1e-5)
 
 
-NODE8 = np.dtype([("p", "<f4", 3), ("scale", "<f4"), ("child_base", "<i4"), ("leaf_base", "<i4"), ("leaf_mask", "<u4"), ("inner_mask", "<u4"),
-                  ("planes", "<u2", (3, 2, 8))])                                      # PtapBvhNode, width 8 (include/ptap.h)
-NODE4 = np.dtype([("p", "<f4", 3), ("order", "<u4"), ("child_base", "<i4"), ("leaf_base", "<i4"), ("leaf_mask", "<u4"), ("inner_mask", "<u4"),
-                  ("planes", "<f4", (3, 2, 4))])                                      # PtapBvhNode, width 4
+NODE = np.dtype([("p", "<f4", 3), ("pad", "<i4"), ("link", "<i4", 4), ("planes", "<f4", (3, 2, 4))])          # PtapBvhNode, include/ptap.h
 
 
 def _bvh_of(scene):
     scene.build_bvh()
     v = scene.view()
-    from pathtracerap_b200 import _native as N
-    NODE = NODE4 if N.lib().ptap_bvh_node_width() == 4 else NODE8
     assert NODE.itemsize == 128
     nodes = np.frombuffer((C.c_char * (v.n_bvh_nodes * 128)).from_address(v.bvh_nodes), NODE).copy()
     tri_id = np.frombuffer((C.c_char * (v.n_bvh_tris * 4)).from_address(v.bvh_tri_id), np.int32).copy()
@@ -79,41 +74,14 @@ def _bvh_of(scene):
 
 
 def _slots(nd):
-    """(slot, lo, hi, kind, count) of the used child slots of a wide node, decoded independently of the library: plane = p + offset,
-    offset = binary32 (width 4) or scale * half (width 8), include/ptap.h."""
+    """(lo, hi, link) of the used child slots of a 4-wide node, decoded independently of the library: plane = p + offset in double
+    (an unused slot holds an inverted box)."""
     out = []
-    p = nd["p"].astype(np.float64)
-    width = nd["planes"].shape[-1]
-    if width == 8:
-        sc = float(nd["scale"])
-        assert sc > 0 and np.log2(sc) == np.round(np.log2(sc))                # a power of two: the decode is exact
-        planes = nd["planes"].view(np.float16).astype(np.float64) * sc
-    else:
-        planes = nd["planes"].astype(np.float64)
-        assert int(nd["order"]) < (1 << 16)
-    assert int(nd["inner_mask"]) >> width == 0 and (width == 8 or int(nd["leaf_mask"]) >> (4 * width) == 0)
-    for c in range(width):
-        inner = (int(nd["inner_mask"]) >> c) & 1
-        nib = (int(nd["leaf_mask"]) >> (4 * c)) & 15
-        assert not (inner and nib)
-        if not (inner or nib):
-            continue
-        lo, hi = p + planes[:, 0, c], p + planes[:, 1, c]
-        assert nib in (0, 1, 3, 7, 15)
-        out.append((c, lo, hi, "inner" if inner else "leaf", bin(nib).count("1")))
+    p, pl = nd["p"].astype(np.float64), nd["planes"].astype(np.float64)
+    for k in range(4):
+        if pl[0, 0, k] <= pl[0, 1, k]:
+            out.append((p + pl[:, 0, k], p + pl[:, 1, k], int(nd["link"][k])))
     return out
-
-
-def _check_order(nd, slots):
-    """Width 4: for every sign octant the node's key must be the two sign bits of its two ordering axes - i.e. (slot ^ key) ascending is a
-    consistent front-to-back order: two octants that agree on the axes' signs share a key, and the keys take all four values."""
-    keys = [(int(nd["order"]) >> (2 * o)) & 3 for o in range(8)]
-    assert sorted(set(keys)) == [0, 1, 2, 3]
-    axes = [k for k in range(3) if any(keys[o] != keys[o ^ (1 << k)] for o in range(8))]
-    assert len(axes) == 2
-    free = [k for k in range(3) if k not in axes][0]
-    assert all(keys[o] == keys[o ^ (1 << free)] for o in range(8))
-    assert keys[0] == 0 and keys[7] == 3
 
 
 def _check_bvh(nodes, tri_id, roots, arrays):
@@ -134,18 +102,16 @@ def _check_bvh(nodes, tri_id, roots, arrays):
             visited.add(n)
             max_depth = max(max_depth, d)
             slots = _slots(nodes[n])
-            assert 1 <= len(slots) <= 8
-            if len(slots) > 1 and 'order' in nodes.dtype.names:
-                _check_order(nodes[n], slots)
-            ki = kl = 0
-            for c, lo, hi, kind, cnt in slots:
+            assert 1 <= len(slots) <= 4
+            for lo, hi, l in slots:
                 lo, hi = np.maximum(lo, alo), np.minimum(hi, ahi)
-                if kind == "inner":
-                    child = int(nodes[n]["child_base"]) + ki; ki += 1
-                    assert child > n                                    # parents precede their children (upload relies on it)
-                    stack.append((child, d + 1, lo, hi))
+                if l >= 0:
+                    assert l > n                                        # parents precede their children
+                    stack.append((l, d + 1, lo, hi))
                 else:
-                    first = int(nodes[n]["leaf_base"]) + kl; kl += cnt
+                    code = ~l
+                    first, cnt = code >> 3, (code & 7) + 1
+                    assert 1 <= cnt <= 8 and code < 0x20000000
                     for k in range(first, first + cnt):
                         t = tris[tri_id[k]]
                         assert meshes[mi]["t_start"] <= tri_id[k] < meshes[mi]["t_end"]
@@ -155,7 +121,7 @@ def _check_bvh(nodes, tri_id, roots, arrays):
                             q = p0 + u * e1 + v * e2
                             assert (q >= lo).all() and (q <= hi).all(), "a box above the leaf does not bound the predicate's tolerance band"
                         seen_leaf.append(k)
-        assert len(seen_leaf) == meshes[mi]["t_end"] - meshes[mi]["t_start"] and len(set(seen_leaf)) == len(seen_leaf)
+        assert len(seen_leaf) == meshes[mi]["t_end"] - meshes[mi]["t_start"]
     return max_depth
 
 
@@ -165,7 +131,7 @@ def test_bvh_builder_invariants_bundled(libptap, golden_scene):
     s = Scene.from_arrays(g["models"], g["meshes"], g["vertices"], g["triangles"])
     nodes, tri_id, roots = _bvh_of(s)
     depth = _check_bvh(nodes, tri_id, roots, g)
-    assert depth + 12 <= 64                                              # kBvhStack (device_types.h): one 8-byte entry per level
+    assert 3 * depth + 12 <= 160                                         # kBvhStack (device_types.h): up to 3 pushes per level
     assert s.validate_bvh() == (0, depth)                                # the library's own checker agrees
 
 
