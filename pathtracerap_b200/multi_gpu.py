@@ -35,6 +35,46 @@ def reduce_film(film, dst: int = 0):
     return film
 
 
+def nccl_unique_id() -> bytes:
+    """The 128-byte NCCL id made by the library (ptap_nccl_unique_id); rank 0 calls this and hands the bytes to every rank."""
+    import ctypes as C
+    from . import _native as N
+    buf = (C.c_char * 128)()
+    rc = N.lib().ptap_nccl_unique_id(C.cast(buf, C.c_void_p))
+    if rc != 0:
+        raise N.PtapError(f"ptap_nccl_unique_id failed with {rc}: libnccl.so.2 could not be loaded (set PTAP_NCCL_LIB)")
+    return bytes(buf)
+
+
+def nccl_join(renderer, rank: int, world: int):
+    """Creates the library's own NCCL communicator on every rank (ptap_nccl_init), the id travelling over torch.distributed - the only
+    thing torch does for the data plane.  Returns a description string, or None when the library could not load NCCL (the caller then
+    falls back to torch.distributed.reduce on the film view; plumbing, not compute)."""
+    import torch
+    import torch.distributed as dist
+    from . import _native as N
+    ok = torch.ones(1, dtype=torch.int32, device=f"cuda:{torch.cuda.current_device()}")
+    idt = torch.zeros(128, dtype=torch.uint8, device=ok.device)
+    if rank == 0:
+        try:
+            idt.copy_(torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8))
+        except N.PtapError:
+            ok.zero_()
+    dist.broadcast(ok, 0)
+    if int(ok.item()) == 0:
+        return None
+    dist.broadcast(idt, 0)
+    try:
+        renderer.nccl_init(bytes(idt.cpu().numpy().tobytes()), world, rank)
+    except N.PtapError:
+        ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) == 0:
+        renderer.nccl_finalize()
+        return None
+    return "ptap_reduce (ncclReduce through the C ABI)"
+
+
 def render_partitioned(renderer, iters: int, rank: int, world: int):
     """renderLoop over this rank's share of `iters` iterations, then the reduce; returns the film tensor (complete on rank 0).
     The collective is issued under the renderer's own stream, so it is ordered after the render without a host synchronisation."""

@@ -61,9 +61,9 @@ class Renderer:
         self.accel = accel
         self._check(N.lib().ptap_build_accel(self.h, accel), "build_accel")
 
-    def set_params(self, width, height, depth, first_hit_cache=True, profile=False, count=False, stamp=False):
+    def set_params(self, width, height, depth, first_hit_cache=True, profile=False, count=False, stamp=False, iter_times=False):
         self.W, self.H, self.depth = width, height, depth
-        self.flags = (N.FLAG_FIRST_HIT_CACHE if first_hit_cache else 0) | (N.FLAG_PROFILE if profile else 0) | (N.FLAG_COUNT if count else 0) | (N.FLAG_STAMP if stamp else 0)
+        self.flags = (N.FLAG_FIRST_HIT_CACHE if first_hit_cache else 0) | (N.FLAG_PROFILE if profile else 0) | (N.FLAG_COUNT if count else 0) | (N.FLAG_STAMP if stamp else 0) | (N.FLAG_ITER_TIMES if iter_times else 0)
         self._check(N.lib().ptap_set_render_params(self.h, width, height, depth, self.flags), "set_render_params")
         self._iters_done = 0
 
@@ -120,6 +120,30 @@ class Renderer:
         rgb = np.ascontiguousarray(rgb, np.float32)
         assert rgb.size == self.W * self.H * 3
         self._check(N.lib().ptap_film_add(self.h, N.ptr(rgb)), "film_add")
+
+    # -- multi-GPU through the C ABI (ptap.h: ptap_nccl_*, ptap_reduce, ptap_reduce_peer) ----------------------------------------
+    def nccl_init(self, unique_id: bytes, nranks: int, rank: int):
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        self._check(N.lib().ptap_nccl_init(self.h, C.cast(buf, C.c_void_p), nranks, rank), "nccl_init")
+
+    def reduce(self, root: int = 0):
+        """ncclReduce(sum) of the film onto `root`, in place, on the renderer's own stream (asynchronous)."""
+        self._check(N.lib().ptap_reduce(self.h, root), "reduce")
+
+    def reduce_peer(self, src: "Renderer"):
+        """film(self) += film(src) for two renderers of this process (peer copy + add, fixed order: bit-reproducible)."""
+        self._check(N.lib().ptap_reduce_peer(self.h, src.h), "reduce_peer")
+
+    def nccl_finalize(self):
+        N.lib().ptap_nccl_finalize(self.h)
+
+    def iteration_times(self) -> np.ndarray:
+        """Device time (ms since the start of the last render call) at which each of its iterations completed (needs iter_times=True)."""
+        n = C.c_int32(0)
+        self._check(N.lib().ptap_get_iteration_times(self.h, None, 0, C.byref(n)), "get_iteration_times")
+        out = np.zeros(max(n.value, 1), np.float32)
+        self._check(N.lib().ptap_get_iteration_times(self.h, N.ptr(out), n.value, C.byref(n)), "get_iteration_times")
+        return out[:n.value]
 
     def stream_ptr(self) -> int:
         """cudaStream_t of the context (every kernel and copy of this renderer is ordered on it)."""

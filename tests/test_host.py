@@ -332,3 +332,14 @@ def test_header_is_plain_c(tmp_path):
     assert sizes[:8] == [160, 40, 32, 12, 28, 12, 24, 128]
     from pathtracerap_b200 import _native
     assert sizes[8] == C.sizeof(_native.Stats)
+
+
+def test_reference_arm_arrays_equal_product_arrays(libptap, port):
+    """bench.py's CPU arms build their scene WITHOUT the product library (oracle/synth.c); the arrays must be the product's, byte for byte:
+    same synthetic mesh, same glm-composed model matrices, same bounding boxes - so that both arms time the same workload."""
+    import bench
+    for w in ("cornell", "mesh100k"):
+        _, a = bench.build_scene(w)
+        b = bench.reference_arrays(w)
+        for k in ("models", "meshes", "vertices", "triangles"):
+            assert np.ascontiguousarray(a[k]).tobytes() == np.ascontiguousarray(b[k]).tobytes(), f"{w}: {k} differ"
