@@ -6,7 +6,10 @@
 
 namespace ptap {
 
-constexpr int kTraceBlock = 128;
+#ifndef PTAP_TRACE_BLOCK
+#define PTAP_TRACE_BLOCK 128
+#endif
+constexpr int kTraceBlock = PTAP_TRACE_BLOCK;
 constexpr int kShadeBlock = 256;     // slots a CTA of k_shade regroups by material class and shades
 constexpr int kShadeTile = 32;       // one compaction tile = one warp = 32 consecutive slots
 constexpr int kScanBlock = 256, kScanSlots = 2048, kScanTiles = kScanSlots / kShadeTile;   // k_scan: slots per CTA, tiles per CTA

@@ -44,6 +44,13 @@ constexpr unsigned kEnterBit = 0x20000000u, kExitBit = 0x40000000u, kIndexMask =
 #ifndef PTAP_TRACE_MIN_CTAS
 #define PTAP_TRACE_MIN_CTAS 8     // 64 registers: 8 CTAs of 128 threads per SM, as round 1's kernel
 #endif
+#ifndef PTAP_NODE_LDG256
+#define PTAP_NODE_LDG256 0
+#endif
+#ifndef PTAP_SMEM_STACK
+#define PTAP_SMEM_STACK 12
+#endif
+constexpr int kSmemStack = PTAP_SMEM_STACK;   // stack entries per ray kept in shared memory (0: all in local memory)
 #ifndef PTAP_NODE_STEPS
 #define PTAP_NODE_STEPS 1
 #endif
@@ -146,8 +153,22 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
         return;
     }
 
-    int stack[kBvhStack];
-    int sp = 0, node = kDone, i = -1;
+    int sp = 0;
+    // Traversal stack.  Entries 0 .. kSmemStack - 1 of every lane live in shared memory, laid out [entry][thread]: whatever entry each lane
+    // touches, lane l hits bank l, so a warp-wide push or pop is ONE L1 wavefront.  In local memory the same access costs one 32-byte
+    // sector per lane (the lanes' stack pointers differ), and the stack was 25 % of the kernel's L1 sector traffic - the unit that
+    // limits it (profiles/r02).  Deeper entries spill to local memory.
+    __shared__ int s_stack[kSmemStack > 0 ? kSmemStack * kTraceBlock : 1];
+    int l_stack[kBvhStack > kSmemStack ? kBvhStack - kSmemStack : 1];
+    auto push = [&](int v) {
+        if (kSmemStack > 0 && sp < kSmemStack) s_stack[sp * kTraceBlock + threadIdx.x] = v; else l_stack[sp - kSmemStack] = v;
+        ++sp;
+    };
+    auto pop = [&]() {
+        --sp;
+        return (kSmemStack > 0 && sp < kSmemStack) ? s_stack[sp * kTraceBlock + threadIdx.x] : l_stack[sp - kSmemStack];
+    };
+    int node = kDone, i = -1;
     V3 bo = v3(0, 0, 0), bd = v3(0, 0, 0);          // the ray as stored (Ray::base, Primitive.h:160-164)
     V3 winv = v3(0, 0, 0);                          // reciprocal of the normalised world direction (TLAS level)
     unsigned near_off = 0u, wnear_off = 0u;         // byte offsets of the near planes inside a node for the current level / the world ray
@@ -168,6 +189,25 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
             if (node >= 0) {
                 const char* __restrict__ np = reinterpret_cast<const char*>(&sc.nodes[node]);
                 const F8 hd = ldg8(np);                                           // origin, four links
+#if PTAP_NODE_LDG256
+                // variant: the whole node in four 32-byte loads, near / far planes picked per child and axis by min / max
+                const F8 px8 = ldg8(np + 32), py8 = ldg8(np + 64), pz8 = ldg8(np + 96);
+                if (COUNT) cnt.x++;
+                const float cx = (hd.v[0] - ro.x) * rinv.x, cy = (hd.v[1] - ro.y) * rinv.y, cz = (hd.v[2] - ro.z) * rinv.z;
+                const float2 ix = make_float2(rinv.x, rinv.x), iy = make_float2(rinv.y, rinv.y), iz = make_float2(rinv.z, rinv.z);
+                const float2 ccx = make_float2(cx, cx), ccy = make_float2(cy, cy), ccz = make_float2(cz, cz);
+                const float2 lxa = fma2(make_float2(px8.v[0], px8.v[1]), ix, ccx), lxb = fma2(make_float2(px8.v[2], px8.v[3]), ix, ccx), hxa = fma2(make_float2(px8.v[4], px8.v[5]), ix, ccx), hxb = fma2(make_float2(px8.v[6], px8.v[7]), ix, ccx);
+                const float2 lya = fma2(make_float2(py8.v[0], py8.v[1]), iy, ccy), lyb = fma2(make_float2(py8.v[2], py8.v[3]), iy, ccy), hya = fma2(make_float2(py8.v[4], py8.v[5]), iy, ccy), hyb = fma2(make_float2(py8.v[6], py8.v[7]), iy, ccy);
+                const float2 lza = fma2(make_float2(pz8.v[0], pz8.v[1]), iz, ccz), lzb = fma2(make_float2(pz8.v[2], pz8.v[3]), iz, ccz), hza = fma2(make_float2(pz8.v[4], pz8.v[5]), iz, ccz), hzb = fma2(make_float2(pz8.v[6], pz8.v[7]), iz, ccz);
+#define PTAP_MM(l, h, c) fminf(l.c, h.c), fmaxf(l.c, h.c)
+                const float2 nxa = make_float2(fminf(lxa.x, hxa.x), fminf(lxa.y, hxa.y)), fxa = make_float2(fmaxf(lxa.x, hxa.x), fmaxf(lxa.y, hxa.y));
+                const float2 nxb = make_float2(fminf(lxb.x, hxb.x), fminf(lxb.y, hxb.y)), fxb = make_float2(fmaxf(lxb.x, hxb.x), fmaxf(lxb.y, hxb.y));
+                const float2 nya = make_float2(fminf(lya.x, hya.x), fminf(lya.y, hya.y)), fya = make_float2(fmaxf(lya.x, hya.x), fmaxf(lya.y, hya.y));
+                const float2 nyb = make_float2(fminf(lyb.x, hyb.x), fminf(lyb.y, hyb.y)), fyb = make_float2(fmaxf(lyb.x, hyb.x), fmaxf(lyb.y, hyb.y));
+                const float2 nza = make_float2(fminf(lza.x, hza.x), fminf(lza.y, hza.y)), fza = make_float2(fmaxf(lza.x, hza.x), fmaxf(lza.y, hza.y));
+                const float2 nzb = make_float2(fminf(lzb.x, hzb.x), fminf(lzb.y, hzb.y)), fzb = make_float2(fmaxf(lzb.x, hzb.x), fmaxf(lzb.y, hzb.y));
+#undef PTAP_MM
+#else
                 const unsigned nox = near_off & 0xffu, noy = (near_off >> 8) & 0xffu, noz = near_off >> 16;
                 const uint4 NX = ldg4u(np + nox), FX = ldg4u(np + (nox ^ 16u));   // near / far planes by address
                 const uint4 NY = ldg4u(np + noy), FY = ldg4u(np + (noy ^ 16u));
@@ -182,6 +222,7 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
                 const float2 fxa = fma2(make_float2(__uint_as_float(FX.x), __uint_as_float(FX.y)), ix, ccx), fxb = fma2(make_float2(__uint_as_float(FX.z), __uint_as_float(FX.w)), ix, ccx);
                 const float2 fya = fma2(make_float2(__uint_as_float(FY.x), __uint_as_float(FY.y)), iy, ccy), fyb = fma2(make_float2(__uint_as_float(FY.z), __uint_as_float(FY.w)), iy, ccy);
                 const float2 fza = fma2(make_float2(__uint_as_float(FZ.x), __uint_as_float(FZ.y)), iz, ccz), fzb = fma2(make_float2(__uint_as_float(FZ.z), __uint_as_float(FZ.w)), iz, ccz);
+#endif
                 int key[4], lnk[4];
                 key[0] = childKey(nxa.x, nya.x, nza.x, fxa.x, fya.x, fza.x, tmin, tmax);
                 key[1] = childKey(nxa.y, nya.y, nza.y, fxa.y, fya.y, fza.y, tmin, tmax);
@@ -193,10 +234,10 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
                            const int la = sw ? lnk[b] : lnk[a], lb = sw ? lnk[a] : lnk[b]; key[a] = ka; key[b] = kb; lnk[a] = la; lnk[b] = lb; }
                 PTAP_CSWAP(0, 1) PTAP_CSWAP(2, 3) PTAP_CSWAP(0, 2) PTAP_CSWAP(1, 3) PTAP_CSWAP(1, 2)
 #undef PTAP_CSWAP
-                if (key[3] != 0x7f800000) stack[sp++] = lnk[3];
-                if (key[2] != 0x7f800000) stack[sp++] = lnk[2];
-                if (key[1] != 0x7f800000) stack[sp++] = lnk[1];
-                node = key[0] != 0x7f800000 ? lnk[0] : stack[--sp];
+                if (key[3] != 0x7f800000) push(lnk[3]);
+                if (key[2] != 0x7f800000) push(lnk[2]);
+                if (key[1] != 0x7f800000) push(lnk[1]);
+                if (key[0] != 0x7f800000) node = lnk[0]; else node = pop();
             }
         }
         // ---- (2) who waits for what: one warp reduction over 6-bit counters, one per state
@@ -211,7 +252,7 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
         // ---- (3a) one triangle of the held leaf (Renderer.cpp:174-215)
         if (s_tri && n_tri >= min(vote_tri, n_inner)) {
             leafTriangle<UV, COUNT>(sc, ro, rd, tmax, best_tri, best_u, best_v, (int)(code >> 3), cnt);
-            node = (code & 7u) ? (int)~(code + 7u) : stack[--sp];        // (first + 1, count - 1), or pop when the leaf is finished
+            if (code & 7u) node = (int)~(code + 7u); else node = pop();   // (first + 1, count - 1), or pop when the leaf is finished
         }
         // ---- (3b) TLAS leaf: enter instance `im` (Renderer.cpp:381-384)
         if (s_enter && n_enter >= min(vote_inst, n_inner)) {
@@ -233,8 +274,8 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
                 const float tb = (g_dist * sc.prune + sc.c_pad + 1e-4f * (fabsf(bo.x) + fabsf(bo.y) + fabsf(bo.z))) * (mlen * wil) * 1.0001f;
                 if (tb < kFloatMax) tmax = tb;                                  // false for NaN / inf: no bound
             }
-            stack[sp++] = __float_as_int(__fdividef(1.0f, mlen * wil));           // world distance per unit of model-space t, for the exit step
-            stack[sp++] = (int)~(kExitBit | (unsigned)im);
+            push(__float_as_int(__fdividef(1.0f, mlen * wil)));                  // world distance per unit of model-space t, for the exit step
+            push((int)~(kExitBit | (unsigned)im));
             node = __float_as_int(__ldg(&inst->grid.z));                        // BLAS root of the instance's mesh
         }
         // ---- (3c) marker popped: leave instance `im` (Renderer.cpp:388-398).  The nearest-model decision of the reference compares exact
@@ -242,7 +283,7 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
         // exact distances are evaluated only when two candidates are closer than that slack, or when pruning is off.
         if (s_exit && n_exit >= min(vote_inst, n_inner)) {
             const int im = (int)(code & kIndexMask);
-            const float ascale = __int_as_float(stack[--sp]);                    // pushed under the marker at entry
+            const float ascale = __int_as_float(pop());                          // pushed under the marker at entry
             const float cb = sc.c_pad + 1e-4f * (fabsf(bo.x) + fabsf(bo.y) + fabsf(bo.z));
             if (best_tri >= 0) {
                 // |t|: the reference ranks instances by length(hit - origin) >= 0 (Renderer.cpp:391-393), and the predicate accepts
@@ -268,7 +309,7 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
             }
             ro = bo; rinv = winv; near_off = wnear_off;
             tmin = sc.tmin_world; tmax = worldBound(g_dist, sc.prune, cb);
-            node = stack[--sp];
+            node = pop();
         }
         // ---- (3d) retire finished rays, refill the lanes from the warp's batch
         if (n_done > 0 && n_done >= min(vote_refill, n_inner)) {
@@ -303,7 +344,7 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
                 g_dist = kFloatMax; g_model = -1; g_tri = -1; g_t = 0.0f; g_u = 0.0f; g_v = 0.0f;
                 best_tri = -1;
                 if (COUNT) cnt = make_int4(0, 0, 0, 0);
-                stack[0] = kDone; sp = 1;
+                sp = 0; push(kDone);
                 node = sc.tlas_root;
             }
             w_next += min(__popc(m_done), avail);
