@@ -54,10 +54,12 @@ public:
         v.grid_dim[0] = GRID_X; v.grid_dim[1] = GRID_Y; v.grid_dim[2] = GRID_Z;
         // PTAP_RANKS = N: N GPUs of this process (devices PTAP_DEVICE ..), scene replicated, iterations split, films summed onto rank 0
         const int ranks = std::max(1, pick("PTAP_RANKS", 0, 1)), dev0 = pick("PTAP_DEVICE", 0, 0);
+        std::vector<int> devices;                             // PTAP_RANK_DEVICES=0,0,1: explicit device of every rank (default dev0 + rank)
+        if (const char* list = std::getenv("PTAP_RANK_DEVICES")) for (const char* q = list; *q;) { devices.push_back(std::atoi(q)); while (*q && *q != ',') ++q; if (*q) ++q; }
         all.assign((size_t)ranks, nullptr);
         for (int r = 0; r < ranks; ++r) {
             ctx = nullptr;
-            check(ptap_create(dev0 + r, 0, &ctx), "ptap_create");
+            check(ptap_create(r < (int)devices.size() ? devices[(size_t)r] : dev0 + r, 0, &ctx), "ptap_create");
             all[(size_t)r] = ctx;
             check(ptap_upload_scene(ctx, &v), "ptap_upload_scene");
             check(ptap_build_accel(ctx, lbvh ? PTAP_ACCEL_BVH_DEVICE : bvh || scene.grids.empty() ? PTAP_ACCEL_BVH : PTAP_ACCEL_GRID_COMPAT), "ptap_build_accel");

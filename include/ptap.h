@@ -190,6 +190,13 @@ const char* ptap_last_error(const ptap_ctx* ctx);
 /* Renderer::allocateOnGPU (Renderer.cpp:65-130): copies the scene into the device arena (repacked). */
 int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* view);
 int ptap_build_accel(ptap_ctx* ctx, int kind);
+/* Scene::addMeshesToGrid (Scene.cpp:318-396) on the DEVICE for the scene last uploaded (`view` must be that scene's view: vertices and
+ * triangles are read again): one gx x gy x gz grid per distinct mesh in model order, built by sorting (cell, triangle) pairs; cells and
+ * reference lists are bit-identical to the host builder's / the reference's (ascending triangle order per cell).  Selects
+ * PTAP_ACCEL_GRID_COMPAT; PtapStats::ms_build reports the device time.  ptap_read_grids copies the result back in the reference's layout
+ * (voxels / refs NULL: counts only; counts = {voxels, references}). */
+int ptap_build_grids_device(ptap_ctx* ctx, const PtapSceneView* view, int32_t gx, int32_t gy, int32_t gz);
+int ptap_read_grids(ptap_ctx* ctx, PtapVoxel* voxels, int32_t* refs, int32_t counts[2]);
 int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, uint32_t flags);
 /* Renderer::renderLoop (Renderer.cpp:567-648) for iterations [iter_begin, iter_end); the film accumulates.
  * Asynchronous on the context stream; ptap_sync / ptap_read_film / ptap_get_stats wait for it. */

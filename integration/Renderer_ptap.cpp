@@ -67,10 +67,12 @@ void Renderer::allocateOnGPU(Scene& scene)
     const char* accel = std::getenv("PTAP_ACCEL");            // default: the reference's own grid walk, bit-compatible hits
     const int kind = !accel ? PTAP_ACCEL_GRID_COMPAT : std::string(accel) == "bvh" ? PTAP_ACCEL_BVH : std::string(accel) == "lbvh" ? PTAP_ACCEL_BVH_DEVICE : PTAP_ACCEL_GRID_COMPAT;
     const int ranks = std::max(1, envInt("PTAP_RANKS", 1)), dev0 = envInt("PTAP_DEVICE", 0);
+    std::vector<int> devices;                                 // PTAP_RANK_DEVICES=0,0,1: explicit device of every rank (default dev0 + rank)
+    if (const char* list = std::getenv("PTAP_RANK_DEVICES")) for (const char* q = list; *q;) { devices.push_back(std::atoi(q)); while (*q && *q != ',') ++q; if (*q) ++q; }
     b.all.assign(ranks, nullptr);
     for (int r = 0; r < ranks; ++r) {
         b.ctx = nullptr;
-        check(b, ptap_create(dev0 + r, 0, &b.ctx), "ptap_create");
+        check(b, ptap_create(r < (int)devices.size() ? devices[r] : dev0 + r, 0, &b.ctx), "ptap_create");
         b.all[r] = b.ctx;
         check(b, ptap_upload_scene(b.ctx, &v), "ptap_upload_scene");
         check(b, ptap_build_accel(b.ctx, kind), "ptap_build_accel");

@@ -62,7 +62,7 @@ EXPORTS = [
     "ptap_scene_add_obj", "ptap_scene_add_mesh", "ptap_scene_add_icosphere", "ptap_scene_add_model", "ptap_compose_trs",
     "ptap_scene_build_grids", "ptap_scene_build_bvh", "ptap_scene_validate_bvh", "ptap_scene_view", "ptap_scene_models", "ptap_scene_destroy", "ptap_scene_last_error",
     "ptap_scene_config_params",
-    "ptap_create", "ptap_destroy", "ptap_last_error", "ptap_upload_scene", "ptap_build_accel", "ptap_set_render_params",
+    "ptap_create", "ptap_destroy", "ptap_last_error", "ptap_upload_scene", "ptap_build_accel", "ptap_build_grids_device", "ptap_read_grids", "ptap_set_render_params",
     "ptap_render", "ptap_timer_start", "ptap_timer_stop", "ptap_frame_begin", "ptap_film_reset", "ptap_sync", "ptap_read_film", "ptap_film_device_ptr", "ptap_film_add",
     "ptap_write_bmp", "ptap_read_film_resolved", "ptap_write_bmp_resolved", "ptap_get_stats", "ptap_stream", "ptap_trace", "ptap_trace_count", "ptap_shade", "ptap_bench_trace", "ptap_render_probe", "ptap_get_iteration_times",
     "ptap_reduce_peer", "ptap_nccl_unique_id", "ptap_nccl_init", "ptap_reduce", "ptap_nccl_finalize",
@@ -106,6 +106,8 @@ def lib():
         L.ptap_last_error.argtypes = [vp]; L.ptap_last_error.restype = C.c_char_p
         L.ptap_upload_scene.argtypes = [vp, C.POINTER(SceneView)]
         L.ptap_build_accel.argtypes = [vp, C.c_int]
+        L.ptap_build_grids_device.argtypes = [vp, C.POINTER(SceneView), ci, ci, ci]
+        L.ptap_read_grids.argtypes = [vp, vp, vp, vp]
         L.ptap_set_render_params.argtypes = [vp, ci, ci, ci, cu]
         L.ptap_render.argtypes = [vp, ci, ci]
         L.ptap_film_reset.argtypes = [vp]

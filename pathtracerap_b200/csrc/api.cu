@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <array>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -89,6 +90,7 @@ struct ptap_ctx {
     std::vector<cudaEvent_t> iter_events;      // completion of every iteration of the last render call (PTAP_FLAG_ITER_TIMES)
     int iter_events_used = 0;
     std::vector<float> iter_ms;
+    int2* gd_cells = nullptr; int* gd_refs = nullptr; size_t gd_ncells = 0, gd_nrefs = 0;   // grids built on the device (own allocation)
     void* nccl_comm = nullptr;                 // ptap_nccl_init
     cudaEvent_t e_peer = nullptr;
     unsigned long long* d_stamps = nullptr;   // PTAP_FLAG_STAMP: (start, end) %globaltimer words of the closest-hit launches of the last render call
@@ -513,6 +515,8 @@ void ptap_destroy(ptap_ctx* ctx)
     for (cudaEvent_t e : {ctx->e_fork, ctx->e_cache}) if (e) cudaEventDestroy(e);
     for (int l = 0; l < kMaxLanes; ++l) { if (ctx->e_join[l]) cudaEventDestroy(ctx->e_join[l]); if (ctx->e_gather[l]) cudaEventDestroy(ctx->e_gather[l]); }
     ctx->scene_arena.release(); ctx->frame_arena.release(); ctx->scratch.release();
+    if (ctx->gd_cells) cudaFree(ctx->gd_cells);
+    if (ctx->gd_refs) cudaFree(ctx->gd_refs);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->iter_events) cudaEventDestroy(e);
     if (ctx->e_peer) cudaEventDestroy(ctx->e_peer);
@@ -1298,6 +1302,125 @@ int ptap_reduce(ptap_ctx* ctx, int32_t root)
     CK(cudaSetDevice(ctx->device));
     const int rc = nccl().Reduce(ctx->wv.film, ctx->wv.film, (size_t)ctx->wv.N * 3, /* ncclFloat32 */ 7, /* ncclSum */ 0, root, ctx->nccl_comm, ctx->stream);
     if (rc != 0) return fail(ctx, PTAP_E_STATE, "ncclReduce: %s", nccl().GetErrorString ? nccl().GetErrorString(rc) : "error");
+    return PTAP_OK;
+}
+
+// Scene::addMeshesToGrid (Scene.cpp:318-396) on the device (grid_device.cu): one grid per distinct mesh in model order, exactly the
+// assignment the reference makes (grid index != mesh index; the grid remembers its creating model, through which the traversal reads
+// the mesh bounds, Renderer.cpp:245-249).  The view must be the one last uploaded (its vertices and triangles are read again: the voxel
+// ranges need the original vertex positions, which the edge-form triangle records on the device do not reproduce bit for bit).
+int ptap_build_grids_device(ptap_ctx* ctx, const PtapSceneView* v, int32_t gx, int32_t gy, int32_t gz)
+{
+    if (!ctx || !ctx->have_scene || !v || !v->vertices || !v->triangles || !v->meshes || !v->models) return fail(ctx, PTAP_E_STATE, "build_grids_device: uploaded scene and its view required");
+    if (gx <= 0 || gy <= 0 || gz <= 0 || (long long)gx * gy * gz > (1ll << 27)) return fail(ctx, PTAP_E_INVALID, "build_grids_device: bad grid dimensions");
+    if (v->ntriangles != ctx->ntris || v->nmodels != (int)ctx->h_models.size() || v->nmeshes != (int)ctx->h_meshes.size()) return fail(ctx, PTAP_E_INVALID, "build_grids_device: the view is not the uploaded scene");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
+    cudaEvent_t b0, b1;
+    CK(cudaEventCreate(&b0)); CK(cudaEventCreate(&b1));
+    CK(cudaEventRecord(b0, ctx->stream));
+    const int nm = v->nmodels, nmesh = v->nmeshes, nt = v->ntriangles;
+    const int gd[3] = {gx, gy, gz};
+    const size_t ncell = (size_t)gx * gy * gz;
+    // grid list, as Scene.cpp:322-339
+    std::vector<int> grid_of_mesh(nmesh, -1), grid_mesh, grid_owner, model_grid(nm, -1);
+    for (int i = 0; i < nm; ++i) {
+        const int mi = v->models[i].mesh_index;
+        if (mi < 0 || mi >= nmesh) return fail(ctx, PTAP_E_INVALID, "build_grids_device: model %d has no mesh", i);
+        if (grid_of_mesh[mi] < 0) { grid_of_mesh[mi] = (int)grid_mesh.size(); grid_mesh.push_back(mi); grid_owner.push_back(i); }
+        model_grid[i] = grid_of_mesh[mi];
+    }
+    const int ng = (int)grid_mesh.size();
+    // vertex positions per triangle (9 floats), gathered on the host once
+    std::vector<float> pos((size_t)nt * 9);
+    for (int t = 0; t < nt; ++t)
+        for (int k = 0; k < 3; ++k) {
+            const int vi = v->triangles[t].v[k];
+            if (vi < 0 || vi >= v->nvertices) return fail(ctx, PTAP_E_INVALID, "build_grids_device: triangle %d: vertex index out of range", t);
+            memcpy(&pos[(size_t)t * 9 + 3 * k], v->vertices[vi].position, 12);
+        }
+    int max_tris = 1;
+    for (int g = 0; g < ng; ++g) max_tris = std::max(max_tris, v->meshes[grid_mesh[g]].t_end - v->meshes[grid_mesh[g]].t_start);
+    // phase 1: count the references of every grid
+    float* d_pos = nullptr; int *d_count = nullptr, *d_offset_all = nullptr; void* d_tmp = nullptr;
+    size_t tmp_bytes = gridDeviceTempBytes(max_tris, 1);
+    auto cleanup = [&]() { cudaFree(d_pos); cudaFree(d_count); cudaFree(d_offset_all); cudaFree(d_tmp); cudaEventDestroy(b0); cudaEventDestroy(b1); };
+#define CKG(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return fail(ctx, (int)e_, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
+    CKG(cudaMalloc(&d_pos, pos.size() * sizeof(float) + 16));
+    CKG(cudaMalloc(&d_count, (size_t)max_tris * sizeof(int)));
+    CKG(cudaMalloc(&d_offset_all, (size_t)std::max(nt, 1) * sizeof(int)));
+    CKG(cudaMalloc(&d_tmp, tmp_bytes));
+    CKG(cudaMemcpyAsync(d_pos, pos.data(), pos.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<long long> npairs(ng, 0);
+    std::vector<std::array<float, 3>> widths(ng);
+    long long total = 0, max_pairs = 1;
+    for (int g = 0; g < ng; ++g) {
+        const PtapMesh& mesh = v->meshes[grid_mesh[g]];
+        for (int k = 0; k < 3; ++k) widths[g][k] = (mesh.bb_max[k] - mesh.bb_min[k]) / gd[k];      // Scene.cpp:341-347
+        const int n = std::max(0, mesh.t_end - mesh.t_start);
+        CKG((cudaError_t)gridDeviceCount(d_pos + (size_t)mesh.t_start * 9, mesh.t_start, n, mesh.bb_min, widths[g].data(), gd, d_count, d_offset_all + mesh.t_start,
+                                         d_tmp, tmp_bytes, ctx->stream, &npairs[g]));
+        total += npairs[g]; max_pairs = std::max(max_pairs, npairs[g]);
+    }
+    if (total > 0x7fffffffll) { cleanup(); return fail(ctx, PTAP_E_NOMEM, "build_grids_device: %lld references exceed the 32-bit reference list", total); }
+    // phase 2: pairs, sort, cells
+    if (ctx->gd_cells) { cudaFree(ctx->gd_cells); ctx->gd_cells = nullptr; }
+    if (ctx->gd_refs) { cudaFree(ctx->gd_refs); ctx->gd_refs = nullptr; }
+    int *d_keys = nullptr, *d_vals = nullptr, *d_keys2 = nullptr;
+    cudaFree(d_tmp); d_tmp = nullptr;
+    tmp_bytes = gridDeviceTempBytes(max_tris, max_pairs);
+    auto cleanup2 = [&]() { cudaFree(d_keys); cudaFree(d_vals); cudaFree(d_keys2); cleanup(); };
+#define CKH(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup2(); return fail(ctx, (int)e_, "%s: %s", #call, cudaGetErrorString(e_)); } } while (0)
+    CKH(cudaMalloc(&d_tmp, tmp_bytes));
+    CKH(cudaMalloc(&d_keys, (size_t)max_pairs * sizeof(int))); CKH(cudaMalloc(&d_vals, (size_t)max_pairs * sizeof(int))); CKH(cudaMalloc(&d_keys2, (size_t)max_pairs * sizeof(int)));
+    CKH(cudaMalloc(&ctx->gd_cells, (size_t)ng * ncell * sizeof(int2)));
+    CKH(cudaMalloc(&ctx->gd_refs, (size_t)std::max(total, 1ll) * sizeof(int)));
+    ctx->gd_ncells = (size_t)ng * ncell; ctx->gd_nrefs = (size_t)total;
+    long long ref_base = 0;
+    for (int g = 0; g < ng; ++g) {
+        const PtapMesh& mesh = v->meshes[grid_mesh[g]];
+        const int n = std::max(0, mesh.t_end - mesh.t_start);
+        CKH((cudaError_t)gridDeviceFill(d_pos + (size_t)mesh.t_start * 9, mesh.t_start, n, mesh.bb_min, widths[g].data(), gd, d_offset_all + mesh.t_start, (int)npairs[g],
+                                        d_keys, d_vals, d_keys2, d_tmp, tmp_bytes, (int)ref_base, ctx->gd_refs + ref_base, ctx->gd_cells + (size_t)g * ncell, ctx->stream));
+        ref_base += npairs[g];
+    }
+    // instance records: mesh bounds through the grid's creating model, voxel widths, first voxel (as ptap_upload_scene does for host grids)
+    for (int i = 0; i < nm; ++i) {
+        const int g = model_grid[i];
+        const PtapMesh& mesh = v->meshes[v->models[grid_owner[g]].mesh_index];
+        InstanceTrace& it = ctx->h_inst[i];
+        it.bb_min = make_float4(mesh.bb_min[0], mesh.bb_min[1], mesh.bb_min[2], widths[g][0]);
+        it.bb_max = make_float4(mesh.bb_max[0], mesh.bb_max[1], mesh.bb_max[2], widths[g][1]);
+        it.grid.x = widths[g][2];
+        it.grid.y = __builtin_bit_cast(float, (int)((size_t)g * ncell));
+    }
+    CKH(cudaMemcpyAsync(ctx->d_inst, ctx->h_inst.data(), nm * sizeof(InstanceTrace), cudaMemcpyHostToDevice, ctx->stream));
+    CKH(cudaEventRecord(b1, ctx->stream));
+    CKH(cudaEventSynchronize(b1));
+    cudaEventElapsedTime(&ctx->stats.ms_build, b0, b1);
+#undef CKG
+#undef CKH
+    cleanup2();
+    ctx->sc.cells = ctx->gd_cells; ctx->sc.refs = ctx->gd_refs;
+    ctx->sc.gx = gx; ctx->sc.gy = gy; ctx->sc.gz = gz;
+    ctx->have_grid = true; ctx->accel = PTAP_ACCEL_GRID_COMPAT; ctx->cache_valid = false;
+    ctx->grid_trace = traceGridSize(ctx);
+    return PTAP_OK;
+}
+
+// The grids now on the device in the reference's own layout (Voxel: start, end, entity_type; the reference list).  Two-call protocol:
+// pass voxels / refs NULL to get the counts.
+int ptap_read_grids(ptap_ctx* ctx, PtapVoxel* voxels, int32_t* refs, int32_t counts[2])
+{
+    if (!ctx || !ctx->have_grid || !ctx->gd_cells || !counts) return fail(ctx, PTAP_E_STATE, "read_grids: no device-built grids");
+    CK(cudaSetDevice(ctx->device));
+    counts[0] = (int32_t)ctx->gd_ncells; counts[1] = (int32_t)ctx->gd_nrefs;
+    if (voxels) {
+        std::vector<int2> h(ctx->gd_ncells);
+        CK(cudaMemcpy(h.data(), ctx->gd_cells, h.size() * sizeof(int2), cudaMemcpyDeviceToHost));
+        for (size_t c = 0; c < h.size(); ++c) { voxels[c].start = h[c].x; voxels[c].end = h[c].y; voxels[c].entity_type = 2; }
+    }
+    if (refs && ctx->gd_nrefs) CK(cudaMemcpy(refs, ctx->gd_refs, ctx->gd_nrefs * sizeof(int), cudaMemcpyDeviceToHost));
     return PTAP_OK;
 }
 

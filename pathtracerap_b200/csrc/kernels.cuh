@@ -57,6 +57,13 @@ size_t deviceBvhScratchBytes(int ntris);
 int buildMeshBvhDevice(const TriRec* d_tris, int t0, int t1, const float* bb_min, const float* bb_max, int node_base, BvhNode* out_nodes, int leaf_base,
                        LeafTri* btris, int* btid, char* scratch, size_t scratch_bytes, cudaStream_t stream, int* nnodes, int* depth);
 
+// grid_device.cu: Scene::addMeshesToGrid on the device, one mesh's grid at a time
+int gridDeviceCount(const float* d_pos, int t0, int n, const float bb_min[3], const float width[3], const int gd[3], int* d_count, int* d_offset,
+                    void* d_tmp, size_t tmp_bytes, cudaStream_t stream, long long* npairs);
+int gridDeviceFill(const float* d_pos, int t0, int n, const float bb_min[3], const float width[3], const int gd[3], const int* d_offset, int npairs,
+                   int* d_keys, int* d_vals, int* d_keys2, void* d_tmp, size_t tmp_bytes, int ref_base, int* d_refs, int2* d_cells, cudaStream_t stream);
+size_t gridDeviceTempBytes(int ntris, long long npairs);
+
 // wavefront.cu
 void launchGenerate(const WaveDev& wv, int grid, cudaStream_t stream);
 void launchScan(const SceneDev& sc, const WaveDev& wv, int round, const float4* hit, int remaining, int n_fixed, cudaStream_t stream);

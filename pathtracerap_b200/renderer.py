@@ -67,6 +67,20 @@ class Renderer:
         self._check(N.lib().ptap_set_render_params(self.h, width, height, depth, self.flags), "set_render_params")
         self._iters_done = 0
 
+    def build_grids_device(self, scene: Scene, gx=25, gy=25, gz=25):
+        """Scene::addMeshesToGrid on the GPU for the scene last uploaded (`scene` must be that scene); selects the grid walk."""
+        v = scene.view()
+        self._check(N.lib().ptap_build_grids_device(self.h, C.byref(v), gx, gy, gz), "build_grids_device")
+        self.accel = N.ACCEL_GRID_COMPAT
+
+    def read_grids(self):
+        """(voxels, refs) of the device-built grids in the reference's layout."""
+        cnt = (C.c_int32 * 2)()
+        self._check(N.lib().ptap_read_grids(self.h, None, None, cnt), "read_grids")
+        vox = np.zeros(cnt[0], N.VOXEL); refs = np.zeros(max(cnt[1], 1), np.int32)
+        self._check(N.lib().ptap_read_grids(self.h, N.ptr(vox), N.ptr(refs), cnt), "read_grids")
+        return vox, refs[:cnt[1]]
+
     def build_stats(self) -> dict:
         """Device time, node count and depth of the last PTAP_ACCEL_BVH_DEVICE build."""
         st = self.stats()

@@ -264,6 +264,40 @@ def test_obj_loader_edge_cases(libptap, tmp_path):
         s.add_obj(str(tmp_path / "does_not_exist.obj"))
 
 
+def test_obj_multi_object_quads_and_missing_normals(libptap, tmp_path):
+    """Files beyond the bundled ones.  The reference keeps ONE Mesh per file and overwrites its index ranges for every
+    aiMesh Assimp returns (Scene.cpp:240-252, 266, 277), so a multi-object file leaves only its LAST object reachable while the bounding
+    box covers all of them - a bug, single-object files being the only ones it was run on.  This reader does the evident thing: `o` / `g`
+    groups are concatenated into one mesh in file order, polygons are fan-triangulated (corner 0, k, k+1), corners without `vn` get the
+    face's geometric normal scaled by BASE_MODEL_SCALE like imported normals (Scene.cpp:255-262), `vt` indices are skipped."""
+    from pathtracerap_b200 import Scene
+    (tmp_path / "multi.obj").write_text(
+        "# two objects, a quad, a face without normals, texture indices\n"
+        "o first\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvn 0 0 1\n"
+        "f 1/1/1 2/1/1 3/1/1 4/1/1\n"
+        "g second\no second\nv 0 0 2\nv 2 0 2\nv 0 2 2\n"
+        "f 5 6 7\n"
+        "f 5//1 7//1 6//1\n")
+    s = Scene.empty()
+    mi = s.add_obj(str(tmp_path / "multi.obj"))
+    a = s.arrays()
+    assert mi == 0 and len(a["meshes"]) == 1
+    m = a["meshes"][0]
+    assert (m["t_start"], m["t_end"], m["v_start"], m["v_end"]) == (0, 4, 0, 12)          # quad -> 2 triangles, + 2: every object is reachable
+    P = a["vertices"]["position"] / 1000.0
+    assert np.array_equal(a["triangles"]["v"], np.arange(12).reshape(4, 3))             # one vertex per face corner, in file order
+    assert np.allclose(P[0:3], [[0, 0, 0], [1, 0, 0], [1, 1, 0]]) and np.allclose(P[3:6], [[0, 0, 0], [1, 1, 0], [0, 1, 0]])   # fan: (0,1,2), (0,2,3)
+    assert np.allclose(P[6:9], [[0, 0, 2], [2, 0, 2], [0, 2, 2]])
+    N = a["vertices"]["normal"]
+    assert np.allclose(N[0:6], [[0, 0, 1000]] * 6)                                       # vn scaled by BASE_MODEL_SCALE
+    assert np.allclose(N[6:9], [[0, 0, 1000]] * 3)                                       # no vn: geometric normal of (5,6,7), same scale
+    assert np.allclose(N[9:12], [[0, 0, 1000]] * 3)                                      # explicit vn wins over the (opposite) winding
+    assert np.allclose(m["bb_min"], [0, 0, 0]) and np.allclose(m["bb_max"], [2000, 2000, 2000])
+    s.add_model(mi)
+    s.build_grids(); s.build_bvh()
+    assert s.validate_bvh()[0] == 0
+
+
 def test_iteration_range_partition():
     from pathtracerap_b200.multi_gpu import iteration_range
     for iters in (0, 1, 7, 64, 1024):

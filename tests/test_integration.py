@@ -92,6 +92,21 @@ def test_cpp_flow_matches_python_api(libptap, tmp_path):
     p = subprocess.run([exe], cwd=tmp_path, env=env, capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
     assert "Full run:" in p.stdout
+    # the reference's per-iteration timing lines (Renderer.cpp:641-643), one per iteration, non-negative
+    its = [l for l in p.stdout.splitlines() if l.startswith("Iteration ")]
+    assert [l.split(":")[0] for l in its] == [f"Iteration {k + 1}" for k in range(IT)]
+    assert all(int(l.split(":")[1].split()[0]) >= 0 for l in its)
+    one_rank = (tmp_path / "Render.bmp").read_bytes()
+    # PTAP_RANKS: several contexts of ONE process share the iterations and the films are summed over peer copies (ptap_reduce_peer).
+    # On a one-GPU box both ranks sit on device 0; the image equals the one-rank image up to float reassociation of the film sum.
+    p2 = subprocess.run([exe], cwd=tmp_path, env=dict(env, PTAP_RANKS="2", PTAP_RANK_DEVICES="0,0"), capture_output=True, text=True)
+    assert p2.returncode == 0, p2.stderr
+    assert "on 2 GPU(s)" in p2.stdout
+    two_rank = (tmp_path / "Render.bmp").read_bytes()
+    a1 = np.frombuffer(one_rank, np.uint8, offset=54).astype(int); a2 = np.frombuffer(two_rank, np.uint8, offset=54).astype(int)
+    assert one_rank[:54] == two_rank[:54] and np.abs(a1 - a2).max() <= 1 and np.mean(a1 == a2) > 0.999
+    p = subprocess.run([exe], cwd=tmp_path, env=env, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
     s = Scene(None, root=str(tmp_path))
     r = Renderer(width=W, height=H, iters=IT, depth=5, accel=ACCEL_GRID_COMPAT)
     r.allocateOnGPU(s)
