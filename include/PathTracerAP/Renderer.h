@@ -64,6 +64,7 @@ public:
             check(ptap_upload_scene(ctx, &v), "ptap_upload_scene");
             check(ptap_build_accel(ctx, lbvh ? PTAP_ACCEL_BVH_DEVICE : bvh || scene.grids.empty() ? PTAP_ACCEL_BVH : PTAP_ACCEL_GRID_COMPAT), "ptap_build_accel");
             check(ptap_set_render_params(ctx, width * samples_x, height * samples_y, depth, PTAP_FLAG_FIRST_HIT_CACHE | PTAP_FLAG_ITER_TIMES), "ptap_set_render_params");
+            if (scene.config_has_camera) check(ptap_set_camera(ctx, &scene.config_camera), "ptap_set_camera");
         }
         ctx = all[0];
     }

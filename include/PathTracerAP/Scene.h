@@ -33,6 +33,7 @@ public:
         int32_t p[4] = {0, 0, 0, 0};
         ptap_scene_config_params(s, p);
         config_width = p[0]; config_height = p[1]; config_iter = p[2]; config_depth = p[3];
+        config_has_camera = ptap_scene_config_camera(s, &config_camera) != 0;
         PtapSceneView v;
         ptap_scene_view(s, &v);
         models.assign(v.models, v.models + v.nmodels);
@@ -57,4 +58,7 @@ public:
 
     // RESOLUTION / ITER / DEPTH keys of a parsed Config.txt, 0 when absent (an extension: the reference has compile-time macros only)
     int config_width = 0, config_height = 0, config_iter = 0, config_depth = 0;
+    // CAMERA_ORIGIN / CAMERA_PLANE / CAMERA_SPAN / JITTER keys (the reference hard-codes its camera, Renderer.cpp:538-545)
+    bool config_has_camera = false;
+    PtapCamera config_camera{{0.0f, 0.0f, 920.0f}, {-10.0f, -4.0f, 900.0f}, {20.0f, 16.0f}, 0, 0u};
 };

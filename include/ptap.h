@@ -131,6 +131,20 @@ typedef struct {
     float ms_trace_sum;           /* PTAP_FLAG_STAMP: summed residency of its closest-hit launches (lanes overlap: may exceed ms_render) */
 } PtapStats;
 
+/* Camera of generateRaysKernel (Renderer.cpp:527-548), whose numbers the reference hard-codes: rays start at `origin` and pass through
+ * pixel (x, y)'s lower-left corner plane_min + (x * span[0] / W, y * span[1] / H, 0) of an axis-aligned image plane (un-normalised
+ * directions, non-square pixels unless span matches the aspect ratio - as the reference).  jitter != 0 adds a per-iteration sub-pixel
+ * offset in [0, 1)^2 (a hash of jitter_seed, iteration and pixel); camera rays then differ between iterations, so the first-hit cache
+ * (Renderer.cpp:594-613) is not used whatever PTAP_FLAG_FIRST_HIT_CACHE says.  Parity: with the default values the rays are bit-identical
+ * to the reference's; everything else is an extension with no reference behaviour (tested against a numpy restatement). */
+typedef struct {
+    float origin[3];          /* (0, 0, 920) */
+    float plane_min[3];       /* (-10, -4, 900) */
+    float span[2];            /* (20, 16) */
+    int32_t jitter;
+    uint32_t jitter_seed;
+} PtapCamera;
+
 typedef struct ptap_scene ptap_scene;   /* host-side scene: replaces class Scene (Scene.h:21-39) */
 typedef struct ptap_ctx ptap_ctx;       /* per-GPU render context: replaces class Renderer + RenderData (Renderer.h:19-55) */
 
@@ -167,6 +181,9 @@ void ptap_scene_destroy(ptap_scene* s);
 const char* ptap_scene_last_error(const ptap_scene* s);
 /* RESOLUTION / ITER / DEPTH keys of a parsed Config.txt (0 when absent): out4 = {W, H, iters, depth} */
 int ptap_scene_config_params(const ptap_scene* s, int32_t out4[4]);
+/* CAMERA_ORIGIN / CAMERA_PLANE / CAMERA_SPAN / JITTER keys of a parsed Config.txt: returns 1 and fills *out when any of them was given
+ * (missing ones keep the reference's values), 0 otherwise */
+int ptap_scene_config_camera(const ptap_scene* s, PtapCamera* out);
 
 /* ---- device context: replaces Renderer (Renderer.h:46-55) -------------------------------- */
 
@@ -198,6 +215,8 @@ int ptap_build_accel(ptap_ctx* ctx, int kind);
 int ptap_build_grids_device(ptap_ctx* ctx, const PtapSceneView* view, int32_t gx, int32_t gy, int32_t gz);
 int ptap_read_grids(ptap_ctx* ctx, PtapVoxel* voxels, int32_t* refs, int32_t counts[2]);
 int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, uint32_t flags);
+/* NULL restores the reference's camera.  May be called before or after ptap_set_render_params. */
+int ptap_set_camera(ptap_ctx* ctx, const PtapCamera* camera);
 /* Renderer::renderLoop (Renderer.cpp:567-648) for iterations [iter_begin, iter_end); the film accumulates.
  * Asynchronous on the context stream; ptap_sync / ptap_read_film / ptap_get_stats wait for it. */
 int ptap_render(ptap_ctx* ctx, int32_t iter_begin, int32_t iter_end);

@@ -48,6 +48,10 @@ class SceneView(C.Structure):
                 ("tri_recs", C.c_void_p), ("n_tri_recs", C.c_int32)]
 
 
+class Camera(C.Structure):
+    _fields_ = [("origin", C.c_float * 3), ("plane_min", C.c_float * 3), ("span", C.c_float * 2), ("jitter", C.c_int32), ("jitter_seed", C.c_uint32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("rays_traced", C.c_int64), ("paths", C.c_int64), ("kernel_launches", C.c_int64),
                 ("active_per_round", C.c_int64 * 16), ("ms_render", C.c_float), ("ms_trace", C.c_float),
@@ -61,7 +65,7 @@ EXPORTS = [
     "ptap_scene_create_builtin", "ptap_scene_create_from_config", "ptap_scene_create_empty", "ptap_scene_create_from_view",
     "ptap_scene_add_obj", "ptap_scene_add_mesh", "ptap_scene_add_icosphere", "ptap_scene_add_model", "ptap_compose_trs",
     "ptap_scene_build_grids", "ptap_scene_build_bvh", "ptap_scene_validate_bvh", "ptap_scene_view", "ptap_scene_models", "ptap_scene_destroy", "ptap_scene_last_error",
-    "ptap_scene_config_params",
+    "ptap_scene_config_params", "ptap_scene_config_camera", "ptap_set_camera",
     "ptap_create", "ptap_destroy", "ptap_last_error", "ptap_upload_scene", "ptap_build_accel", "ptap_build_grids_device", "ptap_read_grids", "ptap_set_render_params",
     "ptap_render", "ptap_timer_start", "ptap_timer_stop", "ptap_frame_begin", "ptap_film_reset", "ptap_sync", "ptap_read_film", "ptap_film_device_ptr", "ptap_film_add",
     "ptap_write_bmp", "ptap_read_film_resolved", "ptap_write_bmp_resolved", "ptap_get_stats", "ptap_stream", "ptap_trace", "ptap_trace_count", "ptap_shade", "ptap_bench_trace", "ptap_render_probe", "ptap_get_iteration_times",
@@ -101,6 +105,8 @@ def lib():
         L.ptap_scene_destroy.argtypes = [vp]; L.ptap_scene_destroy.restype = None
         L.ptap_scene_last_error.argtypes = [vp]; L.ptap_scene_last_error.restype = C.c_char_p
         L.ptap_scene_config_params.argtypes = [vp, vp]
+        L.ptap_scene_config_camera.argtypes = [vp, C.POINTER(Camera)]
+        L.ptap_set_camera.argtypes = [vp, C.POINTER(Camera)]
         L.ptap_create.argtypes = [C.c_int, C.c_size_t, pp]
         L.ptap_destroy.argtypes = [vp]; L.ptap_destroy.restype = None
         L.ptap_last_error.argtypes = [vp]; L.ptap_last_error.restype = C.c_char_p

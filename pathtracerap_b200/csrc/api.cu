@@ -87,6 +87,7 @@ struct ptap_ctx {
     int grid_trace = 0, grid_shade = 0, grid_gen = 0;
     int trace_ctas = 0;              // PTAP_TRACE_CTAS: CTAs per SM of the closest-hit kernels (0 = occupancy query)
     PtapStats stats{};
+    PtapCamera camera{{0.0f, 0.0f, 920.0f}, {-10.0f, -4.0f, 900.0f}, {20.0f, 16.0f}, 0, 0u};      // Renderer.cpp:538-545
     std::vector<cudaEvent_t> iter_events;      // completion of every iteration of the last render call (PTAP_FLAG_ITER_TIMES)
     int iter_events_used = 0;
     std::vector<float> iter_ms;
@@ -144,6 +145,15 @@ void resetStats(ptap_ctx* c)
     c->stats = PtapStats{};
     c->stats.scene_bytes = old.scene_bytes; c->stats.ms_build = old.ms_build; c->stats.bvh_nodes = old.bvh_nodes; c->stats.bvh_depth = old.bvh_depth;
     c->stats.lanes = c->lanes;
+}
+
+// camera numbers into a wavefront descriptor: step = span / resolution in double, rounded once (Renderer.cpp:538-539, SAMPLESX = SAMPLESY = 1)
+void applyCamera(const ptap_ctx* c, WaveDev& wv)
+{
+    wv.step_x = (float)((double)c->camera.span[0] / (double)wv.W);
+    wv.step_y = (float)((double)c->camera.span[1] / (double)wv.H);
+    for (int k = 0; k < 3; ++k) { wv.cam_o[k] = c->camera.origin[k]; wv.cam_p[k] = c->camera.plane_min[k]; }
+    wv.jitter = c->camera.jitter; wv.jitter_seed = c->camera.jitter_seed;
 }
 
 int traceGridSize(ptap_ctx* c)
@@ -715,8 +725,7 @@ int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, u
     ctx->d_stamps = A.alloc<unsigned long long>(2 * kMaxStamps); ctx->stamps_used = 0;
     if (!ctx->d_stamps || !wv.st || !wv.tile_status || !wv.tile_offset || !wv.tile_ballot || !wv.perm || !wv.film) return fail(ctx, PTAP_E_NOMEM, "frame arena exhausted");
     wv.W = W; wv.H = H; wv.N = N; wv.depth = depth; wv.ntiles = ntiles; wv.nscan = nscan;
-    wv.step_x = (float)(20.0 / (double)W);                       // Renderer.cpp:538-539 (SAMPLESX = SAMPLESY = 1)
-    wv.step_y = (float)(16.0 / (double)H);
+    applyCamera(ctx, wv);
     wv.iter_stride = 1; wv.contrib = nullptr;
     if (ctx->lanes > 1) wv.contrib = A.alloc<float>((size_t)N * 3);
     for (int l = 1; l < ctx->lanes; ++l) {
@@ -743,6 +752,23 @@ int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, u
     return PTAP_OK;
 }
 
+int ptap_set_camera(ptap_ctx* ctx, const PtapCamera* cam)
+{
+    if (!ctx) return PTAP_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
+    const PtapCamera ref{{0.0f, 0.0f, 920.0f}, {-10.0f, -4.0f, 900.0f}, {20.0f, 16.0f}, 0, 0u};
+    const PtapCamera c = cam ? *cam : ref;
+    if (!(c.span[0] > 0.0f) || !(c.span[1] > 0.0f)) return fail(ctx, PTAP_E_INVALID, "set_camera: the image plane needs a positive extent");
+    ctx->camera = c;
+    ctx->cache_valid = false;
+    if (ctx->have_frame) {
+        applyCamera(ctx, ctx->wv);
+        for (int l = 1; l < kMaxLanes; ++l) if (ctx->wvx[l].st) { WaveDev& w = ctx->wvx[l]; w.step_x = ctx->wv.step_x; w.step_y = ctx->wv.step_y; for (int k = 0; k < 3; ++k) { w.cam_o[k] = ctx->wv.cam_o[k]; w.cam_p[k] = ctx->wv.cam_p[k]; } w.jitter = ctx->wv.jitter; w.jitter_seed = ctx->wv.jitter_seed; }
+    }
+    return PTAP_OK;
+}
+
 int ptap_render(ptap_ctx* ctx, int32_t iter_begin, int32_t iter_end)
 {
     if (!ctx || !ctx->have_scene || !ctx->have_frame) return fail(ctx, PTAP_E_STATE, "render: scene and render parameters required");
@@ -750,7 +776,8 @@ int ptap_render(ptap_ctx* ctx, int32_t iter_begin, int32_t iter_end)
     if (iter_end < iter_begin) return fail(ctx, PTAP_E_INVALID, "render: empty iteration range");
     CK(cudaSetDevice(ctx->device));
     if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
-    const bool cache = ctx->flags & PTAP_FLAG_FIRST_HIT_CACHE;
+    // jittered camera rays differ from iteration to iteration: the first-hit cache (Renderer.cpp:594-613) is meaningless then and is not used
+    const bool cache = (ctx->flags & PTAP_FLAG_FIRST_HIT_CACHE) && !ctx->camera.jitter;
     // several lanes only for plain frames (the per-class event timing and the counting build stay on one stream)
     const int L = (ctx->flags & (PTAP_FLAG_PROFILE | PTAP_FLAG_COUNT)) ? 1 : std::max(1, std::min(ctx->lanes, iter_end - iter_begin));
     WaveDev lane[kMaxLanes];
@@ -778,7 +805,7 @@ int ptap_render(ptap_ctx* ctx, int32_t iter_begin, int32_t iter_end)
         const WaveDev& wv = lane[l];
         cudaStream_t S = ctx->streams[l];
         profMark(ctx, 0);
-        launchGenerate(wv, ctx->grid_gen, S); ++launches;
+        launchGenerate(wv, it, ctx->grid_gen, S); ++launches;
         int in = 0;
         for (int round = 0; round < wv.depth; ++round) {
             float4* hitbuf = (round == 0 && cache) ? wv.hit_cache : wv.hit;
@@ -1144,7 +1171,7 @@ int ptap_render_probe(ptap_ctx* ctx, int32_t iter, int32_t round, float* rays_od
     cudaStream_t S = ctx->stream;
     ctx->cache_valid = false;
     launchSetIter(wv.st, iter, S);
-    launchGenerate(wv, ctx->grid_gen, S);
+    launchGenerate(wv, iter, ctx->grid_gen, S);
     int in = 0;
     for (int r = 0; r <= round; ++r) {
         launchTrace(ctx, wv.st, wv.O[in], wv.D[in], wv.hit, nullptr, nullptr, r, -1, false, S);       // the instantiation ptap_render launches

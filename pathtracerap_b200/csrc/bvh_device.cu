@@ -205,20 +205,32 @@ __global__ void k_lbvh_collapse(const int2* __restrict__ child, const Box6* __re
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nfrontier) return;
     const int2 item = frontier[f];
-    int ent[4]; int ne = 0;
-    const int2 ch = child[item.x];
-    const int two[2] = {ch.x, ch.y};
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        if (two[k] >= 0) { const int2 g = child[two[k]]; ent[ne++] = g.x; ent[ne++] = g.y; }
-        else ent[ne++] = two[k];
+    // up to four entries (>= 0: binary internal node, < 0: leaf ~index): starting from the node's two children, the internal entry with
+    // the largest box is replaced by its own two children - the same greedy rule as the host collapse (bvh_build.cpp), which keeps big,
+    // often-hit boxes out of the wide node instead of always taking the four grandchildren
+    int ent[4]; Box6 ebox[4]; int ne = 2;
+    { const int2 ch = child[item.x]; ent[0] = ch.x; ent[1] = ch.y; }
+    for (int k = 0; k < 2; ++k) ebox[k] = ent[k] >= 0 ? node_box[ent[k]] : leaf_box[~ent[k]];
+    while (ne < 4) {
+        int best = -1; float best_area = -1.0f;
+        for (int k = 0; k < ne; ++k) {
+            if (ent[k] < 0) continue;
+            const float dx = ebox[k].hi[0] - ebox[k].lo[0], dy = ebox[k].hi[1] - ebox[k].lo[1], dz = ebox[k].hi[2] - ebox[k].lo[2];
+            const float a = dx * dy + dy * dz + dz * dx;
+            if (a > best_area) { best_area = a; best = k; }
+        }
+        if (best < 0) break;
+        const int2 g = child[ent[best]];
+        ent[best] = g.x; ebox[best] = g.x >= 0 ? node_box[g.x] : leaf_box[~g.x];
+        ent[ne] = g.y; ebox[ne] = g.y >= 0 ? node_box[g.y] : leaf_box[~g.y];
+        ++ne;
     }
     BvhNode nd;
     Box6 boxes[4];
     for (int k = 0; k < 4; ++k) {
         if (k < ne) {
             const int e = ent[k];
-            boxes[k] = e >= 0 ? node_box[e] : leaf_box[~e];
+            boxes[k] = ebox[k];
             if (e >= 0) {
                 const int idx = atomicAdd(&counters[0], 1);
                 next[atomicAdd(&counters[1], 1)] = make_int2(e, idx);

@@ -124,6 +124,8 @@ struct WaveDev {
     FrameState* st;
     int W, H, N, depth, ntiles, nscan;   // ntiles = ceil(N / 32), nscan = ceil(N / 2048)
     float step_x, step_y;
+    float cam_o[3], cam_p[3];   // camera origin and lower-left corner of the image plane (Renderer.cpp:541-545: (0, 0, 920) and (-10, -4, 900))
+    int jitter; unsigned jitter_seed;   // sub-pixel jitter per iteration (an extension; 0 = the reference's fixed pixel corners)
     int iter_stride;            // iterations between two consecutive iterations of this lane (= lanes in use)
 };
 

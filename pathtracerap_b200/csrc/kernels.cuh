@@ -65,7 +65,7 @@ int gridDeviceFill(const float* d_pos, int t0, int n, const float bb_min[3], con
 size_t gridDeviceTempBytes(int ntris, long long npairs);
 
 // wavefront.cu
-void launchGenerate(const WaveDev& wv, int grid, cudaStream_t stream);
+void launchGenerate(const WaveDev& wv, int iter /* the iteration being generated: seeds the camera jitter */, int grid, cudaStream_t stream);
 void launchScan(const SceneDev& sc, const WaveDev& wv, int round, const float4* hit, int remaining, int n_fixed, cudaStream_t stream);
 void launchShade(const SceneDev& sc, const WaveDev& wv, int round, int in_buf, const float4* hit, int remaining, int n_fixed,
                  int iter_fixed, int* slot_pos, int grid, cudaStream_t stream);

@@ -39,6 +39,8 @@ struct ptap_scene {
     int32_t grid_dim[3] = {25, 25, 25};
     // Config.txt extensions (not part of the reference's Scene)
     int32_t cfg_width = 0, cfg_height = 0, cfg_iter = 0, cfg_depth = 0;
+    bool cfg_has_camera = false;
+    PtapCamera cfg_camera{{0.0f, 0.0f, 920.0f}, {-10.0f, -4.0f, 900.0f}, {20.0f, 16.0f}, 0, 0u};
     // optional BVH (ptap_scene_build_bvh); invalidated by any mesh edit
     ptap::BvhBuildResult bvh;
     bool have_bvh = false;
@@ -502,6 +504,17 @@ int parseConfig(ptap_scene* s, const std::string& path)
                 mats[name] = m; ++i;
                 continue;
             }
+            if (up == "CAMERA_ORIGIN" || up == "CAMERA_PLANE" || up == "CAMERA_SPAN" || up == "JITTER") {
+                if (i + 1 >= b.size()) { s->err = path + ": " + up + " needs a value"; return PTAP_E_PARSE; }
+                bool ok = true;
+                if (up == "CAMERA_ORIGIN") ok = parseVec(b[i + 1], s->cfg_camera.origin, 3);
+                else if (up == "CAMERA_PLANE") ok = parseVec(b[i + 1], s->cfg_camera.plane_min, 3);
+                else if (up == "CAMERA_SPAN") ok = parseVec(b[i + 1], s->cfg_camera.span, 2);
+                else { s->cfg_camera.jitter = 1; s->cfg_camera.jitter_seed = (uint32_t)strtoul(b[i + 1].c_str(), nullptr, 10); }
+                if (!ok) { s->err = path + ": bad " + up; return PTAP_E_PARSE; }
+                s->cfg_has_camera = true;
+                i += 2; continue;
+            }
             if (up == "RESOLUTION" || up == "ITER" || up == "DEPTH" || up == "GRID") {
                 if (i + 1 >= b.size()) { s->err = path + ": " + up + " needs a value"; return PTAP_E_PARSE; }
                 float v[3] = {0, 0, 0};
@@ -772,6 +785,13 @@ int ptap_scene_view(const ptap_scene* s, PtapSceneView* out)
 }
 
 PtapModel* ptap_scene_models(ptap_scene* s) { return s ? s->models.data() : nullptr; }
+
+int ptap_scene_config_camera(const ptap_scene* s, PtapCamera* out)
+{
+    if (!s || !out) return 0;
+    *out = s->cfg_camera;
+    return s->cfg_has_camera ? 1 : 0;
+}
 
 int ptap_scene_config_params(const ptap_scene* s, int32_t out4[4])
 {

@@ -118,7 +118,7 @@ __device__ __forceinline__ void stVolatile(unsigned long long* p, unsigned long 
 }  // namespace
 
 // generateRaysKernel (Renderer.cpp:521-555) + per-iteration reset of the device-side frame state.
-__global__ void __launch_bounds__(kGenBlock) k_generate(WaveDev wv)
+__global__ void __launch_bounds__(kGenBlock) k_generate(WaveDev wv, int iter_now)
 {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     const int stride = gridDim.x * blockDim.x;
@@ -134,11 +134,18 @@ __global__ void __launch_bounds__(kGenBlock) k_generate(WaveDev wv)
     for (int i = tid; i < nwords; i += stride) wv.tile_status[i] = 0ull;      // one look-back word per 2048-slot scan block and round
     for (int i = tid; i < wv.N; i += stride) {
         const int y = i / wv.W, x = i % wv.W;
-        // float world_x = -10.0 + x * step_x  (double add of a float product, Renderer.cpp:541-542)
-        const float wx = (float)(-10.0 + (double)xmul((float)x, wv.step_x));
-        const float wy = (float)(-4.0 + (double)xmul((float)y, wv.step_y));
-        wv.O[0][i] = make_float4(0.0f, 0.0f, 920.0f, __int_as_float(i));
-        wv.D[0][i] = make_float4(xsub(wx, 0.0f), xsub(wy, 0.0f), xsub(900.0f, 920.0f), 0.0f);
+        // float world_x = -10.0 + x * step_x  (double add of a float product, Renderer.cpp:541-542); the camera's numbers are parameters
+        // (ptap_set_camera), the arithmetic is the reference's: with its own camera the rays are bit-identical
+        float fx = (float)x, fy = (float)y;
+        if (wv.jitter) {        // sub-pixel offset in [0, 1)^2, a hash of (seed, iteration, pixel): the reference has no jitter (Renderer.cpp:527-548)
+            const unsigned h = utilHash(wv.jitter_seed ^ utilHash((unsigned)iter_now + 0x9e3779b9u)) ^ utilHash((unsigned)i);
+            fx = xadd(fx, xmul((float)(utilHash(h) >> 8), 5.9604644775390625e-8f));
+            fy = xadd(fy, xmul((float)(utilHash(h ^ 0x85ebca6bu) >> 8), 5.9604644775390625e-8f));
+        }
+        const float wx = (float)((double)wv.cam_p[0] + (double)xmul(fx, wv.step_x));
+        const float wy = (float)((double)wv.cam_p[1] + (double)xmul(fy, wv.step_y));
+        wv.O[0][i] = make_float4(wv.cam_o[0], wv.cam_o[1], wv.cam_o[2], __int_as_float(i));
+        wv.D[0][i] = make_float4(xsub(wx, wv.cam_o[0]), xsub(wy, wv.cam_o[1]), xsub(wv.cam_p[2], wv.cam_o[2]), 0.0f);
         wv.C[0][i] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
     }
 }
@@ -418,7 +425,7 @@ __global__ void k_film_add(float* __restrict__ film, const float* __restrict__ a
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) film[i] += add[i];
 }
 
-void launchGenerate(const WaveDev& wv, int grid, cudaStream_t stream) { k_generate<<<grid, kGenBlock, 0, stream>>>(wv); }
+void launchGenerate(const WaveDev& wv, int iter, int grid, cudaStream_t stream) { k_generate<<<grid, kGenBlock, 0, stream>>>(wv, iter); }
 
 void launchScan(const SceneDev& sc, const WaveDev& wv, int round, const float4* hit, int remaining, int n_fixed, cudaStream_t stream)
 {

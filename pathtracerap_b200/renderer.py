@@ -67,6 +67,11 @@ class Renderer:
         self._check(N.lib().ptap_set_render_params(self.h, width, height, depth, self.flags), "set_render_params")
         self._iters_done = 0
 
+    def set_camera(self, origin=(0.0, 0.0, 920.0), plane_min=(-10.0, -4.0, 900.0), span=(20.0, 16.0), jitter=False, jitter_seed=0):
+        """generateRaysKernel's camera (Renderer.cpp:527-548) as parameters; the defaults are the reference's hard-coded numbers."""
+        cam = N.Camera((C.c_float * 3)(*origin), (C.c_float * 3)(*plane_min), (C.c_float * 2)(*span), int(bool(jitter)), int(jitter_seed))
+        self._check(N.lib().ptap_set_camera(self.h, C.byref(cam)), "set_camera")
+
     def build_grids_device(self, scene: Scene, gx=25, gy=25, gz=25):
         """Scene::addMeshesToGrid on the GPU for the scene last uploaded (`scene` must be that scene); selects the grid walk."""
         v = scene.view()

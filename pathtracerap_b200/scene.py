@@ -161,6 +161,13 @@ class Scene:
         N.lib().ptap_scene_config_params(self.h, N.ptr(out))
         return {"W": int(out[0]), "H": int(out[1]), "iters": int(out[2]), "depth": int(out[3])}
 
+    def config_camera(self):
+        """CAMERA_* / JITTER keys of a parsed Config.txt as keyword arguments for Renderer.set_camera, or None when absent."""
+        cam = N.Camera()
+        if not N.lib().ptap_scene_config_camera(self.h, C.byref(cam)):
+            return None
+        return dict(origin=tuple(cam.origin), plane_min=tuple(cam.plane_min), span=tuple(cam.span), jitter=bool(cam.jitter), jitter_seed=int(cam.jitter_seed))
+
     def close(self):
         if getattr(self, "h", None):
             N.lib().ptap_scene_destroy(self.h)

@@ -255,3 +255,65 @@ def test_errors_are_loud(libptap):
     with pytest.raises(PtapError):
         r.set_params(32, 32, 99)            # depth beyond the reserved rounds
     r.free()
+
+
+def test_camera_parameters_and_jitter(gpu_scene):
+    """generateRaysKernel's camera as parameters (ptap_set_camera).  Parity unpinned beyond the default (the reference
+    hard-codes its camera, Renderer.cpp:538-545, and has no jitter): the rays of a custom camera and of a jittered one are compared bit for
+    bit with a numpy restatement of the documented arithmetic (include/ptap.h); the default camera still gives the reference's rays; with
+    jitter the first-hit cache is not used and two renders are bit-identical."""
+    from pathtracerap_b200 import ACCEL_BVH, Renderer
+    W, H, depth = 96, 64, 5
+    r = Renderer(width=W, height=H, depth=depth, accel=ACCEL_BVH, first_hit_cache=True)
+    r.allocateOnGPU(gpu_scene)
+    f32 = np.float32
+
+    def expect(origin, pmin, span, jit=None):
+        i = np.arange(W * H)
+        fx, fy = (i % W).astype(f32), (i // W).astype(f32)
+        if jit is not None:
+            fx, fy = fx + jit[0], fy + jit[1]
+        sx, sy = f32(np.float64(f32(span[0])) / W), f32(np.float64(f32(span[1])) / H)
+        wx = (np.float64(f32(pmin[0])) + (fx * sx).astype(np.float64)).astype(f32)
+        wy = (np.float64(f32(pmin[1])) + (fy * sy).astype(np.float64)).astype(f32)
+        out = np.zeros((W * H, 6), f32)
+        out[:, :3] = f32(origin)
+        out[:, 3], out[:, 4], out[:, 5] = wx - f32(origin[0]), wy - f32(origin[1]), f32(pmin[2]) - f32(origin[2])
+        return out
+
+    rays, pix, _ = r.render_probe(0, 0)
+    assert np.array_equal(rays, expect((0, 0, 920), (-10, -4, 900), (20, 16)))              # the reference's camera (Renderer.cpp:538-548)
+    cam = dict(origin=(35.5, 120.25, 880.0), plane_min=(-7.0, -2.5, 861.0), span=(14.0, 9.75))
+    r.set_camera(**cam)
+    rays, pix, _ = r.render_probe(0, 0)
+    assert np.array_equal(rays, expect(cam["origin"], cam["plane_min"], cam["span"])) and np.array_equal(pix, np.arange(W * H))
+
+    def hash32(a):                                                                          # utility.h:43-53
+        a = a.astype(np.uint32)
+        a = (a + np.uint32(0x7ed55d16)) + (a << np.uint32(12)); a = (a ^ np.uint32(0xc761c23c)) ^ (a >> np.uint32(19))
+        a = (a + np.uint32(0x165667b1)) + (a << np.uint32(5)); a = (a + np.uint32(0xd3a2646c)) ^ (a << np.uint32(9))
+        a = (a + np.uint32(0xfd7046c5)) + (a << np.uint32(3)); a = (a ^ np.uint32(0xb55a4f09)) ^ (a >> np.uint32(16))
+        return a
+
+    seed = 1234
+    r.set_camera(jitter=True, jitter_seed=seed)
+    seen = []
+    with np.errstate(over="ignore"):
+        for it in (0, 5):
+            i = np.arange(W * H, dtype=np.uint32)
+            h = hash32(np.uint32(seed) ^ hash32(np.array([it], np.uint32) + np.uint32(0x9e3779b9))) ^ hash32(i)
+            jx = (hash32(h) >> np.uint32(8)).astype(f32) * f32(2.0 ** -24)
+            jy = (hash32(h ^ np.uint32(0x85ebca6b)) >> np.uint32(8)).astype(f32) * f32(2.0 ** -24)
+            assert jx.min() >= 0 and jx.max() < 1 and jy.max() < 1
+            rays, _, _ = r.render_probe(it, 0)
+            assert np.array_equal(rays, expect((0, 0, 920), (-10, -4, 900), (20, 16), (jx, jy))), f"jittered rays of iteration {it}"
+            seen.append(rays)
+    assert not np.array_equal(seen[0], seen[1])
+    r.frame_begin(); r.render(0, 4); a = r.film(); st = r.stats()
+    assert st["rays_traced"] >= 4 * W * H                                                   # every iteration traces its own camera rays: no first-hit cache
+    r.frame_begin(); r.render(0, 4)
+    assert np.array_equal(r.film(), a)
+    r.set_camera()                                                                          # back to the reference's camera: cache in use again
+    r.frame_begin(); r.render(0, 4)
+    assert r.stats()["rays_traced"] < st["rays_traced"]
+    r.free()

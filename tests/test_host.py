@@ -218,6 +218,11 @@ def test_config_txt_parser(libptap, tmp_path):
     m = a["models"]["model_to_world"][1].reshape(4, 4).T
     assert np.allclose(m, [[2, 0, 0, 1], [0, 2, 0, 2], [0, 0, 2, 3], [0, 0, 0, 1]])
     assert len(a["grids"]) == 3 and len(a["voxels"]) == 3 * 25 ** 3
+    assert s.config_camera() is None                                                          # no CAMERA_* key: the reference's camera
+    cfg2 = tmp_path / "Config2.txt"
+    cfg2.write_text(CONFIG + "\nCAMERA_ORIGIN\n[1, 2, 930]\n\nCAMERA_SPAN\n[16, 9]\n\nJITTER\n77\n")
+    cam = Scene(str(cfg2)).config_camera()
+    assert cam == dict(origin=(1.0, 2.0, 930.0), plane_min=(-10.0, -4.0, 900.0), span=(16.0, 9.0), jitter=True, jitter_seed=77)
     # errors are loud
     bad = tmp_path / "bad.txt"
     bad.write_text("TORUS\nx\n")
