@@ -28,10 +28,21 @@ r.allocateOnGPU(s)
 t = multi_gpu.render_partitioned(r, 8, rank, world)
 r.sync(); torch.cuda.synchronize()
 if rank == 0:
-    np.save({out!r}, t.cpu().numpy().reshape(120, 160, 3))
+    via_torch = t.cpu().numpy().reshape(120, 160, 3).copy()
+    np.save({out!r}, via_torch)
     st = r.stats()
     print("RANK0_DONE", st["rays_traced"])
 dist.barrier()
+# the same frame with the reduce issued through the library's C ABI (ptap_nccl_init + ptap_reduce: its own communicator, its own stream)
+how = multi_gpu.nccl_join(r, rank, world)
+assert how is not None, "ptap_nccl_init failed: libnccl not loadable"
+b, e = multi_gpu.iteration_range(rank, world, 8)
+r.frame_begin(); r.render(b, e); r.reduce(0); r.sync()
+if rank == 0:
+    assert np.array_equal(r.film(), via_torch), "ptap_reduce differs from torch.distributed.reduce"
+    print("C_ABI_REDUCE_OK")
+dist.barrier()
+r.nccl_finalize()
 r.free()
 dist.destroy_process_group()
 """
@@ -49,7 +60,7 @@ def test_two_gpu_frame_equals_one_gpu_frame(libptap, tmp_path):
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29544", str(w)], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stderr[-3000:]
-    assert "RANK0_DONE" in p.stdout
+    assert "RANK0_DONE" in p.stdout and "C_ABI_REDUCE_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
     film2 = np.load(out)
     g = np.load(scene_path)
     s = Scene.from_arrays(g["models"], g["meshes"], g["vertices"], g["triangles"])
