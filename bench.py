@@ -263,6 +263,11 @@ def main():
         return
 
     # -------- our arm
+    # stdout carries exactly ONE line, the JSON: native libraries that print to file descriptor 1 (NCCL announces its version there when
+    # a communicator is created) are sent to stderr for the whole run, and the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from pathtracerap_b200 import ACCEL_BVH, ACCEL_BVH_DEVICE, ACCEL_GRID_COMPAT, Renderer
@@ -510,7 +515,7 @@ def main():
                            "host_accel_build_s, is done once per scene like the reference's addMeshesToGrid and is NOT in this figure - see extras.e2e_build_included) "
                            "+ renderLoop + film read-back to pinned host memory"},
            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "extras": extras}
-    print(json.dumps(out))
+    real_stdout.write(json.dumps(out) + "\n"); real_stdout.flush()
     if world > 1:
         dist.destroy_process_group()
 
