@@ -10,13 +10,22 @@
 //   6  k_lbvh_collapse  breadth-first, one launch per level: a binary node and its two children become one 4-wide BvhNode, its child boxes
 //                       encoded as outward-rounded offsets from a node-local origin exactly as the host builder does (bvh_build.cpp: encodeNode)
 //
+// PTAP_DEVICE_BUILDER=ploc (default) replaces steps 4-5 by PLOC (Meister & Bittner 2018, "Parallel locally-ordered clustering"): the
+// Morton-sorted leaves are merged bottom-up, every cluster pairing with the neighbour (within kPlocRadius positions) whose union with it
+// has the smallest surface area whenever the choice is mutual; the surviving clusters are compacted and the round repeats until one is
+// left.  Boxes are made at the merges, no refit pass is needed, and the tree is close to a SAH tree where the radix tree is not.
+// PTAP_DEVICE_BUILDER=lbvh keeps the radix tree.
+//
 // The tree is a different one than the host builder's, so rays visit different boxes; hits are bit-identical all the same, because the
 // boxes are conservative for the reference's predicate and the triangle arithmetic is the exact one (tests/test_gpu_device_bvh.py).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <string>
 #include <utility>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "kernels.cuh"
 
@@ -252,6 +261,67 @@ __global__ void k_lbvh_single(const Box6* __restrict__ leaf_box, int n, int leaf
     out[0] = nd;
 }
 
+// ---- PLOC ------------------------------------------------------------------------------------------------------------------------
+
+constexpr int kPlocRadius = 8;
+
+__device__ __forceinline__ float unionArea(const Box6& a, const Box6& b)
+{
+    const float dx = fmaxf(a.hi[0], b.hi[0]) - fminf(a.lo[0], b.lo[0]), dy = fmaxf(a.hi[1], b.hi[1]) - fminf(a.lo[1], b.lo[1]), dz = fmaxf(a.hi[2], b.hi[2]) - fminf(a.lo[2], b.lo[2]);
+    return dx * dy + dy * dz + dz * dx;
+}
+
+__global__ void k_ploc_init(const Box6* __restrict__ leaf_box, int n, Box6* __restrict__ cbox, int* __restrict__ cnode)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { cbox[i] = leaf_box[i]; cnode[i] = ~i; }
+}
+
+// nearest[i] = the position within the radius whose union with cluster i has the smallest area (ties: the lower position)
+__global__ void k_ploc_nearest(const Box6* __restrict__ cbox, int n, int* __restrict__ nearest)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Box6 me = cbox[i];
+    float best = 3e38f; int bj = -1;
+    const int j0 = max(0, i - kPlocRadius), j1 = min(n - 1, i + kPlocRadius);
+    for (int j = j0; j <= j1; ++j) {
+        if (j == i) continue;
+        const float a = unionArea(me, cbox[j]);
+        if (a < best) { best = a; bj = j; }
+    }
+    nearest[i] = bj;
+}
+
+// mutual nearest neighbours merge into a new binary node (stored at the lower position); the partner's slot is dropped
+__global__ void k_ploc_merge(Box6* __restrict__ cbox, int* __restrict__ cnode, const int* __restrict__ nearest, int n, int2* __restrict__ child,
+                             Box6* __restrict__ node_box, int* __restrict__ counter, int* __restrict__ keep)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int j = nearest[i];
+    if (j >= 0 && nearest[j] == i) {
+        if (i < j) {
+            const Box6 a = cbox[i], b = cbox[j];
+            Box6 u;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { u.lo[k] = fminf(a.lo[k], b.lo[k]); u.hi[k] = fmaxf(a.hi[k], b.hi[k]); }
+            const int id = atomicAdd(counter, 1);
+            child[id] = make_int2(cnode[i], cnode[j]);
+            node_box[id] = u;
+            cbox[i] = u; cnode[i] = id;      // nobody else reads slot i in this launch: its only reader is its partner, which reads nothing
+            keep[i] = 1;
+        } else keep[i] = 0;
+    } else keep[i] = 1;
+}
+
+__global__ void k_ploc_compact(const Box6* __restrict__ cbox, const int* __restrict__ cnode, const int* __restrict__ keep, const int* __restrict__ pos, int n,
+                               Box6* __restrict__ obox, int* __restrict__ onode)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && keep[i]) { obox[pos[i]] = cbox[i]; onode[pos[i]] = cnode[i]; }
+}
+
 template <typename T> T* carve(char*& p, size_t count)
 {
     T* r = reinterpret_cast<T*>(p);
@@ -266,7 +336,10 @@ size_t deviceBvhScratchBytes(int ntris)
     const size_t n = (size_t)std::max(ntris, 1), L = (n + kCluster - 1) / kCluster;
     size_t cub_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned*)nullptr, (unsigned*)nullptr, (const int*)nullptr, (int*)nullptr, (int)n, 0, 30);
-    return 4 * ((n * 4 + 255) & ~size_t(255)) + cub_bytes + 256 + 2 * ((L * sizeof(Box6) + 255) & ~size_t(255)) + ((L * 8 + 255) & ~size_t(255)) * 4 +
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, (int)n);
+    cub_bytes = std::max(cub_bytes, scan_bytes);
+    return 4 * ((n * 4 + 255) & ~size_t(255)) + cub_bytes + 256 + 4 * ((L * sizeof(Box6) + 255) & ~size_t(255)) + ((L * 8 + 255) & ~size_t(255)) * 4 +
            ((L * 4 + 255) & ~size_t(255)) * 3 + 4096;
 }
 
@@ -284,8 +357,10 @@ int buildMeshBvhDevice(const TriRec* d_tris, int t0, int t1, const float* bb_min
     int* ids = carve<int>(p, n); int* ids2 = carve<int>(p, n);
     size_t cub_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const unsigned*)keys, keys2, (const int*)ids, ids2, n, 0, 30);
+    { size_t scan_bytes = 0; cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, n); cub_bytes = std::max(cub_bytes, scan_bytes); }
     void* cub_tmp = carve<char>(p, cub_bytes + 1);
     Box6* leaf_box = carve<Box6>(p, L); Box6* node_box = carve<Box6>(p, L);
+    Box6* cbox_a = carve<Box6>(p, L); Box6* cbox_b = carve<Box6>(p, L);
     unsigned long long* leaf_key = carve<unsigned long long>(p, L);
     int2* child = carve<int2>(p, L); int2* fr_a = carve<int2>(p, L); int2* fr_b = carve<int2>(p, L);
     int* parent_internal = carve<int>(p, L); int* parent_leaf = carve<int>(p, L); int* arrived = carve<int>(p, L);
@@ -311,12 +386,45 @@ int buildMeshBvhDevice(const TriRec* d_tris, int t0, int t1, const float* bb_min
         *nnodes = 1; *depth = 1;
         return cudaGetLastError();
     }
-    k_lbvh_topology<<<(L - 1 + B - 1) / B, B, 0, stream>>>(leaf_key, L, child, parent_internal, parent_leaf);
-    e = cudaMemsetAsync(arrived, 0, (size_t)L * sizeof(int), stream);
-    if (e != cudaSuccess) return e;
-    k_lbvh_refit<<<(L + B - 1) / B, B, 0, stream>>>(child, parent_internal, parent_leaf, leaf_box, L, node_box, arrived);
-    // breadth-first collapse: the root is 4-wide node 0
-    const int2 root = make_int2(0, 0);
+    int root_node = 0;
+    const char* which = getenv("PTAP_DEVICE_BUILDER");
+    if (which && std::string(which) == "lbvh") {
+        k_lbvh_topology<<<(L - 1 + B - 1) / B, B, 0, stream>>>(leaf_key, L, child, parent_internal, parent_leaf);
+        e = cudaMemsetAsync(arrived, 0, (size_t)L * sizeof(int), stream);
+        if (e != cudaSuccess) return e;
+        k_lbvh_refit<<<(L + B - 1) / B, B, 0, stream>>>(child, parent_internal, parent_leaf, leaf_box, L, node_box, arrived);
+    } else {
+        // PLOC: clusters (box, node) in Morton order, double-buffered across the compaction; scratch arrays of the radix-tree path are reused
+        Box6 *cb = cbox_a, *cb2 = cbox_b;
+        int *cn = parent_internal, *cn2 = parent_leaf, *nearest = arrived, *keep = reinterpret_cast<int*>(keys), *pos = ids;
+        e = cudaMemsetAsync(counters + 8, 0, sizeof(int), stream);
+        if (e != cudaSuccess) return e;
+        k_ploc_init<<<(L + B - 1) / B, B, 0, stream>>>(leaf_box, L, cb, cn);
+        int m = L, rounds = 0;
+        while (m > 1) {
+            const int g = (m + B - 1) / B;
+            k_ploc_nearest<<<g, B, 0, stream>>>(cb, m, nearest);
+            k_ploc_merge<<<g, B, 0, stream>>>(cb, cn, nearest, m, child, node_box, counters + 8, keep);
+            e = cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, keep, pos, m, stream);
+            if (e != cudaSuccess) return e;
+            k_ploc_compact<<<g, B, 0, stream>>>(cb, cn, keep, pos, m, cb2, cn2);
+            int last[2];
+            e = cudaMemcpyAsync(&last[0], pos + m - 1, sizeof(int), cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&last[1], keep + m - 1, sizeof(int), cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) return e;
+            const int m2 = last[0] + last[1];
+            if (m2 >= m || ++rounds > 4096) return cudaErrorUnknown;      // every round merges at least the globally best pair
+            m = m2;
+            std::swap(cb, cb2); std::swap(cn, cn2);
+        }
+        e = cudaMemcpyAsync(&root_node, cn, sizeof(int), cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) return e;
+        if (root_node < 0) return cudaErrorUnknown;
+    }
+    // breadth-first collapse from the binary root: it becomes 4-wide node 0
+    const int2 root = make_int2(root_node, 0);
     const int init[2] = {1, 0};
     e = cudaMemcpyAsync(fr_a, &root, sizeof root, cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(counters, init, sizeof init, cudaMemcpyHostToDevice, stream);
