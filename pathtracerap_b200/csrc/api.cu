@@ -238,34 +238,6 @@ bool invert3(const double m[9], double out[9])
     return true;
 }
 
-// World-space box of an instance for k_trace_grid's conservative reject: the mesh bounds (those the grid walk tests, i.e. of the grid's
-// creating model's mesh) mapped through the INVERSE of world_to_model - the kernel maps rays into model space with world_to_model
-// (Renderer.cpp:381-382), so this is exactly the set of world points whose image lies in the box - then padded by 1e-3 of its size and of
-// the coordinates involved, three orders of magnitude above the rounding of the exact slab test it guards (Renderer.cpp:150-170).
-void worldBoxOf(InstanceTrace& it, const float* W)
-{
-    it.wb_min = make_float4(0, 0, 0, 0); it.wb_max = make_float4(0, 0, 0, 0);
-    const double w3[9] = {W[0], W[4], W[8], W[1], W[5], W[9], W[2], W[6], W[10]};
-    double wi[9];
-    if (!invert3(w3, wi)) return;
-    const float mn[3] = {it.bb_min.x, it.bb_min.y, it.bb_min.z}, mx[3] = {it.bb_max.x, it.bb_max.y, it.bb_max.z};
-    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, mag = 0.0;
-    for (int c = 0; c < 8; ++c) {
-        const double p[3] = {((c & 1) ? mx[0] : mn[0]) - (double)W[12], ((c & 2) ? mx[1] : mn[1]) - (double)W[13], ((c & 4) ? mx[2] : mn[2]) - (double)W[14]};
-        for (int r = 0; r < 3; ++r) {
-            const double w = wi[3 * r] * p[0] + wi[3 * r + 1] * p[1] + wi[3 * r + 2] * p[2];
-            if (!std::isfinite(w)) return;
-            lo[r] = std::min(lo[r], w); hi[r] = std::max(hi[r], w); mag = std::max(mag, std::fabs(w));
-        }
-    }
-    double ext = 0.0;
-    for (int r = 0; r < 3; ++r) ext = std::max(ext, hi[r] - lo[r]);
-    // EPSILON of the entry test (Renderer.cpp:256-259) and of the predicate, in world units, is far below this pad for any sane scale
-    const double pad = 1e-3 * (ext + mag) + 1e-2;
-    it.wb_min = make_float4((float)(lo[0] - pad), (float)(lo[1] - pad), (float)(lo[2] - pad), 1.0f);
-    it.wb_max = make_float4((float)(hi[0] + pad), (float)(hi[1] + pad), (float)(hi[2] + pad), 1.0f);
-}
-
 struct TlasItem { float lo[3], hi[3]; int inst; };
 
 float boxArea(const float* lo, const float* hi)
@@ -598,7 +570,6 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
         InstanceTrace& it = inst[i];
         for (int r = 0; r < 3; ++r) { it.w2m[r] = row(m.world_to_model, r); it.m2w[r] = row(m.model_to_world, r); }
         it.bb_min = make_float4(0, 0, 0, 1); it.bb_max = make_float4(0, 0, 0, 1); it.grid = make_float4(1, 0, 0, 0);
-        it.wb_min = make_float4(0, 0, 0, 0); it.wb_max = make_float4(0, 0, 0, 0);
         if (grid) {
             const PtapGrid& g = v->grids[m.grid_index];
             // the bbox is reached through the grid's creating model, not the traced one (Renderer.cpp:245-249)
@@ -609,7 +580,6 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
             it.bb_max = make_float4(mesh.bb_max[0], mesh.bb_max[1], mesh.bb_max[2], g.width[1]);
             it.grid.x = g.width[2];
             it.grid.y = __builtin_bit_cast(float, (int)g.v_start);
-            worldBoxOf(it, m.world_to_model);
         }
         float nmx[9];
         hm::normal_matrix(m.model_to_world, nmx);
@@ -1450,7 +1420,6 @@ int ptap_build_grids_device(ptap_ctx* ctx, const PtapSceneView* v, int32_t gx, i
         it.bb_max = make_float4(mesh.bb_max[0], mesh.bb_max[1], mesh.bb_max[2], widths[g][1]);
         it.grid.x = widths[g][2];
         it.grid.y = __builtin_bit_cast(float, (int)((size_t)g * ncell));
-        worldBoxOf(it, v->models[i].world_to_model);
     }
     CKH(cudaMemcpyAsync(ctx->d_inst, ctx->h_inst.data(), nm * sizeof(InstanceTrace), cudaMemcpyHostToDevice, ctx->stream));
     CKH(cudaEventRecord(b1, ctx->stream));

@@ -263,7 +263,10 @@ __global__ void k_lbvh_single(const Box6* __restrict__ leaf_box, int n, int leaf
 
 // ---- PLOC ------------------------------------------------------------------------------------------------------------------------
 
-constexpr int kPlocRadius = 8;
+#ifndef PTAP_PLOC_RADIUS
+#define PTAP_PLOC_RADIUS 16
+#endif
+constexpr int kPlocRadius = PTAP_PLOC_RADIUS;
 
 __device__ __forceinline__ float unionArea(const Box6& a, const Box6& b)
 {

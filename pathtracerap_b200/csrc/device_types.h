@@ -12,7 +12,7 @@ constexpr float kFloatMin = -9999990.0f;    // Config.h:6
 constexpr int kMaxDepth = 16;               // rounds per iteration the context reserves state for
 constexpr int kBvhStack = 160;              // traversal stack entries per ray (upload fails for deeper trees)
 
-// Per-model record read by the closest-hit kernels: 11 x float4 = 176 B.
+// Per-model record read by the closest-hit kernels: 9 x float4 = 144 B.
 // Rows 0..2 of the reference's column-major mat4s (the w row is never used by
 // transformPosition/transformDirection, utility.h:71-80).
 struct InstanceTrace {
@@ -21,8 +21,6 @@ struct InstanceTrace {
     float4 bb_min;      // mesh bbox min (through the grid's creating model, Renderer.cpp:245-249); .w = voxel width x
     float4 bb_max;      // mesh bbox max; .w = voxel width y
     float4 grid;        // .x = voxel width z, .y = bits(first voxel of the grid), .z = bits(BLAS root node), .w = bits(first BVH triangle)
-    float4 wb_min;      // world-space box that contains the pre-image of the mesh bounds under world_to_model, padded; .w = 1 when usable
-    float4 wb_max;      //   (k_trace_grid: conservative reject before the exact per-model ray set-up)
 };
 
 // Per-model record read by the shade kernel: 4 x float4 = 64 B.

@@ -22,10 +22,6 @@ struct GridRay {
     float best_u, best_v;
 };
 
-// traversal-only reciprocal for the conservative world-space reject: guarded against 0 (a zero component gives +-1e30: the axis then
-// passes exactly when the origin lies inside the padded slab, the geometric answer)
-__device__ __forceinline__ float gridSafeInv(float d) { return __fdividef(1.0f, fabsf(d) > 1e-30f ? d : copysignf(1e-30f, d)); }
-
 // Renderer.cpp:174-215 without the normal (looked up later from the id)
 template <bool COUNT>
 __device__ __forceinline__ bool rayTriangle(const TriRec* __restrict__ tris, GridRay& r, int itri, int4& cnt)
@@ -68,11 +64,8 @@ enum : unsigned { F_INTERSECT = 1u, F_ANY = 2u, F_POST = 4u, F_MODEL_HIT = 8u };
 
 }  // namespace
 
-#ifndef PTAP_GRID_MIN_CTAS
-#define PTAP_GRID_MIN_CTAS 1
-#endif
 template <bool UV, bool COUNT>
-__global__ void __launch_bounds__(kTraceBlock, PTAP_GRID_MIN_CTAS)
+__global__ void __launch_bounds__(kTraceBlock)
 k_trace_grid(SceneDev sc, const float4* __restrict__ O, const float4* __restrict__ D, float4* __restrict__ hit,
              float2* __restrict__ uv, int4* __restrict__ counts, FrameState* st, int round, int n_fixed, unsigned long long* __restrict__ stamp)
 {
@@ -88,7 +81,7 @@ k_trace_grid(SceneDev sc, const float4* __restrict__ O, const float4* __restrict
 
     unsigned state = G_DONE, flags = 0;
     int i = -1, im = -1;
-    V3 bo = v3(0, 0, 0), bd = v3(0, 0, 0), winv = v3(0, 0, 0);    // the stored ray; reciprocal of its direction (world-space reject only)
+    V3 bo = v3(0, 0, 0), bd = v3(0, 0, 0);
     GridRay r; r.o = v3(0, 0, 0); r.d = v3(0, 0, 1); r.inv = v3(0, 0, 0); r.best_t = kFloatMax; r.best_tri = -1; r.best_u = 0.0f; r.best_v = 0.0f;
     float g_dist = kFloatMax, g_t = 0.0f, g_u = 0.0f, g_v = 0.0f;
     int g_model = -1, g_tri = -1;
@@ -199,27 +192,8 @@ k_trace_grid(SceneDev sc, const float4* __restrict__ O, const float4* __restrict
             else {
                 const InstanceTrace* __restrict__ inst = &sc.inst[im];
                 const float4 w0 = ldg4(&inst->w2m[0]), w1 = ldg4(&inst->w2m[1]), w2 = ldg4(&inst->w2m[2]);
-                const V3 dm = xmat4(w0, w1, w2, bd, 0.0f);                           // Renderer.cpp:382, before the normalisation
-                // Conservative reject in WORLD space before the exact per-model set-up (85 % of the set-ups of the reference's scene end in
-                // a missed mesh box).  The reference's slab test is not purely geometric: a direction component that is exactly zero in
-                // MODEL space makes its axis pass whatever the origin (Renderer.cpp:150-170), so the shortcut is taken only when no
-                // component of the model-space direction can be (or underflow to) zero; then "the exact test passes" implies that the
-                // world ray crosses the padded world box of the instance (api.cu: worldBoxOf) with a non-negative exit parameter, and
-                // a ray that clearly does not is skipped.  Fast arithmetic with slack: it only ever answers "clearly outside".
-                const float4 wlo = ldg4(&inst->wb_min), whi = ldg4(&inst->wb_max);
-                bool skip = false;
-                if (wlo.w != 0.0f && fminf(fminf(fabsf(dm.x), fabsf(dm.y)), fabsf(dm.z)) > 1e-25f) {
-                    const float x0 = (wlo.x - bo.x) * winv.x, x1 = (whi.x - bo.x) * winv.x;
-                    const float y0 = (wlo.y - bo.y) * winv.y, y1 = (whi.y - bo.y) * winv.y;
-                    const float z0 = (wlo.z - bo.z) * winv.z, z1 = (whi.z - bo.z) * winv.z;
-                    const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
-                    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
-                    const float slack = fmaxf(fabsf(tn), fabsf(tf)) * 1e-5f + 1e-6f;
-                    skip = tf < -slack || tn > tf + slack;
-                }
-                if (skip) { /* stay in MODEL: the next round takes the next model */ } else {
                 r.o = xmat4(w0, w1, w2, bo, 1.0f);                                   // Renderer.cpp:381
-                r.d = xnormalize(dm);                                                // Renderer.cpp:382
+                r.d = xnormalize(xmat4(w0, w1, w2, bd, 0.0f));                       // Renderer.cpp:382
                 r.inv = v3(xdiv(1.0f, r.d.x), xdiv(1.0f, r.d.y), xdiv(1.0f, r.d.z)); // Renderer.cpp:383
                 r.best_t = kFloatMax; r.best_tri = -1; r.best_u = 0.0f; r.best_v = 0.0f;   // Renderer.cpp:384
                 const V3 mn = v3(ldg4(&inst->bb_min)), mx = v3(ldg4(&inst->bb_max));
@@ -233,7 +207,6 @@ k_trace_grid(SceneDev sc, const float4* __restrict__ O, const float4* __restrict
                 const float tmin = max_std(max_std(min_std(t1, t2), min_std(t3, t4)), min_std(t5, t6));
                 const float tmax = min_std(min_std(max_std(t1, t2), max_std(t3, t4)), max_std(t5, t6));
                 if (!(tmax < 0 || tmin > tmax)) { t_entry = tmin; state = G_INIT; }      // else: stay in MODEL, the next round takes the next model
-                }
             }
         }
         // ---- DONE: retire finished rays, refill the lanes from the warp's batch
@@ -259,7 +232,6 @@ k_trace_grid(SceneDev sc, const float4* __restrict__ O, const float4* __restrict
             if (s_done && live && rank < avail) {
                 i = w_next + rank;
                 bo = v3(O[i]); bd = v3(D[i]);
-                winv = v3(gridSafeInv(bd.x), gridSafeInv(bd.y), gridSafeInv(bd.z));
                 g_dist = kFloatMax; g_model = -1; g_tri = -1; g_t = 0.0f; g_u = 0.0f; g_v = 0.0f;
                 if (COUNT) cnt = make_int4(0, 0, 0, 0);
                 im = -1; flags = 0;
