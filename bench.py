@@ -2,7 +2,7 @@
 """bench.py - headline benchmark of the render hot path (BASELINE.json: Mrays/s, all bounces; ms/frame at 2800x2240, 64 spp).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload mesh100k|mesh1m|mesh5m|bundled|cornell|mesh1m4k]
-                    [--accel bvh|lbvh|grid] [--scaling weak|strong] [--impl ptap|reference]
+                    [--accel bvh|lbvh|grid|emu] [--scaling weak|strong] [--impl ptap|reference]
 
 A "step" is one whole frame of the workload: Renderer::renderLoop for `spp` iterations (ray generation, closest hit,
 shading + compaction, film accumulation for every bounce).  Rays = rays actually traced, summed over closest-hit launches
@@ -223,7 +223,7 @@ def main():
     ap.add_argument("--impl", default="ptap", choices=["ptap", "reference"])
     ap.add_argument("--workload", default="mesh1m", choices=sorted(WORKLOADS))
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel of the workload")
-    ap.add_argument("--accel", default="bvh", choices=["bvh", "lbvh", "grid"], help="bvh: host-built SAH tree (default); lbvh: tree built on the GPU at upload; grid: the reference's uniform grid")
+    ap.add_argument("--accel", default="bvh", choices=["bvh", "lbvh", "grid", "emu"], help="bvh: host-built SAH tree (default); lbvh: tree built on the GPU at upload; grid: the reference's uniform grid, walked; emu: the walk's results (bit-identical) through the BVH")
     ap.add_argument("--grid-dim", type=int, default=25, help="voxels per axis of the uniform grid (--accel grid); the reference fixes 25 (Config.h:8-10)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N > 1: weak = spp iterations per GPU; strong = the frame's spp split over the GPUs")
     ap.add_argument("--no-cache", action="store_true", help="disable the first-hit cache (Renderer.cpp:594-613)")
@@ -270,7 +270,7 @@ def main():
     os.dup2(2, 1)
     import torch
     import torch.distributed as dist
-    from pathtracerap_b200 import ACCEL_BVH, ACCEL_BVH_DEVICE, ACCEL_GRID_COMPAT, Renderer
+    from pathtracerap_b200 import ACCEL_BVH, ACCEL_BVH_DEVICE, ACCEL_GRID_COMPAT, ACCEL_GRID_EMULATED, Renderer
     from pathtracerap_b200 import _native as N
     from pathtracerap_b200 import multi_gpu
 
@@ -282,12 +282,14 @@ def main():
     torch.cuda.init()
 
     scene, arrays = build_scene(args.workload)
-    accel = {"bvh": ACCEL_BVH, "lbvh": ACCEL_BVH_DEVICE, "grid": ACCEL_GRID_COMPAT}[args.accel]
+    accel = {"bvh": ACCEL_BVH, "lbvh": ACCEL_BVH_DEVICE, "grid": ACCEL_GRID_COMPAT, "emu": ACCEL_GRID_EMULATED}[args.accel]
     t0 = time.perf_counter()
     if accel == ACCEL_BVH:
         scene.build_bvh()                 # host-side, part of scene construction like the reference's addMeshesToGrid
     elif accel == ACCEL_GRID_COMPAT:
         scene.build_grids(args.grid_dim, args.grid_dim, args.grid_dim)
+    elif accel == ACCEL_GRID_EMULATED:
+        scene.build_grids(args.grid_dim, args.grid_dim, args.grid_dim); scene.build_bvh()
     build_s = time.perf_counter() - t0     # lbvh: built on the GPU inside Renderer.allocateOnGPU / upload
     ntris = len(arrays["triangles"])
     cache = not args.no_cache
@@ -418,7 +420,10 @@ def main():
         r2.render(it0, it0 + 1); r2.sync()
         c2 = r2.stats(); ref_nodes, ref_tris, denom = c2["avg_nodes"], c2["avg_tris"], "host SAH tree of the same scene (fixed denominator)"
         r2.free()
-    if accel != ACCEL_GRID_COMPAT:
+    if accel == ACCEL_GRID_EMULATED:
+        bytes_per_ray = 48.0 + 128.0 * ref_nodes + 64.0 * ref_tris
+        formula = "48 + 128 * nodes_per_ray + 64 * tris_per_ray (leaf-order triangle record; the replayed voxels read nothing)"
+    elif accel != ACCEL_GRID_COMPAT:
         bytes_per_ray = 48.0 + 128.0 * ref_nodes + 48.0 * ref_tris
         formula = "48 + 128 * nodes_per_ray + 48 * tris_per_ray"
     else:
@@ -432,7 +437,7 @@ def main():
         evidence = json.load(open(ep)).get(f"{args.workload}:{args.accel}")
         if evidence:
             traffic = evidence.get("dram_bytes_per_launch")
-    kernel = "k_trace_bvh" if accel != ACCEL_GRID_COMPAT else "k_trace_grid"
+    kernel = "k_trace_emu" if accel == ACCEL_GRID_EMULATED else "k_trace_bvh" if accel != ACCEL_GRID_COMPAT else "k_trace_grid"
     roofline = {"bound": "issue", "bound_note": "instruction issue x SIMT fill; NOT memory-bound: DRAM traffic is a few % of the HBM peak (evidence). `frac` is the "
                 "contract's algorithmic-bytes figure against the HBM peak and says how far the kernel is from becoming memory-bound, not what limits it",
                 "kernel": kernel, "achieved": round(achieved, 1) if achieved else None, "peak": peak, "unit": "GB/s",
@@ -457,7 +462,7 @@ def main():
             rb = Renderer(device=dev, width=2800, height=2240, depth=5, accel=ACCEL_BVH, first_hit_cache=True)
             rb.allocateOnGPU(bs)
             frames = {}
-            for name, acc, nfr in (("bvh", ACCEL_BVH, 3), ("grid_compat", ACCEL_GRID_COMPAT, 2)):
+            for name, acc, nfr in (("bvh", ACCEL_BVH, 3), ("grid_compat", ACCEL_GRID_COMPAT, 2), ("grid_emulated", ACCEL_GRID_EMULATED, 3)):
                 rb.set_accel(acc)
                 rb.set_params(2800, 2240, 5, first_hit_cache=True)
                 rb.frame_begin(); rb.render(0, 64); rb.sync()
@@ -466,7 +471,7 @@ def main():
                     rb.timer_start(); rb.frame_begin(); rb.render(0, 64); ms += rb.timer_stop(); rays_b += rb.stats()["rays_traced"]
                 frames[name] = {"ms_per_frame": round(ms / nfr, 2), "Mrays_s": round(rays_b / ms / 1e3, 1), "frames": nfr}
             rb.free()
-            extras["ms_per_frame_2800x2240_64spp"] = dict(frames, scene="bundled (configs[2])", note="grid_compat = the reference's own 25^3 grid walk, bit-identical hits (the drop-in default); bvh = exact closest hit")
+            extras["ms_per_frame_2800x2240_64spp"] = dict(frames, scene="bundled (configs[2])", note="grid_compat = the reference's own 25^3 grid walk; grid_emulated = the same hits, bit for bit, through the BVH (the drop-in default); bvh = exact closest hit")
         # ---- end to end with the acceleration structure built INSIDE the timed region (tree built on the GPU at upload)
         if accel == ACCEL_BVH and args.workload != "cornell":
             rl = Renderer(device=dev, width=W, height=H, depth=depth, accel=ACCEL_BVH_DEVICE, first_hit_cache=cache)
@@ -504,7 +509,7 @@ def main():
            "ms_per_step": round(t_max / args.steps * 1e3, 3), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
            "config": {"workload": args.workload, "description": desc, "resolution": [W, H], "spp_per_gpu": it1 - it0, "spp_total": total_spp, "depth": depth,
-                      "triangles": ntris, "models": len(arrays["models"]), "accel": args.accel if args.accel != "grid" else f"grid {args.grid_dim}^3", "first_hit_cache": cache, "lanes": lanes,
+                      "triangles": ntris, "models": len(arrays["models"]), "accel": {"grid": f"grid {args.grid_dim}^3 (walked)", "emu": f"grid {args.grid_dim}^3 (emulated through the BVH)"}.get(args.accel, args.accel), "first_hit_cache": cache, "lanes": lanes,
                       "parallelism": par,
                       "l2": "wavefront state (6 float4 queues + hits, >300 MB at 1080p) exceeds L2 every bounce; the scene is small and L2-resident by design",
                       "host_accel_build_s": round(build_s, 3)},

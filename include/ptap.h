@@ -43,7 +43,8 @@ enum {
     PTAP_E_NOMEM = -3,        /* device arena exhausted */
     PTAP_E_IO = -4,           /* file could not be read / written */
     PTAP_E_PARSE = -5,        /* malformed OBJ / Config.txt */
-    PTAP_E_STATE = -6         /* scene / accel / render parameters missing */
+    PTAP_E_STATE = -6,        /* scene / accel / render parameters missing */
+    PTAP_E_UNSUPPORTED = -7   /* the request is valid but this input cannot take the fast path asked for; the message names the alternative */
 };
 
 /* ---- PODs with the reference's exact layouts (Primitive.h:10-179) ----------------------- */
@@ -190,7 +191,14 @@ int ptap_scene_config_camera(const ptap_scene* s, PtapCamera* out);
 enum { PTAP_ACCEL_GRID_COMPAT = 0,  /* the reference's per-mesh uniform grid walked exactly as Renderer.cpp:238-360 (oracle tier R0) */
        PTAP_ACCEL_BVH = 1,          /* two-level BVH, exact closest hit under the reference's triangle predicate (oracle tier R1);
                                        the per-mesh trees are the host's binned-SAH ones (ptap_scene_build_bvh, or built at this call) */
-       PTAP_ACCEL_BVH_DEVICE = 2 }; /* same traversal and results, per-mesh trees built on the GPU (LBVH) in milliseconds */
+       PTAP_ACCEL_BVH_DEVICE = 2,   /* same traversal and results, per-mesh trees built on the GPU (PLOC) in milliseconds */
+       PTAP_ACCEL_GRID_EMULATED = 3 };
+                                    /* the RESULTS of PTAP_ACCEL_GRID_COMPAT (tier R0, bit for bit: the walk's misses and early exits
+                                       included) computed through the BVH: all hits of a model, then a replay of the walk's voxel sequence
+                                       over the voxel boxes of the hit triangles (trace_emu.cu).  Needs the grids (their lists define the
+                                       result) and builds a BVH on the device if none is there.  ptap_build_accel fails with
+                                       PTAP_E_UNSUPPORTED when the lists on the device do not have the shape Scene::addMeshesToGrid
+                                       produces (Scene.cpp:357-374); PTAP_ACCEL_GRID_COMPAT then remains available. */
 
 enum { PTAP_FLAG_FIRST_HIT_CACHE = 1,   /* Renderer.cpp:580,594-613 */
        PTAP_FLAG_PROFILE = 2,           /* per-kernel CUDA-event split in PtapStats (adds event records) */

@@ -34,7 +34,8 @@ assert GRID.itemsize == 28 and VOXEL.itemsize == 12 and HIT.itemsize == 40 and P
 
 FLOAT_MAX = np.float32(9999999.0)
 DIFFUSE, SPECULAR, REFLECTIVE, REFRACTIVE, EMISSIVE, COAT, METAL = range(7)
-ACCEL_GRID_COMPAT, ACCEL_BVH, ACCEL_BVH_DEVICE = 0, 1, 2
+ACCEL_GRID_COMPAT, ACCEL_BVH, ACCEL_BVH_DEVICE, ACCEL_GRID_EMULATED = 0, 1, 2, 3
+E_UNSUPPORTED = -7
 FLAG_FIRST_HIT_CACHE, FLAG_PROFILE, FLAG_COUNT, FLAG_STAMP, FLAG_ITER_TIMES = 1, 2, 4, 8, 16
 
 

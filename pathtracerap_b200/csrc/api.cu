@@ -91,6 +91,8 @@ struct ptap_ctx {
     std::vector<cudaEvent_t> iter_events;      // completion of every iteration of the last render call (PTAP_FLAG_ITER_TIMES)
     int iter_events_used = 0;
     std::vector<float> iter_ms;
+    int2* d_tri_box = nullptr; size_t tri_box_cap = 0; bool emu_ok = false;   // PTAP_ACCEL_GRID_EMULATED: per-triangle voxel boxes (own allocation)
+    std::vector<int> h_grid_first, h_model_grid;     // first voxel of every grid on the device / grid of every model
     int2* gd_cells = nullptr; int* gd_refs = nullptr; size_t gd_ncells = 0, gd_nrefs = 0;   // grids built on the device (own allocation)
     void* nccl_comm = nullptr;                 // ptap_nccl_init
     cudaEvent_t e_peer = nullptr;
@@ -120,11 +122,17 @@ float4 row(const float* m, int r) { return make_float4(m[0 + r], m[4 + r], m[8 +
 
 constexpr int kMaxStamps = 8192;     // closest-hit launches of one render call that can be stamped (PTAP_FLAG_STAMP)
 
+// replay: N ints the emulated grid walk may fill with the slots it hands to the walk itself (PTAP_ACCEL_GRID_EMULATED only)
 void launchTrace(ptap_ctx* c, FrameState* st, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, int round, int n_fixed,
-                 bool count_totals = false, cudaStream_t stream = nullptr, unsigned long long* stamp = nullptr)
+                 int* replay, bool count_totals = false, cudaStream_t stream = nullptr, unsigned long long* stamp = nullptr)
 {
     if (!stream) stream = c->stream;
-    if (c->accel != PTAP_ACCEL_GRID_COMPAT) launchTraceBvh(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, stream, stamp);
+    if (c->accel == PTAP_ACCEL_GRID_EMULATED) {
+        launchTraceEmu(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, stream, stamp, replay);
+        // second launch: the walk itself for the (normally zero) slots with more hits in one model than the emulation keeps
+        launchTraceGrid(c->sc, O, D, hit, uv, counts, false, st, round, n_fixed, c->sms, stream, nullptr, replay);
+    }
+    else if (c->accel != PTAP_ACCEL_GRID_COMPAT) launchTraceBvh(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, stream, stamp);
     else launchTraceGrid(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, stream, stamp);
 }
 
@@ -158,7 +166,7 @@ void applyCamera(const ptap_ctx* c, WaveDev& wv)
 
 int traceGridSize(ptap_ctx* c)
 {
-    int occ = c->accel != PTAP_ACCEL_GRID_COMPAT ? traceBvhOccupancy() : traceGridOccupancy();
+    int occ = c->accel == PTAP_ACCEL_GRID_EMULATED ? traceEmuOccupancy() : c->accel != PTAP_ACCEL_GRID_COMPAT ? traceBvhOccupancy() : traceGridOccupancy();
     if (c->trace_ctas > 0) occ = std::min(occ, c->trace_ctas);
     return c->sms * std::max(occ, 1);
 }
@@ -526,6 +534,7 @@ void ptap_destroy(ptap_ctx* ctx)
     for (int l = 0; l < kMaxLanes; ++l) { if (ctx->e_join[l]) cudaEventDestroy(ctx->e_join[l]); if (ctx->e_gather[l]) cudaEventDestroy(ctx->e_gather[l]); }
     ctx->scene_arena.release(); ctx->frame_arena.release(); ctx->scratch.release();
     if (ctx->gd_cells) cudaFree(ctx->gd_cells);
+    if (ctx->d_tri_box) cudaFree(ctx->d_tri_box);
     if (ctx->gd_refs) cudaFree(ctx->gd_refs);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     for (cudaEvent_t e : ctx->iter_events) cudaEventDestroy(e);
@@ -549,7 +558,7 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
     const int nm = v->nmodels, nt = v->ntriangles;
     const bool grid = v->grids && v->voxels && v->refs && v->ngrids > 0;
     // the scene arena is about to be overwritten: whatever was uploaded before is gone even if this call fails half-way
-    ctx->have_scene = false; ctx->have_grid = false; ctx->have_bvh = false; ctx->bvh_kind = -1; ctx->cache_valid = false;
+    ctx->have_scene = false; ctx->have_grid = false; ctx->have_bvh = false; ctx->bvh_kind = -1; ctx->cache_valid = false; ctx->emu_ok = false;
     ctx->sc.tlas_root = -1; ctx->sc.nmodels = 0;
     for (int i = 0; i < nm; ++i) {
         const PtapModel& m = v->models[i];
@@ -597,6 +606,11 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
     ctx->ntris = nt;
     ctx->h_meshes.assign(v->meshes, v->meshes + v->nmeshes);
     ctx->h_models.assign(v->models, v->models + nm);
+    ctx->h_grid_first.clear(); ctx->h_model_grid.clear();
+    if (grid) {
+        for (int g = 0; g < v->ngrids; ++g) ctx->h_grid_first.push_back(v->grids[g].v_start);
+        for (int i = 0; i < nm; ++i) ctx->h_model_grid.push_back(v->models[i].grid_index);
+    }
 
     std::vector<int2> cells;
     if (grid) {
@@ -609,6 +623,10 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
         }
         for (int i = 0; i < v->nrefs; ++i)
             if (v->refs[i] < 0 || v->refs[i] >= nt) return fail(ctx, PTAP_E_INVALID, "ref %d: triangle index out of range", i);
+        if (v->grid_dim[0] <= 0 || v->grid_dim[1] <= 0 || v->grid_dim[2] <= 0) return fail(ctx, PTAP_E_INVALID, "grid_dim must be positive");
+        const long long ncell = (long long)v->grid_dim[0] * v->grid_dim[1] * v->grid_dim[2];
+        for (int g = 0; g < v->ngrids; ++g)
+            if (v->grids[g].v_start < 0 || v->grids[g].v_start + ncell > v->nvoxels) return fail(ctx, PTAP_E_INVALID, "grid %d: voxel range out of bounds", g);
     }
 
     // ---- one arena for everything scene-lifetime; BVH storage is reserved up front (2T-1 BLAS nodes + 2M TLAS nodes bound)
@@ -687,6 +705,33 @@ int ptap_build_accel(ptap_ctx* ctx, int kind)
             cudaEventElapsedTime(&ctx->stats.ms_build, b0, b1);
             cudaEventDestroy(b0); cudaEventDestroy(b1);
         }
+    } else if (kind == PTAP_ACCEL_GRID_EMULATED) {
+        // the walk's results through the BVH (trace_emu.cu): needs the grids (their lists define the result), a BVH over the same triangles
+        // (whichever builder made the one on the device; else the device builder), and lists of the shape the emulation relies on
+        if (!ctx->have_grid) return fail(ctx, PTAP_E_STATE, "build_accel: the uploaded scene carries no grids (call ptap_scene_build_grids first)");
+        if (!ctx->have_bvh) { const int rc = buildBvhOnDevice(ctx); if (rc) return rc; }
+        if (!ctx->emu_ok) {
+            const int nt = ctx->ntris, ng = (int)ctx->h_grid_first.size();
+            if ((size_t)nt > ctx->tri_box_cap) {
+                if (ctx->d_tri_box) { cudaFree(ctx->d_tri_box); ctx->d_tri_box = nullptr; ctx->tri_box_cap = 0; }
+                CK(cudaMalloc(&ctx->d_tri_box, (size_t)std::max(nt, 1) * sizeof(int2)));
+                ctx->tri_box_cap = (size_t)nt;
+            }
+            std::vector<int> range(2 * (size_t)std::max(ng, 1), 0);
+            int ok = 0;
+            const int e = gridTriBoxes(ctx->sc.cells, ctx->sc.refs, ng, ctx->h_grid_first.data(), ctx->sc.gx, ctx->sc.gy, ctx->sc.gz, nt, ctx->d_tri_box, range.data(), &ok, ctx->stream);
+            if (e != 0) return fail(ctx, e, "build_accel: voxel boxes: %s", cudaGetErrorString((cudaError_t)e));
+            if (!ok) return fail(ctx, PTAP_E_UNSUPPORTED, "build_accel: the voxel lists are not box-shaped ascending registrations of one grid per triangle; use PTAP_ACCEL_GRID_COMPAT");
+            // every triangle a model's grid lists must belong to the model's own mesh (the BVH the emulation traverses is the mesh's)
+            for (size_t i = 0; i < ctx->h_models.size(); ++i) {
+                const int g = ctx->h_model_grid[i];
+                const PtapMesh& mesh = ctx->h_meshes[ctx->h_models[i].mesh_index];
+                if (range[2 * g] <= range[2 * g + 1] && (range[2 * g] < mesh.t_start || range[2 * g + 1] >= mesh.t_end))
+                    return fail(ctx, PTAP_E_UNSUPPORTED, "build_accel: grid %d lists triangles outside the mesh of model %d; use PTAP_ACCEL_GRID_COMPAT", g, (int)i);
+            }
+            ctx->sc.tri_box = ctx->d_tri_box;
+            ctx->emu_ok = true;
+        }
     } else return fail(ctx, PTAP_E_INVALID, "build_accel: unknown kind %d", kind);
     ctx->accel = kind;
     ctx->cache_valid = false;
@@ -706,10 +751,10 @@ int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, u
     const int ntiles = (N + kShadeTile - 1) / kShadeTile, nscan = (N + kScanSlots - 1) / kScanSlots;
     size_t need = Arena::need(N, sizeof(float4)) * 8 + Arena::need(N, sizeof(float2)) + Arena::need((size_t)N * 3, sizeof(float)) +
                   Arena::need((size_t)nscan * kMaxDepth, sizeof(unsigned long long)) + Arena::need(ntiles, sizeof(int)) * 2 +
-                  Arena::need((size_t)nscan * kScanSlots, 1) + Arena::need(1, sizeof(FrameState)) + Arena::need(2 * kMaxStamps, sizeof(unsigned long long)) + 4096;
+                  Arena::need((size_t)nscan * kScanSlots, 1) + Arena::need(1, sizeof(FrameState)) + Arena::need(2 * kMaxStamps, sizeof(unsigned long long)) + Arena::need(N, sizeof(int)) + 4096;
     if (ctx->lanes > 1)            // every further lane: its own queues, hits, scan state; one contribution buffer per lane (lane 0 too)
         need += (size_t)(ctx->lanes - 1) * (Arena::need(N, sizeof(float4)) * 7 + Arena::need((size_t)nscan * kMaxDepth, sizeof(unsigned long long)) +
-                                            Arena::need(ntiles, sizeof(int)) * 2 + Arena::need((size_t)nscan * kScanSlots, 1) + Arena::need(1, sizeof(FrameState)) + 4096) +
+                                            Arena::need(ntiles, sizeof(int)) * 2 + Arena::need((size_t)nscan * kScanSlots, 1) + Arena::need(1, sizeof(FrameState)) + Arena::need(N, sizeof(int)) + 4096) +
                 (size_t)ctx->lanes * Arena::need((size_t)N * 3, sizeof(float));
     if (need > ctx->frame_arena.cap) CK(ctx->frame_arena.reserve(need)); else ctx->frame_arena.used = 0;
     Arena& A = ctx->frame_arena;
@@ -722,8 +767,9 @@ int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, u
     wv.tile_ballot = A.alloc<unsigned>(ntiles);
     wv.perm = A.alloc<unsigned char>((size_t)nscan * kScanSlots);
     wv.st = A.alloc<FrameState>(1);
+    wv.replay = A.alloc<int>(N);
     ctx->d_stamps = A.alloc<unsigned long long>(2 * kMaxStamps); ctx->stamps_used = 0;
-    if (!ctx->d_stamps || !wv.st || !wv.tile_status || !wv.tile_offset || !wv.tile_ballot || !wv.perm || !wv.film) return fail(ctx, PTAP_E_NOMEM, "frame arena exhausted");
+    if (!ctx->d_stamps || !wv.replay || !wv.st || !wv.tile_status || !wv.tile_offset || !wv.tile_ballot || !wv.perm || !wv.film) return fail(ctx, PTAP_E_NOMEM, "frame arena exhausted");
     wv.W = W; wv.H = H; wv.N = N; wv.depth = depth; wv.ntiles = ntiles; wv.nscan = nscan;
     applyCamera(ctx, wv);
     wv.iter_stride = 1; wv.contrib = nullptr;
@@ -737,8 +783,9 @@ int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, u
         w2.tile_offset = A.alloc<int>(ntiles); w2.tile_ballot = A.alloc<unsigned>(ntiles);
         w2.perm = A.alloc<unsigned char>((size_t)nscan * kScanSlots);
         w2.st = A.alloc<FrameState>(1);
+        w2.replay = A.alloc<int>(N);
         w2.contrib = A.alloc<float>((size_t)N * 3);
-        if (!w2.st || !w2.contrib || !wv.contrib || !w2.perm || !w2.hit) return fail(ctx, PTAP_E_NOMEM, "frame arena exhausted (lane %d)", l);
+        if (!w2.st || !w2.replay || !w2.contrib || !wv.contrib || !w2.perm || !w2.hit) return fail(ctx, PTAP_E_NOMEM, "frame arena exhausted (lane %d)", l);
         CK(cudaMemsetAsync(w2.st, 0, sizeof(FrameState), ctx->stream));
     }
     CK(cudaMemsetAsync(wv.film, 0, (size_t)N * 3 * sizeof(float), ctx->stream));   // initImageKernel, Renderer.cpp:557-565
@@ -772,7 +819,7 @@ int ptap_set_camera(ptap_ctx* ctx, const PtapCamera* cam)
 int ptap_render(ptap_ctx* ctx, int32_t iter_begin, int32_t iter_end)
 {
     if (!ctx || !ctx->have_scene || !ctx->have_frame) return fail(ctx, PTAP_E_STATE, "render: scene and render parameters required");
-    if (ctx->accel == PTAP_ACCEL_GRID_COMPAT && !ctx->have_grid) return fail(ctx, PTAP_E_STATE, "render: no grid in the uploaded scene; build the BVH");
+    if ((ctx->accel == PTAP_ACCEL_GRID_COMPAT || ctx->accel == PTAP_ACCEL_GRID_EMULATED) && !ctx->have_grid) return fail(ctx, PTAP_E_STATE, "render: no grid in the uploaded scene; build the BVH");
     if (iter_end < iter_begin) return fail(ctx, PTAP_E_INVALID, "render: empty iteration range");
     CK(cudaSetDevice(ctx->device));
     if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
@@ -812,7 +859,7 @@ int ptap_render(ptap_ctx* ctx, int32_t iter_begin, int32_t iter_end)
             if (!(round == 0 && cache && ctx->cache_valid)) {                    // Renderer.cpp:594-620
                 profMark(ctx, 1);
                 unsigned long long* stamp = stamping && ctx->stamps_used < kMaxStamps ? ctx->d_stamps + 2 * (size_t)ctx->stamps_used++ : nullptr;
-                launchTrace(ctx, wv.st, wv.O[in], wv.D[in], hitbuf, nullptr, nullptr, round, -1, (ctx->flags & PTAP_FLAG_COUNT) != 0, S, stamp); ++launches; ++trace_launches;
+                launchTrace(ctx, wv.st, wv.O[in], wv.D[in], hitbuf, nullptr, nullptr, round, -1, wv.replay, (ctx->flags & PTAP_FLAG_COUNT) != 0, S, stamp); ++launches; ++trace_launches;
                 if (L > 1 && round == 0 && cache) { CK(cudaEventRecord(ctx->e_cache, S)); cache_lane = l; cache_waited = 1u << l; }
             } else if (L > 1 && cache_lane >= 0 && !(cache_waited >> l & 1u)) {
                 CK(cudaStreamWaitEvent(S, ctx->e_cache, 0)); cache_waited |= 1u << l;
@@ -1013,17 +1060,18 @@ int ptap_read_film_resolved(ptap_ctx* ctx, int32_t sx, int32_t sy, float* rgb)
 static int traceImpl(ptap_ctx* ctx, const float* rays_od, int32_t n, PtapHit* out, int32_t* counts)
 {
     if (!ctx || !ctx->have_scene || !rays_od || !out || n < 0) return fail(ctx, PTAP_E_STATE, "trace: scene and buffers required");
-    if (ctx->accel == PTAP_ACCEL_GRID_COMPAT && !ctx->have_grid) return fail(ctx, PTAP_E_STATE, "trace: no grid in the uploaded scene");
+    if ((ctx->accel == PTAP_ACCEL_GRID_COMPAT || ctx->accel == PTAP_ACCEL_GRID_EMULATED) && !ctx->have_grid) return fail(ctx, PTAP_E_STATE, "trace: no grid in the uploaded scene");
     if (n == 0) return PTAP_OK;
     CK(cudaSetDevice(ctx->device));
     if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
     size_t need = Arena::need(n, sizeof(float4)) * 3 + Arena::need(n, sizeof(float2)) + Arena::need(n, sizeof(PtapHit)) + Arena::need(n, sizeof(int4)) +
-                  Arena::need((size_t)n * 6, sizeof(float)) + Arena::need(1, sizeof(FrameState)) + 4096;
+                  Arena::need((size_t)n * 6, sizeof(float)) + Arena::need(1, sizeof(FrameState)) + Arena::need(n, sizeof(int)) + 4096;
     if (need > ctx->scratch.cap) CK(ctx->scratch.reserve(need)); else ctx->scratch.used = 0;
     Arena& A = ctx->scratch;
     float4* O = A.alloc<float4>(n); float4* D = A.alloc<float4>(n); float4* hit = A.alloc<float4>(n);
     float2* uv = A.alloc<float2>(n); PtapHit* dout = A.alloc<PtapHit>(n); int4* dcnt = A.alloc<int4>(n);
     FrameState* st = A.alloc<FrameState>(1);
+    int* replay = A.alloc<int>(n);
     std::vector<float4> hO(n), hD(n);
     for (int i = 0; i < n; ++i) {
         hO[i] = make_float4(rays_od[6 * (size_t)i], rays_od[6 * (size_t)i + 1], rays_od[6 * (size_t)i + 2], 0.f);
@@ -1033,7 +1081,7 @@ static int traceImpl(ptap_ctx* ctx, const float* rays_od, int32_t n, PtapHit* ou
     CK(cudaMemcpyAsync(D, hD.data(), n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(st, 0, sizeof(FrameState), ctx->stream));
     if (!ctx->grid_trace) ctx->grid_trace = traceGridSize(ctx);
-    launchTrace(ctx, st, O, D, hit, uv, counts ? dcnt : nullptr, 0, n);
+    launchTrace(ctx, st, O, D, hit, uv, counts ? dcnt : nullptr, 0, n, replay);
     launchResolveHits(ctx->sc, O, D, hit, uv, n, dout, ctx->stream);
     CK(cudaMemcpyAsync(out, dout, n * sizeof(PtapHit), cudaMemcpyDeviceToHost, ctx->stream));
     if (counts) CK(cudaMemcpyAsync(counts, dcnt, n * sizeof(int4), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1127,11 +1175,12 @@ int ptap_bench_trace(ptap_ctx* ctx, const float* rays_od, int32_t n, int32_t rep
     if (!ctx || !ctx->have_scene || !rays_od || n <= 0 || reps <= 0 || !ms_per_launch) return fail(ctx, PTAP_E_INVALID, "bench_trace: bad arguments");
     CK(cudaSetDevice(ctx->device));
     if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
-    size_t need = Arena::need(n, sizeof(float4)) * 3 + Arena::need(1, sizeof(FrameState)) + 4096;
+    size_t need = Arena::need(n, sizeof(float4)) * 3 + Arena::need(1, sizeof(FrameState)) + Arena::need(n, sizeof(int)) + 4096;
     if (need > ctx->scratch.cap) CK(ctx->scratch.reserve(need)); else ctx->scratch.used = 0;
     Arena& A = ctx->scratch;
     float4* O = A.alloc<float4>(n); float4* D = A.alloc<float4>(n); float4* hit = A.alloc<float4>(n);
     FrameState* st = A.alloc<FrameState>(1);
+    int* replay = A.alloc<int>(n);
     std::vector<float4> hO(n), hD(n);
     for (int i = 0; i < n; ++i) {
         hO[i] = make_float4(rays_od[6 * (size_t)i], rays_od[6 * (size_t)i + 1], rays_od[6 * (size_t)i + 2], 0.f);
@@ -1140,9 +1189,9 @@ int ptap_bench_trace(ptap_ctx* ctx, const float* rays_od, int32_t n, int32_t rep
     CK(cudaMemcpy(O, hO.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(D, hD.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
     CK(cudaMemset(st, 0, sizeof(FrameState)));
-    for (int w = 0; w < 3; ++w) { CK(cudaMemsetAsync(st, 0, sizeof(FrameState), ctx->stream)); launchTrace(ctx, st, O, D, hit, nullptr, nullptr, 0, n); }
+    for (int w = 0; w < 3; ++w) { CK(cudaMemsetAsync(st, 0, sizeof(FrameState), ctx->stream)); launchTrace(ctx, st, O, D, hit, nullptr, nullptr, 0, n, replay); }
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    for (int r = 0; r < reps; ++r) { CK(cudaMemsetAsync(st, 0, sizeof(FrameState), ctx->stream)); launchTrace(ctx, st, O, D, hit, nullptr, nullptr, 0, n); }   // the memset re-arms the work-stealing cursor
+    for (int r = 0; r < reps; ++r) { CK(cudaMemsetAsync(st, 0, sizeof(FrameState), ctx->stream)); launchTrace(ctx, st, O, D, hit, nullptr, nullptr, 0, n, replay); }   // the memset re-arms the work-stealing cursor
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
@@ -1162,7 +1211,7 @@ int ptap_bench_trace(ptap_ctx* ctx, const float* rays_od, int32_t n, int32_t rep
 int ptap_render_probe(ptap_ctx* ctx, int32_t iter, int32_t round, float* rays_od, int32_t* pixels, PtapHit* hits, int32_t cap, int32_t* n_out)
 {
     if (!ctx || !ctx->have_scene || !ctx->have_frame) return fail(ctx, PTAP_E_STATE, "render_probe: scene and render parameters required");
-    if (ctx->accel == PTAP_ACCEL_GRID_COMPAT && !ctx->have_grid) return fail(ctx, PTAP_E_STATE, "render_probe: no grid in the uploaded scene");
+    if ((ctx->accel == PTAP_ACCEL_GRID_COMPAT || ctx->accel == PTAP_ACCEL_GRID_EMULATED) && !ctx->have_grid) return fail(ctx, PTAP_E_STATE, "render_probe: no grid in the uploaded scene");
     if (round < 0 || round >= ctx->wv.depth || !n_out || cap < 0) return fail(ctx, PTAP_E_INVALID, "render_probe: bad arguments");
     CK(cudaSetDevice(ctx->device));
     if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
@@ -1174,7 +1223,7 @@ int ptap_render_probe(ptap_ctx* ctx, int32_t iter, int32_t round, float* rays_od
     launchGenerate(wv, iter, ctx->grid_gen, S);
     int in = 0;
     for (int r = 0; r <= round; ++r) {
-        launchTrace(ctx, wv.st, wv.O[in], wv.D[in], wv.hit, nullptr, nullptr, r, -1, false, S);       // the instantiation ptap_render launches
+        launchTrace(ctx, wv.st, wv.O[in], wv.D[in], wv.hit, nullptr, nullptr, r, -1, wv.replay, false, S);       // the instantiation ptap_render launches
         if (r == round) break;
         launchScan(ctx->sc, wv, r, wv.hit, wv.depth - r, -1, S);
         launchShade(ctx->sc, wv, r, in, wv.hit, wv.depth - r, -1, 0, nullptr, ctx->grid_shade, S);
@@ -1429,6 +1478,8 @@ int ptap_build_grids_device(ptap_ctx* ctx, const PtapSceneView* v, int32_t gx, i
 #undef CKH
     cleanup2();
     ctx->sc.cells = ctx->gd_cells; ctx->sc.refs = ctx->gd_refs;
+    ctx->h_grid_first.resize(ng); ctx->h_model_grid.assign(model_grid.begin(), model_grid.end()); ctx->emu_ok = false;
+    for (int g = 0; g < ng; ++g) ctx->h_grid_first[g] = (int)((size_t)g * ncell);
     ctx->sc.gx = gx; ctx->sc.gy = gy; ctx->sc.gz = gz;
     ctx->have_grid = true; ctx->accel = PTAP_ACCEL_GRID_COMPAT; ctx->cache_valid = false;
     ctx->grid_trace = traceGridSize(ctx);

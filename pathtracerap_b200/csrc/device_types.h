@@ -77,6 +77,8 @@ struct FrameState {
     int n_active[kMaxDepth + 2];        // rays entering round r
     unsigned int ticket[kMaxDepth + 2]; // tile tickets of the shade kernel, per round
     unsigned int fetch[kMaxDepth + 2];  // work-stealing cursors of the trace kernel, per round
+    unsigned int n_replay[kMaxDepth + 2];      // k_trace_emu: rays of the round handed to the grid walk itself (more hits in one model than it keeps)
+    unsigned int fetch_replay[kMaxDepth + 2];  // work-stealing cursors of that second launch
     int iter_cur, iter_next;
     int cache_valid;                    // first-hit cache holds round-0 hits
     int pad;
@@ -92,6 +94,7 @@ struct SceneDev {
     const float4* normals;      // flat shading normal per GLOBAL triangle id (copy of the TriRec .w lanes, 16-byte gather for k_shade)
     const int2* cells;          // grid voxels: (start, end) into refs
     const int* refs;            // global triangle ids
+    const int2* tri_box;        // per GLOBAL triangle id: the box of voxels that list it, (lo, hi) packed x | y << 10 | z << 20 (k_trace_emu)
     const BvhNode* nodes;       // all BLAS nodes, then the TLAS nodes
     const LeafTri* bvh_tris;    // triangles in BVH leaf order
     const int* bvh_tri_id;      // leaf-order position -> global triangle id (build-time input of k_gather_tris; the kernels read LeafTri::id)
@@ -115,6 +118,7 @@ struct WaveDev {
     float4* hit;                // (dist, bits(tri), bits(model), t_model) per slot; dist < 0: hit whose exact distance the consumer evaluates
     float4* hit_cache;          // round-0 hits (first-hit cache, Renderer.cpp:594-613)
     float2* uv;                 // parity entry only
+    int* replay;                // k_trace_emu: slots of the round that the grid walk itself must answer (N ints; null unless PTAP_ACCEL_GRID_EMULATED)
     float* film;                // W*H*3 running sum (Pixel, Primitive.h:145-148)
     float* contrib;             // multi-lane rendering: this iteration's sqrt(throughput) per pixel, added to the film in iteration order; else null
     unsigned long long* tile_status;   // k_scan look-back words: rounds x 2048-slot scan blocks

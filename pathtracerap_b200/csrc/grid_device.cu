@@ -109,6 +109,86 @@ int gridDeviceFill(const float* d_pos, int t0, int n, const float bb_min[3], con
     return cudaGetLastError();
 }
 
+// ---- per-triangle voxel boxes (PTAP_ACCEL_GRID_EMULATED, trace_emu.cu) ------------------------------------------------------------------
+// Scene::addMeshesToGrid lists a triangle in every voxel of the index box its bounds cover (Scene.cpp:357-374), so "is triangle T listed
+// in voxel v" is a box test - IF the lists on the device really have that shape.  They may come from anywhere (the reference's own
+// Scene.cpp in the integration build, ptap_scene_build_grids, the device builder, a caller's arrays), so the boxes are DERIVED from the
+// lists and the shape is VERIFIED: per triangle the bounding index box of the voxels that list it, the number of listings (must equal
+// the box volume), the grid that lists it (must be one), and per voxel an ascending list (the order the walk tests in decides exact-t ties).
+namespace {
+
+struct TriAcc { int lo[3], hi[3], cnt, gid; };
+
+__global__ void k_tribox_init(TriAcc* acc, int ntris, int* grange, int ngrids)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < ntris) { TriAcc a; a.lo[0] = a.lo[1] = a.lo[2] = 0x7fffffff; a.hi[0] = a.hi[1] = a.hi[2] = -1; a.cnt = 0; a.gid = -1; acc[t] = a; }
+    if (t < ngrids) { grange[2 * t] = 0x7fffffff; grange[2 * t + 1] = -1; }
+}
+
+__global__ void k_tribox_cells(const int2* __restrict__ cells, const int* __restrict__ refs, const int* __restrict__ first_cell, int ngrids, int gx, int gy, int gz,
+                               int ntris, TriAcc* acc, int* grange, int* bad)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ncell = gx * gy * gz;
+    if (idx >= (long long)ngrids * ncell) return;
+    const int g = (int)(idx / ncell), l = (int)(idx % ncell);
+    const int x = l % gx, y = (l / gx) % gy, z = l / (gx * gy);
+    const int2 cell = cells[first_cell[g] + l];
+    int prev = -1;
+    for (int r = cell.x; r < cell.y; ++r) {
+        const int t = refs[r];
+        if (t < 0 || t >= ntris || t <= prev) { *bad = 1; continue; }
+        prev = t;
+        atomicMin(&acc[t].lo[0], x); atomicMin(&acc[t].lo[1], y); atomicMin(&acc[t].lo[2], z);
+        atomicMax(&acc[t].hi[0], x); atomicMax(&acc[t].hi[1], y); atomicMax(&acc[t].hi[2], z);
+        atomicAdd(&acc[t].cnt, 1);
+        const int old = atomicCAS(&acc[t].gid, -1, g);
+        if (old != -1 && old != g) *bad = 1;
+        atomicMin(&grange[2 * g], t); atomicMax(&grange[2 * g + 1], t);
+    }
+}
+
+__global__ void k_tribox_finish(const TriAcc* __restrict__ acc, int ntris, int2* __restrict__ tri_box, int* bad)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntris) return;
+    const TriAcc a = acc[t];
+    if (a.cnt == 0) { tri_box[t] = make_int2(0x3fffffff, 0); return; }          // listed nowhere: lo > hi on every axis, no voxel is inside
+    const long long vol = (long long)(a.hi[0] - a.lo[0] + 1) * (a.hi[1] - a.lo[1] + 1) * (a.hi[2] - a.lo[2] + 1);
+    if (vol != (long long)a.cnt) *bad = 1;
+    tri_box[t] = make_int2(a.lo[0] | (a.lo[1] << 10) | (a.lo[2] << 20), a.hi[0] | (a.hi[1] << 10) | (a.hi[2] << 20));
+}
+
+}  // namespace
+
+int gridTriBoxes(const int2* cells, const int* refs, int ngrids, const int* grid_first_cell, int gx, int gy, int gz, int ntris, int2* tri_box,
+                 int* grid_tri_range_host, int* ok, cudaStream_t stream)
+{
+    *ok = 0;
+    if (ngrids <= 0 || ntris <= 0 || gx > 1023 || gy > 1023 || gz > 1023) return cudaSuccess;      // 10 bits per packed index
+    TriAcc* acc = nullptr; int* d_small = nullptr;       // d_small: first cells, grid ranges, the flag
+    cudaError_t e = cudaMalloc(&acc, (size_t)ntris * sizeof(TriAcc));
+    if (e == cudaSuccess) e = cudaMalloc(&d_small, ((size_t)3 * ngrids + 1) * sizeof(int));
+    if (e != cudaSuccess) { cudaFree(acc); cudaFree(d_small); return e; }
+    int* d_first = d_small, *d_range = d_small + ngrids, *d_bad = d_small + 3 * ngrids;
+    cudaMemcpyAsync(d_first, grid_first_cell, ngrids * sizeof(int), cudaMemcpyHostToDevice, stream);
+    cudaMemsetAsync(d_bad, 0, sizeof(int), stream);
+    const int nmax = std::max(ntris, ngrids);
+    k_tribox_init<<<(nmax + 255) / 256, 256, 0, stream>>>(acc, ntris, d_range, ngrids);
+    const long long total = (long long)ngrids * gx * gy * gz;
+    k_tribox_cells<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(cells, refs, d_first, ngrids, gx, gy, gz, ntris, acc, d_range, d_bad);
+    k_tribox_finish<<<(ntris + 255) / 256, 256, 0, stream>>>(acc, ntris, tri_box, d_bad);
+    int bad = 1;
+    e = cudaMemcpyAsync(grid_tri_range_host, d_range, 2 * ngrids * sizeof(int), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(acc); cudaFree(d_small);
+    if (e != cudaSuccess) return e;
+    *ok = bad ? 0 : 1;
+    return cudaGetLastError();
+}
+
 size_t gridDeviceTempBytes(int ntris, long long npairs)
 {
     size_t a = 0, b = 0;

@@ -30,17 +30,14 @@
 // unbounded for axis-parallel rays, which is why round 1's kernel spent a subtract and a multiply per plane.  Two children share one
 // FFMA2 (packed binary32 FMA, new on sm_100), and the near / far planes of an axis are picked by ADDRESS from the direction's sign
 // bits (they lie 16 bytes apart) instead of by a min / max pair per child and axis.
-#include "kernels.cuh"
+#include "bvh_traverse.cuh"
 
 namespace ptap {
 
+using namespace bvh;
+
 namespace {
 
-constexpr unsigned kFull = 0xffffffffu;
-constexpr int kDone = (int)0x80000000u;        // ~0x7fffffff: bottom-of-stack sentinel
-// A negative `node` is ~code with the lane's state in code >> 29:
-//   0: triangle leaf (first << 3 | count - 1), 1: TLAS leaf = enter instance (code & kIndexMask), 2: marker = leave instance, 3: done
-constexpr unsigned kEnterBit = 0x20000000u, kExitBit = 0x40000000u, kIndexMask = 0x1fffffffu;
 #ifndef PTAP_TRACE_MIN_CTAS
 #define PTAP_TRACE_MIN_CTAS 8     // 64 registers: 8 CTAs of 128 threads per SM, as round 1's kernel
 #endif
@@ -80,53 +77,6 @@ __device__ __forceinline__ void leafTriangle(const SceneDev& sc, const V3& o, co
     if (reject || !(t <= tmax)) return;                        // the second test only catches NaN (a degenerate det passes none of the above as true)
     const int id = __float_as_int(tb.v[1]);
     if (t < tmax || (best_tri >= 0 && id < best_tri)) { tmax = t; best_tri = id; if (UV) { best_u = u; best_v = v; } }
-}
-
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)          // FFMA2 (sm_100): two binary32 FMAs per issue slot
-{
-    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rc = *reinterpret_cast<unsigned long long*>(&c), rd;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-    return *reinterpret_cast<float2*>(&rd);
-}
-
-__device__ __forceinline__ uint4 ldg4u(const void* p)
-{
-    uint4 r;
-    asm("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-
-// Entry distance of a child as an order-preserving integer key (a missed child sorts last): interval test with relative slack on the
-// entry / exit parameters of the six planes (near / far already selected by the ray's direction signs).
-__device__ __forceinline__ int childKey(float nx, float ny, float nz, float fx, float fy, float fz, float tmin, float tmax)
-{
-    const float tn = fmaxf(fmaxf(fmaxf(nx, ny), nz), tmin);
-    const float tf = fminf(fminf(fminf(fx, fy), fz), tmax);
-    const bool h = tn <= tf + __fmaf_rn(fabsf(tf), 2e-6f, 1e-6f);
-    return h ? __float_as_int(fmaxf(tn, 0.0f)) : 0x7f800000;
-}
-
-// direction-sign bits, taken from the SIGN BIT (not d < 0) so that they agree with safeInv for -0.0f: they decide which plane of a pair
-// is the near one, and a near / far swap against the sign of the reciprocal would turn every box into a miss.
-// Result: byte offsets (x | y << 8 | z << 16) of the near planes inside a node: lower planes at 32 / 64 / 96, upper planes 16 further.
-__device__ __forceinline__ unsigned nearOffsets(const V3& d)
-{
-    const unsigned sx = __float_as_uint(d.x) >> 31, sy = __float_as_uint(d.y) >> 31, sz = __float_as_uint(d.z) >> 31;
-    return (32u + (sx << 4)) | ((64u + (sy << 4)) << 8) | ((96u + (sz << 4)) << 16);
-}
-
-// traversal-only reciprocal: guarded against 0 (the exact predicate never uses it)
-__device__ __forceinline__ float safeInv(float d)
-{
-    const float ooeps = 1e-30f;
-    return __fdividef(1.0f, fabsf(d) > ooeps ? d : copysignf(ooeps, d));     // 1-ulp reciprocal: inside the slab test's 2e-6 slack
-}
-
-// TLAS pruning bound once some instance reported world distance g_dist: g_dist may be the approximation t * |d_w| / |W3 d_w| of the exact
-// distance (off by at most g_dist * tie + cb, tie < prune - 1), so the bound carries the same absolute slack cb as the instance-entry bound
-__device__ __forceinline__ float worldBound(float g_dist, float prune, float cb)
-{
-    return g_dist < kFloatMax ? g_dist * prune + cb + 1e-3f : 3.0e38f;
 }
 
 }  // namespace

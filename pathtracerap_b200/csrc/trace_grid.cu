@@ -67,13 +67,15 @@ enum : unsigned { F_INTERSECT = 1u, F_ANY = 2u, F_POST = 4u, F_MODEL_HIT = 8u };
 template <bool UV, bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock)
 k_trace_grid(SceneDev sc, const float4* __restrict__ O, const float4* __restrict__ D, float4* __restrict__ hit,
-             float2* __restrict__ uv, int4* __restrict__ counts, FrameState* st, int round, int n_fixed, unsigned long long* __restrict__ stamp)
+             float2* __restrict__ uv, int4* __restrict__ counts, FrameState* st, int round, int n_fixed, unsigned long long* __restrict__ stamp,
+             const int* __restrict__ list)
 {
     constexpr unsigned kFull = 0xffffffffu;
-    const int n = n_fixed >= 0 ? n_fixed : st->n_active[round];
-    if (blockIdx.x == 0 && threadIdx.x == 0 && n_fixed < 0) st->rays_traced += (unsigned long long)n;
+    // list != null: the second launch of PTAP_ACCEL_GRID_EMULATED - only the slots k_trace_emu (trace_emu.cu) handed over are walked
+    const int n = list ? (int)st->n_replay[round] : n_fixed >= 0 ? n_fixed : st->n_active[round];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n_fixed < 0 && !list) st->rays_traced += (unsigned long long)n;
     if (stamp && threadIdx.x == 0) atomicMin(stamp, globalTimerNs());
-    unsigned int* cursor = &st->fetch[round];
+    unsigned int* cursor = list ? &st->fetch_replay[round] : &st->fetch[round];
     const int lane = threadIdx.x & 31;
     const int GX = sc.gx, GY = sc.gy, GZ = sc.gz;
     unsigned long long tot_x = 0, tot_y = 0, tot_z = 0;
@@ -230,7 +232,7 @@ k_trace_grid(SceneDev sc, const float4* __restrict__ O, const float4* __restrict
             const int avail = w_end - w_next;
             const int rank = __popc(m_done & ((1u << lane) - 1u));
             if (s_done && live && rank < avail) {
-                i = w_next + rank;
+                i = list ? __ldg(&list[w_next + rank]) : w_next + rank;
                 bo = v3(O[i]); bd = v3(D[i]);
                 g_dist = kFloatMax; g_model = -1; g_tri = -1; g_t = 0.0f; g_u = 0.0f; g_v = 0.0f;
                 if (COUNT) cnt = make_int4(0, 0, 0, 0);
@@ -251,11 +253,11 @@ k_trace_grid(SceneDev sc, const float4* __restrict__ O, const float4* __restrict
 }
 
 void launchTraceGrid(const SceneDev& sc, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, bool count_totals,
-                     FrameState* st, int round, int n_fixed, int grid, cudaStream_t stream, unsigned long long* stamp)
+                     FrameState* st, int round, int n_fixed, int grid, cudaStream_t stream, unsigned long long* stamp, const int* list)
 {
-    if (counts || count_totals) k_trace_grid<true, true><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, stamp);
-    else if (uv) k_trace_grid<true, false><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, stamp);
-    else k_trace_grid<false, false><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, stamp);
+    if (counts || count_totals) k_trace_grid<true, true><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, stamp, list);
+    else if (uv) k_trace_grid<true, false><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, stamp, list);
+    else k_trace_grid<false, false><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, stamp, list);
 }
 
 int traceGridOccupancy()

@@ -1,0 +1,166 @@
+"""PTAP_ACCEL_GRID_EMULATED (csrc/trace_emu.cu): the RESULTS of the reference's grid walk - oracle tier R0, its misses and early exits
+included - computed through the BVH (all hits of a model, then a replay of the walk's voxel sequence over the voxel boxes of the hit
+triangles).  The contract is bit equality with the walk on everything: ids, t, u, v, distance, whole films."""
+import numpy as np
+import pytest
+
+from conftest import have_gpu
+from test_gpu_trace import _random_rays, assert_hits_equal
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_gpu(), reason="no CUDA device")]
+
+
+@pytest.fixture(scope="module")
+def renderer(gpu_scene):
+    from pathtracerap_b200 import ACCEL_GRID_EMULATED, Renderer
+    r = Renderer(width=64, height=32, depth=5, accel=ACCEL_GRID_EMULATED)      # no BVH in the scene: built on the device at this call
+    r.allocateOnGPU(gpu_scene)
+    yield r
+    r.free()
+
+
+def test_emulated_vs_reference_golden(renderer, golden_trace):
+    from pathtracerap_b200 import ACCEL_GRID_COMPAT, ACCEL_GRID_EMULATED
+    renderer.set_accel(ACCEL_GRID_EMULATED)
+    got = renderer.trace(golden_trace["rays"])
+    assert_hits_equal(got, golden_trace["r0"], "emulated walk vs reference R0 (golden)")
+    assert not np.array_equal(golden_trace["r0"]["tri"], golden_trace["r1"]["tri"])      # the fixture does hold rays the walk loses
+    renderer.set_accel(ACCEL_GRID_COMPAT)
+    assert_hits_equal(got, renderer.trace(golden_trace["rays"]), "emulated walk vs k_trace_grid")
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_emulated_random_rays_vs_oracle(renderer, oracle_scene, seed):
+    """Origins anywhere in the room (inside mesh boxes too: the walk then starts BEHIND the origin), un-normalised directions,
+    zero components and axis-parallel rays (the reference's slab test is not geometric there)."""
+    from pathtracerap_b200 import ACCEL_GRID_EMULATED
+    rays = _random_rays(300_000, seed)
+    renderer.set_accel(ACCEL_GRID_EMULATED)
+    got, cnt = renderer.trace(rays, counts=True)
+    assert_hits_equal(got, oracle_scene.trace(rays, 0), "emulated walk vs oracle R0 (random rays)")
+    assert_hits_equal(renderer.trace(rays), got, "UV build vs counting build")
+    # nodes visited, voxels replayed, triangles tested per ray: far below the walk's ~40 voxels and ~32 tests
+    assert cnt[:, 2].mean() < 12 and cnt[:, 1].mean() < 20
+
+
+def test_emulated_with_host_bvh_and_device_grids(gpu_scene, oracle_scene, golden_trace):
+    """Same answers whichever builder made the tree and the grids: host SAH tree + host grids, then the grids rebuilt on the device."""
+    from pathtracerap_b200 import ACCEL_BVH, ACCEL_GRID_EMULATED, Renderer
+    r = Renderer(width=64, height=32, depth=5, accel=ACCEL_BVH)
+    r.allocateOnGPU(gpu_scene)
+    rays = _random_rays(100_000, 7)
+    want = oracle_scene.trace(rays, 0)
+    r.set_accel(ACCEL_GRID_EMULATED)
+    assert_hits_equal(r.trace(rays), want, "host SAH tree + host grids")
+    r.build_grids_device(gpu_scene, 25, 25, 25)
+    r.set_accel(ACCEL_GRID_EMULATED)
+    assert_hits_equal(r.trace(rays), want, "host SAH tree + device grids")
+    r.free()
+
+
+def test_emulated_film_is_the_walks_film(gpu_scene):
+    """Whole frames, multi-lane schedule, first-hit cache on and off: the film must equal k_trace_grid's bit for bit."""
+    from pathtracerap_b200 import ACCEL_GRID_COMPAT, ACCEL_GRID_EMULATED, Renderer
+    W, H, depth, iters = 320, 240, 8, 6
+    films = {}
+    for accel in (ACCEL_GRID_COMPAT, ACCEL_GRID_EMULATED):
+        r = Renderer(width=W, height=H, depth=depth, accel=accel, first_hit_cache=True)
+        r.allocateOnGPU(gpu_scene)
+        for cache in (True, False):
+            r.set_params(W, H, depth, first_hit_cache=cache)
+            r.frame_begin(); r.render(0, iters); r.sync()
+            films[(accel, cache)] = (r.film().copy(), r.stats()["rays_traced"], list(r.stats()["active_per_round"]))
+        r.free()
+    for cache in (True, False):
+        a, b = films[(ACCEL_GRID_COMPAT, cache)], films[(ACCEL_GRID_EMULATED, cache)]
+        assert a[1] == b[1] and a[2] == b[2]
+        assert np.array_equal(a[0], b[0]), f"cache={cache}: {(a[0] != b[0]).any(axis=-1).sum()} pixels differ"
+
+
+def _stacked_scene(copies):
+    """One model whose mesh is `copies` coincident copies of two big triangles (plus a floor quad so that the grid has more than one
+    layer): a ray through them hits `copies` triangles of ONE model, more than the emulation keeps per (ray, model)."""
+    from pathtracerap_b200 import DIFFUSE, Scene, VERTEX
+    quad = np.array([[-1, -1, 0], [1, -1, 0], [1, 1, 0], [-1, 1, 0]], np.float32)
+    verts, idx = [], []
+    for c in range(copies):
+        base = len(verts)
+        verts += [tuple(p) for p in quad]
+        idx += [(base, base + 1, base + 2), (base, base + 2, base + 3)]
+    base = len(verts)
+    verts += [(-1, -1, -1), (1, -1, -1), (1, 1, -1), (-1, 1, -1)]
+    idx += [(base, base + 1, base + 2), (base, base + 2, base + 3)]
+    v = np.zeros(len(verts), VERTEX)
+    v["position"] = np.array(verts, np.float32); v["normal"] = (0, 0, 1)
+    s = Scene.empty()
+    mi = s.add_mesh(v, np.array(idx, np.int32))
+    s.add_model(mi, translate=(3, 2, 1), rotate_y_degrees=20.0, scale=(50, 40, 30), material=DIFFUSE)
+    s.add_model(mi, translate=(-80, 10, -5), rotate_y_degrees=-35.0, scale=(20, 60, 10), material=DIFFUSE)
+    s.build_grids(25, 25, 25)
+    return s
+
+
+@pytest.mark.parametrize("copies", [3, 12])
+def test_more_hits_than_slots_goes_to_the_walk(port, copies):
+    """12 coincident copies: every ray through the quad has 12 (or 24, on the diagonal) hits in one model - beyond the 8 the replay keeps -
+    and must be answered by the walk itself in the second launch; 3 copies stay inside the emulation.  Both must equal the oracle's R0,
+    exact-t ties included (coincident triangles have bit-equal t: the lowest id listed first wins, Renderer.cpp:209)."""
+    from pathtracerap_b200 import ACCEL_GRID_COMPAT, ACCEL_GRID_EMULATED, Renderer
+    s = _stacked_scene(copies)
+    a = s.arrays()
+    osc = port.OracleScene({k: a[k] for k in ("models", "meshes", "vertices", "triangles")})
+    rs = np.random.RandomState(5)
+    n = 60_000
+    o = np.stack([rs.uniform(-150, 100, n), rs.uniform(-80, 80, n), rs.uniform(-100, 100, n)], 1)
+    tgt = np.stack([rs.uniform(-120, 60, n), rs.uniform(-50, 50, n), rs.uniform(-40, 40, n)], 1)
+    rays = np.concatenate([o, tgt - o], 1).astype(np.float32)
+    want = osc.trace(rays, 0)
+    assert (want["model"] >= 0).mean() > 0.2
+    r = Renderer(width=64, height=32, depth=5, accel=ACCEL_GRID_EMULATED)
+    r.allocateOnGPU(s)
+    assert_hits_equal(r.trace(rays), want, f"{copies} coincident copies, emulated")
+    r.set_accel(ACCEL_GRID_COMPAT)
+    assert_hits_equal(r.trace(rays), want, f"{copies} coincident copies, walked")
+    # the production instantiation too: one probed round of a frame whose camera looks at the models
+    r.set_accel(ACCEL_GRID_EMULATED)
+    r.set_params(96, 64, 3, first_hit_cache=False)
+    r.set_camera(origin=(0.0, 0.0, 300.0), plane_min=(-120.0, -80.0, 100.0), span=(240.0, 160.0))
+    rays_p, _, hits_p = r.render_probe(0, 0)
+    want_p = osc.trace(rays_p, 0)
+    for f in ("model", "tri", "t_model", "dist"):
+        assert np.array_equal(hits_p[f], want_p[f]), f
+    r.free()
+
+
+def test_lists_that_are_not_boxes_are_refused(gpu_scene):
+    """The emulation relies on box-shaped, ascending lists (Scene.cpp:357-374).  A grid whose lists were edited by hand is walked, not
+    emulated: ptap_build_accel(PTAP_ACCEL_GRID_EMULATED) fails with PTAP_E_UNSUPPORTED and PTAP_ACCEL_GRID_COMPAT keeps working."""
+    from pathtracerap_b200 import ACCEL_GRID_COMPAT, ACCEL_GRID_EMULATED, PtapError, Renderer, Scene
+    a = gpu_scene.arrays()
+    vox, refs = a["voxels"].copy(), a["refs"].copy()
+    # take a triangle listed in many voxels and drop it from the list of the middle one: its bounding box of voxels stays, one listing is gone
+    tri = int(np.bincount(refs).argmax())
+    listing = [c for c in np.flatnonzero(vox["end"] > vox["start"]) if tri in refs[vox["start"][c]:vox["end"][c]]]
+    assert len(listing) >= 9
+    k = int(listing[len(listing) // 2])
+    s0, e0 = int(vox["start"][k]), int(vox["end"][k])
+    keep = [t for t in refs[s0:e0] if t != tri]
+    refs[s0:s0 + len(keep)] = keep
+    vox["end"][k] = s0 + len(keep)
+    s = Scene.from_arrays(a["models"], a["meshes"], a["vertices"], a["triangles"], a["grids"], vox, refs)
+    r = Renderer(width=64, height=32, depth=5, accel=ACCEL_GRID_COMPAT)
+    r.allocateOnGPU(s)
+    with pytest.raises(PtapError, match="box-shaped"):
+        r.set_accel(ACCEL_GRID_EMULATED)
+    r.set_accel(ACCEL_GRID_COMPAT)
+    assert len(r.trace(_random_rays(1000, 3))) == 1000
+    # descending order inside one voxel: refused as well
+    vox, refs = a["voxels"].copy(), a["refs"].copy()
+    k = int(np.flatnonzero(vox["end"] - vox["start"] >= 2)[0])
+    s0, e0 = int(vox["start"][k]), int(vox["end"][k])
+    refs[s0:e0] = refs[s0:e0][::-1].copy()
+    s2 = Scene.from_arrays(a["models"], a["meshes"], a["vertices"], a["triangles"], a["grids"], vox, refs)
+    r.allocateOnGPU(s2)
+    with pytest.raises(PtapError, match="box-shaped"):
+        r.set_accel(ACCEL_GRID_EMULATED)
+    r.free()

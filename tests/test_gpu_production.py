@@ -54,13 +54,13 @@ def renderer(gpu_scene):
     r.free()
 
 
-@pytest.mark.parametrize("accel_name,mode", [("grid", 0), ("bvh", 1), ("lbvh", 1)])
+@pytest.mark.parametrize("accel_name,mode", [("grid", 0), ("emu", 0), ("bvh", 1), ("lbvh", 1)])
 def test_production_kernels_round_by_round(renderer, oracle_scene, accel_name, mode):
-    """Every round of a real iteration: the rays the production kernel read, re-traced by the oracle (R0 for the grid walk, R1 for the
-    BVHs), must give bit-equal ids, model t, world distance (for the BVH: the value deferred to the consumer), normal and material;
+    """Every round of a real iteration: the rays the production kernel read, re-traced by the oracle (R0 for the grid walk and for its
+    emulation through the BVH, R1 for the BVHs), must give bit-equal ids, model t, world distance (for the BVH: the value deferred to the consumer), normal and material;
     and the next round's wavefront must be exactly the survivors, in stable order, restarted at hit + 0.1 n."""
-    from pathtracerap_b200 import ACCEL_BVH, ACCEL_BVH_DEVICE, ACCEL_GRID_COMPAT
-    accel = {"grid": ACCEL_GRID_COMPAT, "bvh": ACCEL_BVH, "lbvh": ACCEL_BVH_DEVICE}[accel_name]
+    from pathtracerap_b200 import ACCEL_BVH, ACCEL_BVH_DEVICE, ACCEL_GRID_COMPAT, ACCEL_GRID_EMULATED
+    accel = {"grid": ACCEL_GRID_COMPAT, "emu": ACCEL_GRID_EMULATED, "bvh": ACCEL_BVH, "lbvh": ACCEL_BVH_DEVICE}[accel_name]
     W, H, depth = 256, 192, 5
     renderer.set_accel(accel)
     for cache in (False, True):
