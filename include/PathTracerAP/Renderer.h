@@ -8,11 +8,12 @@
 //
 // Resolution, iteration count and depth come from Config.h's macros (the reference's only configuration), overridden by the
 // RESOLUTION / ITER / DEPTH keys of a parsed Config.txt, overridden by the environment (PTAP_WIDTH, PTAP_HEIGHT, PTAP_ITER,
-// PTAP_DEPTH, PTAP_ACCEL=grid|bvh|lbvh, PTAP_DEVICE, PTAP_RANKS = GPUs of this process that share the iterations).  The acceleration structure defaults to the reference's own 25^3 grid walk
-// (bit-compatible hits); PTAP_ACCEL=bvh selects the BVH (built on the host), lbvh the same built on the GPU.  All errors throw std::runtime_error: there is no CPU fallback.
+// PTAP_DEPTH, PTAP_ACCEL=emu|grid|bvh|lbvh, PTAP_DEVICE, PTAP_RANKS = GPUs of this process that share the iterations).  The default reproduces the reference's own 25^3 grid walk
+// bit for bit - through the BVH (PTAP_ACCEL_GRID_EMULATED) when the grids have the shape Scene.cpp builds, else by walking them (also PTAP_ACCEL=grid); PTAP_ACCEL=bvh selects the BVH (built on the host), lbvh the same built on the GPU.  All errors throw std::runtime_error: there is no CPU fallback.
 #pragma once
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <iostream>
 #include <stdexcept>
@@ -40,9 +41,10 @@ public:
         depth = pick("PTAP_DEPTH", scene.config_depth, MAX_DEPTH);
         samples_x = std::max(1, pick("PTAP_SAMPLESX", 0, SAMPLESX));   // Config.h:14-15: camera rays per pixel, on one W*SX x H*SY lattice
         samples_y = std::max(1, pick("PTAP_SAMPLESY", 0, SAMPLESY));
-        const char* a = std::getenv("PTAP_ACCEL");
-        const bool lbvh = a && std::string(a) == "lbvh";          // tree built on the GPU at this call
-        const bool bvh = a && std::string(a) == "bvh";
+        const std::string a = std::getenv("PTAP_ACCEL") ? std::getenv("PTAP_ACCEL") : "";
+        const bool lbvh = a == "lbvh";                            // tree built on the GPU at this call
+        const bool bvh = a == "bvh";
+        const bool walk = a == "grid";                            // walk the grids instead of emulating the walk through the BVH
         PtapSceneView v{};
         v.models = scene.models.data(); v.nmodels = (int32_t)scene.models.size();
         v.meshes = scene.meshes.data(); v.nmeshes = (int32_t)scene.meshes.size();
@@ -62,7 +64,13 @@ public:
             check(ptap_create(r < (int)devices.size() ? devices[(size_t)r] : dev0 + r, 0, &ctx), "ptap_create");
             all[(size_t)r] = ctx;
             check(ptap_upload_scene(ctx, &v), "ptap_upload_scene");
-            check(ptap_build_accel(ctx, lbvh ? PTAP_ACCEL_BVH_DEVICE : bvh || scene.grids.empty() ? PTAP_ACCEL_BVH : PTAP_ACCEL_GRID_COMPAT), "ptap_build_accel");
+            const int kind = lbvh ? PTAP_ACCEL_BVH_DEVICE : bvh || scene.grids.empty() ? PTAP_ACCEL_BVH : walk ? PTAP_ACCEL_GRID_COMPAT : PTAP_ACCEL_GRID_EMULATED;
+            int rc = ptap_build_accel(ctx, kind);
+            const int rc_first = rc;
+            if (rc == PTAP_E_UNSUPPORTED && kind == PTAP_ACCEL_GRID_EMULATED) rc = ptap_build_accel(ctx, PTAP_ACCEL_GRID_COMPAT);   // same results, walked
+            check(rc, "ptap_build_accel");
+            if (r == 0) std::fprintf(stderr, "ptap: acceleration structure: %s\n", kind == PTAP_ACCEL_BVH ? "BVH (host build)" : kind == PTAP_ACCEL_BVH_DEVICE ? "BVH (device build)" :
+                                     kind == PTAP_ACCEL_GRID_COMPAT ? "the reference's grids, walked" : rc_first == 0 ? "the reference's grids, emulated through the BVH" : "the reference's grids, walked (lists not box-shaped)");
             check(ptap_set_render_params(ctx, width * samples_x, height * samples_y, depth, PTAP_FLAG_FIRST_HIT_CACHE | PTAP_FLAG_ITER_TIMES), "ptap_set_render_params");
             if (scene.config_has_camera) check(ptap_set_camera(ctx, &scene.config_camera), "ptap_set_camera");
         }

@@ -64,8 +64,10 @@ void Renderer::allocateOnGPU(Scene& scene)
     v.voxels = reinterpret_cast<const PtapVoxel*>(scene.voxels.data()); v.nvoxels = (int32_t)scene.voxels.size();
     v.refs = scene.per_voxel_data_pool.data(); v.nrefs = (int32_t)scene.per_voxel_data_pool.size();
     v.grid_dim[0] = GRID_X; v.grid_dim[1] = GRID_Y; v.grid_dim[2] = GRID_Z;
-    const char* accel = std::getenv("PTAP_ACCEL");            // default: the reference's own grid walk, bit-compatible hits
-    const int kind = !accel ? PTAP_ACCEL_GRID_COMPAT : std::string(accel) == "bvh" ? PTAP_ACCEL_BVH : std::string(accel) == "lbvh" ? PTAP_ACCEL_BVH_DEVICE : PTAP_ACCEL_GRID_COMPAT;
+    // default: the reference's own hits, bit for bit (tier R0) - through the BVH when the grids have the shape Scene.cpp builds
+    // (PTAP_ACCEL_GRID_EMULATED), else by walking them (PTAP_ACCEL_GRID_COMPAT; also PTAP_ACCEL=grid).  bvh / lbvh: exact closest hit.
+    const std::string accel = std::getenv("PTAP_ACCEL") ? std::getenv("PTAP_ACCEL") : "";
+    const int kind = accel == "bvh" ? PTAP_ACCEL_BVH : accel == "lbvh" ? PTAP_ACCEL_BVH_DEVICE : accel == "grid" ? PTAP_ACCEL_GRID_COMPAT : PTAP_ACCEL_GRID_EMULATED;
     const int ranks = std::max(1, envInt("PTAP_RANKS", 1)), dev0 = envInt("PTAP_DEVICE", 0);
     std::vector<int> devices;                                 // PTAP_RANK_DEVICES=0,0,1: explicit device of every rank (default dev0 + rank)
     if (const char* list = std::getenv("PTAP_RANK_DEVICES")) for (const char* q = list; *q;) { devices.push_back(std::atoi(q)); while (*q && *q != ',') ++q; if (*q) ++q; }
@@ -75,7 +77,12 @@ void Renderer::allocateOnGPU(Scene& scene)
         check(b, ptap_create(r < (int)devices.size() ? devices[r] : dev0 + r, 0, &b.ctx), "ptap_create");
         b.all[r] = b.ctx;
         check(b, ptap_upload_scene(b.ctx, &v), "ptap_upload_scene");
-        check(b, ptap_build_accel(b.ctx, kind), "ptap_build_accel");
+        int rc = ptap_build_accel(b.ctx, kind);
+        const int rc_first = rc;
+        if (rc == PTAP_E_UNSUPPORTED && kind == PTAP_ACCEL_GRID_EMULATED) rc = ptap_build_accel(b.ctx, PTAP_ACCEL_GRID_COMPAT);   // same results, walked
+        check(b, rc, "ptap_build_accel");
+        if (r == 0) std::fprintf(stderr, "ptap: acceleration structure: %s\n", kind == PTAP_ACCEL_BVH ? "BVH (host build)" : kind == PTAP_ACCEL_BVH_DEVICE ? "BVH (device build)" :
+                                 kind == PTAP_ACCEL_GRID_COMPAT ? "the reference's grids, walked" : rc_first == 0 ? "the reference's grids, emulated through the BVH" : "the reference's grids, walked (lists not box-shaped)");
         // nrays = RESOLUTION * SAMPLES camera rays on one lattice (Renderer.cpp:96, 527-542); SAMPLESX = SAMPLESY = 1 in Config.h:14-15
         check(b, ptap_set_render_params(b.ctx, RESOLUTION_X * SAMPLESX, RESOLUTION_Y * SAMPLESY, MAX_DEPTH, PTAP_FLAG_FIRST_HIT_CACHE | PTAP_FLAG_ITER_TIMES), "ptap_set_render_params");
     }

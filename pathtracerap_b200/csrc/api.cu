@@ -91,6 +91,8 @@ struct ptap_ctx {
     std::vector<cudaEvent_t> iter_events;      // completion of every iteration of the last render call (PTAP_FLAG_ITER_TIMES)
     int iter_events_used = 0;
     std::vector<float> iter_ms;
+    int emu_replay_ctas = 8, emu_walk_ctas = 2;
+    Arena emu_arena; int emu_lanes = 0;          // PTAP_ACCEL_GRID_EMULATED: per-slot buffers of the render lanes
     int2* d_tri_box = nullptr; size_t tri_box_cap = 0; bool emu_ok = false;   // PTAP_ACCEL_GRID_EMULATED: per-triangle voxel boxes (own allocation)
     std::vector<int> h_grid_first, h_model_grid;     // first voxel of every grid on the device / grid of every model
     int2* gd_cells = nullptr; int* gd_refs = nullptr; size_t gd_ncells = 0, gd_nrefs = 0;   // grids built on the device (own allocation)
@@ -122,18 +124,45 @@ float4 row(const float* m, int r) { return make_float4(m[0 + r], m[4 + r], m[8 +
 
 constexpr int kMaxStamps = 8192;     // closest-hit launches of one render call that can be stamped (PTAP_FLAG_STAMP)
 
-// replay: N ints the emulated grid walk may fill with the slots it hands to the walk itself (PTAP_ACCEL_GRID_EMULATED only)
+// emu: per-slot buffers of the emulated grid walk (PTAP_ACCEL_GRID_EMULATED only; see emuFromArena / ensureEmuBuffers)
 void launchTrace(ptap_ctx* c, FrameState* st, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, int round, int n_fixed,
-                 int* replay, bool count_totals = false, cudaStream_t stream = nullptr, unsigned long long* stamp = nullptr)
+                 const EmuBuf& emu, bool count_totals = false, cudaStream_t stream = nullptr, unsigned long long* stamp = nullptr)
 {
     if (!stream) stream = c->stream;
     if (c->accel == PTAP_ACCEL_GRID_EMULATED) {
-        launchTraceEmu(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, stream, stamp, replay);
-        // second launch: the walk itself for the (normally zero) slots with more hits in one model than the emulation keeps
-        launchTraceGrid(c->sc, O, D, hit, uv, counts, false, st, round, n_fixed, c->sms, stream, nullptr, replay);
+        // closest hit + the hits of the nearest model, then the replay of that model's walk (trace_emu.cu) ...
+        launchTraceEmu(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, c->sms * c->emu_replay_ctas, stream, stamp, emu);
+        // ... and the walk itself for the slots the replay could not confirm (the 0.3-0.6 % of rays on which the walk is not a closest-hit query)
+        launchTraceGrid(c->sc, O, D, hit, uv, nullptr, false, st, round, n_fixed, c->sms * c->emu_walk_ctas, stream, nullptr, emu.list);
     }
     else if (c->accel != PTAP_ACCEL_GRID_COMPAT) launchTraceBvh(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, stream, stamp);
     else launchTraceGrid(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, stream, stamp);
+}
+
+// Per-slot buffers of PTAP_ACCEL_GRID_EMULATED: hit count, kEmuHits x (triangle id, t), the list for the walk.  72 B per slot.
+size_t emuArenaNeed(size_t n) { return Arena::need(n, sizeof(int)) * 2 + Arena::need(n * kEmuHits, sizeof(int)) + Arena::need(n * kEmuHits, sizeof(float)); }
+
+EmuBuf emuFromArena(Arena& A, size_t n)
+{
+    EmuBuf e;
+    e.n = A.alloc<int>(n); e.list = A.alloc<int>(n); e.id = A.alloc<int>(n * kEmuHits); e.t = A.alloc<float>(n * kEmuHits); e.stride = (int)n;
+    return e;
+}
+
+// The render lanes' buffers: one allocation of their own (the frame arena is sized before the acceleration structure is chosen), made
+// the first time a frame is rendered through the emulation at this resolution.
+int ensureEmuBuffers(ptap_ctx* ctx)
+{
+    if (ctx->accel != PTAP_ACCEL_GRID_EMULATED) return PTAP_OK;
+    const size_t N = (size_t)ctx->wv.N, per_lane = emuArenaNeed(N), need = per_lane * (size_t)ctx->lanes + 4096;
+    bool moved = false;
+    if (ctx->emu_arena.cap < need) { CK(ctx->emu_arena.reserve(need)); moved = true; }
+    if (!moved && ctx->wv.emu.n && ctx->wv.emu.stride == (int)N && ctx->emu_lanes == ctx->lanes) return PTAP_OK;
+    ctx->emu_arena.used = 0;
+    ctx->wv.emu = emuFromArena(ctx->emu_arena, N);
+    for (int l = 1; l < ctx->lanes; ++l) ctx->wvx[l].emu = emuFromArena(ctx->emu_arena, N);
+    ctx->emu_lanes = ctx->lanes;
+    return PTAP_OK;
 }
 
 void profMark(ptap_ctx* c, int kind)
@@ -515,6 +544,8 @@ int ptap_create(int device, size_t arena_bytes, ptap_ctx** out)
         if (!ok) { ptap_destroy(ctx); return PTAP_E_NOMEM; }
     }      // measured slower on every workload (profiles/r01/README.md): opt-in
     ctx->trace_ctas = std::max(0, envInt("PTAP_TRACE_CTAS", 0));
+    ctx->emu_replay_ctas = std::max(1, envInt("PTAP_EMU_REPLAY_CTAS", 8));     // per SM: k_emu_replay / k_trace_grid in list mode (tuning only)
+    ctx->emu_walk_ctas = std::max(1, envInt("PTAP_EMU_WALK_CTAS", 2));
     if (arena_bytes) {                                          // caller-sized arena: split 1/4 scene, 3/4 frame
         if (ctx->scene_arena.reserve(arena_bytes / 4) != cudaSuccess || ctx->frame_arena.reserve(arena_bytes - arena_bytes / 4) != cudaSuccess) {
             ptap_destroy(ctx); return PTAP_E_NOMEM;
@@ -532,7 +563,7 @@ void ptap_destroy(ptap_ctx* ctx)
     for (int l = 1; l < kMaxLanes; ++l) if (ctx->streams[l]) { cudaStreamSynchronize(ctx->streams[l]); cudaStreamDestroy(ctx->streams[l]); }
     for (cudaEvent_t e : {ctx->e_fork, ctx->e_cache}) if (e) cudaEventDestroy(e);
     for (int l = 0; l < kMaxLanes; ++l) { if (ctx->e_join[l]) cudaEventDestroy(ctx->e_join[l]); if (ctx->e_gather[l]) cudaEventDestroy(ctx->e_gather[l]); }
-    ctx->scene_arena.release(); ctx->frame_arena.release(); ctx->scratch.release();
+    ctx->scene_arena.release(); ctx->frame_arena.release(); ctx->scratch.release(); ctx->emu_arena.release();
     if (ctx->gd_cells) cudaFree(ctx->gd_cells);
     if (ctx->d_tri_box) cudaFree(ctx->d_tri_box);
     if (ctx->gd_refs) cudaFree(ctx->gd_refs);
@@ -751,10 +782,10 @@ int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, u
     const int ntiles = (N + kShadeTile - 1) / kShadeTile, nscan = (N + kScanSlots - 1) / kScanSlots;
     size_t need = Arena::need(N, sizeof(float4)) * 8 + Arena::need(N, sizeof(float2)) + Arena::need((size_t)N * 3, sizeof(float)) +
                   Arena::need((size_t)nscan * kMaxDepth, sizeof(unsigned long long)) + Arena::need(ntiles, sizeof(int)) * 2 +
-                  Arena::need((size_t)nscan * kScanSlots, 1) + Arena::need(1, sizeof(FrameState)) + Arena::need(2 * kMaxStamps, sizeof(unsigned long long)) + Arena::need(N, sizeof(int)) + 4096;
+                  Arena::need((size_t)nscan * kScanSlots, 1) + Arena::need(1, sizeof(FrameState)) + Arena::need(2 * kMaxStamps, sizeof(unsigned long long)) + 4096;
     if (ctx->lanes > 1)            // every further lane: its own queues, hits, scan state; one contribution buffer per lane (lane 0 too)
         need += (size_t)(ctx->lanes - 1) * (Arena::need(N, sizeof(float4)) * 7 + Arena::need((size_t)nscan * kMaxDepth, sizeof(unsigned long long)) +
-                                            Arena::need(ntiles, sizeof(int)) * 2 + Arena::need((size_t)nscan * kScanSlots, 1) + Arena::need(1, sizeof(FrameState)) + Arena::need(N, sizeof(int)) + 4096) +
+                                            Arena::need(ntiles, sizeof(int)) * 2 + Arena::need((size_t)nscan * kScanSlots, 1) + Arena::need(1, sizeof(FrameState)) + 4096) +
                 (size_t)ctx->lanes * Arena::need((size_t)N * 3, sizeof(float));
     if (need > ctx->frame_arena.cap) CK(ctx->frame_arena.reserve(need)); else ctx->frame_arena.used = 0;
     Arena& A = ctx->frame_arena;
@@ -767,9 +798,9 @@ int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, u
     wv.tile_ballot = A.alloc<unsigned>(ntiles);
     wv.perm = A.alloc<unsigned char>((size_t)nscan * kScanSlots);
     wv.st = A.alloc<FrameState>(1);
-    wv.replay = A.alloc<int>(N);
+    wv.emu = EmuBuf{};
     ctx->d_stamps = A.alloc<unsigned long long>(2 * kMaxStamps); ctx->stamps_used = 0;
-    if (!ctx->d_stamps || !wv.replay || !wv.st || !wv.tile_status || !wv.tile_offset || !wv.tile_ballot || !wv.perm || !wv.film) return fail(ctx, PTAP_E_NOMEM, "frame arena exhausted");
+    if (!ctx->d_stamps || !wv.st || !wv.tile_status || !wv.tile_offset || !wv.tile_ballot || !wv.perm || !wv.film) return fail(ctx, PTAP_E_NOMEM, "frame arena exhausted");
     wv.W = W; wv.H = H; wv.N = N; wv.depth = depth; wv.ntiles = ntiles; wv.nscan = nscan;
     applyCamera(ctx, wv);
     wv.iter_stride = 1; wv.contrib = nullptr;
@@ -783,9 +814,8 @@ int ptap_set_render_params(ptap_ctx* ctx, int32_t W, int32_t H, int32_t depth, u
         w2.tile_offset = A.alloc<int>(ntiles); w2.tile_ballot = A.alloc<unsigned>(ntiles);
         w2.perm = A.alloc<unsigned char>((size_t)nscan * kScanSlots);
         w2.st = A.alloc<FrameState>(1);
-        w2.replay = A.alloc<int>(N);
         w2.contrib = A.alloc<float>((size_t)N * 3);
-        if (!w2.st || !w2.replay || !w2.contrib || !wv.contrib || !w2.perm || !w2.hit) return fail(ctx, PTAP_E_NOMEM, "frame arena exhausted (lane %d)", l);
+        if (!w2.st || !w2.contrib || !wv.contrib || !w2.perm || !w2.hit) return fail(ctx, PTAP_E_NOMEM, "frame arena exhausted (lane %d)", l);
         CK(cudaMemsetAsync(w2.st, 0, sizeof(FrameState), ctx->stream));
     }
     CK(cudaMemsetAsync(wv.film, 0, (size_t)N * 3 * sizeof(float), ctx->stream));   // initImageKernel, Renderer.cpp:557-565
@@ -823,6 +853,7 @@ int ptap_render(ptap_ctx* ctx, int32_t iter_begin, int32_t iter_end)
     if (iter_end < iter_begin) return fail(ctx, PTAP_E_INVALID, "render: empty iteration range");
     CK(cudaSetDevice(ctx->device));
     if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
+    { const int rc = ensureEmuBuffers(ctx); if (rc) return rc; }
     // jittered camera rays differ from iteration to iteration: the first-hit cache (Renderer.cpp:594-613) is meaningless then and is not used
     const bool cache = (ctx->flags & PTAP_FLAG_FIRST_HIT_CACHE) && !ctx->camera.jitter;
     // several lanes only for plain frames (the per-class event timing and the counting build stay on one stream)
@@ -859,7 +890,7 @@ int ptap_render(ptap_ctx* ctx, int32_t iter_begin, int32_t iter_end)
             if (!(round == 0 && cache && ctx->cache_valid)) {                    // Renderer.cpp:594-620
                 profMark(ctx, 1);
                 unsigned long long* stamp = stamping && ctx->stamps_used < kMaxStamps ? ctx->d_stamps + 2 * (size_t)ctx->stamps_used++ : nullptr;
-                launchTrace(ctx, wv.st, wv.O[in], wv.D[in], hitbuf, nullptr, nullptr, round, -1, wv.replay, (ctx->flags & PTAP_FLAG_COUNT) != 0, S, stamp); ++launches; ++trace_launches;
+                launchTrace(ctx, wv.st, wv.O[in], wv.D[in], hitbuf, nullptr, nullptr, round, -1, wv.emu, (ctx->flags & PTAP_FLAG_COUNT) != 0, S, stamp); ++launches; ++trace_launches;
                 if (L > 1 && round == 0 && cache) { CK(cudaEventRecord(ctx->e_cache, S)); cache_lane = l; cache_waited = 1u << l; }
             } else if (L > 1 && cache_lane >= 0 && !(cache_waited >> l & 1u)) {
                 CK(cudaStreamWaitEvent(S, ctx->e_cache, 0)); cache_waited |= 1u << l;
@@ -1065,13 +1096,13 @@ static int traceImpl(ptap_ctx* ctx, const float* rays_od, int32_t n, PtapHit* ou
     CK(cudaSetDevice(ctx->device));
     if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
     size_t need = Arena::need(n, sizeof(float4)) * 3 + Arena::need(n, sizeof(float2)) + Arena::need(n, sizeof(PtapHit)) + Arena::need(n, sizeof(int4)) +
-                  Arena::need((size_t)n * 6, sizeof(float)) + Arena::need(1, sizeof(FrameState)) + Arena::need(n, sizeof(int)) + 4096;
+                  Arena::need((size_t)n * 6, sizeof(float)) + Arena::need(1, sizeof(FrameState)) + emuArenaNeed(n) + 4096;
     if (need > ctx->scratch.cap) CK(ctx->scratch.reserve(need)); else ctx->scratch.used = 0;
     Arena& A = ctx->scratch;
     float4* O = A.alloc<float4>(n); float4* D = A.alloc<float4>(n); float4* hit = A.alloc<float4>(n);
     float2* uv = A.alloc<float2>(n); PtapHit* dout = A.alloc<PtapHit>(n); int4* dcnt = A.alloc<int4>(n);
     FrameState* st = A.alloc<FrameState>(1);
-    int* replay = A.alloc<int>(n);
+    const EmuBuf emu = emuFromArena(A, n);
     std::vector<float4> hO(n), hD(n);
     for (int i = 0; i < n; ++i) {
         hO[i] = make_float4(rays_od[6 * (size_t)i], rays_od[6 * (size_t)i + 1], rays_od[6 * (size_t)i + 2], 0.f);
@@ -1081,7 +1112,7 @@ static int traceImpl(ptap_ctx* ctx, const float* rays_od, int32_t n, PtapHit* ou
     CK(cudaMemcpyAsync(D, hD.data(), n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(st, 0, sizeof(FrameState), ctx->stream));
     if (!ctx->grid_trace) ctx->grid_trace = traceGridSize(ctx);
-    launchTrace(ctx, st, O, D, hit, uv, counts ? dcnt : nullptr, 0, n, replay);
+    launchTrace(ctx, st, O, D, hit, uv, counts ? dcnt : nullptr, 0, n, emu);
     launchResolveHits(ctx->sc, O, D, hit, uv, n, dout, ctx->stream);
     CK(cudaMemcpyAsync(out, dout, n * sizeof(PtapHit), cudaMemcpyDeviceToHost, ctx->stream));
     if (counts) CK(cudaMemcpyAsync(counts, dcnt, n * sizeof(int4), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1175,12 +1206,12 @@ int ptap_bench_trace(ptap_ctx* ctx, const float* rays_od, int32_t n, int32_t rep
     if (!ctx || !ctx->have_scene || !rays_od || n <= 0 || reps <= 0 || !ms_per_launch) return fail(ctx, PTAP_E_INVALID, "bench_trace: bad arguments");
     CK(cudaSetDevice(ctx->device));
     if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
-    size_t need = Arena::need(n, sizeof(float4)) * 3 + Arena::need(1, sizeof(FrameState)) + Arena::need(n, sizeof(int)) + 4096;
+    size_t need = Arena::need(n, sizeof(float4)) * 3 + Arena::need(1, sizeof(FrameState)) + emuArenaNeed(n) + 4096;
     if (need > ctx->scratch.cap) CK(ctx->scratch.reserve(need)); else ctx->scratch.used = 0;
     Arena& A = ctx->scratch;
     float4* O = A.alloc<float4>(n); float4* D = A.alloc<float4>(n); float4* hit = A.alloc<float4>(n);
     FrameState* st = A.alloc<FrameState>(1);
-    int* replay = A.alloc<int>(n);
+    const EmuBuf emu = emuFromArena(A, n);
     std::vector<float4> hO(n), hD(n);
     for (int i = 0; i < n; ++i) {
         hO[i] = make_float4(rays_od[6 * (size_t)i], rays_od[6 * (size_t)i + 1], rays_od[6 * (size_t)i + 2], 0.f);
@@ -1189,9 +1220,9 @@ int ptap_bench_trace(ptap_ctx* ctx, const float* rays_od, int32_t n, int32_t rep
     CK(cudaMemcpy(O, hO.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(D, hD.data(), n * sizeof(float4), cudaMemcpyHostToDevice));
     CK(cudaMemset(st, 0, sizeof(FrameState)));
-    for (int w = 0; w < 3; ++w) { CK(cudaMemsetAsync(st, 0, sizeof(FrameState), ctx->stream)); launchTrace(ctx, st, O, D, hit, nullptr, nullptr, 0, n, replay); }
+    for (int w = 0; w < 3; ++w) { CK(cudaMemsetAsync(st, 0, sizeof(FrameState), ctx->stream)); launchTrace(ctx, st, O, D, hit, nullptr, nullptr, 0, n, emu); }
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    for (int r = 0; r < reps; ++r) { CK(cudaMemsetAsync(st, 0, sizeof(FrameState), ctx->stream)); launchTrace(ctx, st, O, D, hit, nullptr, nullptr, 0, n, replay); }   // the memset re-arms the work-stealing cursor
+    for (int r = 0; r < reps; ++r) { CK(cudaMemsetAsync(st, 0, sizeof(FrameState), ctx->stream)); launchTrace(ctx, st, O, D, hit, nullptr, nullptr, 0, n, emu); }   // the memset re-arms the work-stealing cursor
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
@@ -1215,6 +1246,7 @@ int ptap_render_probe(ptap_ctx* ctx, int32_t iter, int32_t round, float* rays_od
     if (round < 0 || round >= ctx->wv.depth || !n_out || cap < 0) return fail(ctx, PTAP_E_INVALID, "render_probe: bad arguments");
     CK(cudaSetDevice(ctx->device));
     if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
+    { const int rc = ensureEmuBuffers(ctx); if (rc) return rc; }
     WaveDev wv = ctx->wv;
     wv.iter_stride = 1; wv.contrib = nullptr;
     cudaStream_t S = ctx->stream;
@@ -1223,7 +1255,7 @@ int ptap_render_probe(ptap_ctx* ctx, int32_t iter, int32_t round, float* rays_od
     launchGenerate(wv, iter, ctx->grid_gen, S);
     int in = 0;
     for (int r = 0; r <= round; ++r) {
-        launchTrace(ctx, wv.st, wv.O[in], wv.D[in], wv.hit, nullptr, nullptr, r, -1, wv.replay, false, S);       // the instantiation ptap_render launches
+        launchTrace(ctx, wv.st, wv.O[in], wv.D[in], wv.hit, nullptr, nullptr, r, -1, wv.emu, false, S);       // the instantiation ptap_render launches
         if (r == round) break;
         launchScan(ctx->sc, wv, r, wv.hit, wv.depth - r, -1, S);
         launchShade(ctx->sc, wv, r, in, wv.hit, wv.depth - r, -1, 0, nullptr, ctx->grid_shade, S);

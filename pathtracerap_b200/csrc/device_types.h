@@ -10,6 +10,7 @@ constexpr float kEpsilon = 0.005f;          // Config.h:4
 constexpr float kFloatMax = 9999999.0f;     // Config.h:5
 constexpr float kFloatMin = -9999990.0f;    // Config.h:6
 constexpr int kMaxDepth = 16;               // rounds per iteration the context reserves state for
+constexpr int kEmuHits = 8;                 // PTAP_ACCEL_GRID_EMULATED: hits of a (ray, model) that are kept for the replay of the walk
 constexpr int kBvhStack = 160;              // traversal stack entries per ray (upload fails for deeper trees)
 
 // Per-model record read by the closest-hit kernels: 9 x float4 = 144 B.
@@ -94,7 +95,7 @@ struct SceneDev {
     const float4* normals;      // flat shading normal per GLOBAL triangle id (copy of the TriRec .w lanes, 16-byte gather for k_shade)
     const int2* cells;          // grid voxels: (start, end) into refs
     const int* refs;            // global triangle ids
-    const int2* tri_box;        // per GLOBAL triangle id: the box of voxels that list it, (lo, hi) packed x | y << 10 | z << 20 (k_trace_emu)
+    const int2* tri_box;        // per GLOBAL triangle id: the box of voxels that list it, (lo, hi) packed x | y << 10 | z << 20, indices < 512 (trace_emu.cu)
     const BvhNode* nodes;       // all BLAS nodes, then the TLAS nodes
     const LeafTri* bvh_tris;    // triangles in BVH leaf order
     const int* bvh_tri_id;      // leaf-order position -> global triangle id (build-time input of k_gather_tris; the kernels read LeafTri::id)
@@ -111,6 +112,15 @@ struct SceneDev {
     float prune;                // relative slack of cross-instance pruning (1.0001), +inf when some model's matrices are not inverses
 };
 
+// PTAP_ACCEL_GRID_EMULATED: what k_trace_emu hands to k_emu_replay for every wavefront slot, and the list of slots for the walk itself
+struct EmuBuf {
+    int* n;                     // [slot] hits of the ray in its nearest model (> kEmuHits: not all kept - the walk answers that ray)
+    int* id;                    // [hit][slot] their global triangle ids (stride slots per hit)
+    float* t;                   // [hit][slot] their model-space t
+    int* list;                  // slots that k_trace_grid must answer (FrameState::n_replay of them)
+    int stride;
+};
+
 struct WaveDev {
     float4* O[2];               // (orig.xyz, bits(ipixel)) ping-pong
     float4* D[2];               // (dir.xyz, unused)
@@ -118,7 +128,7 @@ struct WaveDev {
     float4* hit;                // (dist, bits(tri), bits(model), t_model) per slot; dist < 0: hit whose exact distance the consumer evaluates
     float4* hit_cache;          // round-0 hits (first-hit cache, Renderer.cpp:594-613)
     float2* uv;                 // parity entry only
-    int* replay;                // k_trace_emu: slots of the round that the grid walk itself must answer (N ints; null unless PTAP_ACCEL_GRID_EMULATED)
+    EmuBuf emu;                 // PTAP_ACCEL_GRID_EMULATED only (api.cu: ensureEmuBuffers), else null pointers
     float* film;                // W*H*3 running sum (Pixel, Primitive.h:145-148)
     float* contrib;             // multi-lane rendering: this iteration's sqrt(throughput) per pixel, added to the film in iteration order; else null
     unsigned long long* tile_status;   // k_scan look-back words: rounds x 2048-slot scan blocks

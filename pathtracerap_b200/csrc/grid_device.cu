@@ -154,7 +154,7 @@ __global__ void k_tribox_finish(const TriAcc* __restrict__ acc, int ntris, int2*
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntris) return;
     const TriAcc a = acc[t];
-    if (a.cnt == 0) { tri_box[t] = make_int2(0x3fffffff, 0); return; }          // listed nowhere: lo > hi on every axis, no voxel is inside
+    if (a.cnt == 0) { tri_box[t] = make_int2(511 | (511 << 10) | (511 << 20), 0); return; }   // listed nowhere: lo > hi on every axis, no voxel is inside
     const long long vol = (long long)(a.hi[0] - a.lo[0] + 1) * (a.hi[1] - a.lo[1] + 1) * (a.hi[2] - a.lo[2] + 1);
     if (vol != (long long)a.cnt) *bad = 1;
     tri_box[t] = make_int2(a.lo[0] | (a.lo[1] << 10) | (a.lo[2] << 20), a.hi[0] | (a.hi[1] << 10) | (a.hi[2] << 20));
@@ -166,7 +166,7 @@ int gridTriBoxes(const int2* cells, const int* refs, int ngrids, const int* grid
                  int* grid_tri_range_host, int* ok, cudaStream_t stream)
 {
     *ok = 0;
-    if (ngrids <= 0 || ntris <= 0 || gx > 1023 || gy > 1023 || gz > 1023) return cudaSuccess;      // 10 bits per packed index
+    if (ngrids <= 0 || ntris <= 0 || gx > 512 || gy > 512 || gz > 512) return cudaSuccess;      // 9 bits per packed index + a guard bit (trace_emu.cu)
     TriAcc* acc = nullptr; int* d_small = nullptr;       // d_small: first cells, grid ranges, the flag
     cudaError_t e = cudaMalloc(&acc, (size_t)ntris * sizeof(TriAcc));
     if (e == cudaSuccess) e = cudaMalloc(&d_small, ((size_t)3 * ngrids + 1) * sizeof(int));

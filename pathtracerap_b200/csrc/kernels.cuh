@@ -48,9 +48,10 @@ __device__ __forceinline__ float exactHitDistance(const SceneDev& sc, V3 bo, V3 
 // list (may be null): walk only the slots list[0 .. st->n_replay[round]) - the second launch of PTAP_ACCEL_GRID_EMULATED.
 void launchTraceGrid(const SceneDev& sc, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, bool count_totals,
                      FrameState* st, int round, int n_fixed, int grid, cudaStream_t stream, unsigned long long* stamp = nullptr, const int* list = nullptr);
-// trace_emu.cu: the results of the grid walk (tier R0) through the BVH; slots it cannot answer are appended to `replay`
+// trace_emu.cu: the results of the grid walk (tier R0) through the BVH, in two launches: nearest model + all of the ray's hits in it,
+// then the replay of the walk over those hits; slots the replay cannot confirm are appended to emu.list for launchTraceGrid(list)
 void launchTraceEmu(const SceneDev& sc, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, bool count_totals,
-                    FrameState* st, int round, int n_fixed, int grid, cudaStream_t stream, unsigned long long* stamp, int* replay);
+                    FrameState* st, int round, int n_fixed, int grid, int grid_replay, cudaStream_t stream, unsigned long long* stamp, const EmuBuf& emu);
 int traceEmuOccupancy();
 // grid_device.cu: per-triangle voxel boxes of the grids on the device + the checks that make the emulation exact; *ok = 0 when some list is
 // not what a box-shaped registration produces (the caller then keeps the walk).  grid_tri_range: 2 ints per grid (lowest / highest listed id).

@@ -6,23 +6,30 @@
 // nearest hit among the triangles it happened to test.  0.3-0.6 % of the rays get a different answer than brute force, and the drop-in
 // Renderer has to reproduce those too.  Walking the grid costs ~40 voxels and ~32 triangle tests per ray in eleven models (k_trace_grid:
 // 940 warp instructions per ray at 12.6 of 32 lanes, issue-bound; three attempts to make the walk itself cheaper bought nothing,
-// profiles/r02).  This kernel computes the SAME answer from two facts:
-//   1. only triangles the ray actually hits (predicate true, Renderer.cpp:174-215) influence the walk: a miss neither sets the voxel's hit
-//      flag nor updates the nearest hit.  The set H of ALL hits of a (ray, model) is what an any-hit BVH traversal returns (typically 0-3
-//      triangles), and a model the ray hits nowhere cannot report a hit whatever its walk does - so the nine of eleven models that the
-//      reference sets up and slab-tests per ray are never touched here (TLAS), and most of the others end with H empty.
+// profiles/r02).  The same answer follows from three facts:
+//   1. Only triangles the ray actually hits (predicate true, Renderer.cpp:174-215) influence a walk: a miss neither sets the voxel's hit
+//      flag nor updates the nearest hit.  Every model's answer is therefore one of the ray's real hits, and no answer can be nearer than
+//      the exact closest hit D* (tier R1: model m*, parameter t*).
 //   2. Scene::addMeshesToGrid lists a triangle in every voxel of an index BOX (Scene.cpp:357-374); grid_device.cu derives that box per
-//      triangle from the lists on the device and verifies the shape.  "Does voxel v list a triangle of H" is then |H| box tests, so the
-//      walk can be REPLAYED without reading a voxel or testing a triangle: the reference's own slab test, entry point, entry voxel and
-//      DDA stepping (every operation un-contracted, as in k_trace_grid), its hit-voxel bookkeeping and its early exit, with the hits of H
-//      taking effect in the order the walk meets them (first voxel along the path that lists them, ascending triangle id inside a voxel:
-//      that order decides exact-t ties, Renderer.cpp:209).  The replay stops as soon as every box of H is behind the walk.
-// Cross-model bookkeeping (model t -> world distance, nearest model, ties to the lower model index) is k_trace_bvh's.
-// A (ray, model) with more than kEmuHits hits is not replayed: the ray is appended to a list and the walk itself (k_trace_grid in list
-// mode) answers it in a second launch, so the result is exact whatever the geometry.  api.cu refuses this mode (and keeps the walk) when
-// the lists on the device are not box-shaped, not ascending, or list triangles outside the mesh of a model that uses the grid.
-// Parity: tests/test_gpu_emulated.py (bit-equal to the oracle's R0 and to k_trace_grid on every fixture, the production path round by
-// round, and a scene that forces the overflow path).
+//      triangle from the lists on the device and verifies the shape.  Given the set H of ALL hits of the ray in one model (typically 1-4
+//      triangles), "does voxel v list a triangle the ray hits" is |H| box tests, so that model's walk can be REPLAYED without reading a
+//      voxel or testing a triangle: the reference's own slab test, entry point, entry voxel and DDA stepping (every operation
+//      un-contracted, as in k_trace_grid), its hit-voxel bookkeeping and early exit, the hits of H taking effect in the order the walk
+//      meets them (first voxel along the path that lists them, ascending triangle id inside a voxel: that order decides exact-t ties).
+//   3. If the replayed walk of m* returns t* (bit for bit), the reference's answer for the ray is m* with the walk's triangle: every other
+//      model's answer is a real hit, hence not nearer, and a model with a lower index that tied at D* would itself have been m*
+//      (the closest-hit rule breaks ties towards the lower model index exactly as Renderer.cpp:393 does in model order).
+// Two launches: k_trace_emu is k_trace_bvh's state machine (TLAS pruning by the nearest hit so far, cross-instance ranking, deferred exact
+// distance) except that inside an instance the ray interval never shrinks and every hit is recorded; the hits of the currently nearest
+// instance are kept (two buffers in shared memory that swap roles) and written out with the closest hit.  k_emu_replay then runs one
+// thread per slot - full SIMT width, where the same loop inside the traversal kernel ran with two or three lanes and made the first
+// version of this file slower than the walk - and either confirms the hit (fixing the triangle id when the walk's tie rule differs) or
+// appends the slot to a list.  Rays on the list - those where the walk misses the closest hit (the 0.3-0.6 %), and any (ray, model) with
+// more than kEmuHits hits - are answered by the walk itself (k_trace_grid in list mode, third launch), so the result is exact whatever
+// the geometry.  api.cu refuses this mode (and keeps the walk) when the lists on the device are not box-shaped, not ascending, or list
+// triangles outside the mesh of a model that uses the grid.
+// Parity: tests/test_gpu_emulated.py, tests/test_gpu_production.py[emu] (bit-equal to the oracle's R0 and to k_trace_grid: fixtures, random
+// rays, every round of the production path, whole films, and scenes that force the list path).
 #include "bvh_traverse.cuh"
 
 namespace ptap {
@@ -34,34 +41,29 @@ namespace {
 #ifndef PTAP_EMU_MIN_CTAS
 #define PTAP_EMU_MIN_CTAS 7
 #endif
-#ifndef PTAP_EMU_HITS
-#define PTAP_EMU_HITS 8
-#endif
-constexpr int kEmuHits = PTAP_EMU_HITS;       // hits of one (ray, model) kept for the replay
 constexpr int kEmuStack = 12;                 // traversal-stack entries per ray in shared memory (as k_trace_bvh)
-static_assert(kEmuHits >= 1 && kEmuHits <= 31, "hit slots are tracked in 32-bit masks");
+constexpr unsigned kGuard = 0x20080200u;      // bits 9, 19, 29: one guard bit above each 9-bit voxel index of a packed (x | y << 10 | z << 20)
 
 }  // namespace
 
-template <bool UV, bool COUNT>
+// ---- launch 1: exact closest hit + all hits of the ray in the nearest model ------------------------------------------------------------
+template <bool COUNT>
 __global__ void __launch_bounds__(kTraceBlock, PTAP_EMU_MIN_CTAS)
 k_trace_emu(SceneDev sc, const float4* __restrict__ O, const float4* __restrict__ D, float4* __restrict__ hit,
-            float2* __restrict__ uv, int4* __restrict__ counts, FrameState* st, int round, int n_fixed, unsigned long long* __restrict__ stamp,
-            int* __restrict__ replay)
+            int4* __restrict__ counts, FrameState* st, int round, int n_fixed, unsigned long long* __restrict__ stamp, EmuBuf emu)
 {
     const int n = n_fixed >= 0 ? n_fixed : st->n_active[round];
     if (blockIdx.x == 0 && threadIdx.x == 0 && n_fixed < 0) st->rays_traced += (unsigned long long)n;
     if (stamp && threadIdx.x == 0) atomicMin(stamp, globalTimerNs());
     unsigned int* cursor = &st->fetch[round];
     const int lane = threadIdx.x & 31;
-    const int GX = sc.gx, GY = sc.gy, GZ = sc.gz;
-    unsigned long long tot_x = 0, tot_y = 0, tot_z = 0;
-    int4 cnt = make_int4(0, 0, 0, 0);      // counting build: nodes visited, voxels replayed, triangles tested
+    unsigned long long tot_x = 0, tot_z = 0;
+    int4 cnt = make_int4(0, 0, 0, 0);      // counting build: nodes visited, (voxels replayed: launch 2), triangles tested
 
     if (sc.tlas_root < 0) {                            // no instance has triangles: every ray misses
         for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
             hit[k] = make_float4(kFloatMax, __int_as_float(-1), __int_as_float(-1), 0.0f);
-            if (UV && uv) uv[k] = make_float2(0.0f, 0.0f);
+            emu.n[k] = 0;
             if (COUNT && counts) counts[k] = cnt;
         }
         return;
@@ -72,13 +74,15 @@ k_trace_emu(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
     int l_stack[kBvhStack - kEmuStack];
     auto push = [&](int v) { if (sp < kEmuStack) s_stack[sp * kTraceBlock + threadIdx.x] = v; else l_stack[sp - kEmuStack] = v; ++sp; };
     auto pop = [&]() { --sp; return sp < kEmuStack ? s_stack[sp * kTraceBlock + threadIdx.x] : l_stack[sp - kEmuStack]; };
-    // H: the hits of the current (ray, model), [slot][thread] like the stack: triangle id, t, and the triangle's voxel box
-    __shared__ int s_id[kEmuHits * kTraceBlock];
-    __shared__ float s_t[kEmuHits * kTraceBlock];
-    __shared__ int2 s_box[kEmuHits * kTraceBlock];
-    float l_u[UV ? kEmuHits : 1], l_v[UV ? kEmuHits : 1];
-    int nh = 0;                                      // hits of the current model (may exceed kEmuHits: then the ray goes to the walk)
-    bool overflow = false;
+    // the hits of the instance being traversed and of the nearest instance so far: two buffers [buffer][hit][thread] that swap roles
+    __shared__ int s_id[2 * kEmuHits * kTraceBlock];
+    __shared__ float s_t[2 * kEmuHits * kTraceBlock];
+    int cur = 0, nh = 0, nh_best = 0;                // buffer being filled; hits of the current instance / of the nearest one (may exceed kEmuHits)
+    // Fact 3 needs "no model answers nearer than its own closest hit".  A walk's answer t' >= t_min can only be nearer in DISTANCE |t'| when
+    // t_min < 0 (the predicate accepts hits up to EPSILON behind the origin) and the model has a second hit: such an instance is
+    // `ambiguous`.  As the nearest model it is settled by its replay; anywhere else it sends the ray to the walk.
+    int n_amb = 0; bool best_amb = false;
+    float c_t = kFloatMax; int c_tri = -1;           // closest hit of the current instance (Renderer.cpp:209 over every triangle: tier R1)
 
     int node = kDone, i = -1;
     V3 bo = v3(0, 0, 0), bd = v3(0, 0, 0);          // the ray as stored (Ray::base, Primitive.h:160-164)
@@ -86,7 +90,7 @@ k_trace_emu(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
     unsigned near_off = 0u, wnear_off = 0u;
     V3 ro = v3(0, 0, 0), rd = v3(0, 0, 1), rinv = v3(0, 0, 0);   // the ray of the current level: world, or model space of the entered instance (exact)
     float tmin = 0.0f, tmax = 0.0f;
-    float g_dist = kFloatMax, g_t = 0.0f, g_u = 0.0f, g_v = 0.0f;
+    float g_dist = kFloatMax, g_t = 0.0f;
     int g_model = -1, g_tri = -1;
     int w_next = 0, w_end = 0;
     bool exhausted = false;
@@ -129,13 +133,13 @@ k_trace_emu(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
             const bool reject = (xabs(xsub(det, 0.0f)) < kEpsilon) | (u < (0.0f - kEpsilon)) | (u > (1.0f + kEpsilon)) |
                                 (v < (0.0f - kEpsilon)) | (xadd(u, v) > (1.0f + kEpsilon)) | (t < (0.0f - kEpsilon));
             if (!reject) {
+                const int id = __float_as_int(tb.v[1]);
                 if (nh < kEmuHits) {
-                    const int id = __float_as_int(tb.v[1]);
-                    const int slot = nh * kTraceBlock + threadIdx.x;
-                    s_id[slot] = id; s_t[slot] = t; s_box[slot] = __ldg(&sc.tri_box[id]);
-                    if (UV) { l_u[nh] = u; l_v[nh] = v; }
+                    const int slot = ((cur * kEmuHits + nh) * kTraceBlock) + threadIdx.x;
+                    s_id[slot] = id; s_t[slot] = t;
                 }
                 ++nh;
+                if (t < c_t || (t == c_t && c_tri >= 0 && id < c_tri)) { c_t = t; c_tri = id; }      // brute force in index order
             }
             if (code & 7u) node = (int)~(code + 7u); else node = pop();
         }
@@ -153,92 +157,20 @@ k_trace_emu(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
             const float wil = rsqrtf(bd.x * bd.x + bd.y * bd.y + bd.z * bd.z);
             tmin = -(kEpsilon + 1e-4f);                                         // the predicate accepts t >= -EPSILON
             tmax = 3.0e38f;                                                     // all hits: a far one can keep the walk going until it meets a near one
-            nh = 0;
+            nh = 0; c_t = kFloatMax; c_tri = -1;
             push(__float_as_int(__fdividef(1.0f, mlen * wil)));                  // world distance per unit of model-space t, for the exit step
             push((int)~(kExitBit | (unsigned)im));
             node = __float_as_int(__ldg(&inst->grid.z));                        // BLAS root of the instance's mesh
         }
-        // ---- (3c) marker popped: leave instance `im`.  Replay the reference's walk over the hits found (Renderer.cpp:238-360), then the
-        // nearest-model decision (Renderer.cpp:388-398) as k_trace_bvh makes it
+        // ---- (3c) marker popped: leave instance `im`; nearest-model decision (Renderer.cpp:388-398) exactly as k_trace_bvh makes it
         if (s_exit && n_exit >= min(vote_inst, n_inner)) {
             const int im = (int)(code & kIndexMask);
             const float ascale = __int_as_float(pop());
             const float cb = sc.c_pad + 1e-4f * (fabsf(bo.x) + fabsf(bo.y) + fabsf(bo.z));
-            int w_tri = -1; float w_t = kFloatMax, w_u = 0.0f, w_v = 0.0f;
-            if (nh > kEmuHits) overflow = true;
-            else if (nh > 0) {
-                const InstanceTrace* __restrict__ inst = &sc.inst[im];
-                const float4 bbmin_wx = ldg4(&inst->bb_min), bbmax_wy = ldg4(&inst->bb_max), gridrec = ldg4(&inst->grid);
-                const V3 mn = v3(bbmin_wx), mx = v3(bbmax_wy);
-                const V3 inv = v3(xdiv(1.0f, rd.x), xdiv(1.0f, rd.y), xdiv(1.0f, rd.z));   // Renderer.cpp:383
-                // Renderer.cpp:150-170
-                const float t1 = rd.x == 0.0f ? kFloatMin : xmul(xsub(mn.x, ro.x), inv.x);
-                const float t2 = rd.x == 0.0f ? kFloatMax : xmul(xsub(mx.x, ro.x), inv.x);
-                const float t3 = rd.y == 0.0f ? kFloatMin : xmul(xsub(mn.y, ro.y), inv.y);
-                const float t4 = rd.y == 0.0f ? kFloatMax : xmul(xsub(mx.y, ro.y), inv.y);
-                const float t5 = rd.z == 0.0f ? kFloatMin : xmul(xsub(mn.z, ro.z), inv.z);
-                const float t6 = rd.z == 0.0f ? kFloatMax : xmul(xsub(mx.z, ro.z), inv.z);
-                const float sl_min = max_std(max_std(min_std(t1, t2), min_std(t3, t4)), min_std(t5, t6));
-                const float sl_max = min_std(min_std(max_std(t1, t2), max_std(t3, t4)), max_std(t5, t6));
-                const V3 p = xadd(ro, xscale(rd, sl_min));
-                if (!(sl_max < 0 || sl_min > sl_max) &&
-                    !(xsub(p.x, mn.x) < -kEpsilon || xsub(p.y, mn.y) < -kEpsilon || xsub(p.z, mn.z) < -kEpsilon)) {      // Renderer.cpp:252-259
-                    const float wx = bbmin_wx.w, wy = bbmax_wy.w, wz = gridrec.x;
-                    int ix = f2i_x86(xdiv(xabs(xadd(xsub(p.x, mn.x), kEpsilon)), wx));
-                    int iy = f2i_x86(xdiv(xabs(xadd(xsub(p.y, mn.y), kEpsilon)), wy));
-                    int iz = f2i_x86(xdiv(xabs(xadd(xsub(p.z, mn.z), kEpsilon)), wz));
-                    ix = min(max(ix, 0), GX - 1); iy = min(max(iy, 0), GY - 1); iz = min(max(iz, 0), GZ - 1);
-                    float tmx = kFloatMax, tmy = kFloatMax, tmz = kFloatMax, dx = kFloatMax, dy = kFloatMax, dz = kFloatMax;
-                    if (rd.x != 0) { const int nx = rd.x > 0.0f ? ix + 1 : ix; dx = xabs(xmul(wx, inv.x)); tmx = xmul(xsub(xadd(mn.x, xmul((float)nx, wx)), p.x), inv.x); }
-                    if (rd.y != 0) { const int ny = rd.y > 0.0f ? iy + 1 : iy; dy = xabs(xmul(wy, inv.y)); tmy = xmul(xsub(xadd(mn.y, xmul((float)ny, wy)), p.y), inv.y); }
-                    if (rd.z != 0) { const int nz = rd.z > 0.0f ? iz + 1 : iz; dz = xabs(xmul(wz, inv.z)); tmz = xmul(xsub(xadd(mn.z, xmul((float)nz, wz)), p.z), inv.z); }
-                    const bool px = rd.x > 0.0f, py = rd.y > 0.0f, pz = rd.z > 0.0f;
-                    const unsigned all = (1u << nh) - 1u;
-                    unsigned seen = 0u, gone = 0u;      // hits already met by the walk / hits whose box the walk has passed for good
-                    int cx = 0, cy = 0, cz = 0, best_k = -1;
-                    bool inter = false;
-                    for (int k = 0;; ++k) {
-                        if (COUNT) cnt.y++;
-                        bool any = false;
-                        for (int j = 0; j < nh; ++j) {
-                            if ((gone >> j) & 1u) continue;
-                            const int slot = j * kTraceBlock + threadIdx.x;
-                            const int2 bx = s_box[slot];
-                            const int lox = bx.x & 1023, loy = (bx.x >> 10) & 1023, loz = bx.x >> 20, hix = bx.y & 1023, hiy = (bx.y >> 10) & 1023, hiz = bx.y >> 20;
-                            if (ix >= lox && ix <= hix && iy >= loy && iy <= hiy && iz >= loz && iz <= hiz) {
-                                any = true;                                        // the voxel lists a triangle the ray hits (Renderer.cpp:217-236)
-                                if (!((seen >> j) & 1u)) {                         // its first test: the only one that can update the nearest hit
-                                    seen |= 1u << j;
-                                    const float t = s_t[slot]; const int id = s_id[slot];
-                                    if (w_t > t || (w_t == t && best_k == k && id < w_tri)) {      // Renderer.cpp:209, lists ascend inside a voxel
-                                        w_t = t; w_tri = id; best_k = k;
-                                        if (UV) { w_u = l_u[j]; w_v = l_v[j]; }
-                                    }
-                                }
-                            } else if ((px ? ix > hix : ix < lox) || (py ? iy > hiy : iy < loy) || (pz ? iz > hiz : iz < loz)) gone |= 1u << j;   // indices move one way only
-                        }
-                        if (any) { cx = ix; cy = iy; cz = iz; inter = true; }
-                        if (inter && (abs(cx - ix) > 2 || abs(cy - iy) > 2 || abs(cz - iz) > 2)) break;     // Renderer.cpp:326-329
-                        if (gone == all) break;        // no voxel ahead lists a hit triangle: the walk ends with what it has (`return is_intersect`)
-                        if (tmx < tmy && tmx < tmz) {                                                     // Renderer.cpp:331-357
-                            ix += px ? 1 : -1;
-                            if (ix == (px ? GX : -1) || tmx >= kFloatMax) break;
-                            tmx = xadd(tmx, dx);
-                        } else if (tmy < tmz) {
-                            iy += py ? 1 : -1;
-                            if (iy == (py ? GY : -1) || tmy >= kFloatMax) break;
-                            tmy = xadd(tmy, dy);
-                        } else {
-                            iz += pz ? 1 : -1;
-                            if (iz == (pz ? GZ : -1) || tmz >= kFloatMax) break;
-                            tmz = xadd(tmz, dz);
-                        }
-                    }
-                    // (w_tri < 0 although some voxel had a hit: only hits at t >= FLOAT_MAX, which never become the nearest one)
-                }
-            }
-            if (w_tri >= 0) {
-                const float a = fabsf(w_t * ascale);
+            const bool amb = c_tri >= 0 && c_t < 0.0f && nh >= 2;
+            if (amb) ++n_amb;
+            if (c_tri >= 0) {
+                const float a = fabsf(c_t * ascale);
                 const float a_lo = a - (fabsf(a) * sc.tie + cb), a_hi = a + (fabsf(a) * sc.tie + cb);
                 const float g_lo = g_dist - (g_dist * sc.tie + cb), g_hi = g_dist + (g_dist * sc.tie + cb);
                 bool take;
@@ -246,18 +178,19 @@ k_trace_emu(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
                 if (a_hi < g_lo && a_hi < 0.99f * kFloatMax) take = true;
                 else if (g_model >= 0 && a_lo > g_hi) take = false;
                 else {                                                           // near-tie, or no usable bound: the reference's comparison
-                    const float dn = exactHitDistance(sc, bo, bd, im, w_t);
+                    const float dn = exactHitDistance(sc, bo, bd, im, c_t);
                     const float dg = g_model >= 0 ? exactHitDistance(sc, bo, bd, g_model, g_t) : kFloatMax;
                     take = dg > dn || (dg == dn && g_model >= 0 && im < g_model);   // Renderer.cpp:393 in model order
                     nd = dn;
                     if (!take && g_model >= 0) g_dist = dg;
                 }
                 if (take) {
-                    g_dist = nd; g_model = im; g_tri = w_tri; g_t = w_t;
-                    if (UV) { g_u = w_u; g_v = w_v; }
+                    g_dist = nd; g_model = im; g_tri = c_tri; g_t = c_t;
+                    nh_best = nh; cur ^= 1;                                      // the buffer just filled is kept; the next instance fills the other
+                    best_amb = amb;
                 }
             }
-            nh = 0;
+            nh = 0; c_t = kFloatMax; c_tri = -1;
             ro = bo; rinv = winv; near_off = wnear_off;
             tmin = sc.tmin_world; tmax = worldBound(g_dist, sc.prune, cb);
             node = pop();
@@ -266,11 +199,17 @@ k_trace_emu(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
         if (n_done > 0 && n_done >= min(vote_refill, n_inner)) {
             const unsigned m_done = __ballot_sync(kFull, s_done && live);
             if (s_done && i >= 0) {
-                const bool found = g_dist < kFloatMax;
+                const bool found = g_model >= 0;
                 hit[i] = make_float4(found ? -1.0f : kFloatMax, __int_as_float(found ? g_tri : -1), __int_as_float(found ? g_model : -1), g_t);
-                if (UV && uv) uv[i] = make_float2(g_u, g_v);
-                if (COUNT) { if (counts) counts[i] = cnt; tot_x += cnt.x; tot_y += cnt.y; tot_z += cnt.z; }
-                if (overflow) replay[atomicAdd(&st->n_replay[round], 1u)] = i;      // the walk itself answers this one (second launch)
+                emu.n[i] = !found ? 0 : n_amb > (best_amb ? 1 : 0) ? kEmuHits + 1 : nh_best;      // > kEmuHits: not replayed, the walk answers
+                if (found && nh_best > 1) {                                      // a single hit is the one in the hit record
+                    const int kept = min(nh_best, kEmuHits), base = (cur ^ 1) * kEmuHits;
+                    for (int j = 0; j < kept; ++j) {
+                        const int slot = (base + j) * kTraceBlock + threadIdx.x;
+                        emu.id[(size_t)j * emu.stride + i] = s_id[slot]; emu.t[(size_t)j * emu.stride + i] = s_t[slot];
+                    }
+                }
+                if (COUNT) { if (counts) counts[i] = cnt; tot_x += cnt.x; tot_z += cnt.z; }
                 i = -1;
             }
             if (w_next >= w_end && !exhausted) {
@@ -291,8 +230,8 @@ k_trace_emu(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
                 wnear_off = nearOffsets(bd);
                 ro = bo; rinv = winv; near_off = wnear_off;
                 tmin = sc.tmin_world; tmax = 3.0e38f;
-                g_dist = kFloatMax; g_model = -1; g_tri = -1; g_t = 0.0f; g_u = 0.0f; g_v = 0.0f;
-                nh = 0; overflow = false;
+                g_dist = kFloatMax; g_model = -1; g_tri = -1; g_t = 0.0f;
+                nh = 0; nh_best = 0; c_t = kFloatMax; c_tri = -1; n_amb = 0; best_amb = false;
                 if (COUNT) cnt = make_int4(0, 0, 0, 0);
                 sp = 0; push(kDone);
                 node = sc.tlas_root;
@@ -303,25 +242,153 @@ k_trace_emu(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
     if (stamp && (threadIdx.x & 31) == 0) atomicMax(stamp + 1, globalTimerNs());
     if (COUNT) {
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            tot_x += __shfl_xor_sync(kFull, tot_x, d); tot_y += __shfl_xor_sync(kFull, tot_y, d); tot_z += __shfl_xor_sync(kFull, tot_z, d);
+        for (int d = 16; d > 0; d >>= 1) { tot_x += __shfl_xor_sync(kFull, tot_x, d); tot_z += __shfl_xor_sync(kFull, tot_z, d); }
+        if (lane == 0) { atomicAdd(&st->count_nodes, tot_x); atomicAdd(&st->count_tris, tot_z); }
+    }
+}
+
+// ---- launch 2: replay the walk of the nearest model over its hits (Renderer.cpp:238-360); one thread per slot --------------------------
+template <bool UV, bool COUNT>
+__global__ void __launch_bounds__(256)
+k_emu_replay(SceneDev sc, const float4* __restrict__ O, const float4* __restrict__ D, float4* __restrict__ hit, float2* __restrict__ uv,
+             int4* __restrict__ counts, FrameState* st, int round, int n_fixed, EmuBuf emu)
+{
+    const int n = n_fixed >= 0 ? n_fixed : st->n_active[round];
+    const int GX = sc.gx, GY = sc.gy, GZ = sc.gz;
+    unsigned long long steps_total = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 h = hit[i];
+        const int im = __float_as_int(h.z);
+        if (im < 0) { if (UV && uv) uv[i] = make_float2(0.0f, 0.0f); continue; }      // no real hit: no walk finds one
+        const int nh = emu.n[i];
+        const float t_star = h.w;
+        int w_tri = -1; float w_t = kFloatMax;
+        int steps = 0;
+        const V3 bo = v3(O[i]), bd = v3(D[i]);
+        const InstanceTrace* __restrict__ inst = &sc.inst[im];
+        const float4 w0 = ldg4(&inst->w2m[0]), w1 = ldg4(&inst->w2m[1]), w2 = ldg4(&inst->w2m[2]);
+        const V3 ro = xmat4(w0, w1, w2, bo, 1.0f);                               // Renderer.cpp:381
+        const V3 rd = xnormalize(xmat4(w0, w1, w2, bd, 0.0f));                   // Renderer.cpp:382
+        if (nh <= kEmuHits) {
+            // the hits and their voxel boxes; U = the box around all of them (nothing can happen to the walk outside it)
+            int ids[kEmuHits]; float ts[kEmuHits]; unsigned lo[kEmuHits], hi[kEmuHits];
+            unsigned ulo = 0x1ff | (0x1ff << 10) | (0x1ff << 20), uhi = 0u;
+            for (int j = 0; j < nh; ++j) {
+                if (nh == 1) { ids[0] = __float_as_int(h.y); ts[0] = t_star; }
+                else { ids[j] = emu.id[(size_t)j * emu.stride + i]; ts[j] = emu.t[(size_t)j * emu.stride + i]; }
+                const int2 bx = __ldg(&sc.tri_box[ids[j]]);
+                lo[j] = (unsigned)bx.x; hi[j] = (unsigned)bx.y;
+                if (((hi[j] | kGuard) - lo[j] & kGuard) == kGuard) {            // listed somewhere (lo <= hi on every axis)
+                    ulo = min(ulo & 0x1ffu, lo[j] & 0x1ffu) | min(ulo & (0x1ffu << 10), lo[j] & (0x1ffu << 10)) | min(ulo & (0x1ffu << 20), lo[j] & (0x1ffu << 20));
+                    uhi = max(uhi & 0x1ffu, hi[j] & 0x1ffu) | max(uhi & (0x1ffu << 10), hi[j] & (0x1ffu << 10)) | max(uhi & (0x1ffu << 20), hi[j] & (0x1ffu << 20));
+                }
+            }
+            const float4 bbmin_wx = ldg4(&inst->bb_min), bbmax_wy = ldg4(&inst->bb_max), gridrec = ldg4(&inst->grid);
+            const V3 mn = v3(bbmin_wx), mx = v3(bbmax_wy);
+            const V3 inv = v3(xdiv(1.0f, rd.x), xdiv(1.0f, rd.y), xdiv(1.0f, rd.z));   // Renderer.cpp:383
+            // Renderer.cpp:150-170
+            const float t1 = rd.x == 0.0f ? kFloatMin : xmul(xsub(mn.x, ro.x), inv.x);
+            const float t2 = rd.x == 0.0f ? kFloatMax : xmul(xsub(mx.x, ro.x), inv.x);
+            const float t3 = rd.y == 0.0f ? kFloatMin : xmul(xsub(mn.y, ro.y), inv.y);
+            const float t4 = rd.y == 0.0f ? kFloatMax : xmul(xsub(mx.y, ro.y), inv.y);
+            const float t5 = rd.z == 0.0f ? kFloatMin : xmul(xsub(mn.z, ro.z), inv.z);
+            const float t6 = rd.z == 0.0f ? kFloatMax : xmul(xsub(mx.z, ro.z), inv.z);
+            const float sl_min = max_std(max_std(min_std(t1, t2), min_std(t3, t4)), min_std(t5, t6));
+            const float sl_max = min_std(min_std(max_std(t1, t2), max_std(t3, t4)), max_std(t5, t6));
+            const V3 p = xadd(ro, xscale(rd, sl_min));
+            if (!(sl_max < 0 || sl_min > sl_max) &&
+                !(xsub(p.x, mn.x) < -kEpsilon || xsub(p.y, mn.y) < -kEpsilon || xsub(p.z, mn.z) < -kEpsilon)) {      // Renderer.cpp:252-259
+                const float wx = bbmin_wx.w, wy = bbmax_wy.w, wz = gridrec.x;
+                int ix = f2i_x86(xdiv(xabs(xadd(xsub(p.x, mn.x), kEpsilon)), wx));
+                int iy = f2i_x86(xdiv(xabs(xadd(xsub(p.y, mn.y), kEpsilon)), wy));
+                int iz = f2i_x86(xdiv(xabs(xadd(xsub(p.z, mn.z), kEpsilon)), wz));
+                ix = min(max(ix, 0), GX - 1); iy = min(max(iy, 0), GY - 1); iz = min(max(iz, 0), GZ - 1);
+                float tmx = kFloatMax, tmy = kFloatMax, tmz = kFloatMax, dx = kFloatMax, dy = kFloatMax, dz = kFloatMax;
+                if (rd.x != 0) { const int nx = rd.x > 0.0f ? ix + 1 : ix; dx = xabs(xmul(wx, inv.x)); tmx = xmul(xsub(xadd(mn.x, xmul((float)nx, wx)), p.x), inv.x); }
+                if (rd.y != 0) { const int ny = rd.y > 0.0f ? iy + 1 : iy; dy = xabs(xmul(wy, inv.y)); tmy = xmul(xsub(xadd(mn.y, xmul((float)ny, wy)), p.y), inv.y); }
+                if (rd.z != 0) { const int nz = rd.z > 0.0f ? iz + 1 : iz; dz = xabs(xmul(wz, inv.z)); tmz = xmul(xsub(xadd(mn.z, xmul((float)nz, wz)), p.z), inv.z); }
+                const bool px = rd.x > 0.0f, py = rd.y > 0.0f, pz = rd.z > 0.0f;
+                // guard bits of the axes along which the voxel index grows / shrinks: "the walk has passed a box for good" is one mask test
+                const unsigned gpos = (px ? 1u << 9 : 0u) | (py ? 1u << 19 : 0u) | (pz ? 1u << 29 : 0u), gneg = kGuard ^ gpos;
+                const unsigned all = nh >= 32 ? 0xffffffffu : (1u << nh) - 1u;
+                unsigned seen = 0u, gone = 0u;      // hits already met by the walk / hits whose box the walk has passed for good
+                int cx = 0, cy = 0, cz = 0, best_k = -1;
+                bool inter = false;
+                for (int k = 0;; ++k) {
+                    ++steps;
+                    const unsigned v = (unsigned)ix | ((unsigned)iy << 10) | ((unsigned)iz << 20);
+                    bool any = false;
+                    const unsigned u1 = (v | kGuard) - ulo, u2 = (uhi | kGuard) - v;      // per axis: guard bit set <=> lo <= index / index <= hi
+                    if ((u1 & u2 & kGuard) == kGuard) {                                   // inside U: look at the hits one by one
+                        for (int j = 0; j < nh; ++j) {
+                            if ((gone >> j) & 1u) continue;
+                            const unsigned d1 = (v | kGuard) - lo[j], d2 = (hi[j] | kGuard) - v;
+                            if ((d1 & d2 & kGuard) == kGuard) {
+                                any = true;                                        // the voxel lists a triangle the ray hits (Renderer.cpp:217-236)
+                                if (!((seen >> j) & 1u)) {                         // its first test: the only one that can update the nearest hit
+                                    seen |= 1u << j;
+                                    if (w_t > ts[j] || (w_t == ts[j] && best_k == k && ids[j] < w_tri)) { w_t = ts[j]; w_tri = ids[j]; best_k = k; }   // Renderer.cpp:209
+                                }
+                            } else if ((~d2 & gpos) | (~d1 & gneg)) gone |= 1u << j;   // indices move one way only
+                        }
+                    } else if ((~u2 & gpos) | (~u1 & gneg)) gone = all;
+                    // t* is the smallest t of ALL the model's hits: once the walk has met a hit with that t nothing it does later can change
+                    // its answer's t, and a tie for the triangle is settled inside the voxel just closed - the rest of the walk is not needed
+                    if (w_t == t_star) break;
+                    if (any) { cx = ix; cy = iy; cz = iz; inter = true; }
+                    if (inter && (abs(cx - ix) > 2 || abs(cy - iy) > 2 || abs(cz - iz) > 2)) break;     // Renderer.cpp:326-329
+                    if (gone == all) break;        // no voxel ahead lists a hit triangle: the walk ends with what it has (`return is_intersect`)
+                    if (tmx < tmy && tmx < tmz) {                                                     // Renderer.cpp:331-357
+                        ix += px ? 1 : -1;
+                        if (ix == (px ? GX : -1) || tmx >= kFloatMax) break;
+                        tmx = xadd(tmx, dx);
+                    } else if (tmy < tmz) {
+                        iy += py ? 1 : -1;
+                        if (iy == (py ? GY : -1) || tmy >= kFloatMax) break;
+                        tmy = xadd(tmy, dy);
+                    } else {
+                        iz += pz ? 1 : -1;
+                        if (iz == (pz ? GZ : -1) || tmz >= kFloatMax) break;
+                        tmz = xadd(tmz, dz);
+                    }
+                }
+            }
         }
-        if (lane == 0) { atomicAdd(&st->count_nodes, tot_x); atomicAdd(&st->count_cells, tot_y); atomicAdd(&st->count_tris, tot_z); }
+        if (COUNT) { if (counts) counts[i].y = steps; steps_total += steps; }
+        if (w_tri >= 0 && w_t == t_star) {
+            // the walk of the nearest model finds the closest hit: that is the reference's answer (the triangle is the WALK's: its tie rule)
+            if (w_tri != __float_as_int(h.y)) hit[i] = make_float4(h.x, __int_as_float(w_tri), h.z, h.w);
+            if (UV && uv) {                                                          // barycentrics as the predicate computes them (Renderer.cpp:174-201)
+                const float4 a = ldg4(&sc.tris[w_tri].v0), b = ldg4(&sc.tris[w_tri].e1), c = ldg4(&sc.tris[w_tri].e2);
+                const V3 pvec = xcross(rd, v3(c));
+                const float invDet = xdiv(1.0f, xdot(v3(b), pvec));
+                const V3 tvec = xsub(ro, v3(a));
+                uv[i] = make_float2(xmul(xdot(tvec, pvec), invDet), xmul(xdot(rd, xcross(tvec, v3(b))), invDet));
+            }
+        } else emu.list[atomicAdd(&st->n_replay[round], 1u)] = i;                   // the walk itself answers this one (third launch)
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) steps_total += __shfl_xor_sync(0xffffffffu, steps_total, d);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&st->count_cells, steps_total);
     }
 }
 
 void launchTraceEmu(const SceneDev& sc, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, bool count_totals,
-                    FrameState* st, int round, int n_fixed, int grid, cudaStream_t stream, unsigned long long* stamp, int* replay)
+                    FrameState* st, int round, int n_fixed, int grid, int grid_replay, cudaStream_t stream, unsigned long long* stamp, const EmuBuf& emu)
 {
-    if (counts || count_totals) k_trace_emu<true, true><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, stamp, replay);
-    else if (uv) k_trace_emu<true, false><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, stamp, replay);
-    else k_trace_emu<false, false><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, stamp, replay);
+    const bool count = counts || count_totals;
+    if (count) k_trace_emu<true><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, counts, st, round, n_fixed, stamp, emu);
+    else k_trace_emu<false><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, counts, st, round, n_fixed, stamp, emu);
+    if (count) k_emu_replay<true, true><<<grid_replay, 256, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, emu);
+    else if (uv) k_emu_replay<true, false><<<grid_replay, 256, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, emu);
+    else k_emu_replay<false, false><<<grid_replay, 256, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, emu);
 }
 
 int traceEmuOccupancy()
 {
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_emu<false, false>, kTraceBlock, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_trace_emu<false>, kTraceBlock, 0);
     return nb;
 }
 

@@ -18,7 +18,7 @@ class Renderer:
     RESOLUTION_X, RESOLUTION_Y, ITER, DEPTH = 1000, 800, 500, 5
 
     def __init__(self, device: int = 0, width: int | None = None, height: int | None = None, iters: int | None = None,
-                 depth: int | None = None, accel: int = N.ACCEL_GRID_COMPAT, first_hit_cache: bool = True, profile: bool = False,
+                 depth: int | None = None, accel: int = N.ACCEL_GRID_EMULATED, first_hit_cache: bool = True, profile: bool = False,
                  arena_bytes: int = 0):
         self.W = width or self.RESOLUTION_X; self.H = height or self.RESOLUTION_Y
         self.iters = iters or self.ITER; self.depth = depth or self.DEPTH
@@ -39,7 +39,12 @@ class Renderer:
     def allocateOnGPU(self, scene: Scene):
         v = scene.view()
         self._check(N.lib().ptap_upload_scene(self.h, C.byref(v)), "allocateOnGPU/upload_scene")
-        self._check(N.lib().ptap_build_accel(self.h, self.accel), "allocateOnGPU/build_accel")
+        rc = N.lib().ptap_build_accel(self.h, self.accel)
+        if rc == N.E_UNSUPPORTED and self.accel == N.ACCEL_GRID_EMULATED:
+            # grids whose lists are not the box-shaped registrations of Scene.cpp:357-374: the same results by walking them
+            self.accel = N.ACCEL_GRID_COMPAT
+            rc = N.lib().ptap_build_accel(self.h, self.accel)
+        self._check(rc, "allocateOnGPU/build_accel")
         self._check(N.lib().ptap_set_render_params(self.h, self.W, self.H, self.depth, self.flags), "allocateOnGPU/set_render_params")
         self._iters_done = 0
 

@@ -92,6 +92,7 @@ def test_cpp_flow_matches_python_api(libptap, tmp_path):
     p = subprocess.run([exe], cwd=tmp_path, env=env, capture_output=True, text=True)
     assert p.returncode == 0, p.stderr
     assert "Full run:" in p.stdout
+    assert "emulated through the BVH" in p.stderr          # the default: the walk's results without the walk (PTAP_ACCEL_GRID_EMULATED)
     # the reference's per-iteration timing lines (Renderer.cpp:641-643), one per iteration, non-negative
     its = [l for l in p.stdout.splitlines() if l.startswith("Iteration ")]
     assert [l.split(":")[0] for l in its] == [f"Iteration {k + 1}" for k in range(IT)]
@@ -121,6 +122,7 @@ def test_cpp_flow_matches_python_api(libptap, tmp_path):
         write_bundled_objs(str(d2))
         p = subprocess.run([exe2], cwd=d2, env=dict(os.environ, PTAP_ITER="2"), capture_output=True, text=True)
         assert p.returncode == 0, p.stderr
+        assert "emulated through the BVH" in p.stderr      # the lists the reference's own Scene.cpp builds pass the shape checks
         r = Renderer(width=1000, height=800, iters=2, depth=5, accel=ACCEL_GRID_COMPAT)     # Config.h:12-13
         r.allocateOnGPU(Scene(None, root=str(d2)))
         r.renderLoop()
