@@ -213,12 +213,13 @@ int collect(ptap_ctx* ctx)
         FrameState f2;
         CK(cudaMemcpy(&f2, ctx->wvx[l].st, sizeof f2, cudaMemcpyDeviceToHost));
         const bool later = f2.iter_cur > fs.iter_cur && f2.paths > 0;
-        f2.rays_traced += fs.rays_traced; f2.paths += fs.paths;
+        f2.rays_traced += fs.rays_traced; f2.rays_walked += fs.rays_walked; f2.paths += fs.paths;
         f2.count_nodes += fs.count_nodes; f2.count_tris += fs.count_tris; f2.count_cells += fs.count_cells; f2.count_refs += fs.count_refs;
         if (later) fs = f2;
-        else { fs.rays_traced = f2.rays_traced; fs.paths = f2.paths; fs.count_nodes = f2.count_nodes; fs.count_tris = f2.count_tris; fs.count_cells = f2.count_cells; fs.count_refs = f2.count_refs; }
+        else { fs.rays_traced = f2.rays_traced; fs.rays_walked = f2.rays_walked; fs.paths = f2.paths; fs.count_nodes = f2.count_nodes; fs.count_tris = f2.count_tris; fs.count_cells = f2.count_cells; fs.count_refs = f2.count_refs; }
     }
     ctx->stats.rays_traced = (int64_t)fs.rays_traced;
+    ctx->stats.rays_walked = (int64_t)fs.rays_walked;
     ctx->stats.paths = (int64_t)fs.paths;
     for (int i = 0; i < 16; ++i) ctx->stats.active_per_round[i] = i <= kMaxDepth ? fs.n_active[i] : 0;
     const double rt = fs.rays_traced ? (double)fs.rays_traced : 1.0;

@@ -84,6 +84,7 @@ struct FrameState {
     int cache_valid;                    // first-hit cache holds round-0 hits
     int pad;
     unsigned long long rays_traced;
+    unsigned long long rays_walked;     // PTAP_ACCEL_GRID_EMULATED: rays handed to k_trace_grid in list mode
     unsigned long long paths;
     unsigned long long count_nodes, count_tris, count_cells, count_refs;   // counting build only
 };

@@ -71,6 +71,10 @@ def test_emulated_film_is_the_walks_film(gpu_scene):
             r.set_params(W, H, depth, first_hit_cache=cache)
             r.frame_begin(); r.render(0, iters); r.sync()
             films[(accel, cache)] = (r.film().copy(), r.stats()["rays_traced"], list(r.stats()["active_per_round"]))
+            if accel == ACCEL_GRID_EMULATED:
+                walked = r.stats()["rays_walked"] / r.stats()["rays_traced"]
+                print(f"emulated walk, cache={cache}: {walked:.4%} of the rays answered by the walk itself")
+                assert 0 < walked < 0.05                     # the rays on which the walk is not a closest-hit query, and nothing like all of them
         r.free()
     for cache in (True, False):
         a, b = films[(ACCEL_GRID_COMPAT, cache)], films[(ACCEL_GRID_EMULATED, cache)]
