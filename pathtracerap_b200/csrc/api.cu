@@ -91,7 +91,7 @@ struct ptap_ctx {
     std::vector<cudaEvent_t> iter_events;      // completion of every iteration of the last render call (PTAP_FLAG_ITER_TIMES)
     int iter_events_used = 0;
     std::vector<float> iter_ms;
-    int emu_replay_ctas = 8, emu_walk_ctas = 2;
+    int emu_replay_ctas = 6, emu_walk_ctas = 2;
     Arena emu_arena; int emu_lanes = 0;          // PTAP_ACCEL_GRID_EMULATED: per-slot buffers of the render lanes
     int2* d_tri_box = nullptr; size_t tri_box_cap = 0; bool emu_ok = false;   // PTAP_ACCEL_GRID_EMULATED: per-triangle voxel boxes (own allocation)
     std::vector<int> h_grid_first, h_model_grid;     // first voxel of every grid on the device / grid of every model
@@ -545,8 +545,9 @@ int ptap_create(int device, size_t arena_bytes, ptap_ctx** out)
         if (!ok) { ptap_destroy(ctx); return PTAP_E_NOMEM; }
     }      // measured slower on every workload (profiles/r01/README.md): opt-in
     ctx->trace_ctas = std::max(0, envInt("PTAP_TRACE_CTAS", 0));
-    ctx->emu_replay_ctas = std::max(1, envInt("PTAP_EMU_REPLAY_CTAS", 8));     // per SM: k_emu_replay / k_trace_grid in list mode (tuning only)
+    ctx->emu_replay_ctas = std::max(1, envInt("PTAP_EMU_REPLAY_CTAS", 6));     // per SM: k_emu_replay / k_trace_grid in list mode (tuning only)
     ctx->emu_walk_ctas = std::max(1, envInt("PTAP_EMU_WALK_CTAS", 2));
+    ctx->sc.emu_refill = std::min(32, std::max(1, envInt("PTAP_EMU_REFILL", 16)));
     if (arena_bytes) {                                          // caller-sized arena: split 1/4 scene, 3/4 frame
         if (ctx->scene_arena.reserve(arena_bytes / 4) != cudaSuccess || ctx->frame_arena.reserve(arena_bytes - arena_bytes / 4) != cudaSuccess) {
             ptap_destroy(ctx); return PTAP_E_NOMEM;

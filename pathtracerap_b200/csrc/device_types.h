@@ -79,7 +79,8 @@ struct FrameState {
     unsigned int ticket[kMaxDepth + 2]; // tile tickets of the shade kernel, per round
     unsigned int fetch[kMaxDepth + 2];  // work-stealing cursors of the trace kernel, per round
     unsigned int n_replay[kMaxDepth + 2];      // k_trace_emu: rays of the round handed to the grid walk itself (more hits in one model than it keeps)
-    unsigned int fetch_replay[kMaxDepth + 2];  // work-stealing cursors of that second launch
+    unsigned int fetch_replay[kMaxDepth + 2];  // work-stealing cursors of that launch (k_trace_grid in list mode)
+    unsigned int fetch_emu[kMaxDepth + 2];     // work-stealing cursors of k_emu_replay
     int iter_cur, iter_next;
     int cache_valid;                    // first-hit cache holds round-0 hits
     int pad;
@@ -107,6 +108,7 @@ struct SceneDev {
     int batch;                  // rays a warp takes from the work-stealing cursor per atomic (PTAP_BATCH)
     int shade_sort;             // k_shade regroups each block's slots by material class before shading (PTAP_SHADE_SORT=1; default off)
     int vote_grid;              // k_trace_grid: lanes that must wait in a state before its step runs (the most popular state always runs)
+    int emu_refill;             // k_emu_replay: free lanes of a warp that trigger the set-up of the next slots (PTAP_EMU_REFILL)
     int vote_tri, vote_inst, vote_refill;   // lanes that must wait in a state before the warp runs that state's step (PTAP_VOTE_*)
     float c_pad;                // slack of the pruning bound for the residual of model_to_world * world_to_model - I
     float tie;                  // two instances' winners whose approximate world distances differ by less than this relative slack are compared exactly
