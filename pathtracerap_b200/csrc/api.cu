@@ -139,13 +139,15 @@ void launchTrace(ptap_ctx* c, FrameState* st, const float4* O, const float4* D, 
     else launchTraceGrid(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, stream, stamp);
 }
 
-// Per-slot buffers of PTAP_ACCEL_GRID_EMULATED: hit count, kEmuHits x (triangle id, t), the list for the walk.  72 B per slot.
-size_t emuArenaNeed(size_t n) { return Arena::need(n, sizeof(int)) * 2 + Arena::need(n * kEmuHits, sizeof(int)) + Arena::need(n * kEmuHits, sizeof(float)); }
+// Per-slot buffers of PTAP_ACCEL_GRID_EMULATED: hit count, kEmuHits x (triangle id, t), the list for the walk, the queue of replays in
+// progress.  152 B per slot.
+size_t emuArenaNeed(size_t n) { return Arena::need(n, sizeof(int)) * 2 + Arena::need(n * kEmuHits, sizeof(int)) + Arena::need(n * kEmuHits, sizeof(float)) + Arena::need(n * 5, sizeof(uint4)); }
 
 EmuBuf emuFromArena(Arena& A, size_t n)
 {
     EmuBuf e;
     e.n = A.alloc<int>(n); e.list = A.alloc<int>(n); e.id = A.alloc<int>(n * kEmuHits); e.t = A.alloc<float>(n * kEmuHits); e.stride = (int)n;
+    e.cont = A.alloc<uint4>(n * 5); e.cont_cap = (int)n;
     return e;
 }
 
@@ -547,7 +549,7 @@ int ptap_create(int device, size_t arena_bytes, ptap_ctx** out)
     ctx->trace_ctas = std::max(0, envInt("PTAP_TRACE_CTAS", 0));
     ctx->emu_replay_ctas = std::max(1, envInt("PTAP_EMU_REPLAY_CTAS", 6));     // per SM: k_emu_replay / k_trace_grid in list mode (tuning only)
     ctx->emu_walk_ctas = std::max(1, envInt("PTAP_EMU_WALK_CTAS", 2));
-    ctx->sc.emu_refill = std::min(32, std::max(1, envInt("PTAP_EMU_REFILL", 16)));
+    ctx->sc.emu_refill = std::min(32, std::max(1, envInt("PTAP_EMU_REFILL", 8)));
     if (arena_bytes) {                                          // caller-sized arena: split 1/4 scene, 3/4 frame
         if (ctx->scene_arena.reserve(arena_bytes / 4) != cudaSuccess || ctx->frame_arena.reserve(arena_bytes - arena_bytes / 4) != cudaSuccess) {
             ptap_destroy(ctx); return PTAP_E_NOMEM;

@@ -80,7 +80,8 @@ struct FrameState {
     unsigned int fetch[kMaxDepth + 2];  // work-stealing cursors of the trace kernel, per round
     unsigned int n_replay[kMaxDepth + 2];      // k_trace_emu: rays of the round handed to the grid walk itself (more hits in one model than it keeps)
     unsigned int fetch_replay[kMaxDepth + 2];  // work-stealing cursors of that launch (k_trace_grid in list mode)
-    unsigned int fetch_emu[kMaxDepth + 2];     // work-stealing cursors of k_emu_replay
+    unsigned int fetch_emu[kMaxDepth + 2];     // work-stealing cursors of k_emu_tail
+    unsigned int n_cont[kMaxDepth + 2];        // replays that k_emu_setup queued for k_emu_tail
     int iter_cur, iter_next;
     int cache_valid;                    // first-hit cache holds round-0 hits
     int pad;
@@ -121,7 +122,9 @@ struct EmuBuf {
     int* id;                    // [hit][slot] their global triangle ids (stride slots per hit)
     float* t;                   // [hit][slot] their model-space t
     int* list;                  // slots that k_trace_grid must answer (FrameState::n_replay of them)
+    uint4* cont;                // queue of replays in progress, 5 x uint4 each (k_emu_setup -> k_emu_tail)
     int stride;
+    int cont_cap;               // entries the queue holds
 };
 
 struct WaveDev {

@@ -42,7 +42,16 @@ namespace {
 #define PTAP_EMU_MIN_CTAS 7
 #endif
 constexpr int kEmuStack = 12;                 // traversal-stack entries per ray in shared memory (as k_trace_bvh)
-constexpr int kReplayBlock = 128, kReplayBatch = 32;   // k_emu_replay: threads per CTA, slots per cursor fetch
+constexpr int kReplayBlock = 128, kReplayBatch = 32;   // k_emu_tail: threads per CTA, queue entries per cursor fetch
+constexpr int kSetupBlock = 128;                      // k_emu_setup
+#ifndef PTAP_EMU_SETUP_STEPS
+#define PTAP_EMU_SETUP_STEPS 2
+#endif
+#ifndef PTAP_EMU_BURST
+#define PTAP_EMU_BURST 8
+#endif
+constexpr int kBurst = PTAP_EMU_BURST;                // voxels outside the hits' box that one step call may take in a row
+constexpr int kSetupSteps = PTAP_EMU_SETUP_STEPS;     // voxel steps a replay takes in the set-up kernel before it is queued
 constexpr unsigned kGuard = 0x20080200u;      // bits 9, 19, 29: one guard bit above each 9-bit voxel index of a packed (x | y << 10 | z << 20)
 
 }  // namespace
@@ -248,106 +257,246 @@ k_trace_emu(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
     }
 }
 
-// ---- launch 2: replay the walk of the nearest model over its hits (Renderer.cpp:238-360) ------------------------------------------------
+// ---- launches 2 and 3: replay the walk of the nearest model over its hits (Renderer.cpp:238-360) -----------------------------------------
 // Most replays end in the entry voxel (a ray that meets a wall enters the wall's box at the hit), a few take 30-70 steps (a ray that leaves
-// a scaled-up sphere starts its walk at the far side of the sphere's box): one thread per slot ran at 6 of 32 lanes (ncu,
-// profiles/r02/ncu_emu_bundled.txt).  So this is a persistent kernel of independent warps too: a lane owns one replay at a time, every
-// round all lanes with a replay in progress take ONE voxel step, and when enough lanes have finished theirs the warp writes their results
-// and sets up the next slots for them (the set-up - the reference's ray transform, slab test, entry voxel and DDA increments - is the
-// expensive part - ~600 instructions of un-contracted divides and square roots against ~30 per voxel step - so it waits until 24 lanes
-// are free, while the few long replays keep stepping).
+// a scaled-up sphere starts its walk at the far side of the sphere's box).  One thread per slot for the whole replay ran at 6 of 32 lanes
+// (profiles/r02/ncu_emu_bundled.txt); one persistent kernel that sets up new slots for the lanes that finished ran either the set-up or the
+// steps at a quarter of the warp.  So the two parts get a kernel each:
+//   k_emu_setup  one thread per slot, full width: the reference's ray transform, slab test, entry voxel and DDA increments (~600
+//                instructions of un-contracted divides and square roots), then up to kSetupSteps voxel steps; a replay that is not over by
+//                then is written to a queue (80 bytes of DDA state);
+//   k_emu_tail   persistent warps: a lane owns one queued replay at a time, every round all lanes take ONE voxel step, and when enough
+//                lanes are free they load the next queue entries (cheap: no arithmetic to redo).
+namespace {
+
+struct Replay {
+    int i, nh, ix, iy, iz, cx, cy, cz, k, best_k, w_tri, steps;
+    unsigned ulo, uhi, gpos, seen;
+    float tmx, tmy, tmz, dx, dy, dz, w_t, t_star;
+    bool inter, passed;
+};
+
+// one voxel of the walk; true when the replay is over (r.w_tri / r.w_t hold the walk's answer so far)
+__device__ __forceinline__ bool replayStep(Replay& r, int GX, int GY, int GZ, const unsigned* s_lo, const unsigned* s_hi, const float* s_ts, const int* s_ids, int stride)
+{
+    ++r.steps;
+    const unsigned gneg = kGuard ^ r.gpos;
+    const unsigned v = (unsigned)r.ix | ((unsigned)r.iy << 10) | ((unsigned)r.iz << 20);
+    bool any = false, finished = false;
+    const unsigned u1 = (v | kGuard) - r.ulo, u2 = (r.uhi | kGuard) - v;      // per axis: guard bit set <=> lo <= index / index <= hi
+    if ((u1 & u2 & kGuard) == kGuard) {                                       // inside the box around all hits: look at them one by one
+#pragma unroll 1
+        for (int j = 0; j < r.nh; ++j) {
+            const int slot = j * stride + threadIdx.x;
+            const unsigned d1 = (v | kGuard) - s_lo[slot], d2 = (s_hi[slot] | kGuard) - v;
+            if ((d1 & d2 & kGuard) == kGuard) {
+                any = true;                                        // the voxel lists a triangle the ray hits (Renderer.cpp:217-236)
+                if (!((r.seen >> j) & 1u)) {                       // its first test: the only one that can update the nearest hit
+                    r.seen |= 1u << j;
+                    const float tj = s_ts[slot]; const int idj = s_ids[slot];
+                    if (r.w_t > tj || (r.w_t == tj && r.best_k == r.k && idj < r.w_tri)) { r.w_t = tj; r.w_tri = idj; r.best_k = r.k; }   // Renderer.cpp:209
+                }
+            }
+        }
+    } else if ((~u2 & r.gpos) | (~u1 & gneg)) r.passed = true;               // indices move one way only
+    // t* is the smallest t of ALL the model's hits: once the walk has met a hit with that t nothing it does later can change
+    // its answer's t, and a tie for the triangle is settled inside the voxel just closed - the rest of the walk is not needed
+    if (r.w_t == r.t_star) finished = true;
+    else {
+        if (any) { r.cx = r.ix; r.cy = r.iy; r.cz = r.iz; r.inter = true; }
+        if (r.inter && (abs(r.cx - r.ix) > 2 || abs(r.cy - r.iy) > 2 || abs(r.cz - r.iz) > 2)) finished = true;       // Renderer.cpp:326-329
+        else if (r.passed) finished = true;         // no voxel ahead lists a hit triangle: the walk ends with what it has
+        else {                                                                                                       // Renderer.cpp:331-357, without branches
+            const bool px = r.gpos & (1u << 9), py = r.gpos & (1u << 19), pz = r.gpos & (1u << 29);
+            const bool sx = r.tmx < r.tmy && r.tmx < r.tmz, sy = !sx && r.tmy < r.tmz;
+            r.ix += sx ? (px ? 1 : -1) : 0; r.iy += sy ? (py ? 1 : -1) : 0; r.iz += (sx || sy) ? 0 : (pz ? 1 : -1);
+            const float tsel = sx ? r.tmx : sy ? r.tmy : r.tmz;
+            const int isel = sx ? r.ix : sy ? r.iy : r.iz, lim = sx ? (px ? GX : -1) : sy ? (py ? GY : -1) : (pz ? GZ : -1);
+            if (isel == lim || tsel >= kFloatMax) finished = true;
+            else { r.tmx = sx ? xadd(r.tmx, r.dx) : r.tmx; r.tmy = sy ? xadd(r.tmy, r.dy) : r.tmy; r.tmz = (sx || sy) ? r.tmz : xadd(r.tmz, r.dz); }
+        }
+    }
+    ++r.k;
+    // Voxels outside the box around the hits list no hit triangle: nothing but the walk's own exit tests and DDA arithmetic happens there,
+    // so up to kBurst of them are taken at once (a ray that leaves a scaled-up mesh walks a dozen such voxels before it reaches the first hit).
+#pragma unroll 1
+    for (int b = 0; b < kBurst && !finished; ++b) {
+        const unsigned w = (unsigned)r.ix | ((unsigned)r.iy << 10) | ((unsigned)r.iz << 20);
+        const unsigned q1 = (w | kGuard) - r.ulo, q2 = (r.uhi | kGuard) - w;
+        if ((q1 & q2 & kGuard) == kGuard) break;                               // inside: the next call looks at the hits
+        ++r.steps;
+        if ((~q2 & r.gpos) | (~q1 & gneg)) finished = true;                     // passed for good (this voxel is visited, the walk ends after it)
+        else if (r.inter && (abs(r.cx - r.ix) > 2 || abs(r.cy - r.iy) > 2 || abs(r.cz - r.iz) > 2)) finished = true;
+        else {
+            const bool px = r.gpos & (1u << 9), py = r.gpos & (1u << 19), pz = r.gpos & (1u << 29);
+            const bool sx = r.tmx < r.tmy && r.tmx < r.tmz, sy = !sx && r.tmy < r.tmz;
+            r.ix += sx ? (px ? 1 : -1) : 0; r.iy += sy ? (py ? 1 : -1) : 0; r.iz += (sx || sy) ? 0 : (pz ? 1 : -1);
+            const float tsel = sx ? r.tmx : sy ? r.tmy : r.tmz;
+            const int isel = sx ? r.ix : sy ? r.iy : r.iz, lim = sx ? (px ? GX : -1) : sy ? (py ? GY : -1) : (pz ? GZ : -1);
+            if (isel == lim || tsel >= kFloatMax) finished = true;
+            else { r.tmx = sx ? xadd(r.tmx, r.dx) : r.tmx; r.tmy = sy ? xadd(r.tmy, r.dy) : r.tmy; r.tmz = (sx || sy) ? r.tmz : xadd(r.tmz, r.dz); }
+        }
+        ++r.k;
+    }
+    return finished;
+}
+
+// the hits of slot i and their voxel boxes into the lane's shared-memory column; (ulo, uhi) = the box around all of them
+__device__ __forceinline__ void replayLoadHits(const SceneDev& sc, const EmuBuf& emu, int i, int nh, int first_id, float t_star, unsigned& ulo, unsigned& uhi,
+                                               unsigned* s_lo, unsigned* s_hi, float* s_ts, int* s_ids, int stride)
+{
+    ulo = 0x1ffu | (0x1ffu << 10) | (0x1ffu << 20); uhi = 0u;
+#pragma unroll 1
+    for (int j = 0; j < nh; ++j) {
+        const int slot = j * stride + threadIdx.x;
+        const int idj = nh == 1 ? first_id : emu.id[(size_t)j * emu.stride + i];
+        s_ids[slot] = idj; s_ts[slot] = nh == 1 ? t_star : emu.t[(size_t)j * emu.stride + i];
+        const int2 bx = __ldg(&sc.tri_box[idj]);
+        const unsigned lj = (unsigned)bx.x, hj = (unsigned)bx.y;
+        s_lo[slot] = lj; s_hi[slot] = hj;
+        if ((((hj | kGuard) - lj) & kGuard) == kGuard) {                // listed somewhere (lo <= hi on every axis)
+            ulo = min(ulo & 0x1ffu, lj & 0x1ffu) | min(ulo & (0x1ffu << 10), lj & (0x1ffu << 10)) | min(ulo & (0x1ffu << 20), lj & (0x1ffu << 20));
+            uhi = max(uhi & 0x1ffu, hj & 0x1ffu) | max(uhi & (0x1ffu << 10), hj & (0x1ffu << 10)) | max(uhi & (0x1ffu << 20), hj & (0x1ffu << 20));
+        }
+    }
+}
+
+// the end of a replay: confirm the closest hit as the reference's answer, or hand the slot to the walk itself
+template <bool UV>
+__device__ __forceinline__ void replayFinish(const SceneDev& sc, const Replay& r, const float4& h, const float4* __restrict__ O, const float4* __restrict__ D,
+                                             float4* __restrict__ hit, float2* __restrict__ uv, FrameState* st, int round, const EmuBuf& emu)
+{
+    if (r.w_tri >= 0 && r.w_t == r.t_star) {
+        // the walk of the nearest model finds the closest hit: that is the reference's answer (the triangle is the WALK's: its tie rule)
+        if (r.w_tri != __float_as_int(h.y)) hit[r.i] = make_float4(h.x, __int_as_float(r.w_tri), h.z, h.w);
+        if (UV && uv) {                                                          // barycentrics as the predicate computes them (Renderer.cpp:174-201)
+            const InstanceTrace* __restrict__ inst = &sc.inst[__float_as_int(h.z)];
+            const float4 w0 = ldg4(&inst->w2m[0]), w1 = ldg4(&inst->w2m[1]), w2 = ldg4(&inst->w2m[2]);
+            const V3 ro = xmat4(w0, w1, w2, v3(O[r.i]), 1.0f), rd = xnormalize(xmat4(w0, w1, w2, v3(D[r.i]), 0.0f));
+            const float4 a = ldg4(&sc.tris[r.w_tri].v0), b = ldg4(&sc.tris[r.w_tri].e1), c = ldg4(&sc.tris[r.w_tri].e2);
+            const V3 pvec = xcross(rd, v3(c));
+            const float invDet = xdiv(1.0f, xdot(v3(b), pvec));
+            const V3 tvec = xsub(ro, v3(a));
+            uv[r.i] = make_float2(xmul(xdot(tvec, pvec), invDet), xmul(xdot(rd, xcross(tvec, v3(b))), invDet));
+        }
+    } else emu.list[atomicAdd(&st->n_replay[round], 1u)] = r.i;                 // the walk itself answers this one (last launch)
+}
+
+}  // namespace
+
+template <bool UV, bool COUNT>
+__global__ void __launch_bounds__(kSetupBlock)
+k_emu_setup(SceneDev sc, const float4* __restrict__ O, const float4* __restrict__ D, float4* __restrict__ hit, float2* __restrict__ uv,
+            int4* __restrict__ counts, FrameState* st, int round, int n_fixed, EmuBuf emu)
+{
+    const int n = n_fixed >= 0 ? n_fixed : st->n_active[round];
+    const int GX = sc.gx, GY = sc.gy, GZ = sc.gz;
+    __shared__ int s_ids[kEmuHits * kSetupBlock];                  // [hit][thread]: the hits of the thread's replay
+    __shared__ float s_ts[kEmuHits * kSetupBlock];
+    __shared__ unsigned s_lo[kEmuHits * kSetupBlock], s_hi[kEmuHits * kSetupBlock];
+    unsigned long long steps_total = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 h = hit[i];
+        const int im = __float_as_int(h.z);
+        if (im < 0) { if (UV && uv) uv[i] = make_float2(0.0f, 0.0f); continue; }      // no real hit: no walk finds one
+        Replay r;
+        r.i = i; r.nh = emu.n[i]; r.t_star = h.w; r.w_tri = -1; r.w_t = kFloatMax; r.steps = 0;
+        bool walking = false;
+        if (r.nh <= kEmuHits) {
+            const V3 bo = v3(O[i]), bd = v3(D[i]);
+            const InstanceTrace* __restrict__ inst = &sc.inst[im];
+            const float4 w0 = ldg4(&inst->w2m[0]), w1 = ldg4(&inst->w2m[1]), w2 = ldg4(&inst->w2m[2]);
+            const V3 ro = xmat4(w0, w1, w2, bo, 1.0f);                               // Renderer.cpp:381
+            const V3 rd = xnormalize(xmat4(w0, w1, w2, bd, 0.0f));                   // Renderer.cpp:382
+            const float4 bbmin_wx = ldg4(&inst->bb_min), bbmax_wy = ldg4(&inst->bb_max), gridrec = ldg4(&inst->grid);
+            const V3 mn = v3(bbmin_wx), mx = v3(bbmax_wy);
+            const V3 inv = v3(xdiv(1.0f, rd.x), xdiv(1.0f, rd.y), xdiv(1.0f, rd.z));   // Renderer.cpp:383
+            // Renderer.cpp:150-170
+            const float t1 = rd.x == 0.0f ? kFloatMin : xmul(xsub(mn.x, ro.x), inv.x);
+            const float t2 = rd.x == 0.0f ? kFloatMax : xmul(xsub(mx.x, ro.x), inv.x);
+            const float t3 = rd.y == 0.0f ? kFloatMin : xmul(xsub(mn.y, ro.y), inv.y);
+            const float t4 = rd.y == 0.0f ? kFloatMax : xmul(xsub(mx.y, ro.y), inv.y);
+            const float t5 = rd.z == 0.0f ? kFloatMin : xmul(xsub(mn.z, ro.z), inv.z);
+            const float t6 = rd.z == 0.0f ? kFloatMax : xmul(xsub(mx.z, ro.z), inv.z);
+            const float sl_min = max_std(max_std(min_std(t1, t2), min_std(t3, t4)), min_std(t5, t6));
+            const float sl_max = min_std(min_std(max_std(t1, t2), max_std(t3, t4)), max_std(t5, t6));
+            const V3 p = xadd(ro, xscale(rd, sl_min));
+            if (!(sl_max < 0 || sl_min > sl_max) &&
+                !(xsub(p.x, mn.x) < -kEpsilon || xsub(p.y, mn.y) < -kEpsilon || xsub(p.z, mn.z) < -kEpsilon)) {      // Renderer.cpp:252-259
+                const float wx = bbmin_wx.w, wy = bbmax_wy.w, wz = gridrec.x;
+                r.ix = f2i_x86(xdiv(xabs(xadd(xsub(p.x, mn.x), kEpsilon)), wx));
+                r.iy = f2i_x86(xdiv(xabs(xadd(xsub(p.y, mn.y), kEpsilon)), wy));
+                r.iz = f2i_x86(xdiv(xabs(xadd(xsub(p.z, mn.z), kEpsilon)), wz));
+                r.ix = min(max(r.ix, 0), GX - 1); r.iy = min(max(r.iy, 0), GY - 1); r.iz = min(max(r.iz, 0), GZ - 1);
+                r.tmx = kFloatMax; r.tmy = kFloatMax; r.tmz = kFloatMax; r.dx = kFloatMax; r.dy = kFloatMax; r.dz = kFloatMax;
+                if (rd.x != 0) { const int nx = rd.x > 0.0f ? r.ix + 1 : r.ix; r.dx = xabs(xmul(wx, inv.x)); r.tmx = xmul(xsub(xadd(mn.x, xmul((float)nx, wx)), p.x), inv.x); }
+                if (rd.y != 0) { const int ny = rd.y > 0.0f ? r.iy + 1 : r.iy; r.dy = xabs(xmul(wy, inv.y)); r.tmy = xmul(xsub(xadd(mn.y, xmul((float)ny, wy)), p.y), inv.y); }
+                if (rd.z != 0) { const int nz = rd.z > 0.0f ? r.iz + 1 : r.iz; r.dz = xabs(xmul(wz, inv.z)); r.tmz = xmul(xsub(xadd(mn.z, xmul((float)nz, wz)), p.z), inv.z); }
+                // guard bits of the axes along which the voxel index grows: "the walk has passed a box for good" is one mask test
+                r.gpos = (rd.x > 0.0f ? 1u << 9 : 0u) | (rd.y > 0.0f ? 1u << 19 : 0u) | (rd.z > 0.0f ? 1u << 29 : 0u);
+                r.seen = 0u; r.passed = false; r.cx = 0; r.cy = 0; r.cz = 0; r.best_k = -1; r.k = 0; r.inter = false;
+                replayLoadHits(sc, emu, i, r.nh, __float_as_int(h.y), r.t_star, r.ulo, r.uhi, s_lo, s_hi, s_ts, s_ids, kSetupBlock);
+                walking = true;
+#pragma unroll 1
+                for (int s = 0; s < kSetupSteps && walking; ++s) walking = !replayStep(r, GX, GY, GZ, s_lo, s_hi, s_ts, s_ids, kSetupBlock);
+            }
+        }
+        if (walking) {
+            const unsigned q = atomicAdd(&st->n_cont[round], 1u);
+            if (q < (unsigned)emu.cont_cap) {                       // the rest of this replay: k_emu_tail
+                uint4* rec = emu.cont + (size_t)q * 5;
+                rec[0] = make_uint4((unsigned)i, (unsigned)r.ix | ((unsigned)r.iy << 10) | ((unsigned)r.iz << 20), r.gpos | (r.inter ? 1u : 0u) | ((unsigned)r.nh << 1), r.seen);
+                rec[1] = make_uint4(__float_as_uint(r.tmx), __float_as_uint(r.tmy), __float_as_uint(r.tmz), __float_as_uint(r.t_star));
+                rec[2] = make_uint4(__float_as_uint(r.dx), __float_as_uint(r.dy), __float_as_uint(r.dz), __float_as_uint(r.w_t));
+                rec[3] = make_uint4((unsigned)r.w_tri, (unsigned)r.best_k, (unsigned)r.k, (unsigned)r.cx | ((unsigned)r.cy << 10) | ((unsigned)r.cz << 20));
+                rec[4] = make_uint4(r.ulo, r.uhi, (unsigned)r.steps, 0u);
+                continue;
+            }
+            r.w_tri = -1;                                           // queue full (cannot happen with cont_cap = slots): the walk answers
+        }
+        if (COUNT) { if (counts) counts[i].y = r.steps; steps_total += r.steps; }
+        replayFinish<UV>(sc, r, h, O, D, hit, uv, st, round, emu);
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) steps_total += __shfl_xor_sync(0xffffffffu, steps_total, d);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&st->count_cells, steps_total);
+    }
+}
+
 template <bool UV, bool COUNT>
 __global__ void __launch_bounds__(kReplayBlock)
-k_emu_replay(SceneDev sc, const float4* __restrict__ O, const float4* __restrict__ D, float4* __restrict__ hit, float2* __restrict__ uv,
-             int4* __restrict__ counts, FrameState* st, int round, int n_fixed, EmuBuf emu)
+k_emu_tail(SceneDev sc, const float4* __restrict__ O, const float4* __restrict__ D, float4* __restrict__ hit, float2* __restrict__ uv,
+           int4* __restrict__ counts, FrameState* st, int round, EmuBuf emu)
 {
     constexpr unsigned kFullMask = 0xffffffffu;
-    const int n = n_fixed >= 0 ? n_fixed : st->n_active[round];
+    const int n = (int)min(st->n_cont[round], (unsigned)emu.cont_cap);
     unsigned int* cursor = &st->fetch_emu[round];
     const int lane = threadIdx.x & 31;
     const int GX = sc.gx, GY = sc.gy, GZ = sc.gz;
-    unsigned long long steps_total = 0;
-
-    enum : int { R_IDLE = 0, R_STEP = 1, R_DONE = 2 };
-    int state = R_IDLE, i = -1;
-    // the replay in progress
-    __shared__ int s_ids[kEmuHits * kReplayBlock];                 // [hit][thread]: the hits of the lane's replay (conflict-free, no local memory)
+    __shared__ int s_ids[kEmuHits * kReplayBlock];
     __shared__ float s_ts[kEmuHits * kReplayBlock];
     __shared__ unsigned s_lo[kEmuHits * kReplayBlock], s_hi[kEmuHits * kReplayBlock];
-    unsigned ulo = 0u, uhi = 0u, gpos = 0u, seen = 0u;
-    bool passed = false;                                            // the walk has left the box around all hits for good
-    int stx = 1, sty = 1, stz = 1, limx = 0, limy = 0, limz = 0;   // index step and first index outside the grid, per axis
-    int nh = 0, ix = 0, iy = 0, iz = 0, cx = 0, cy = 0, cz = 0, k = 0, best_k = -1, w_tri = -1, steps = 0;
-    float tmx = kFloatMax, tmy = kFloatMax, tmz = kFloatMax, dx = kFloatMax, dy = kFloatMax, dz = kFloatMax, w_t = kFloatMax, t_star = 0.0f;
-    bool inter = false;
-    V3 ro = v3(0, 0, 0), rd = v3(0, 0, 1);      // model-space ray of the slot (UV build: barycentrics of the winner)
-    float4 h = make_float4(0, 0, 0, 0);
+    unsigned long long steps_total = 0;
+    enum : int { R_IDLE = 0, R_STEP = 1, R_DONE = 2 };
+    int state = R_IDLE;
+    Replay r; r.i = -1; r.nh = 0; r.steps = 0;
     int w_next = 0, w_end = 0;
     bool exhausted = false;
 
     for (;;) {
         // ---- one voxel of every replay in progress
-        if (state == R_STEP) {
-            ++steps;
-            const unsigned gneg = kGuard ^ gpos;
-            const unsigned v = (unsigned)ix | ((unsigned)iy << 10) | ((unsigned)iz << 20);
-            bool any = false, finished = false;
-            const unsigned u1 = (v | kGuard) - ulo, u2 = (uhi | kGuard) - v;      // per axis: guard bit set <=> lo <= index / index <= hi
-            if ((u1 & u2 & kGuard) == kGuard) {                                   // inside the box around all hits: look at them one by one
-#pragma unroll 1
-                for (int j = 0; j < nh; ++j) {
-                    const int slot = j * kReplayBlock + threadIdx.x;
-                    const unsigned d1 = (v | kGuard) - s_lo[slot], d2 = (s_hi[slot] | kGuard) - v;
-                    if ((d1 & d2 & kGuard) == kGuard) {
-                        any = true;                                        // the voxel lists a triangle the ray hits (Renderer.cpp:217-236)
-                        if (!((seen >> j) & 1u)) {                         // its first test: the only one that can update the nearest hit
-                            seen |= 1u << j;
-                            const float tj = s_ts[slot]; const int idj = s_ids[slot];
-                            if (w_t > tj || (w_t == tj && best_k == k && idj < w_tri)) { w_t = tj; w_tri = idj; best_k = k; }   // Renderer.cpp:209
-                        }
-                    }
-                }
-            } else if ((~u2 & gpos) | (~u1 & gneg)) passed = true;               // indices move one way only
-            // t* is the smallest t of ALL the model's hits: once the walk has met a hit with that t nothing it does later can change
-            // its answer's t, and a tie for the triangle is settled inside the voxel just closed - the rest of the walk is not needed
-            if (w_t == t_star) finished = true;
-            else {
-                if (any) { cx = ix; cy = iy; cz = iz; inter = true; }
-                if (inter && (abs(cx - ix) > 2 || abs(cy - iy) > 2 || abs(cz - iz) > 2)) finished = true;       // Renderer.cpp:326-329
-                else if (passed) finished = true;           // no voxel ahead lists a hit triangle: the walk ends with what it has
-                else {                                                                                           // Renderer.cpp:331-357, without branches
-                    const bool sx = tmx < tmy && tmx < tmz, sy = !sx && tmy < tmz;
-                    ix += sx ? stx : 0; iy += sy ? sty : 0; iz += (sx || sy) ? 0 : stz;
-                    const float tsel = sx ? tmx : sy ? tmy : tmz;
-                    const int isel = sx ? ix : sy ? iy : iz, lim = sx ? limx : sy ? limy : limz;
-                    if (isel == lim || tsel >= kFloatMax) finished = true;
-                    else { tmx = sx ? xadd(tmx, dx) : tmx; tmy = sy ? xadd(tmy, dy) : tmy; tmz = (sx || sy) ? tmz : xadd(tmz, dz); }
-                }
-            }
-            ++k;
-            if (finished) state = R_DONE;
-        }
+        if (state == R_STEP && replayStep(r, GX, GY, GZ, s_lo, s_hi, s_ts, s_ids, kReplayBlock)) state = R_DONE;
         // ---- who is where
         const unsigned m_step = __ballot_sync(kFullMask, state == R_STEP);
-        const int n_free = 32 - __popc(m_step);
-        if (m_step != 0u && n_free < sc.emu_refill) continue;          // keep stepping until enough lanes are free (or none steps)
+        if (m_step != 0u && 32 - __popc(m_step) < sc.emu_refill) continue;      // keep stepping until enough lanes are free (or none steps)
         // ---- results of the finished replays
         if (state == R_DONE) {
-            if (COUNT) { if (counts) counts[i].y = steps; steps_total += steps; }
-            if (w_tri >= 0 && w_t == t_star) {
-                // the walk of the nearest model finds the closest hit: that is the reference's answer (the triangle is the WALK's: its tie rule)
-                if (w_tri != __float_as_int(h.y)) hit[i] = make_float4(h.x, __int_as_float(w_tri), h.z, h.w);
-                if (UV && uv) {                                                          // barycentrics as the predicate computes them (Renderer.cpp:174-201)
-                    const float4 a = ldg4(&sc.tris[w_tri].v0), b = ldg4(&sc.tris[w_tri].e1), c = ldg4(&sc.tris[w_tri].e2);
-                    const V3 pvec = xcross(rd, v3(c));
-                    const float invDet = xdiv(1.0f, xdot(v3(b), pvec));
-                    const V3 tvec = xsub(ro, v3(a));
-                    uv[i] = make_float2(xmul(xdot(tvec, pvec), invDet), xmul(xdot(rd, xcross(tvec, v3(b))), invDet));
-                }
-            } else emu.list[atomicAdd(&st->n_replay[round], 1u)] = i;                   // the walk itself answers this one (third launch)
-            state = R_IDLE; i = -1;
+            if (COUNT) { if (counts) counts[r.i].y = r.steps; steps_total += r.steps; }
+            replayFinish<UV>(sc, r, hit[r.i], O, D, hit, uv, st, round, emu);
+            state = R_IDLE; r.i = -1;
         }
-        // ---- the next slots for the free lanes
+        // ---- the next queue entries for the free lanes
         if (w_next >= w_end && !exhausted) {
             unsigned b = 0;
             if (lane == 0) b = atomicAdd(cursor, (unsigned)kReplayBatch);
@@ -360,69 +509,17 @@ k_emu_replay(SceneDev sc, const float4* __restrict__ O, const float4* __restrict
         const int avail = w_end - w_next;
         const int rank = __popc(m_idle & ((1u << lane) - 1u));
         if (state == R_IDLE && rank < avail) {
-            i = w_next + rank;
-            h = hit[i];
-            const int im = __float_as_int(h.z);
-            if (im < 0) { if (UV && uv) uv[i] = make_float2(0.0f, 0.0f); i = -1; }      // no real hit: no walk finds one
-            else {
-                nh = emu.n[i];
-                t_star = h.w; w_tri = -1; w_t = kFloatMax; steps = 0;
-                state = R_DONE;                                                           // unless the walk is entered below
-                const V3 bo = v3(O[i]), bd = v3(D[i]);
-                const InstanceTrace* __restrict__ inst = &sc.inst[im];
-                const float4 w0 = ldg4(&inst->w2m[0]), w1 = ldg4(&inst->w2m[1]), w2 = ldg4(&inst->w2m[2]);
-                ro = xmat4(w0, w1, w2, bo, 1.0f);                                        // Renderer.cpp:381
-                rd = xnormalize(xmat4(w0, w1, w2, bd, 0.0f));                            // Renderer.cpp:382
-                if (nh <= kEmuHits) {
-                    // the hits and their voxel boxes; (ulo, uhi) = the box around all of them (nothing can happen to the walk outside it)
-                    ulo = 0x1ffu | (0x1ffu << 10) | (0x1ffu << 20); uhi = 0u;
-#pragma unroll 1
-                    for (int j = 0; j < nh; ++j) {
-                        const int slot = j * kReplayBlock + threadIdx.x;
-                        const int idj = nh == 1 ? __float_as_int(h.y) : emu.id[(size_t)j * emu.stride + i];
-                        s_ids[slot] = idj; s_ts[slot] = nh == 1 ? t_star : emu.t[(size_t)j * emu.stride + i];
-                        const int2 bx = __ldg(&sc.tri_box[idj]);
-                        const unsigned lj = (unsigned)bx.x, hj = (unsigned)bx.y;
-                        s_lo[slot] = lj; s_hi[slot] = hj;
-                        if ((((hj | kGuard) - lj) & kGuard) == kGuard) {                // listed somewhere (lo <= hi on every axis)
-                            ulo = min(ulo & 0x1ffu, lj & 0x1ffu) | min(ulo & (0x1ffu << 10), lj & (0x1ffu << 10)) | min(ulo & (0x1ffu << 20), lj & (0x1ffu << 20));
-                            uhi = max(uhi & 0x1ffu, hj & 0x1ffu) | max(uhi & (0x1ffu << 10), hj & (0x1ffu << 10)) | max(uhi & (0x1ffu << 20), hj & (0x1ffu << 20));
-                        }
-                    }
-                    const float4 bbmin_wx = ldg4(&inst->bb_min), bbmax_wy = ldg4(&inst->bb_max), gridrec = ldg4(&inst->grid);
-                    const V3 mn = v3(bbmin_wx), mx = v3(bbmax_wy);
-                    const V3 inv = v3(xdiv(1.0f, rd.x), xdiv(1.0f, rd.y), xdiv(1.0f, rd.z));   // Renderer.cpp:383
-                    // Renderer.cpp:150-170
-                    const float t1 = rd.x == 0.0f ? kFloatMin : xmul(xsub(mn.x, ro.x), inv.x);
-                    const float t2 = rd.x == 0.0f ? kFloatMax : xmul(xsub(mx.x, ro.x), inv.x);
-                    const float t3 = rd.y == 0.0f ? kFloatMin : xmul(xsub(mn.y, ro.y), inv.y);
-                    const float t4 = rd.y == 0.0f ? kFloatMax : xmul(xsub(mx.y, ro.y), inv.y);
-                    const float t5 = rd.z == 0.0f ? kFloatMin : xmul(xsub(mn.z, ro.z), inv.z);
-                    const float t6 = rd.z == 0.0f ? kFloatMax : xmul(xsub(mx.z, ro.z), inv.z);
-                    const float sl_min = max_std(max_std(min_std(t1, t2), min_std(t3, t4)), min_std(t5, t6));
-                    const float sl_max = min_std(min_std(max_std(t1, t2), max_std(t3, t4)), max_std(t5, t6));
-                    const V3 p = xadd(ro, xscale(rd, sl_min));
-                    if (!(sl_max < 0 || sl_min > sl_max) &&
-                        !(xsub(p.x, mn.x) < -kEpsilon || xsub(p.y, mn.y) < -kEpsilon || xsub(p.z, mn.z) < -kEpsilon)) {      // Renderer.cpp:252-259
-                        const float wx = bbmin_wx.w, wy = bbmax_wy.w, wz = gridrec.x;
-                        ix = f2i_x86(xdiv(xabs(xadd(xsub(p.x, mn.x), kEpsilon)), wx));
-                        iy = f2i_x86(xdiv(xabs(xadd(xsub(p.y, mn.y), kEpsilon)), wy));
-                        iz = f2i_x86(xdiv(xabs(xadd(xsub(p.z, mn.z), kEpsilon)), wz));
-                        ix = min(max(ix, 0), GX - 1); iy = min(max(iy, 0), GY - 1); iz = min(max(iz, 0), GZ - 1);
-                        tmx = kFloatMax; tmy = kFloatMax; tmz = kFloatMax; dx = kFloatMax; dy = kFloatMax; dz = kFloatMax;
-                        if (rd.x != 0) { const int nx = rd.x > 0.0f ? ix + 1 : ix; dx = xabs(xmul(wx, inv.x)); tmx = xmul(xsub(xadd(mn.x, xmul((float)nx, wx)), p.x), inv.x); }
-                        if (rd.y != 0) { const int ny = rd.y > 0.0f ? iy + 1 : iy; dy = xabs(xmul(wy, inv.y)); tmy = xmul(xsub(xadd(mn.y, xmul((float)ny, wy)), p.y), inv.y); }
-                        if (rd.z != 0) { const int nz = rd.z > 0.0f ? iz + 1 : iz; dz = xabs(xmul(wz, inv.z)); tmz = xmul(xsub(xadd(mn.z, xmul((float)nz, wz)), p.z), inv.z); }
-                        // guard bits of the axes along which the voxel index grows: "the walk has passed a box for good" is one mask test
-                        gpos = (rd.x > 0.0f ? 1u << 9 : 0u) | (rd.y > 0.0f ? 1u << 19 : 0u) | (rd.z > 0.0f ? 1u << 29 : 0u);
-                        stx = rd.x > 0.0f ? 1 : -1; sty = rd.y > 0.0f ? 1 : -1; stz = rd.z > 0.0f ? 1 : -1;
-                        limx = rd.x > 0.0f ? GX : -1; limy = rd.y > 0.0f ? GY : -1; limz = rd.z > 0.0f ? GZ : -1;
-                        seen = 0u; passed = false;
-                        cx = 0; cy = 0; cz = 0; best_k = -1; k = 0; inter = false;
-                        state = R_STEP;
-                    }
-                }
-            }
+            const uint4* rec = emu.cont + (size_t)(w_next + rank) * 5;
+            const uint4 a = rec[0], b = rec[1], c = rec[2], d = rec[3], e = rec[4];
+            r.i = (int)a.x; r.ix = a.y & 0x3ff; r.iy = (a.y >> 10) & 0x3ff; r.iz = a.y >> 20;
+            r.gpos = a.z & kGuard; r.inter = a.z & 1u; r.nh = (a.z >> 1) & 0xf; r.seen = a.w; r.passed = false;
+            r.tmx = __uint_as_float(b.x); r.tmy = __uint_as_float(b.y); r.tmz = __uint_as_float(b.z); r.t_star = __uint_as_float(b.w);
+            r.dx = __uint_as_float(c.x); r.dy = __uint_as_float(c.y); r.dz = __uint_as_float(c.z); r.w_t = __uint_as_float(c.w);
+            r.w_tri = (int)d.x; r.best_k = (int)d.y; r.k = (int)d.z; r.cx = d.w & 0x3ff; r.cy = (d.w >> 10) & 0x3ff; r.cz = d.w >> 20;
+            r.steps = (int)e.z;
+            const float4 h = hit[r.i];
+            replayLoadHits(sc, emu, r.i, r.nh, __float_as_int(h.y), r.t_star, r.ulo, r.uhi, s_lo, s_hi, s_ts, s_ids, kReplayBlock);
+            state = R_STEP;
         }
         w_next += min(__popc(m_idle), avail);
     }
@@ -437,11 +534,19 @@ void launchTraceEmu(const SceneDev& sc, const float4* O, const float4* D, float4
                     FrameState* st, int round, int n_fixed, int grid, int grid_replay, cudaStream_t stream, unsigned long long* stamp, const EmuBuf& emu)
 {
     const bool count = counts || count_totals;
+    const int grid_setup = grid_replay * 2;
     if (count) k_trace_emu<true><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, counts, st, round, n_fixed, stamp, emu);
     else k_trace_emu<false><<<grid, kTraceBlock, 0, stream>>>(sc, O, D, hit, counts, st, round, n_fixed, stamp, emu);
-    if (count) k_emu_replay<true, true><<<grid_replay, kReplayBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, emu);
-    else if (uv) k_emu_replay<true, false><<<grid_replay, kReplayBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, emu);
-    else k_emu_replay<false, false><<<grid_replay, kReplayBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, emu);
+    if (count) {
+        k_emu_setup<true, true><<<grid_setup, kSetupBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, emu);
+        k_emu_tail<true, true><<<grid_replay, kReplayBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, emu);
+    } else if (uv) {
+        k_emu_setup<true, false><<<grid_setup, kSetupBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, emu);
+        k_emu_tail<true, false><<<grid_replay, kReplayBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, emu);
+    } else {
+        k_emu_setup<false, false><<<grid_setup, kSetupBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, emu);
+        k_emu_tail<false, false><<<grid_replay, kReplayBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, emu);
+    }
 }
 
 int traceEmuOccupancy()
