@@ -131,6 +131,7 @@ typedef struct {
     float ms_trace_inflight;      /* PTAP_FLAG_STAMP: time of the last ptap_render call during which at least one closest-hit kernel was resident */
     float ms_trace_sum;           /* PTAP_FLAG_STAMP: summed residency of its closest-hit launches (lanes overlap: may exceed ms_render) */
     int64_t rays_walked;          /* PTAP_ACCEL_GRID_EMULATED: rays (of rays_traced) that the grid walk itself had to answer */
+    int64_t rays_reemulated;      /* PTAP_ACCEL_GRID_EMULATED: rays whose nearest model's walk does not return the closest hit (emulated in full) */
 } PtapStats;
 
 /* Camera of generateRaysKernel (Renderer.cpp:527-548), whose numbers the reference hard-codes: rays start at `origin` and pass through

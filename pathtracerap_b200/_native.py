@@ -59,7 +59,7 @@ class Stats(C.Structure):
                 ("ms_shade", C.c_float), ("ms_generate", C.c_float), ("avg_nodes", C.c_float), ("avg_tris", C.c_float),
                 ("avg_cells", C.c_float), ("avg_refs", C.c_float), ("trace_launches", C.c_int64), ("scene_bytes", C.c_int64),
                 ("ms_build", C.c_float), ("bvh_nodes", C.c_int32), ("bvh_depth", C.c_int32), ("lanes", C.c_int32),
-                ("ms_trace_inflight", C.c_float), ("ms_trace_sum", C.c_float), ("rays_walked", C.c_int64)]
+                ("ms_trace_inflight", C.c_float), ("ms_trace_sum", C.c_float), ("rays_walked", C.c_int64), ("rays_reemulated", C.c_int64)]
 
 
 EXPORTS = [

@@ -131,23 +131,31 @@ void launchTrace(ptap_ctx* c, FrameState* st, const float4* O, const float4* D, 
     if (!stream) stream = c->stream;
     if (c->accel == PTAP_ACCEL_GRID_EMULATED) {
         // closest hit + the hits of the nearest model, then the replay of that model's walk (trace_emu.cu) ...
-        launchTraceEmu(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, c->sms * c->emu_replay_ctas, stream, stamp, emu);
+        launchTraceEmu(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, c->sms * c->emu_replay_ctas, c->sms, stream, stamp, emu);
         // ... and the walk itself for the slots the replay could not confirm (the 0.3-0.6 % of rays on which the walk is not a closest-hit query)
-        launchTraceGrid(c->sc, O, D, hit, uv, nullptr, false, st, round, n_fixed, c->sms * c->emu_walk_ctas, stream, nullptr, emu.list);
+        launchTraceGrid(c->sc, O, D, hit, uv, nullptr, false, st, round, n_fixed, c->sms, stream, nullptr, emu.list2);
     }
     else if (c->accel != PTAP_ACCEL_GRID_COMPAT) launchTraceBvh(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, stream, stamp);
     else launchTraceGrid(c->sc, O, D, hit, uv, counts, count_totals, st, round, n_fixed, c->grid_trace, stream, stamp);
 }
 
 // Per-slot buffers of PTAP_ACCEL_GRID_EMULATED: hit count, kEmuHits x (triangle id, t), the list for the walk, the queue of replays in
-// progress.  152 B per slot.
-size_t emuArenaNeed(size_t n) { return Arena::need(n, sizeof(int)) * 2 + Arena::need(n * kEmuHits, sizeof(int)) + Arena::need(n * kEmuHits, sizeof(float)) + Arena::need(n * 5, sizeof(uint4)); }
+// progress: 156 B per slot, plus 33 MB for the hits of grazing rays in k_emu_full.
+// threads of a k_emu_full launch (one CTA per SM: it runs for ~0.5 % of the rays), each with kBigHits x 16 B of global memory for the hits of a grazing ray
+size_t emuFullThreads(const ptap_ctx* c) { return (size_t)c->sms * kTraceBlock; }
 
-EmuBuf emuFromArena(Arena& A, size_t n)
+size_t emuArenaNeed(const ptap_ctx* c, size_t n)
+{
+    return Arena::need(n, sizeof(int)) * 3 + Arena::need(n * kEmuHits, sizeof(int)) + Arena::need(n * kEmuHits, sizeof(float)) + Arena::need(n * 5, sizeof(uint4)) +
+           Arena::need(emuFullThreads(c) * kBigHits, sizeof(uint4));
+}
+
+EmuBuf emuFromArena(const ptap_ctx* c, Arena& A, size_t n)
 {
     EmuBuf e;
-    e.n = A.alloc<int>(n); e.list = A.alloc<int>(n); e.id = A.alloc<int>(n * kEmuHits); e.t = A.alloc<float>(n * kEmuHits); e.stride = (int)n;
+    e.n = A.alloc<int>(n); e.list = A.alloc<int>(n); e.list2 = A.alloc<int>(n); e.id = A.alloc<int>(n * kEmuHits); e.t = A.alloc<float>(n * kEmuHits); e.stride = (int)n;
     e.cont = A.alloc<uint4>(n * 5); e.cont_cap = (int)n;
+    e.big = A.alloc<uint4>(emuFullThreads(c) * kBigHits);
     return e;
 }
 
@@ -156,13 +164,13 @@ EmuBuf emuFromArena(Arena& A, size_t n)
 int ensureEmuBuffers(ptap_ctx* ctx)
 {
     if (ctx->accel != PTAP_ACCEL_GRID_EMULATED) return PTAP_OK;
-    const size_t N = (size_t)ctx->wv.N, per_lane = emuArenaNeed(N), need = per_lane * (size_t)ctx->lanes + 4096;
+    const size_t N = (size_t)ctx->wv.N, per_lane = emuArenaNeed(ctx, N), need = per_lane * (size_t)ctx->lanes + 4096;
     bool moved = false;
     if (ctx->emu_arena.cap < need) { CK(ctx->emu_arena.reserve(need)); moved = true; }
     if (!moved && ctx->wv.emu.n && ctx->wv.emu.stride == (int)N && ctx->emu_lanes == ctx->lanes) return PTAP_OK;
     ctx->emu_arena.used = 0;
-    ctx->wv.emu = emuFromArena(ctx->emu_arena, N);
-    for (int l = 1; l < ctx->lanes; ++l) ctx->wvx[l].emu = emuFromArena(ctx->emu_arena, N);
+    ctx->wv.emu = emuFromArena(ctx, ctx->emu_arena, N);
+    for (int l = 1; l < ctx->lanes; ++l) ctx->wvx[l].emu = emuFromArena(ctx, ctx->emu_arena, N);
     ctx->emu_lanes = ctx->lanes;
     return PTAP_OK;
 }
@@ -215,13 +223,14 @@ int collect(ptap_ctx* ctx)
         FrameState f2;
         CK(cudaMemcpy(&f2, ctx->wvx[l].st, sizeof f2, cudaMemcpyDeviceToHost));
         const bool later = f2.iter_cur > fs.iter_cur && f2.paths > 0;
-        f2.rays_traced += fs.rays_traced; f2.rays_walked += fs.rays_walked; f2.paths += fs.paths;
+        f2.rays_traced += fs.rays_traced; f2.rays_walked += fs.rays_walked; f2.rays_reemulated += fs.rays_reemulated; f2.paths += fs.paths;
         f2.count_nodes += fs.count_nodes; f2.count_tris += fs.count_tris; f2.count_cells += fs.count_cells; f2.count_refs += fs.count_refs;
         if (later) fs = f2;
-        else { fs.rays_traced = f2.rays_traced; fs.rays_walked = f2.rays_walked; fs.paths = f2.paths; fs.count_nodes = f2.count_nodes; fs.count_tris = f2.count_tris; fs.count_cells = f2.count_cells; fs.count_refs = f2.count_refs; }
+        else { fs.rays_traced = f2.rays_traced; fs.rays_walked = f2.rays_walked; fs.rays_reemulated = f2.rays_reemulated; fs.paths = f2.paths; fs.count_nodes = f2.count_nodes; fs.count_tris = f2.count_tris; fs.count_cells = f2.count_cells; fs.count_refs = f2.count_refs; }
     }
     ctx->stats.rays_traced = (int64_t)fs.rays_traced;
     ctx->stats.rays_walked = (int64_t)fs.rays_walked;
+    ctx->stats.rays_reemulated = (int64_t)fs.rays_reemulated;
     ctx->stats.paths = (int64_t)fs.paths;
     for (int i = 0; i < 16; ++i) ctx->stats.active_per_round[i] = i <= kMaxDepth ? fs.n_active[i] : 0;
     const double rt = fs.rays_traced ? (double)fs.rays_traced : 1.0;
@@ -1100,13 +1109,13 @@ static int traceImpl(ptap_ctx* ctx, const float* rays_od, int32_t n, PtapHit* ou
     CK(cudaSetDevice(ctx->device));
     if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
     size_t need = Arena::need(n, sizeof(float4)) * 3 + Arena::need(n, sizeof(float2)) + Arena::need(n, sizeof(PtapHit)) + Arena::need(n, sizeof(int4)) +
-                  Arena::need((size_t)n * 6, sizeof(float)) + Arena::need(1, sizeof(FrameState)) + emuArenaNeed(n) + 4096;
+                  Arena::need((size_t)n * 6, sizeof(float)) + Arena::need(1, sizeof(FrameState)) + (ctx->accel == PTAP_ACCEL_GRID_EMULATED ? emuArenaNeed(ctx, n) : 0) + 4096;
     if (need > ctx->scratch.cap) CK(ctx->scratch.reserve(need)); else ctx->scratch.used = 0;
     Arena& A = ctx->scratch;
     float4* O = A.alloc<float4>(n); float4* D = A.alloc<float4>(n); float4* hit = A.alloc<float4>(n);
     float2* uv = A.alloc<float2>(n); PtapHit* dout = A.alloc<PtapHit>(n); int4* dcnt = A.alloc<int4>(n);
     FrameState* st = A.alloc<FrameState>(1);
-    const EmuBuf emu = emuFromArena(A, n);
+    const EmuBuf emu = ctx->accel == PTAP_ACCEL_GRID_EMULATED ? emuFromArena(ctx, A, n) : EmuBuf{};
     std::vector<float4> hO(n), hD(n);
     for (int i = 0; i < n; ++i) {
         hO[i] = make_float4(rays_od[6 * (size_t)i], rays_od[6 * (size_t)i + 1], rays_od[6 * (size_t)i + 2], 0.f);
@@ -1210,12 +1219,12 @@ int ptap_bench_trace(ptap_ctx* ctx, const float* rays_od, int32_t n, int32_t rep
     if (!ctx || !ctx->have_scene || !rays_od || n <= 0 || reps <= 0 || !ms_per_launch) return fail(ctx, PTAP_E_INVALID, "bench_trace: bad arguments");
     CK(cudaSetDevice(ctx->device));
     if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
-    size_t need = Arena::need(n, sizeof(float4)) * 3 + Arena::need(1, sizeof(FrameState)) + emuArenaNeed(n) + 4096;
+    size_t need = Arena::need(n, sizeof(float4)) * 3 + Arena::need(1, sizeof(FrameState)) + (ctx->accel == PTAP_ACCEL_GRID_EMULATED ? emuArenaNeed(ctx, n) : 0) + 4096;
     if (need > ctx->scratch.cap) CK(ctx->scratch.reserve(need)); else ctx->scratch.used = 0;
     Arena& A = ctx->scratch;
     float4* O = A.alloc<float4>(n); float4* D = A.alloc<float4>(n); float4* hit = A.alloc<float4>(n);
     FrameState* st = A.alloc<FrameState>(1);
-    const EmuBuf emu = emuFromArena(A, n);
+    const EmuBuf emu = ctx->accel == PTAP_ACCEL_GRID_EMULATED ? emuFromArena(ctx, A, n) : EmuBuf{};
     std::vector<float4> hO(n), hD(n);
     for (int i = 0; i < n; ++i) {
         hO[i] = make_float4(rays_od[6 * (size_t)i], rays_od[6 * (size_t)i + 1], rays_od[6 * (size_t)i + 2], 0.f);

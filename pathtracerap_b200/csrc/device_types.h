@@ -10,6 +10,7 @@ constexpr float kEpsilon = 0.005f;          // Config.h:4
 constexpr float kFloatMax = 9999999.0f;     // Config.h:5
 constexpr float kFloatMin = -9999990.0f;    // Config.h:6
 constexpr int kMaxDepth = 16;               // rounds per iteration the context reserves state for
+constexpr int kBigHits = 108;               // k_emu_full: further hits of a (ray, model) kept per thread in global memory (128 with the 20 in shared memory)
 constexpr int kEmuHits = 8;                 // PTAP_ACCEL_GRID_EMULATED: hits of a (ray, model) that are kept for the replay of the walk
 constexpr int kBvhStack = 160;              // traversal stack entries per ray (upload fails for deeper trees)
 
@@ -78,8 +79,10 @@ struct FrameState {
     int n_active[kMaxDepth + 2];        // rays entering round r
     unsigned int ticket[kMaxDepth + 2]; // tile tickets of the shade kernel, per round
     unsigned int fetch[kMaxDepth + 2];  // work-stealing cursors of the trace kernel, per round
-    unsigned int n_replay[kMaxDepth + 2];      // k_trace_emu: rays of the round handed to the grid walk itself (more hits in one model than it keeps)
-    unsigned int fetch_replay[kMaxDepth + 2];  // work-stealing cursors of that launch (k_trace_grid in list mode)
+    unsigned int n_replay[kMaxDepth + 2];      // PTAP_ACCEL_GRID_EMULATED: slots of the round whose replay did not confirm the closest hit (-> k_emu_full)
+    unsigned int fetch_replay[kMaxDepth + 2];  // work-stealing cursors of k_emu_full
+    unsigned int n_walk[kMaxDepth + 2];        // slots that only the grid walk itself can answer (-> k_trace_grid in list mode)
+    unsigned int fetch_walk[kMaxDepth + 2];    // work-stealing cursors of that launch
     unsigned int fetch_emu[kMaxDepth + 2];     // work-stealing cursors of k_emu_tail
     unsigned int n_cont[kMaxDepth + 2];        // replays that k_emu_setup queued for k_emu_tail
     int iter_cur, iter_next;
@@ -87,6 +90,7 @@ struct FrameState {
     int pad;
     unsigned long long rays_traced;
     unsigned long long rays_walked;     // PTAP_ACCEL_GRID_EMULATED: rays handed to k_trace_grid in list mode
+    unsigned long long rays_reemulated; // PTAP_ACCEL_GRID_EMULATED: rays handed to k_emu_full
     unsigned long long paths;
     unsigned long long count_nodes, count_tris, count_cells, count_refs;   // counting build only
 };
@@ -121,8 +125,10 @@ struct EmuBuf {
     int* n;                     // [slot] hits of the ray in its nearest model (> kEmuHits: not all kept - the walk answers that ray)
     int* id;                    // [hit][slot] their global triangle ids (stride slots per hit)
     float* t;                   // [hit][slot] their model-space t
-    int* list;                  // slots that k_trace_grid must answer (FrameState::n_replay of them)
+    int* list;                  // slots that k_emu_full must answer (FrameState::n_replay of them)
+    int* list2;                 // slots that k_trace_grid must answer (FrameState::n_walk of them)
     uint4* cont;                // queue of replays in progress, 5 x uint4 each (k_emu_setup -> k_emu_tail)
+    uint4* big;                 // k_emu_full: kBigHits x uint4 per thread of its grid (one CTA per SM)
     int stride;
     int cont_cap;               // entries the queue holds
 };

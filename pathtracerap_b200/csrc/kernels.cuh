@@ -45,13 +45,13 @@ __device__ __forceinline__ float exactHitDistance(const SceneDev& sc, V3 bo, V3 
 // closest hit, grid-compat (trace_grid.cu) and BVH (trace_bvh.cu).  n_fixed < 0: read the count from st->n_active[round].
 // stamp (may be null): two 64-bit words that receive the earliest start and the latest end of the launch in %globaltimer nanoseconds
 // (atomicMin / atomicMax by every CTA), so that bench.py can time the closest-hit kernel inside the real multi-lane schedule.
-// list (may be null): walk only the slots list[0 .. st->n_replay[round]) - the second launch of PTAP_ACCEL_GRID_EMULATED.
+// list (may be null): walk only the slots list[0 .. st->n_walk[round]) - the last launch of PTAP_ACCEL_GRID_EMULATED.
 void launchTraceGrid(const SceneDev& sc, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, bool count_totals,
                      FrameState* st, int round, int n_fixed, int grid, cudaStream_t stream, unsigned long long* stamp = nullptr, const int* list = nullptr);
 // trace_emu.cu: the results of the grid walk (tier R0) through the BVH, in two launches: nearest model + all of the ray's hits in it,
 // then the replay of the walk over those hits; slots the replay cannot confirm are appended to emu.list for launchTraceGrid(list)
 void launchTraceEmu(const SceneDev& sc, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, bool count_totals,
-                    FrameState* st, int round, int n_fixed, int grid, int grid_replay, cudaStream_t stream, unsigned long long* stamp, const EmuBuf& emu);
+                    FrameState* st, int round, int n_fixed, int grid, int grid_replay, int grid_full, cudaStream_t stream, unsigned long long* stamp, const EmuBuf& emu);
 int traceEmuOccupancy();
 // grid_device.cu: per-triangle voxel boxes of the grids on the device + the checks that make the emulation exact; *ok = 0 when some list is
 // not what a box-shaped registration produces (the caller then keeps the walk).  grid_tri_range: 2 ints per grid (lowest / highest listed id).

@@ -17,17 +17,19 @@
 //      un-contracted, as in k_trace_grid), its hit-voxel bookkeeping and early exit, the hits of H taking effect in the order the walk
 //      meets them (first voxel along the path that lists them, ascending triangle id inside a voxel: that order decides exact-t ties).
 //   3. If the replayed walk of m* returns t* (bit for bit), the reference's answer for the ray is m* with the walk's triangle: every other
-//      model's answer is a real hit, hence not nearer, and a model with a lower index that tied at D* would itself have been m*
-//      (the closest-hit rule breaks ties towards the lower model index exactly as Renderer.cpp:393 does in model order).
-// Two launches: k_trace_emu is k_trace_bvh's state machine (TLAS pruning by the nearest hit so far, cross-instance ranking, deferred exact
+//      model's answer is a real hit, hence not nearer (with one exception, handled in k_trace_emu: `ambiguous` instances), and a model
+//      with a lower index that tied at D* would itself have been m* (the closest-hit rule breaks ties towards the lower model index
+//      exactly as Renderer.cpp:393 does in model order).
+// Launches: k_trace_emu is k_trace_bvh's state machine (TLAS pruning by the nearest hit so far, cross-instance ranking, deferred exact
 // distance) except that inside an instance the ray interval never shrinks and every hit is recorded; the hits of the currently nearest
-// instance are kept (two buffers in shared memory that swap roles) and written out with the closest hit.  k_emu_replay then runs one
-// thread per slot - full SIMT width, where the same loop inside the traversal kernel ran with two or three lanes and made the first
-// version of this file slower than the walk - and either confirms the hit (fixing the triangle id when the walk's tie rule differs) or
-// appends the slot to a list.  Rays on the list - those where the walk misses the closest hit (the 0.3-0.6 %), and any (ray, model) with
-// more than kEmuHits hits - are answered by the walk itself (k_trace_grid in list mode, third launch), so the result is exact whatever
-// the geometry.  api.cu refuses this mode (and keeps the walk) when the lists on the device are not box-shaped, not ascending, or list
-// triangles outside the mesh of a model that uses the grid.
+// instance are kept (two buffers in shared memory that swap roles) and written out with the closest hit.  k_emu_setup + k_emu_tail then
+// replay the walk of that model (see there for why two kernels) and either confirm the hit - fixing the triangle id when the walk's tie
+// rule differs - or append the slot to a list.  Rays on the list - those where the walk misses the closest hit (the 0.3-0.6 %), any
+// (ray, model) with more than kEmuHits hits, and the ambiguous ones of fact 3 - are answered by the walk itself (k_trace_grid in list
+// mode, last launch), so the result is exact whatever the geometry.  api.cu refuses this mode (and keeps the walk) when the lists on the
+// device are not box-shaped, not ascending, or list triangles outside the mesh of a model that uses the grid.  The first version ran the
+// replay inside this kernel's exit step and was slower than the walk: a 30-step loop for the two or three lanes that leave an instance
+// together.
 // Parity: tests/test_gpu_emulated.py, tests/test_gpu_production.py[emu] (bit-equal to the oracle's R0 and to k_trace_grid: fixtures, random
 // rays, every round of the production path, whole films, and scenes that force the list path).
 #include "bvh_traverse.cuh"
@@ -41,6 +43,7 @@ namespace {
 #ifndef PTAP_EMU_MIN_CTAS
 #define PTAP_EMU_MIN_CTAS 7
 #endif
+constexpr int kFullHits = 20;                 // hits of a (ray, model) that k_emu_full keeps in shared memory (46 KB per CTA with the stack)
 constexpr int kEmuStack = 12;                 // traversal-stack entries per ray in shared memory (as k_trace_bvh)
 constexpr int kReplayBlock = 128, kReplayBatch = 32;   // k_emu_tail: threads per CTA, queue entries per cursor fetch
 constexpr int kSetupBlock = 128;                      // k_emu_setup
@@ -341,6 +344,39 @@ __device__ __forceinline__ bool replayStep(Replay& r, int GX, int GY, int GZ, co
     return finished;
 }
 
+// the start of a model's walk (Renderer.cpp:150-170, 252-311): slab test against the mesh box, entry point, entry voxel, DDA increments.
+// false: the reference does not enter the grid (its answer for the model is "no hit")
+__device__ __forceinline__ bool replayEnter(const InstanceTrace* __restrict__ inst, const V3& ro, const V3& rd, int GX, int GY, int GZ, Replay& r)
+{
+    const float4 bbmin_wx = ldg4(&inst->bb_min), bbmax_wy = ldg4(&inst->bb_max), gridrec = ldg4(&inst->grid);
+    const V3 mn = v3(bbmin_wx), mx = v3(bbmax_wy);
+    const V3 inv = v3(xdiv(1.0f, rd.x), xdiv(1.0f, rd.y), xdiv(1.0f, rd.z));   // Renderer.cpp:383
+    // Renderer.cpp:150-170
+    const float t1 = rd.x == 0.0f ? kFloatMin : xmul(xsub(mn.x, ro.x), inv.x);
+    const float t2 = rd.x == 0.0f ? kFloatMax : xmul(xsub(mx.x, ro.x), inv.x);
+    const float t3 = rd.y == 0.0f ? kFloatMin : xmul(xsub(mn.y, ro.y), inv.y);
+    const float t4 = rd.y == 0.0f ? kFloatMax : xmul(xsub(mx.y, ro.y), inv.y);
+    const float t5 = rd.z == 0.0f ? kFloatMin : xmul(xsub(mn.z, ro.z), inv.z);
+    const float t6 = rd.z == 0.0f ? kFloatMax : xmul(xsub(mx.z, ro.z), inv.z);
+    const float sl_min = max_std(max_std(min_std(t1, t2), min_std(t3, t4)), min_std(t5, t6));
+    const float sl_max = min_std(min_std(max_std(t1, t2), max_std(t3, t4)), max_std(t5, t6));
+    const V3 p = xadd(ro, xscale(rd, sl_min));
+    if ((sl_max < 0 || sl_min > sl_max) || (xsub(p.x, mn.x) < -kEpsilon || xsub(p.y, mn.y) < -kEpsilon || xsub(p.z, mn.z) < -kEpsilon)) return false;   // Renderer.cpp:252-259
+    const float wx = bbmin_wx.w, wy = bbmax_wy.w, wz = gridrec.x;
+    r.ix = f2i_x86(xdiv(xabs(xadd(xsub(p.x, mn.x), kEpsilon)), wx));
+    r.iy = f2i_x86(xdiv(xabs(xadd(xsub(p.y, mn.y), kEpsilon)), wy));
+    r.iz = f2i_x86(xdiv(xabs(xadd(xsub(p.z, mn.z), kEpsilon)), wz));
+    r.ix = min(max(r.ix, 0), GX - 1); r.iy = min(max(r.iy, 0), GY - 1); r.iz = min(max(r.iz, 0), GZ - 1);
+    r.tmx = kFloatMax; r.tmy = kFloatMax; r.tmz = kFloatMax; r.dx = kFloatMax; r.dy = kFloatMax; r.dz = kFloatMax;
+    if (rd.x != 0) { const int nx = rd.x > 0.0f ? r.ix + 1 : r.ix; r.dx = xabs(xmul(wx, inv.x)); r.tmx = xmul(xsub(xadd(mn.x, xmul((float)nx, wx)), p.x), inv.x); }
+    if (rd.y != 0) { const int ny = rd.y > 0.0f ? r.iy + 1 : r.iy; r.dy = xabs(xmul(wy, inv.y)); r.tmy = xmul(xsub(xadd(mn.y, xmul((float)ny, wy)), p.y), inv.y); }
+    if (rd.z != 0) { const int nz = rd.z > 0.0f ? r.iz + 1 : r.iz; r.dz = xabs(xmul(wz, inv.z)); r.tmz = xmul(xsub(xadd(mn.z, xmul((float)nz, wz)), p.z), inv.z); }
+    // guard bits of the axes along which the voxel index grows: "the walk has passed a box for good" is one mask test
+    r.gpos = (rd.x > 0.0f ? 1u << 9 : 0u) | (rd.y > 0.0f ? 1u << 19 : 0u) | (rd.z > 0.0f ? 1u << 29 : 0u);
+    r.seen = 0u; r.passed = false; r.cx = 0; r.cy = 0; r.cz = 0; r.best_k = -1; r.k = 0; r.inter = false;
+    return true;
+}
+
 // the hits of slot i and their voxel boxes into the lane's shared-memory column; (ulo, uhi) = the box around all of them
 __device__ __forceinline__ void replayLoadHits(const SceneDev& sc, const EmuBuf& emu, int i, int nh, int first_id, float t_star, unsigned& ulo, unsigned& uhi,
                                                unsigned* s_lo, unsigned* s_hi, float* s_ts, int* s_ids, int stride)
@@ -408,33 +444,7 @@ k_emu_setup(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
             const float4 w0 = ldg4(&inst->w2m[0]), w1 = ldg4(&inst->w2m[1]), w2 = ldg4(&inst->w2m[2]);
             const V3 ro = xmat4(w0, w1, w2, bo, 1.0f);                               // Renderer.cpp:381
             const V3 rd = xnormalize(xmat4(w0, w1, w2, bd, 0.0f));                   // Renderer.cpp:382
-            const float4 bbmin_wx = ldg4(&inst->bb_min), bbmax_wy = ldg4(&inst->bb_max), gridrec = ldg4(&inst->grid);
-            const V3 mn = v3(bbmin_wx), mx = v3(bbmax_wy);
-            const V3 inv = v3(xdiv(1.0f, rd.x), xdiv(1.0f, rd.y), xdiv(1.0f, rd.z));   // Renderer.cpp:383
-            // Renderer.cpp:150-170
-            const float t1 = rd.x == 0.0f ? kFloatMin : xmul(xsub(mn.x, ro.x), inv.x);
-            const float t2 = rd.x == 0.0f ? kFloatMax : xmul(xsub(mx.x, ro.x), inv.x);
-            const float t3 = rd.y == 0.0f ? kFloatMin : xmul(xsub(mn.y, ro.y), inv.y);
-            const float t4 = rd.y == 0.0f ? kFloatMax : xmul(xsub(mx.y, ro.y), inv.y);
-            const float t5 = rd.z == 0.0f ? kFloatMin : xmul(xsub(mn.z, ro.z), inv.z);
-            const float t6 = rd.z == 0.0f ? kFloatMax : xmul(xsub(mx.z, ro.z), inv.z);
-            const float sl_min = max_std(max_std(min_std(t1, t2), min_std(t3, t4)), min_std(t5, t6));
-            const float sl_max = min_std(min_std(max_std(t1, t2), max_std(t3, t4)), max_std(t5, t6));
-            const V3 p = xadd(ro, xscale(rd, sl_min));
-            if (!(sl_max < 0 || sl_min > sl_max) &&
-                !(xsub(p.x, mn.x) < -kEpsilon || xsub(p.y, mn.y) < -kEpsilon || xsub(p.z, mn.z) < -kEpsilon)) {      // Renderer.cpp:252-259
-                const float wx = bbmin_wx.w, wy = bbmax_wy.w, wz = gridrec.x;
-                r.ix = f2i_x86(xdiv(xabs(xadd(xsub(p.x, mn.x), kEpsilon)), wx));
-                r.iy = f2i_x86(xdiv(xabs(xadd(xsub(p.y, mn.y), kEpsilon)), wy));
-                r.iz = f2i_x86(xdiv(xabs(xadd(xsub(p.z, mn.z), kEpsilon)), wz));
-                r.ix = min(max(r.ix, 0), GX - 1); r.iy = min(max(r.iy, 0), GY - 1); r.iz = min(max(r.iz, 0), GZ - 1);
-                r.tmx = kFloatMax; r.tmy = kFloatMax; r.tmz = kFloatMax; r.dx = kFloatMax; r.dy = kFloatMax; r.dz = kFloatMax;
-                if (rd.x != 0) { const int nx = rd.x > 0.0f ? r.ix + 1 : r.ix; r.dx = xabs(xmul(wx, inv.x)); r.tmx = xmul(xsub(xadd(mn.x, xmul((float)nx, wx)), p.x), inv.x); }
-                if (rd.y != 0) { const int ny = rd.y > 0.0f ? r.iy + 1 : r.iy; r.dy = xabs(xmul(wy, inv.y)); r.tmy = xmul(xsub(xadd(mn.y, xmul((float)ny, wy)), p.y), inv.y); }
-                if (rd.z != 0) { const int nz = rd.z > 0.0f ? r.iz + 1 : r.iz; r.dz = xabs(xmul(wz, inv.z)); r.tmz = xmul(xsub(xadd(mn.z, xmul((float)nz, wz)), p.z), inv.z); }
-                // guard bits of the axes along which the voxel index grows: "the walk has passed a box for good" is one mask test
-                r.gpos = (rd.x > 0.0f ? 1u << 9 : 0u) | (rd.y > 0.0f ? 1u << 19 : 0u) | (rd.z > 0.0f ? 1u << 29 : 0u);
-                r.seen = 0u; r.passed = false; r.cx = 0; r.cy = 0; r.cz = 0; r.best_k = -1; r.k = 0; r.inter = false;
+            if (replayEnter(inst, ro, rd, GX, GY, GZ, r)) {
                 replayLoadHits(sc, emu, i, r.nh, __float_as_int(h.y), r.t_star, r.ulo, r.uhi, s_lo, s_hi, s_ts, s_ids, kSetupBlock);
                 walking = true;
 #pragma unroll 1
@@ -530,8 +540,241 @@ k_emu_tail(SceneDev sc, const float4* __restrict__ O, const float4* __restrict__
     }
 }
 
+// ---- launch 4: the rays the replay could not confirm, emulated in FULL -----------------------------------------------------------------
+// For a ray on the list the walk of the nearest model does not return the closest hit, so the reference's answer may come from any model.
+// This kernel answers it without the voxel lists all the same: every instance the ray's line meets is traversed for ALL its hits (no
+// pruning by distance: a farther model may hold the answer), every such model's walk is replayed on the spot, and the models' answers are
+// combined exactly as Renderer.cpp:388-398 does (exact world distances, ties to the lower model index).  It runs for ~0.5 % of the rays;
+// walking the grids for them instead (k_trace_grid in list mode) cost 0.4 ms per bounce on the reference's scene and milliseconds on a
+// dense mesh (one lane testing the hundreds of triangles of every voxel), for any number of rays.  It keeps kFullHits + kBigHits hits
+// per model (rays with more than kEmuHits in their nearest model come here too: a ray that grazes a finely tessellated surface crosses
+// it dozens of times); what still goes to the walk is a ray with more than that.
+template <bool UV>
+__global__ void __launch_bounds__(kTraceBlock, 4)
+k_emu_full(SceneDev sc, const float4* __restrict__ O, const float4* __restrict__ D, float4* __restrict__ hit, float2* __restrict__ uv,
+           FrameState* st, int round, EmuBuf emu)
+{
+    // hits beyond the kFullHits kept in shared memory: kBigHits more per thread in global memory, (id, t, lo | seen flag, hi) each
+    uint4* __restrict__ big = emu.big + (size_t)(blockIdx.x * blockDim.x + threadIdx.x) * kBigHits;
+    const int n = (int)st->n_replay[round];
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->rays_reemulated += (unsigned long long)n;
+    unsigned int* cursor = &st->fetch_replay[round];
+    const int lane = threadIdx.x & 31;
+    const int GX = sc.gx, GY = sc.gy, GZ = sc.gz;
+    if (n == 0 || sc.tlas_root < 0) return;
+
+    int sp = 0;
+    __shared__ int s_stack[kEmuStack * kTraceBlock];
+    int l_stack[kBvhStack - kEmuStack];
+    auto push = [&](int v) { if (sp < kEmuStack) s_stack[sp * kTraceBlock + threadIdx.x] = v; else l_stack[sp - kEmuStack] = v; ++sp; };
+    auto pop = [&]() { --sp; return sp < kEmuStack ? s_stack[sp * kTraceBlock + threadIdx.x] : l_stack[sp - kEmuStack]; };
+    __shared__ int s_ids[kFullHits * kTraceBlock];                  // [hit][thread]: the hits of the instance being traversed
+    __shared__ float s_ts[kFullHits * kTraceBlock];
+    __shared__ unsigned s_lo[kFullHits * kTraceBlock], s_hi[kFullHits * kTraceBlock];
+    int nh = 0;
+    float c_t = kFloatMax;                          // smallest t of the instance's hits: the replay may stop when the walk meets it
+    bool overflow = false;
+
+    int node = kDone, i = -1;
+    V3 bo = v3(0, 0, 0), bd = v3(0, 0, 0), winv = v3(0, 0, 0);
+    unsigned near_off = 0u, wnear_off = 0u;
+    V3 ro = v3(0, 0, 0), rd = v3(0, 0, 1), rinv = v3(0, 0, 0);
+    float tmin = 0.0f, tmax = 0.0f;
+    float g_dist = kFloatMax, g_t = 0.0f;
+    int g_model = -1, g_tri = -1;
+    int w_next = 0, w_end = 0;
+    bool exhausted = false;
+    const int vote_tri = sc.vote_tri, vote_inst = sc.vote_inst, vote_refill = sc.vote_refill;
+
+    for (;;) {
+        if (node >= 0) {
+            int key[4], lnk[4];
+            nodeChildren(reinterpret_cast<const char*>(&sc.nodes[node]), ro, rinv, near_off, tmin, tmax, key, lnk);
+            if (key[3] != 0x7f800000) push(lnk[3]);
+            if (key[2] != 0x7f800000) push(lnk[2]);
+            if (key[1] != 0x7f800000) push(lnk[1]);
+            if (key[0] != 0x7f800000) node = lnk[0]; else node = pop();
+        }
+        const unsigned code = ~(unsigned)node;
+        const unsigned state = min(code >> 29, 4u);             // 0 tri, 1 enter, 2 exit, 3 done, 4 inner
+        const bool live = state != 3u || i >= 0 || !exhausted;
+        const unsigned sum = __reduce_add_sync(kFull, live ? 1u << (6u * state) : 0u);
+        if (sum == 0u) break;
+        const int n_tri = sum & 63u, n_enter = (sum >> 6) & 63u, n_exit = (sum >> 12) & 63u, n_done = (sum >> 18) & 63u, n_inner = (sum >> 24) & 63u;
+        const bool s_tri = state == 0u, s_enter = state == 1u, s_exit = state == 2u, s_done = state == 3u;
+
+        // ---- one triangle of the held leaf: the reference's predicate (Renderer.cpp:174-201), every hit recorded with its voxel box
+        if (s_tri && n_tri >= min(vote_tri, n_inner)) {
+            const int k = (int)(code >> 3);
+            const F8 ta = ldg8(&sc.bvh_tris[k]), tb = ldg8(reinterpret_cast<const char*>(&sc.bvh_tris[k]) + 32);
+            const V3 v0 = v3(ta.v[0], ta.v[1], ta.v[2]), v0v1 = v3(ta.v[3], ta.v[4], ta.v[5]), v0v2 = v3(ta.v[6], ta.v[7], tb.v[0]);
+            const V3 pvec = xcross(rd, v0v2);
+            const float det = xdot(v0v1, pvec);
+            const float invDet = xdiv(1.0f, det);
+            const V3 tvec = xsub(ro, v0);
+            const float u = xmul(xdot(tvec, pvec), invDet);
+            const V3 qvec = xcross(tvec, v0v1);
+            const float v = xmul(xdot(rd, qvec), invDet);
+            const float t = xmul(xdot(v0v2, qvec), invDet);
+            const bool reject = (xabs(xsub(det, 0.0f)) < kEpsilon) | (u < (0.0f - kEpsilon)) | (u > (1.0f + kEpsilon)) |
+                                (v < (0.0f - kEpsilon)) | (xadd(u, v) > (1.0f + kEpsilon)) | (t < (0.0f - kEpsilon));
+            if (!reject) {
+                if (nh < kFullHits + kBigHits) {
+                    const int id = __float_as_int(tb.v[1]);
+                    const int2 bx = __ldg(&sc.tri_box[id]);
+                    if (nh < kFullHits) {
+                        const int slot = nh * kTraceBlock + threadIdx.x;
+                        s_ids[slot] = id; s_ts[slot] = t; s_lo[slot] = (unsigned)bx.x; s_hi[slot] = (unsigned)bx.y;
+                    } else big[nh - kFullHits] = make_uint4((unsigned)id, __float_as_uint(t), (unsigned)bx.x, (unsigned)bx.y);
+                }
+                ++nh;
+                if (t < c_t) c_t = t;
+            }
+            if (code & 7u) node = (int)~(code + 7u); else node = pop();
+        }
+        // ---- enter instance `im` (Renderer.cpp:381-384)
+        if (s_enter && n_enter >= min(vote_inst, n_inner)) {
+            const int im = (int)(code & kIndexMask);
+            const InstanceTrace* __restrict__ inst = &sc.inst[im];
+            const float4 w0 = ldg4(&inst->w2m[0]), w1 = ldg4(&inst->w2m[1]), w2 = ldg4(&inst->w2m[2]);
+            ro = xmat4(w0, w1, w2, bo, 1.0f);                                   // Renderer.cpp:381
+            rd = xnormalize(xmat4(w0, w1, w2, bd, 0.0f));                       // Renderer.cpp:382
+            rinv = v3(safeInv(rd.x), safeInv(rd.y), safeInv(rd.z));
+            near_off = nearOffsets(rd);
+            tmin = -(kEpsilon + 1e-4f); tmax = 3.0e38f;
+            nh = 0; c_t = kFloatMax;
+            push((int)~(kExitBit | (unsigned)im));
+            node = __float_as_int(__ldg(&inst->grid.z));
+        }
+        // ---- leave instance `im`: replay its walk over the hits found, then the reference's nearest-model rule (Renderer.cpp:388-398)
+        if (s_exit && n_exit >= min(vote_inst, n_inner)) {
+            const int im = (int)(code & kIndexMask);
+            if (nh > kFullHits + kBigHits) overflow = true;
+            else if (nh > kFullHits) {
+                // a ray that grazes a finely tessellated surface: the same replay with the further hits read from global memory (no box
+                // around all hits, no burst: rare)
+                Replay r;
+                r.i = i; r.nh = nh; r.t_star = c_t; r.w_tri = -1; r.w_t = kFloatMax; r.steps = 0;
+                if (replayEnter(&sc.inst[im], ro, rd, GX, GY, GZ, r)) {
+                    const bool px = r.gpos & (1u << 9), py = r.gpos & (1u << 19), pz = r.gpos & (1u << 29);
+                    for (;;) {
+                        const unsigned v = (unsigned)r.ix | ((unsigned)r.iy << 10) | ((unsigned)r.iz << 20);
+                        bool any = false;
+#pragma unroll 1
+                        for (int j = 0; j < nh; ++j) {
+                            unsigned lj, hj; float tj; int idj; bool was_seen;
+                            if (j < kFullHits) {
+                                const int slot = j * kTraceBlock + threadIdx.x;
+                                lj = s_lo[slot]; hj = s_hi[slot]; tj = s_ts[slot]; idj = s_ids[slot]; was_seen = (r.seen >> j) & 1u;
+                            } else {
+                                const uint4 e = big[j - kFullHits];
+                                idj = (int)e.x; tj = __uint_as_float(e.y); lj = e.z & 0x7fffffffu; hj = e.w; was_seen = e.z >> 31;
+                            }
+                            const unsigned d1 = (v | kGuard) - lj, d2 = (hj | kGuard) - v;
+                            if ((d1 & d2 & kGuard) != kGuard) continue;
+                            any = true;
+                            if (was_seen) continue;
+                            if (j < kFullHits) r.seen |= 1u << j; else big[j - kFullHits].z = lj | 0x80000000u;
+                            if (r.w_t > tj || (r.w_t == tj && r.best_k == r.k && idj < r.w_tri)) { r.w_t = tj; r.w_tri = idj; r.best_k = r.k; }
+                        }
+                        if (r.w_t == r.t_star) break;
+                        if (any) { r.cx = r.ix; r.cy = r.iy; r.cz = r.iz; r.inter = true; }
+                        if (r.inter && (abs(r.cx - r.ix) > 2 || abs(r.cy - r.iy) > 2 || abs(r.cz - r.iz) > 2)) break;
+                        const bool sx = r.tmx < r.tmy && r.tmx < r.tmz, sy = !sx && r.tmy < r.tmz;
+                        r.ix += sx ? (px ? 1 : -1) : 0; r.iy += sy ? (py ? 1 : -1) : 0; r.iz += (sx || sy) ? 0 : (pz ? 1 : -1);
+                        const float tsel = sx ? r.tmx : sy ? r.tmy : r.tmz;
+                        const int isel = sx ? r.ix : sy ? r.iy : r.iz, lim = sx ? (px ? GX : -1) : sy ? (py ? GY : -1) : (pz ? GZ : -1);
+                        if (isel == lim || tsel >= kFloatMax) break;
+                        r.tmx = sx ? xadd(r.tmx, r.dx) : r.tmx; r.tmy = sy ? xadd(r.tmy, r.dy) : r.tmy; r.tmz = (sx || sy) ? r.tmz : xadd(r.tmz, r.dz);
+                        ++r.k;
+                    }
+                    if (r.w_tri >= 0) {
+                        const float dn = exactHitDistance(sc, bo, bd, im, r.w_t);
+                        if (g_dist > dn || (g_dist == dn && g_model >= 0 && im < g_model)) { g_dist = dn; g_model = im; g_tri = r.w_tri; g_t = r.w_t; }
+                    }
+                }
+            }
+            else if (nh > 0) {
+                Replay r;
+                r.i = i; r.nh = nh; r.t_star = c_t; r.w_tri = -1; r.w_t = kFloatMax; r.steps = 0;
+                if (replayEnter(&sc.inst[im], ro, rd, GX, GY, GZ, r)) {
+                    r.ulo = 0x1ffu | (0x1ffu << 10) | (0x1ffu << 20); r.uhi = 0u;
+#pragma unroll 1
+                    for (int j = 0; j < nh; ++j) {
+                        const unsigned lj = s_lo[j * kTraceBlock + threadIdx.x], hj = s_hi[j * kTraceBlock + threadIdx.x];
+                        if ((((hj | kGuard) - lj) & kGuard) == kGuard) {
+                            r.ulo = min(r.ulo & 0x1ffu, lj & 0x1ffu) | min(r.ulo & (0x1ffu << 10), lj & (0x1ffu << 10)) | min(r.ulo & (0x1ffu << 20), lj & (0x1ffu << 20));
+                            r.uhi = max(r.uhi & 0x1ffu, hj & 0x1ffu) | max(r.uhi & (0x1ffu << 10), hj & (0x1ffu << 10)) | max(r.uhi & (0x1ffu << 20), hj & (0x1ffu << 20));
+                        }
+                    }
+#pragma unroll 1
+                    while (!replayStep(r, GX, GY, GZ, s_lo, s_hi, s_ts, s_ids, kTraceBlock)) { }
+                    if (r.w_tri >= 0) {
+                        const float dn = exactHitDistance(sc, bo, bd, im, r.w_t);
+                        if (g_dist > dn || (g_dist == dn && g_model >= 0 && im < g_model)) { g_dist = dn; g_model = im; g_tri = r.w_tri; g_t = r.w_t; }   // Renderer.cpp:393 in model order
+                    }
+                }
+            }
+            nh = 0; c_t = kFloatMax;
+            ro = bo; rinv = winv; near_off = wnear_off;
+            tmin = sc.tmin_world; tmax = 3.0e38f;                                // no pruning by distance: a farther model may hold the answer
+            node = pop();
+        }
+        // ---- retire finished rays, refill the lanes from the warp's batch of the list
+        if (n_done > 0 && n_done >= min(vote_refill, n_inner)) {
+            const unsigned m_done = __ballot_sync(kFull, s_done && live);
+            if (s_done && i >= 0) {
+                if (overflow) emu.list2[atomicAdd(&st->n_walk[round], 1u)] = i;      // more hits in one model than are kept: the walk itself
+                else {
+                    const bool found = g_dist < kFloatMax;
+                    hit[i] = make_float4(found ? g_dist : kFloatMax, __int_as_float(found ? g_tri : -1), __int_as_float(found ? g_model : -1), found ? g_t : 0.0f);
+                    if (UV && uv) {
+                        float2 w = make_float2(0.0f, 0.0f);
+                        if (found) {                                                     // barycentrics as the predicate computes them
+                            const InstanceTrace* __restrict__ inst = &sc.inst[g_model];
+                            const float4 w0 = ldg4(&inst->w2m[0]), w1 = ldg4(&inst->w2m[1]), w2 = ldg4(&inst->w2m[2]);
+                            const V3 mo = xmat4(w0, w1, w2, bo, 1.0f), md = xnormalize(xmat4(w0, w1, w2, bd, 0.0f));
+                            const float4 a = ldg4(&sc.tris[g_tri].v0), b = ldg4(&sc.tris[g_tri].e1), c = ldg4(&sc.tris[g_tri].e2);
+                            const V3 pvec = xcross(md, v3(c));
+                            const float invDet = xdiv(1.0f, xdot(v3(b), pvec));
+                            const V3 tvec = xsub(mo, v3(a));
+                            w = make_float2(xmul(xdot(tvec, pvec), invDet), xmul(xdot(md, xcross(tvec, v3(b))), invDet));
+                        }
+                        uv[i] = w;
+                    }
+                }
+                i = -1;
+            }
+            if (w_next >= w_end && !exhausted) {
+                unsigned b = 0;
+                if (lane == 0) b = atomicAdd(cursor, 32u);
+                b = __shfl_sync(kFull, b, 0);
+                if (b >= (unsigned)n) { exhausted = true; w_next = w_end = n; }
+                else { w_next = (int)b; w_end = min((int)b + 32, n); }
+            }
+            const int avail = w_end - w_next;
+            const int rank = __popc(m_done & ((1u << lane) - 1u));
+            if (s_done && live && rank < avail) {
+                i = __ldg(&emu.list[w_next + rank]);
+                const float4 o4 = O[i], d4 = D[i];
+                bo = v3(o4); bd = v3(d4);
+                const float il = rsqrtf(bd.x * bd.x + bd.y * bd.y + bd.z * bd.z);
+                winv = v3(safeInv(bd.x * il), safeInv(bd.y * il), safeInv(bd.z * il));
+                wnear_off = nearOffsets(bd);
+                ro = bo; rinv = winv; near_off = wnear_off;
+                tmin = sc.tmin_world; tmax = 3.0e38f;
+                g_dist = kFloatMax; g_model = -1; g_tri = -1; g_t = 0.0f;
+                nh = 0; c_t = kFloatMax; overflow = false;
+                sp = 0; push(kDone);
+                node = sc.tlas_root;
+            }
+            w_next += min(__popc(m_done), avail);
+        }
+    }
+}
+
 void launchTraceEmu(const SceneDev& sc, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, bool count_totals,
-                    FrameState* st, int round, int n_fixed, int grid, int grid_replay, cudaStream_t stream, unsigned long long* stamp, const EmuBuf& emu)
+                    FrameState* st, int round, int n_fixed, int grid, int grid_replay, int grid_full, cudaStream_t stream, unsigned long long* stamp, const EmuBuf& emu)
 {
     const bool count = counts || count_totals;
     const int grid_setup = grid_replay * 2;
@@ -547,6 +790,8 @@ void launchTraceEmu(const SceneDev& sc, const float4* O, const float4* D, float4
         k_emu_setup<false, false><<<grid_setup, kSetupBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, n_fixed, emu);
         k_emu_tail<false, false><<<grid_replay, kReplayBlock, 0, stream>>>(sc, O, D, hit, uv, counts, st, round, emu);
     }
+    if (uv) k_emu_full<true><<<grid_full, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, st, round, emu);
+    else k_emu_full<false><<<grid_full, kTraceBlock, 0, stream>>>(sc, O, D, hit, uv, st, round, emu);
 }
 
 int traceEmuOccupancy()

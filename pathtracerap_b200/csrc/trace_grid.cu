@@ -72,11 +72,11 @@ k_trace_grid(SceneDev sc, const float4* __restrict__ O, const float4* __restrict
 {
     constexpr unsigned kFull = 0xffffffffu;
     // list != null: the second launch of PTAP_ACCEL_GRID_EMULATED - only the slots k_trace_emu (trace_emu.cu) handed over are walked
-    const int n = list ? (int)st->n_replay[round] : n_fixed >= 0 ? n_fixed : st->n_active[round];
+    const int n = list ? (int)st->n_walk[round] : n_fixed >= 0 ? n_fixed : st->n_active[round];
     if (blockIdx.x == 0 && threadIdx.x == 0 && n_fixed < 0 && !list) st->rays_traced += (unsigned long long)n;
     if (blockIdx.x == 0 && threadIdx.x == 0 && list) st->rays_walked += (unsigned long long)n;
     if (stamp && threadIdx.x == 0) atomicMin(stamp, globalTimerNs());
-    unsigned int* cursor = list ? &st->fetch_replay[round] : &st->fetch[round];
+    unsigned int* cursor = list ? &st->fetch_walk[round] : &st->fetch[round];
     const int lane = threadIdx.x & 31;
     const int GX = sc.gx, GY = sc.gy, GZ = sc.gz;
     unsigned long long tot_x = 0, tot_y = 0, tot_z = 0;

@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kGenBlock) k_generate(WaveDev wv, int iter_now
         st->paths += (unsigned long long)wv.N;
     }
     if (tid >= 1 && tid <= kMaxDepth + 1) st->n_active[tid] = 0;
-    if (tid < kMaxDepth + 2) { st->ticket[tid] = 0u; st->fetch[tid] = 0u; st->n_replay[tid] = 0u; st->fetch_replay[tid] = 0u; st->fetch_emu[tid] = 0u; st->n_cont[tid] = 0u; }
+    if (tid < kMaxDepth + 2) { st->ticket[tid] = 0u; st->fetch[tid] = 0u; st->n_replay[tid] = 0u; st->fetch_replay[tid] = 0u; st->fetch_emu[tid] = 0u; st->n_cont[tid] = 0u; st->n_walk[tid] = 0u; st->fetch_walk[tid] = 0u; }
     const int nwords = wv.nscan * wv.depth;
     for (int i = tid; i < nwords; i += stride) wv.tile_status[i] = 0ull;      // one look-back word per 2048-slot scan block and round
     for (int i = tid; i < wv.N; i += stride) {

@@ -72,9 +72,11 @@ def test_emulated_film_is_the_walks_film(gpu_scene):
             r.frame_begin(); r.render(0, iters); r.sync()
             films[(accel, cache)] = (r.film().copy(), r.stats()["rays_traced"], list(r.stats()["active_per_round"]))
             if accel == ACCEL_GRID_EMULATED:
-                walked = r.stats()["rays_walked"] / r.stats()["rays_traced"]
-                print(f"emulated walk, cache={cache}: {walked:.4%} of the rays answered by the walk itself")
-                assert 0 < walked < 0.05                     # the rays on which the walk is not a closest-hit query, and nothing like all of them
+                st = r.stats()
+                full, walked = st["rays_reemulated"] / st["rays_traced"], st["rays_walked"] / st["rays_traced"]
+                print(f"emulated walk, cache={cache}: {full:.4%} of the rays emulated in full, {walked:.4%} answered by the walk itself")
+                assert 0 < full < 0.05                       # the rays on which the walk is not a closest-hit query, and nothing like all of them
+                assert walked < 0.001                        # only rays with more than 8 hits in one model are ever walked
         r.free()
     for cache in (True, False):
         a, b = films[(ACCEL_GRID_COMPAT, cache)], films[(ACCEL_GRID_EMULATED, cache)]
@@ -105,11 +107,12 @@ def _stacked_scene(copies):
     return s
 
 
-@pytest.mark.parametrize("copies", [3, 12])
+@pytest.mark.parametrize("copies", [3, 12, 30])
 def test_more_hits_than_slots_goes_to_the_walk(port, copies):
-    """12 coincident copies: every ray through the quad has 12 (or 24, on the diagonal) hits in one model - beyond the 8 the replay keeps -
-    and must be answered by the walk itself in the second launch; 3 copies stay inside the emulation.  Both must equal the oracle's R0,
-    exact-t ties included (coincident triangles have bit-equal t: the lowest id listed first wins, Renderer.cpp:209)."""
+    """3 coincident copies stay inside the fast path; with 12, every ray through the quad has 12 (24 on the diagonal) hits in one model -
+    beyond the 8 the replay keeps - and is emulated in full (k_emu_full keeps 20); with 30 it must be answered by the walk itself in the
+    last launch.  All must equal the oracle's R0, exact-t ties included (coincident triangles have bit-equal t: the lowest id listed
+    first wins, Renderer.cpp:209)."""
     from pathtracerap_b200 import ACCEL_GRID_COMPAT, ACCEL_GRID_EMULATED, Renderer
     s = _stacked_scene(copies)
     a = s.arrays()
@@ -168,4 +171,65 @@ def test_lists_that_are_not_boxes_are_refused(gpu_scene):
     r.allocateOnGPU(s2)
     with pytest.raises(PtapError, match="box-shaped"):
         r.set_accel(ACCEL_GRID_EMULATED)
+    r.free()
+
+
+def test_emulated_on_the_million_triangle_mesh(libptap):
+    """BASELINE configs[3]'s mesh (1.3 M triangles) through the reference's fixed 25^3 grid: ~84 triangles per voxel, and rays that graze the
+    displaced surface cross it dozens of times (more hits in one model than the fast path or the shared-memory part of k_emu_full keep).
+    GPU against GPU: the emulation must equal the walk on camera rays, bounce rays and rays aimed at the silhouette."""
+    import bench
+    from pathtracerap_b200 import ACCEL_BVH, ACCEL_GRID_EMULATED, Renderer
+    from test_gpu_large import _bounce_rays, _camera_rays
+    scene, arrays = bench.build_scene("mesh1m")
+    r = Renderer(width=64, height=32, depth=5, accel=ACCEL_BVH)
+    r.allocateOnGPU(scene)
+    r.build_grids_device(scene, 25, 25, 25)
+    cam = _camera_rays(320, 180)
+    rs = np.random.RandomState(17)
+    # tangent rays: from outside towards points at one displaced radius from the sphere's centre, perpendicular to the radius
+    n = 20_000
+    c = np.array([25.0, 230.0, -50.0]); radius = 250.0            # bench.ICO_MODEL: radius 1000 x scale 0.25, displaced by +-5 %
+    u = rs.randn(n, 3); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    w = np.cross(u, rs.randn(n, 3)); w /= np.linalg.norm(w, axis=1, keepdims=True)
+    p = c + u * (radius * rs.uniform(0.95, 1.05, (n, 1)))
+    graze = np.concatenate([p - w * 400.0, w], 1).astype(np.float32)
+    rays = np.concatenate([cam, _bounce_rays(40_000, 12), graze])
+    walked = r.trace(rays)
+    assert (walked["model"] == len(arrays["models"]) - 1).mean() > 0.2
+    r.set_accel(ACCEL_GRID_EMULATED)
+    assert_hits_equal(r.trace(rays), walked, "mesh1m 25^3: emulated vs walked")
+    r.free()
+
+
+@pytest.mark.parametrize("dim", [25, 64])
+def test_emulated_on_a_dense_mesh(libptap, port, dim):
+    """An 82 k-triangle displaced icosphere in the room (BASELINE configs[1]) through a 25^3 and a 64^3 grid built ON THE DEVICE: hundreds
+    of triangles per voxel at 25^3, a handful at 64^3.  The emulation must equal the walk (GPU against GPU on 400 k camera + bounce rays,
+    and a whole frame), and both the oracle's R0 on a subset."""
+    import bench
+    from pathtracerap_b200 import ACCEL_BVH, ACCEL_GRID_COMPAT, ACCEL_GRID_EMULATED, Renderer
+    from test_gpu_large import _bounce_rays, _camera_rays
+    scene, arrays = bench.build_scene("mesh100k")
+    r = Renderer(width=64, height=32, depth=5, accel=ACCEL_BVH)        # uploaded without grids; device-built tree
+    r.allocateOnGPU(scene)
+    r.build_grids_device(scene, dim, dim, dim)
+    cam = _camera_rays(640, 360)
+    rays = np.concatenate([cam, _bounce_rays(170_000, 11)])
+    walked = r.trace(rays)
+    r.set_accel(ACCEL_GRID_EMULATED)
+    emulated = r.trace(rays)
+    assert_hits_equal(emulated, walked, f"mesh100k {dim}^3: emulated vs walked")
+    assert (walked["model"] == len(arrays["models"]) - 1).mean() > 0.2
+    sub = rays[:: len(rays) // 3000]
+    oscene = port.OracleScene(arrays, grid_dim=(dim, dim, dim))
+    assert_hits_equal(r.trace(sub), oscene.trace(sub, 0), f"mesh100k {dim}^3: emulated vs oracle R0")
+    W, H, depth, iters = 320, 180, 5, 4
+    films = []
+    for accel in (ACCEL_GRID_COMPAT, ACCEL_GRID_EMULATED):
+        r.set_accel(accel)
+        r.set_params(W, H, depth, first_hit_cache=True)
+        r.frame_begin(); r.render(0, iters); r.sync()
+        films.append(r.film().copy())
+    assert np.array_equal(films[0], films[1])
     r.free()
