@@ -44,6 +44,9 @@ namespace {
 #ifndef PTAP_NODE_LDG256
 #define PTAP_NODE_LDG256 0
 #endif
+#ifndef PTAP_COLD_SMEM
+#define PTAP_COLD_SMEM 0
+#endif
 #ifndef PTAP_SMEM_STACK
 #define PTAP_SMEM_STACK 12
 #endif
@@ -119,14 +122,32 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
         return (kSmemStack > 0 && sp < kSmemStack) ? s_stack[sp * kTraceBlock + threadIdx.x] : l_stack[sp - kSmemStack];
     };
     int node = kDone, i = -1;
-    V3 bo = v3(0, 0, 0), bd = v3(0, 0, 0);          // the ray as stored (Ray::base, Primitive.h:160-164)
-    V3 winv = v3(0, 0, 0);                          // reciprocal of the normalised world direction (TLAS level)
-    unsigned near_off = 0u, wnear_off = 0u;         // byte offsets of the near planes inside a node for the current level / the world ray
+    // What only the instance enter / exit and the retire / refill steps touch - the ray as stored (bo, bd: Ray::base, Primitive.h:160-164),
+    // the reciprocal of its normalised direction and its near-plane offsets (TLAS level), the nearest model so far (g_*) - lives in
+    // shared memory, [word][thread] like the stack, when PTAP_COLD_SMEM is set: 16 registers fewer are live across the node and triangle
+    // steps, so that more warps fit an SM (the kernel waits on dependent node loads; `profiles/r02`).
+#if PTAP_COLD_SMEM
+    __shared__ float s_cold[16 * kTraceBlock];
+    float* const cold = s_cold + threadIdx.x;
+#define CF(k) cold[(k) * kTraceBlock]
+#else
+    float cold_regs[16];
+#define CF(k) cold_regs[k]
+#endif
+#define C_BO v3(CF(0), CF(1), CF(2))
+#define C_BD v3(CF(3), CF(4), CF(5))
+#define C_WINV v3(CF(6), CF(7), CF(8))
+#define C_WNEAR CF(9)
+#define g_dist CF(10)
+#define g_t CF(11)
+#define g_model_f CF(12)
+#define g_tri_f CF(13)
+#define g_u CF(14)
+#define g_v CF(15)
+    unsigned near_off = 0u;                         // byte offsets of the near planes inside a node for the current level
     V3 ro = v3(0, 0, 0), rd = v3(0, 0, 1), rinv = v3(0, 0, 0);   // the ray of the current level: world, or model space of the entered instance
     float tmin = 0.0f, tmax = 0.0f;
     int best_tri = -1; float best_u = 0.0f, best_v = 0.0f;
-    float g_dist = kFloatMax, g_t = 0.0f, g_u = 0.0f, g_v = 0.0f;
-    int g_model = -1, g_tri = -1;
     int w_next = 0, w_end = 0;
     bool exhausted = false;
     const int vote_tri = sc.vote_tri, vote_inst = sc.vote_inst, vote_refill = sc.vote_refill;
@@ -209,6 +230,7 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
             const int im = (int)(code & kIndexMask);
             const InstanceTrace* __restrict__ inst = &sc.inst[im];
             const float4 w0 = ldg4(&inst->w2m[0]), w1 = ldg4(&inst->w2m[1]), w2 = ldg4(&inst->w2m[2]);
+            const V3 bo = C_BO, bd = C_BD;
             ro = xmat4(w0, w1, w2, bo, 1.0f);                                   // Renderer.cpp:381
             const V3 dm = xmat4(w0, w1, w2, bd, 0.0f);
             const float mlen = xsqrt(xdot(dm, dm));
@@ -234,6 +256,8 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
         if (s_exit && n_exit >= min(vote_inst, n_inner)) {
             const int im = (int)(code & kIndexMask);
             const float ascale = __int_as_float(pop());                          // pushed under the marker at entry
+            const V3 bo = C_BO, bd = C_BD;
+            const int g_model = __float_as_int(g_model_f);
             const float cb = sc.c_pad + 1e-4f * (fabsf(bo.x) + fabsf(bo.y) + fabsf(bo.z));
             if (best_tri >= 0) {
                 // |t|: the reference ranks instances by length(hit - origin) >= 0 (Renderer.cpp:391-393), and the predicate accepts
@@ -253,11 +277,11 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
                     if (!take && g_model >= 0) g_dist = dg;
                 }
                 if (take) {
-                    g_dist = nd; g_model = im; g_tri = best_tri; g_t = tmax;
+                    g_dist = nd; g_model_f = __int_as_float(im); g_tri_f = __int_as_float(best_tri); g_t = tmax;
                     if (UV) { g_u = best_u; g_v = best_v; }
                 }
             }
-            ro = bo; rinv = winv; near_off = wnear_off;
+            ro = bo; rinv = C_WINV; near_off = __float_as_uint(C_WNEAR);
             tmin = sc.tmin_world; tmax = worldBound(g_dist, sc.prune, cb);
             node = pop();
         }
@@ -268,7 +292,7 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
                 const bool found = g_dist < kFloatMax;
                 // hit.x < 0 (a constant: the consumers only test the sign) tells the consumer to evaluate the exact world distance
                 // from (model, t) (kernels.cuh: exactHitDistance)
-                hit[i] = make_float4(found ? -1.0f : kFloatMax, __int_as_float(found ? g_tri : -1), __int_as_float(found ? g_model : -1), g_t);
+                hit[i] = make_float4(found ? -1.0f : kFloatMax, found ? g_tri_f : __int_as_float(-1), found ? g_model_f : __int_as_float(-1), g_t);
                 if (UV && uv) uv[i] = make_float2(g_u, g_v);
                 if (COUNT) { if (counts) counts[i] = cnt; tot_x += cnt.x; tot_z += cnt.z; }
                 i = -1;
@@ -285,13 +309,15 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
             if (s_done && live && rank < avail) {
                 i = w_next + rank;
                 const float4 o4 = O[i], d4 = D[i];
-                bo = v3(o4); bd = v3(d4);
+                const V3 bo = v3(o4), bd = v3(d4);
                 const float il = rsqrtf(bd.x * bd.x + bd.y * bd.y + bd.z * bd.z);
-                winv = v3(safeInv(bd.x * il), safeInv(bd.y * il), safeInv(bd.z * il));
-                wnear_off = nearOffsets(bd);          // the normalisation keeps the sign bits
+                const V3 winv = v3(safeInv(bd.x * il), safeInv(bd.y * il), safeInv(bd.z * il));
+                const unsigned wnear_off = nearOffsets(bd);          // the normalisation keeps the sign bits
+                CF(0) = bo.x; CF(1) = bo.y; CF(2) = bo.z; CF(3) = bd.x; CF(4) = bd.y; CF(5) = bd.z;
+                CF(6) = winv.x; CF(7) = winv.y; CF(8) = winv.z; C_WNEAR = __uint_as_float(wnear_off);
                 ro = bo; rinv = winv; near_off = wnear_off;
                 tmin = sc.tmin_world; tmax = 3.0e38f;
-                g_dist = kFloatMax; g_model = -1; g_tri = -1; g_t = 0.0f; g_u = 0.0f; g_v = 0.0f;
+                g_dist = kFloatMax; g_model_f = __int_as_float(-1); g_tri_f = __int_as_float(-1); g_t = 0.0f; g_u = 0.0f; g_v = 0.0f;
                 best_tri = -1;
                 if (COUNT) cnt = make_int4(0, 0, 0, 0);
                 sp = 0; push(kDone);
@@ -307,6 +333,18 @@ k_trace_bvh(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
         if (lane == 0) { atomicAdd(&st->count_nodes, tot_x); atomicAdd(&st->count_tris, tot_z); }
     }
 }
+
+#undef CF
+#undef C_BO
+#undef C_BD
+#undef C_WINV
+#undef C_WNEAR
+#undef g_dist
+#undef g_t
+#undef g_model_f
+#undef g_tri_f
+#undef g_u
+#undef g_v
 
 void launchTraceBvh(const SceneDev& sc, const float4* O, const float4* D, float4* hit, float2* uv, int4* counts, bool count_totals,
                      FrameState* st, int round, int n_fixed, int grid, cudaStream_t stream, unsigned long long* stamp)
