@@ -11,11 +11,14 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "bvh_build.h"
@@ -119,6 +122,18 @@ int fail(ptap_ctx* c, int code, const char* fmt, ...)
         cudaError_t e_ = (call);                                                                       \
         if (e_ != cudaSuccess) return fail(ctx, (int)e_, "%s: %s", #call, cudaGetErrorString(e_));   \
     } while (0)
+
+// fn(begin, end) over [0, n) on up to 8 host threads (the calling one included)
+template <typename F> void parallelFor(int n, F fn)
+{
+    const int workers = n < (1 << 16) ? 1 : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    if (workers <= 1) { fn(0, n); return; }
+    std::vector<std::thread> pool;
+    const int chunk = (n + workers - 1) / workers;
+    for (int w = 1; w < workers; ++w) pool.emplace_back([=]() { fn(std::min(n, w * chunk), std::min(n, (w + 1) * chunk)); });
+    fn(0, std::min(n, chunk));
+    for (std::thread& t : pool) t.join();
+}
 
 float4 row(const float* m, int r) { return make_float4(m[0 + r], m[4 + r], m[8 + r], m[12 + r]); }
 
@@ -419,14 +434,22 @@ int uploadBvh(ptap_ctx* ctx, const BvhNode* nodes, int nnodes, const int* tri_id
 {
     const int nt = ctx->ntris, nm = (int)ctx->h_models.size();
     if ((size_t)nnodes > ctx->nodes_cap) return fail(ctx, PTAP_E_NOMEM, "BVH has more nodes than reserved (2 per triangle)");
-    for (int i = 0; i < nnodes; ++i)
-        for (int k = 0; k < 4; ++k) {
-            const int l = nodes[i].link[k];
-            if (l >= nnodes) return fail(ctx, PTAP_E_INVALID, "BVH node %d: child index out of range", i);
-            if (l < 0) { const int code = ~l, first = code >> 3, cnt = (code & 7) + 1; if (code >= 0x20000000 || first < 0 || first + cnt > nt) return fail(ctx, PTAP_E_INVALID, "BVH node %d: leaf range out of bounds", i); }
-        }
-    for (int k = 0; k < nt; ++k)
-        if (tri_id[k] < 0 || tri_id[k] >= nt) return fail(ctx, PTAP_E_INVALID, "BVH leaf order entry %d out of range", k);
+    // range checks of every link and leaf-order entry: 90 MB of host memory for a 1.3 M-triangle scene, on every upload - spread over threads
+    {
+        std::atomic<int> bad_node{-1}, bad_leaf{-1}, bad_entry{-1};
+        parallelFor(nnodes, [&](int b, int e) {
+            for (int i = b; i < e; ++i)
+                for (int k = 0; k < 4; ++k) {
+                    const int l = nodes[i].link[k];
+                    if (l >= nnodes) bad_node = i;
+                    if (l < 0) { const int code = ~l, first = code >> 3, cnt = (code & 7) + 1; if (code >= 0x20000000 || first < 0 || first + cnt > nt) bad_leaf = i; }
+                }
+        });
+        parallelFor(nt, [&](int b, int e) { for (int k = b; k < e; ++k) if (tri_id[k] < 0 || tri_id[k] >= nt) bad_entry = k; });
+        if (bad_node >= 0) return fail(ctx, PTAP_E_INVALID, "BVH node %d: child index out of range", bad_node.load());
+        if (bad_leaf >= 0) return fail(ctx, PTAP_E_INVALID, "BVH node %d: leaf range out of bounds", bad_leaf.load());
+        if (bad_entry >= 0) return fail(ctx, PTAP_E_INVALID, "BVH leaf order entry %d out of range", bad_entry.load());
+    }
     for (size_t m = 0; m < ctx->h_meshes.size(); ++m)
         if (mesh_root[m] >= nnodes) return fail(ctx, PTAP_E_INVALID, "mesh %d: BVH root out of range", (int)m);
     // Depth of every BLAS (the traversal stack is fixed-size).  Always computed from the nodes: a caller-supplied depth is only a hint that
@@ -599,6 +622,15 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
     if (!ctx || !v || !v->models || !v->meshes || !v->vertices || !v->triangles || v->nmodels <= 0) return fail(ctx, PTAP_E_INVALID, "upload_scene: missing arrays");
     CK(cudaSetDevice(ctx->device));
     if (ctx->render_pending) { int rc = collect(ctx); if (rc) return rc; }
+    const bool timing = getenv("PTAP_UPLOAD_TIMING") != nullptr;          // host-side phases of this call on stderr (diagnostics)
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto t_last = t_begin;
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "ptap_upload_scene: %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     const int nm = v->nmodels, nt = v->ntriangles;
     const bool grid = v->grids && v->voxels && v->refs && v->ngrids > 0;
     // the scene arena is about to be overwritten: whatever was uploaded before is gone even if this call fails half-way
@@ -673,6 +705,7 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
             if (v->grids[g].v_start < 0 || v->grids[g].v_start + ncell > v->nvoxels) return fail(ctx, PTAP_E_INVALID, "grid %d: voxel range out of bounds", g);
     }
 
+    lap("validate + repack (host)");
     // ---- one arena for everything scene-lifetime; BVH storage is reserved up front (2T-1 BLAS nodes + 2M TLAS nodes bound)
     const size_t nodes_cap = (size_t)std::max(nt, 1) * 2 + (size_t)nm * 2 + 2;
     size_t need = Arena::need(nm, sizeof(InstanceTrace)) + Arena::need(nm, sizeof(InstanceShade)) +
@@ -704,6 +737,7 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
     ctx->h_inst = inst;
     ctx->d_inst = d_inst; ctx->d_nodes = d_nodes; ctx->nodes_cap = nodes_cap; ctx->d_btris = d_btris; ctx->d_btid = d_btid;
     ctx->have_bvh = false; ctx->bvh_kind = -1;
+    lap("enqueue scene copies");
     if (v->bvh_nodes && v->n_bvh_nodes > 0 && v->bvh_tri_id && v->bvh_mesh_root) {
         if (v->n_bvh_tris != nt || v->n_bvh_roots != v->nmeshes) return fail(ctx, PTAP_E_INVALID, "upload_scene: prebuilt BVH does not match the triangle / mesh counts");
         size_t bb = 0;
@@ -711,7 +745,9 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
         if (rc) return rc;
         bytes += bb;
     }
+    lap("BVH checks + TLAS (host)");
     CK(cudaStreamSynchronize(ctx->stream));
+    lap("wait for the device");
     ctx->stats.scene_bytes = (int64_t)bytes;
     ctx->sc.inst = d_inst; ctx->sc.shade = d_shade; ctx->sc.tris = d_tris; ctx->sc.normals = d_normals;
     ctx->sc.cells = d_cells; ctx->sc.refs = d_refs; ctx->sc.nodes = d_nodes; ctx->sc.bvh_tris = d_btris; ctx->sc.bvh_tri_id = d_btid;

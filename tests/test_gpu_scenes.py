@@ -50,7 +50,18 @@ def _scene_and_oracle(port, models, meshes, vertices, triangles):
     r = Renderer(width=32, height=32, depth=5, accel=ACCEL_BVH)
     r.allocateOnGPU(s)
     o = port.OracleScene({"models": models, "meshes": meshes, "vertices": vertices, "triangles": triangles})
+    r._scene = s
     return r, o
+
+
+def _check_grid_tiers(r, o, rays, what):
+    """The same scene through the reference's grids (built on the device): walked and emulated through the BVH, both against the oracle's R0."""
+    from pathtracerap_b200 import ACCEL_GRID_EMULATED
+    want = o.trace(rays, 0)
+    r.build_grids_device(r._scene, 25, 25, 25)
+    _assert_equal(r.trace(rays), want, what + ": grid walk vs oracle R0")
+    r.set_accel(ACCEL_GRID_EMULATED)
+    _assert_equal(r.trace(rays), want, what + ": emulated walk vs oracle R0")
 
 
 def test_many_instances_arbitrary_transforms(libptap, port, golden_scene):
@@ -80,6 +91,7 @@ def test_many_instances_arbitrary_transforms(libptap, port, golden_scene):
     assert 0.3 < hit.mean() < 0.999
     assert (want["model"] == 3).sum() > 100 and (want["model"] == 95).sum() == 0
     assert len(np.unique(want["model"][hit])) > 60
+    _check_grid_tiers(r, o, rays[:60_000], "96 instances")
     r.free()
 
 
@@ -97,6 +109,7 @@ def test_matrices_that_are_not_inverses(libptap, port, golden_scene):
     r, o = _scene_and_oracle(port, models, g["meshes"], g["vertices"], g["triangles"])
     rays = _rays(100_000, 6, -450.0, 850.0)
     _assert_equal(r.trace(rays), o.trace(rays, 1), "inconsistent matrices")
+    _check_grid_tiers(r, o, rays, "inconsistent matrices")
     r.free()
 
 
@@ -128,6 +141,7 @@ def test_empty_and_tiny_meshes(libptap, port, golden_scene):
     want = o.trace(rays, 1)
     _assert_equal(r.trace(rays), want, "tiny meshes")
     assert (want["model"] == 1).any() and (want["model"] == 3).any() and not (want["model"] == 2).any()
+    _check_grid_tiers(r, o, rays, "tiny meshes")
     r.free()
 
 
