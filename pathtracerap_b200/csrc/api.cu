@@ -939,7 +939,7 @@ int ptap_render(ptap_ctx* ctx, int32_t iter_begin, int32_t iter_end)
             if (!(round == 0 && cache && ctx->cache_valid)) {                    // Renderer.cpp:594-620
                 profMark(ctx, 1);
                 unsigned long long* stamp = stamping && ctx->stamps_used < kMaxStamps ? ctx->d_stamps + 2 * (size_t)ctx->stamps_used++ : nullptr;
-                launchTrace(ctx, wv.st, wv.O[in], wv.D[in], hitbuf, nullptr, nullptr, round, -1, wv.emu, (ctx->flags & PTAP_FLAG_COUNT) != 0, S, stamp); ++launches; ++trace_launches;
+                launchTrace(ctx, wv.st, wv.O[in], wv.D[in], hitbuf, nullptr, nullptr, round, -1, wv.emu, (ctx->flags & PTAP_FLAG_COUNT) != 0, S, stamp); launches += ctx->accel == PTAP_ACCEL_GRID_EMULATED ? 5 : 1; ++trace_launches;
                 if (L > 1 && round == 0 && cache) { CK(cudaEventRecord(ctx->e_cache, S)); cache_lane = l; cache_waited = 1u << l; }
             } else if (L > 1 && cache_lane >= 0 && !(cache_waited >> l & 1u)) {
                 CK(cudaStreamWaitEvent(S, ctx->e_cache, 0)); cache_waited |= 1u << l;

@@ -15,11 +15,11 @@ if len(sys.argv) > 2:
 keys = sorted(grid)
 for combo in itertools.product(*(grid[k] for k in keys)):
     env = dict(os.environ, **dict(zip(keys, combo)))
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", workload, "--steps", "2", "--warmup", "3", "--no-cpu-baseline"],
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", workload, "--steps", "2", "--warmup", "3", "--no-cpu-baseline", "--no-extras"],
                        env=env, capture_output=True, text=True)
     line = p.stdout.strip().splitlines()[-1] if p.stdout.strip() else ""
     try:
         j = json.loads(line)
-        print(dict(zip(keys, combo)), "value", j["value"], "trace_Mrays/s", j["roofline"]["trace_Mrays_per_s"], "share", j["roofline"]["share_of_step"], flush=True)
+        print(dict(zip(keys, combo)), "value", j["value"], "ms_per_step", j["ms_per_step"], "trace_Mrays/s", j["roofline"].get("trace_Mrays_per_s"), flush=True)
     except Exception:
         print(dict(zip(keys, combo)), "FAILED", p.stderr[-400:], flush=True)
