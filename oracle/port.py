@@ -48,6 +48,9 @@ def lib():
         L.oracle_normal_matrix.argtypes = [vp, vp]
         L.oracle_build_grids.argtypes = [vp, ci, vp, ci, vp, vp, vp, vp, vp, vp, vp, vp, vp]; L.oracle_build_grids.restype = ci
         L.oracle_trace.argtypes = [vp, vp, ci, ci, vp]
+        L.oracle_model_hits.argtypes = [vp, vp, ci, ci, vp, vp]; L.oracle_model_hits.restype = ci
+        L.oracle_grid_path.argtypes = [vp, vp, ci, ci, vp]; L.oracle_grid_path.restype = ci
+        L.oracle_hit_distance.argtypes = [vp, vp, ci, C.c_float]; L.oracle_hit_distance.restype = C.c_float
         L.oracle_wavefront_create.argtypes = [vp, ci, ci, ci]; L.oracle_wavefront_create.restype = vp
         L.oracle_wavefront_free.argtypes = [vp]
         L.oracle_wavefront_set_mode.argtypes = [vp, ci]
@@ -111,6 +114,28 @@ class OracleScene:
 
     def arrays(self):
         return self.a
+
+    # -- probes of single steps (tests/test_emulation_model.py) --------------------------------------------------------------------
+    def model_hits(self, ray_od, imodel, cap=64):
+        """(global triangle ids, model-space t) of every triangle of the model that the reference's predicate accepts for the ray."""
+        ray = np.ascontiguousarray(ray_od, np.float32).reshape(6)
+        tri = np.zeros(cap, np.int32); t = np.zeros(cap, np.float32)
+        n = lib().oracle_model_hits(C.byref(self.c), _ptr(ray), imodel, cap, _ptr(tri), _ptr(t))
+        assert n <= cap
+        return tri[:n].copy(), t[:n].copy()
+
+    def grid_path(self, ray_od, imodel):
+        """The (n, 3) voxel indices the model's grid walk visits when nothing is hit; empty when the walk is not entered."""
+        ray = np.ascontiguousarray(ray_od, np.float32).reshape(6)
+        cap = int(sum(self.c.grid_dim)) + 3
+        out = np.zeros((cap, 3), np.int32)
+        n = lib().oracle_grid_path(C.byref(self.c), _ptr(ray), imodel, cap, _ptr(out))
+        assert n <= cap
+        return out[:n].copy()
+
+    def hit_distance(self, ray_od, imodel, t) -> np.float32:
+        ray = np.ascontiguousarray(ray_od, np.float32).reshape(6)
+        return np.float32(lib().oracle_hit_distance(C.byref(self.c), _ptr(ray), imodel, C.c_float(float(t))))
 
     def trace(self, rays_od, mode=0) -> np.ndarray:
         rays_od = np.ascontiguousarray(rays_od, np.float32).reshape(-1, 6)

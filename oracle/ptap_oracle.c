@@ -409,6 +409,91 @@ static void loop_end(ModelLoop* L, OHitRecord* h, OHit* probe)
     if (probe) *probe = L->g_probe;
 }
 
+/* ---- probes of single steps of the path, for tests of algorithms that must reproduce ray_grid without walking the lists
+ * (tests/test_emulation_model.py: the CPU model of PTAP_ACCEL_GRID_EMULATED).  Nothing here is used by oracle_trace. */
+
+/* Every triangle of model `imodel`'s mesh that the reference's predicate accepts for the ray (Renderer.cpp:174-201 with the model's ray
+ * set-up, :381-384), in triangle order: global triangle ids and model-space t.  Returns the number of hits (at most `cap` are stored). */
+int oracle_model_hits(const OScene* s, const float* ray_od, int imodel, int cap, int* tri, float* t)
+{
+    const OModel* model = &s->models[imodel];
+    const OMesh* mesh = &s->meshes[model->mesh_index];
+    RayCtx c; memset(&c, 0, sizeof c);
+    model_setup(model, ld3(ray_od), ld3(ray_od + 3), &c);
+    int n = 0;
+    for (int k = mesh->t_start; k < mesh->t_end; ++k) {
+        c.dist = O_FLOAT_MAX; c.tri = -1;                                /* every triangle on its own: no nearest-hit state */
+        if (!ray_triangle(s, &c, k)) continue;
+        if (n < cap) { tri[n] = k; t[n] = c.tri == k ? c.t : O_FLOAT_MAX; }
+        ++n;
+    }
+    return n;
+}
+
+/* The voxels computeRayGridIntersection (Renderer.cpp:238-360) visits for the ray in model `imodel` when no listed triangle is ever hit:
+ * its slab test, entry point, entry voxel and DDA stepping, to the end of the grid.  ixyz receives up to `cap` (ix, iy, iz) triplets;
+ * returns the number of voxels, 0 when the walk is not entered.  The statements are those of ray_grid above. */
+int oracle_grid_path(const OScene* s, const float* ray_od, int imodel, int cap, int* ixyz)
+{
+    const OModel* model = &s->models[imodel];
+    RayCtx cc; memset(&cc, 0, sizeof cc);
+    model_setup(model, ld3(ray_od), ld3(ray_od + 3), &cc);
+    const RayCtx* c = &cc;
+    const OGrid* g = &s->grids[model->grid_index];
+    const OMesh* mesh = &s->meshes[s->models[g->entity_index].mesh_index];
+    const float* mn = mesh->bb_min;
+    const int GX = s->grid_dim[0], GY = s->grid_dim[1], GZ = s->grid_dim[2];
+    float t_box;
+    if (!ray_bbox(c, mn, mesh->bb_max, &t_box)) return 0;
+    v3 p = add(c->o, scale(c->d, t_box));
+    if ((p.x - mn[0]) < -O_EPSILON || (p.y - mn[1]) < -O_EPSILON || (p.z - mn[2]) < -O_EPSILON) return 0;
+    int ix = f2i(O_ABS(p.x - mn[0] + O_EPSILON) / g->width[0]);
+    int iy = f2i(O_ABS(p.y - mn[1] + O_EPSILON) / g->width[1]);
+    int iz = f2i(O_ABS(p.z - mn[2] + O_EPSILON) / g->width[2]);
+    ix = O_CLAMP(ix, 0, GX - 1); iy = O_CLAMP(iy, 0, GY - 1); iz = O_CLAMP(iz, 0, GZ - 1);
+    float tmx = O_FLOAT_MAX, tmy = O_FLOAT_MAX, tmz = O_FLOAT_MAX;
+    float dx = O_FLOAT_MAX, dy = O_FLOAT_MAX, dz = O_FLOAT_MAX;
+    int step_x = c->d.x > 0.0f ? 1 : -1, step_y = c->d.y > 0.0f ? 1 : -1, step_z = c->d.z > 0.0f ? 1 : -1;
+    int out_x = c->d.x > 0.0f ? GX : -1, out_y = c->d.y > 0.0f ? GY : -1, out_z = c->d.z > 0.0f ? GZ : -1;
+    int nx = c->d.x > 0.0f ? ix + 1 : ix; float px = mn[0] + nx * g->width[0];
+    int ny = c->d.y > 0.0f ? iy + 1 : iy; float py = mn[1] + ny * g->width[1];
+    int nz = c->d.z > 0.0f ? iz + 1 : iz; float pz = mn[2] + nz * g->width[2];
+    if (c->d.x != 0) { dx = O_ABS(g->width[0] * c->inv.x); tmx = (px - p.x) * c->inv.x; }
+    if (c->d.y != 0) { dy = O_ABS(g->width[1] * c->inv.y); tmy = (py - p.y) * c->inv.y; }
+    if (c->d.z != 0) { dz = O_ABS(g->width[2] * c->inv.z); tmz = (pz - p.z) * c->inv.z; }
+    int n = 0;
+    for (;;) {
+        if (n < cap) { ixyz[3 * n] = ix; ixyz[3 * n + 1] = iy; ixyz[3 * n + 2] = iz; }
+        ++n;
+        if (tmx < tmy && tmx < tmz) {
+            ix += step_x;
+            if (ix == out_x || tmx >= O_FLOAT_MAX) return n;
+            tmx += dx;
+        } else if (tmy < tmz) {
+            iy += step_y;
+            if (iy == out_y || tmy >= O_FLOAT_MAX) return n;
+            tmy += dy;
+        } else {
+            iz += step_z;
+            if (iz == out_z || tmz >= O_FLOAT_MAX) return n;
+            tmz += dz;
+        }
+    }
+}
+
+/* World distance of the hit at model-space parameter t of model `imodel` along the ray, as Renderer.cpp:388-391 computes it. */
+float oracle_hit_distance(const OScene* s, const float* ray_od, int imodel, float t)
+{
+    const OModel* model = &s->models[imodel];
+    RayCtx c; memset(&c, 0, sizeof c);
+    v3 bo = ld3(ray_od);
+    model_setup(model, bo, ld3(ray_od + 3), &c);
+    v3 nd = normalize(c.d);
+    v3 pm = add(c.o, scale(nd, t));
+    v3 pw = mat4_mul(model->m2w, pm, 1.0f);
+    return length3(sub(pw, bo));
+}
+
 /* One thread of computeRaySceneIntersectionKernel (Renderer.cpp:363-409); h->dist on entry is the slot's incoming
  * hit_info->impact_distance.  Returns the final hit_info fields through *h, ids through *probe. */
 static void trace_one(const OScene* s, v3 bo, v3 bd, int mode, OHitRecord* h, OHit* probe)

@@ -76,6 +76,12 @@ int oracle_build_grids(OModel* models, int nmodels, const OMesh* meshes, int nme
  * mode 0 = R0 (grid walk, Renderer.cpp:238-360); mode 1 = R1 (every triangle of the model's mesh). */
 void oracle_trace(const OScene* s, const float* rays_od, int n, int mode, OHit* out);
 
+/* Probes of single steps of the path (tests/test_emulation_model.py): all hits of one model under the reference's predicate, the voxel
+ * sequence of one model's grid walk when nothing is hit, and the reference's model-t -> world-distance conversion. */
+int oracle_model_hits(const OScene* s, const float* ray_od, int imodel, int cap, int* tri, float* t);
+int oracle_grid_path(const OScene* s, const float* ray_od, int imodel, int cap, int* ixyz);
+float oracle_hit_distance(const OScene* s, const float* ray_od, int imodel, float t);
+
 /* Wavefront state for one frame buffer; mirrors RenderData (Renderer.h:19-35). */
 typedef struct OWavefront OWavefront;
 OWavefront* oracle_wavefront_create(const OScene* s, int W, int H, int depth);
