@@ -43,6 +43,10 @@ namespace {
 #ifndef PTAP_EMU_MIN_CTAS
 #define PTAP_EMU_MIN_CTAS 7
 #endif
+#ifndef PTAP_EMU_FULL_BATCH
+#define PTAP_EMU_FULL_BATCH 8
+#endif
+constexpr int kFullBatch = PTAP_EMU_FULL_BATCH;   // list entries a warp of k_emu_full takes per fetch: few, so that a short list spreads over all warps (the kernel is latency-bound)
 constexpr int kFullHits = 20;                 // hits of a (ray, model) that k_emu_full keeps in shared memory (46 KB per CTA with the stack)
 constexpr int kEmuStack = 12;                 // traversal-stack entries per ray in shared memory (as k_trace_bvh)
 constexpr int kReplayBlock = 128, kReplayBatch = 32;   // k_emu_tail: threads per CTA, queue entries per cursor fetch
@@ -747,10 +751,10 @@ k_emu_full(SceneDev sc, const float4* __restrict__ O, const float4* __restrict__
             }
             if (w_next >= w_end && !exhausted) {
                 unsigned b = 0;
-                if (lane == 0) b = atomicAdd(cursor, 32u);
+                if (lane == 0) b = atomicAdd(cursor, (unsigned)kFullBatch);
                 b = __shfl_sync(kFull, b, 0);
                 if (b >= (unsigned)n) { exhausted = true; w_next = w_end = n; }
-                else { w_next = (int)b; w_end = min((int)b + 32, n); }
+                else { w_next = (int)b; w_end = min((int)b + kFullBatch, n); }
             }
             const int avail = w_end - w_next;
             const int rank = __popc(m_done & ((1u << lane) - 1u));
