@@ -58,6 +58,10 @@ constexpr int kSetupBlock = 128;                      // k_emu_setup
 #define PTAP_EMU_BURST 8
 #endif
 constexpr int kBurst = PTAP_EMU_BURST;                // voxels outside the hits' box that one step call may take in a row
+#ifndef PTAP_EMU_SETUP_BURST
+#define PTAP_EMU_SETUP_BURST PTAP_EMU_BURST
+#endif
+constexpr int kSetupBurst = PTAP_EMU_SETUP_BURST;    // the same inside the set-up kernel (its threads wait for the longest burst of their warp)
 constexpr int kSetupSteps = PTAP_EMU_SETUP_STEPS;     // voxel steps a replay takes in the set-up kernel before it is queued
 constexpr unsigned kGuard = 0x20080200u;      // bits 9, 19, 29: one guard bit above each 9-bit voxel index of a packed (x | y << 10 | z << 20)
 
@@ -284,6 +288,7 @@ struct Replay {
 };
 
 // one voxel of the walk; true when the replay is over (r.w_tri / r.w_t hold the walk's answer so far)
+template <int BURST = kBurst>
 __device__ __forceinline__ bool replayStep(Replay& r, int GX, int GY, int GZ, const unsigned* s_lo, const unsigned* s_hi, const float* s_ts, const int* s_ids, int stride)
 {
     ++r.steps;
@@ -327,7 +332,7 @@ __device__ __forceinline__ bool replayStep(Replay& r, int GX, int GY, int GZ, co
     // Voxels outside the box around the hits list no hit triangle: nothing but the walk's own exit tests and DDA arithmetic happens there,
     // so up to kBurst of them are taken at once (a ray that leaves a scaled-up mesh walks a dozen such voxels before it reaches the first hit).
 #pragma unroll 1
-    for (int b = 0; b < kBurst && !finished; ++b) {
+    for (int b = 0; b < BURST && !finished; ++b) {
         const unsigned w = (unsigned)r.ix | ((unsigned)r.iy << 10) | ((unsigned)r.iz << 20);
         const unsigned q1 = (w | kGuard) - r.ulo, q2 = (r.uhi | kGuard) - w;
         if ((q1 & q2 & kGuard) == kGuard) break;                               // inside: the next call looks at the hits
@@ -452,7 +457,7 @@ k_emu_setup(SceneDev sc, const float4* __restrict__ O, const float4* __restrict_
                 replayLoadHits(sc, emu, i, r.nh, __float_as_int(h.y), r.t_star, r.ulo, r.uhi, s_lo, s_hi, s_ts, s_ids, kSetupBlock);
                 walking = true;
 #pragma unroll 1
-                for (int s = 0; s < kSetupSteps && walking; ++s) walking = !replayStep(r, GX, GY, GZ, s_lo, s_hi, s_ts, s_ids, kSetupBlock);
+                for (int s = 0; s < kSetupSteps && walking; ++s) walking = !replayStep<kSetupBurst>(r, GX, GY, GZ, s_lo, s_hi, s_ts, s_ids, kSetupBlock);
             }
         }
         if (walking) {
