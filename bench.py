@@ -290,6 +290,8 @@ def main():
         scene.build_grids(args.grid_dim, args.grid_dim, args.grid_dim)
     elif accel == ACCEL_GRID_EMULATED:
         scene.build_grids(args.grid_dim, args.grid_dim, args.grid_dim); scene.build_bvh()
+    else:
+        scene.pack()                      # triangle records in page-locked memory; the tree itself is built on the GPU at every upload
     build_s = time.perf_counter() - t0     # lbvh: built on the GPU inside Renderer.allocateOnGPU / upload
     ntris = len(arrays["triangles"])
     cache = not args.no_cache
@@ -478,15 +480,17 @@ def main():
             extras["ms_per_frame_2800x2240_64spp"] = dict(frames, scene="bundled (configs[2])", note="grid_compat = the reference's own 25^3 grid walk; grid_emulated = the same hits, bit for bit, through the BVH (the drop-in default); bvh = exact closest hit")
         # ---- end to end with the acceleration structure built INSIDE the timed region (tree built on the GPU at upload)
         if accel == ACCEL_BVH and args.workload != "cornell":
+            scene_l, _ = build_scene(args.workload)      # the same scene WITHOUT a host tree: triangle records only
+            scene_l.pack()
             rl = Renderer(device=dev, width=W, height=H, depth=depth, accel=ACCEL_BVH_DEVICE, first_hit_cache=cache)
-            rl.allocateOnGPU(scene)
+            rl.allocateOnGPU(scene_l)
             rl.render(it0, it1); rl.sync()
             t0 = time.perf_counter(); n_l = 0; k = min(args.steps, 3)
             for _ in range(k):
-                rl.upload(scene); rl.frame_begin(); rl.render(it0, it1)
+                rl.upload(scene_l); rl.frame_begin(); rl.render(it0, it1)
                 N.lib().ptap_read_film(rl.h, N.ptr(film_host)); n_l += rl.stats()["rays_traced"]
             dt = time.perf_counter() - t0
-            extras["e2e_build_included"] = {"value": round(n_l / dt / 1e6, 2), "unit": unit, "accel": "lbvh (tree built on the GPU inside every step)",
+            extras["e2e_build_included"] = {"value": round(n_l / dt / 1e6, 2), "unit": unit, "accel": "lbvh (triangles uploaded, tree built on the GPU by PLOC + a host SAH top inside every step)",
                                             "device_bvh_build_ms": round(rl.stats()["ms_build"], 3), "ms_per_step": round(dt / k * 1e3, 3)}
             rl.free()
     r.free()

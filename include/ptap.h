@@ -86,7 +86,7 @@ typedef struct {
     const int32_t* bvh_tri_id; int32_t n_bvh_tris;    /* leaf-order position -> global triangle index */
     const int32_t* bvh_mesh_root; int32_t n_bvh_roots;/* per mesh: root node, -1 if empty */
     int32_t bvh_depth;                                /* deepest BLAS level (a hint: upload always recomputes it from the nodes) */
-    /* optional triangle records prepared by ptap_scene_build_bvh (48 B per triangle: v0, v1-v0, v2-v0, flat normal in the .w lanes,
+    /* optional triangle records prepared by ptap_scene_build_bvh / ptap_scene_pack_triangles (48 B per triangle: v0, v1-v0, v2-v0, flat normal in the .w lanes,
      * reference arithmetic); NULL/0: ptap_upload_scene derives them from vertices + triangles.  ptap_scene keeps its upload-bound
      * arrays (these, the BVH nodes, the leaf order) in page-locked host memory when a CUDA device is present. */
     const void* tri_recs; int32_t n_tri_recs;
@@ -175,6 +175,9 @@ int ptap_scene_build_grids(ptap_scene* s, int32_t gx, int32_t gy, int32_t gz);
 /* Builds one BVH per mesh on the host (binned SAH); part of scene construction like addMeshesToGrid, so that
  * Renderer::allocateOnGPU only uploads.  Bounds are conservative for the reference's tolerance band. */
 int ptap_scene_build_bvh(ptap_scene* s);
+/* Only the upload-bound triangle records (page-locked), without a host BVH: for PTAP_ACCEL_BVH_DEVICE and the grid modes, so that
+ * ptap_upload_scene copies instead of repacking every triangle on every call.  ptap_scene_build_bvh implies it. */
+int ptap_scene_pack_triangles(ptap_scene* s);
 /* Host-side check of that BVH: the number of triangles whose tolerance band (what the reference's predicate can accept) sticks out of a
  * compressed child box on its path from the root, plus structural errors; 0 for a correct tree. */
 int ptap_scene_validate_bvh(const ptap_scene* s, int64_t* violations, int32_t* depth);

@@ -65,7 +65,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "ptap_scene_create_builtin", "ptap_scene_create_from_config", "ptap_scene_create_empty", "ptap_scene_create_from_view",
     "ptap_scene_add_obj", "ptap_scene_add_mesh", "ptap_scene_add_icosphere", "ptap_scene_add_model", "ptap_compose_trs",
-    "ptap_scene_build_grids", "ptap_scene_build_bvh", "ptap_scene_validate_bvh", "ptap_scene_view", "ptap_scene_models", "ptap_scene_destroy", "ptap_scene_last_error",
+    "ptap_scene_build_grids", "ptap_scene_build_bvh", "ptap_scene_pack_triangles", "ptap_scene_validate_bvh", "ptap_scene_view", "ptap_scene_models", "ptap_scene_destroy", "ptap_scene_last_error",
     "ptap_scene_config_params", "ptap_scene_config_camera", "ptap_set_camera",
     "ptap_create", "ptap_destroy", "ptap_last_error", "ptap_upload_scene", "ptap_build_accel", "ptap_build_grids_device", "ptap_read_grids", "ptap_set_render_params",
     "ptap_render", "ptap_timer_start", "ptap_timer_stop", "ptap_frame_begin", "ptap_film_reset", "ptap_sync", "ptap_read_film", "ptap_film_device_ptr", "ptap_film_add",
@@ -101,6 +101,7 @@ def lib():
         L.ptap_scene_build_grids.argtypes = [vp, ci, ci, ci]
         L.ptap_scene_view.argtypes = [vp, C.POINTER(SceneView)]
         L.ptap_scene_build_bvh.argtypes = [vp]
+        L.ptap_scene_pack_triangles.argtypes = [vp]
         L.ptap_scene_validate_bvh.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(ci)]
         L.ptap_scene_models.argtypes = [vp]; L.ptap_scene_models.restype = vp
         L.ptap_scene_destroy.argtypes = [vp]; L.ptap_scene_destroy.restype = None

@@ -641,7 +641,7 @@ int ptap_upload_scene(ptap_ctx* ctx, const PtapSceneView* v)
         if (m.mesh_index < 0 || m.mesh_index >= v->nmeshes) return fail(ctx, PTAP_E_INVALID, "model %d: mesh_index %d out of range", i, m.mesh_index);
         if (grid && (m.grid_index < 0 || m.grid_index >= v->ngrids)) return fail(ctx, PTAP_E_INVALID, "model %d: grid_index %d out of range", i, m.grid_index);
     }
-    const bool prepacked = v->tri_recs && v->n_tri_recs == nt && v->bvh_nodes && v->n_bvh_nodes > 0;      // ptap_scene_build_bvh made the records
+    const bool prepacked = v->tri_recs && v->n_tri_recs == nt;      // ptap_scene_build_bvh / ptap_scene_pack_triangles made the records (indices checked there)
     if (!prepacked)
         for (int t = 0; t < nt; ++t)
             for (int k = 0; k < 3; ++k)
@@ -768,7 +768,11 @@ int ptap_build_accel(ptap_ctx* ctx, int kind)
     } else if (kind == PTAP_ACCEL_BVH) {
         if (!ctx->have_bvh || ctx->bvh_kind != PTAP_ACCEL_BVH) {
             BvhBuildResult res;
-            if ((int)ctx->h_tris.size() != ctx->ntris) return fail(ctx, PTAP_E_STATE, "build_accel: the triangle records were not kept on the host");
+            if ((int)ctx->h_tris.size() != ctx->ntris) {        // the view brought prepacked records: read them back from the device
+                ctx->h_tris.resize(ctx->ntris);
+                CK(cudaMemcpyAsync(ctx->h_tris.data(), ctx->d_tris, (size_t)ctx->ntris * sizeof(TriRec), cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+            }
             buildSceneBvh(ctx->h_tris.data(), (int)ctx->h_tris.size(), ctx->h_meshes.data(), (int)ctx->h_meshes.size(), res);
             int rc = uploadBvh(ctx, res.nodes.data(), (int)res.nodes.size(), res.tri_id.data(), res.mesh_root.data(), res.max_depth + 1, nullptr);
             if (rc) return rc;

@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <string>
 #include <utility>
+#include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -267,6 +268,10 @@ __global__ void k_lbvh_single(const Box6* __restrict__ leaf_box, int n, int leaf
 #define PTAP_PLOC_RADIUS 16
 #endif
 constexpr int kPlocRadius = PTAP_PLOC_RADIUS;
+#ifndef PTAP_PLOC_TOP
+#define PTAP_PLOC_TOP 4096
+#endif
+constexpr int kPlocTop = PTAP_PLOC_TOP;
 
 __device__ __forceinline__ float unionArea(const Box6& a, const Box6& b)
 {
@@ -323,6 +328,57 @@ __global__ void k_ploc_compact(const Box6* __restrict__ cbox, const int* __restr
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && keep[i]) { obox[pos[i]] = cbox[i]; onode[pos[i]] = cnode[i]; }
+}
+
+// Top of the tree: once PLOC has merged the leaves down to a few thousand clusters, the levels above them are built on the HOST by the
+// same binned SAH as bvh_build.cpp uses (16 bins on the centroid axis with the lowest cost), over the cluster boxes - a few thousand items,
+// well under a millisecond.  PLOC's merges are local in Morton order (radius 16): good near the leaves, arbitrary near the root, where a
+// bad split costs every ray; this puts the surface-area heuristic where it matters and leaves the bulk of the work on the device.
+struct TopItem { Box6 box; float c[3]; int link; };
+
+int buildTopSah(std::vector<TopItem>& it, int begin, int end, int base, std::vector<int2>& out_child, std::vector<Box6>& out_box, Box6& bounds)
+{
+    auto grow = [](Box6& a, const Box6& b) { for (int k = 0; k < 3; ++k) { a.lo[k] = std::min(a.lo[k], b.lo[k]); a.hi[k] = std::max(a.hi[k], b.hi[k]); } };
+    auto area = [](const Box6& b) { const float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2]; return dx < 0 ? 0.0f : dx * dy + dy * dz + dz * dx; };
+    auto empty = []() { Box6 b; for (int k = 0; k < 3; ++k) { b.lo[k] = 3e38f; b.hi[k] = -3e38f; } return b; };
+    bounds = empty();
+    float clo[3] = {3e38f, 3e38f, 3e38f}, chi[3] = {-3e38f, -3e38f, -3e38f};
+    for (int i = begin; i < end; ++i) { grow(bounds, it[i].box); for (int k = 0; k < 3; ++k) { clo[k] = std::min(clo[k], it[i].c[k]); chi[k] = std::max(chi[k], it[i].c[k]); } }
+    if (end - begin == 1) return it[begin].link;
+    constexpr int kBins = 16;
+    int best_axis = -1, best_bin = -1; float best_cost = 3e38f;
+    for (int axis = 0; axis < 3; ++axis) {
+        const float ext = chi[axis] - clo[axis];
+        if (!(ext > 0.0f)) continue;
+        Box6 bb[kBins]; int cnt[kBins];
+        for (int b = 0; b < kBins; ++b) { bb[b] = empty(); cnt[b] = 0; }
+        const float scale = kBins / ext;
+        for (int i = begin; i < end; ++i) { const int b = std::min(kBins - 1, std::max(0, (int)((it[i].c[axis] - clo[axis]) * scale))); grow(bb[b], it[i].box); cnt[b]++; }
+        float right_area[kBins]; int right_cnt[kBins];
+        Box6 acc = empty(); int c = 0;
+        for (int b = kBins - 1; b > 0; --b) { grow(acc, bb[b]); c += cnt[b]; right_area[b] = area(acc); right_cnt[b] = c; }
+        acc = empty(); c = 0;
+        for (int b = 0; b < kBins - 1; ++b) {
+            grow(acc, bb[b]); c += cnt[b];
+            if (c == 0 || right_cnt[b + 1] == 0) continue;
+            const float cost = area(acc) * c + right_area[b + 1] * right_cnt[b + 1];
+            if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
+        }
+    }
+    int mid = begin + (end - begin) / 2;
+    if (best_axis >= 0) {
+        const float lo = clo[best_axis], scale = kBins / (chi[best_axis] - clo[best_axis]);
+        auto m = std::partition(it.begin() + begin, it.begin() + end, [&](const TopItem& t) { return std::min(kBins - 1, std::max(0, (int)((t.c[best_axis] - lo) * scale))) <= best_bin; });
+        const int k = (int)(m - it.begin());
+        if (k > begin && k < end) mid = k;
+    }
+    const int me = (int)out_child.size();
+    out_child.push_back(make_int2(0, 0)); out_box.push_back(bounds);
+    Box6 b0, b1;
+    const int l0 = buildTopSah(it, begin, mid, base, out_child, out_box, b0);
+    const int l1 = buildTopSah(it, mid, end, base, out_child, out_box, b1);
+    out_child[me] = make_int2(l0, l1);
+    return base + me;
 }
 
 template <typename T> T* carve(char*& p, size_t count)
@@ -404,7 +460,9 @@ int buildMeshBvhDevice(const TriRec* d_tris, int t0, int t1, const float* bb_min
         if (e != cudaSuccess) return e;
         k_ploc_init<<<(L + B - 1) / B, B, 0, stream>>>(leaf_box, L, cb, cn);
         int m = L, rounds = 0;
-        while (m > 1) {
+        const char* top_env = getenv("PTAP_PLOC_TOP");
+        const int top = top_env ? atoi(top_env) : kPlocTop;       // clusters handed to the host's SAH build of the upper levels (0: PLOC to the root)
+        while (m > 1 && !(top > 1 && m <= top)) {
             const int g = (m + B - 1) / B;
             k_ploc_nearest<<<g, B, 0, stream>>>(cb, m, nearest);
             k_ploc_merge<<<g, B, 0, stream>>>(cb, cn, nearest, m, child, node_box, counters + 8, keep);
@@ -421,9 +479,31 @@ int buildMeshBvhDevice(const TriRec* d_tris, int t0, int t1, const float* bb_min
             m = m2;
             std::swap(cb, cb2); std::swap(cn, cn2);
         }
-        e = cudaMemcpyAsync(&root_node, cn, sizeof(int), cudaMemcpyDeviceToHost, stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-        if (e != cudaSuccess) return e;
+        if (m > 1) {
+            // the upper levels on the host: cluster boxes and links down, new binary nodes back up (appended after PLOC's)
+            std::vector<Box6> hb(m); std::vector<int> hl(m);
+            int made = 0;
+            e = cudaMemcpyAsync(hb.data(), cb, (size_t)m * sizeof(Box6), cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(hl.data(), cn, (size_t)m * sizeof(int), cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(&made, counters + 8, sizeof(int), cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) return e;
+            if (made + m - 1 > L) return cudaErrorUnknown;                 // L leaves have L - 1 internal nodes
+            std::vector<TopItem> items(m);
+            for (int k = 0; k < m; ++k) { items[k].box = hb[k]; items[k].link = hl[k]; for (int a = 0; a < 3; ++a) items[k].c[a] = 0.5f * (hb[k].lo[a] + hb[k].hi[a]); }
+            std::vector<int2> tc; std::vector<Box6> tb;
+            tc.reserve(m); tb.reserve(m);
+            Box6 bounds;
+            root_node = buildTopSah(items, 0, m, made, tc, tb, bounds);
+            e = cudaMemcpyAsync(child + made, tc.data(), tc.size() * sizeof(int2), cudaMemcpyHostToDevice, stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(node_box + made, tb.data(), tb.size() * sizeof(Box6), cudaMemcpyHostToDevice, stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);       // tc / tb are stack-owned
+            if (e != cudaSuccess) return e;
+        } else {
+            e = cudaMemcpyAsync(&root_node, cn, sizeof(int), cudaMemcpyDeviceToHost, stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+            if (e != cudaSuccess) return e;
+        }
         if (root_node < 0) return cudaErrorUnknown;
     }
     // breadth-first collapse from the binary root: it becomes 4-wide node 0

@@ -44,6 +44,7 @@ struct ptap_scene {
     // optional BVH (ptap_scene_build_bvh); invalidated by any mesh edit
     ptap::BvhBuildResult bvh;
     bool have_bvh = false;
+    bool have_recs = false;       // st_recs holds the triangle records of the current meshes (ptap_scene_pack_triangles / ptap_scene_build_bvh)
     int bvh_nnodes = 0;
     // upload-bound copies of the BVH arrays and the triangle records, page-locked when a CUDA device exists (plain malloc otherwise)
     struct Staging {
@@ -179,7 +180,7 @@ int appendMesh(ptap_scene* s, const PtapVertex* verts, int nverts, const int32_t
     }
     mesh.t_end = (int)s->triangles.size();
     s->meshes.push_back(mesh);
-    s->have_bvh = false;
+    s->have_bvh = false; s->have_recs = false;
     return (int)s->meshes.size() - 1;
 }
 
@@ -717,7 +718,24 @@ int ptap_scene_build_bvh(ptap_scene* s)
         !s->st_recs.fill(recs.data(), recs.size() * sizeof(ptap::TriRec))) { s->err = "build_bvh: out of host memory"; return PTAP_E_NOMEM; }
     s->bvh.nodes.clear(); s->bvh.nodes.shrink_to_fit();          // the staging copies are the ones handed out by ptap_scene_view
     s->bvh_nnodes = (int)(s->st_nodes.bytes / sizeof(ptap::BvhNode));
-    s->have_bvh = true;
+    s->have_bvh = true; s->have_recs = true;
+    return PTAP_OK;
+}
+
+// The upload-bound triangle records (v0, e1, e2, flat normal: the reference's own arithmetic) without a host BVH: for callers that let the
+// GPU build the tree (PTAP_ACCEL_BVH_DEVICE) or walk / emulate the grids, so that ptap_upload_scene is a copy from page-locked memory
+// instead of a repack of every triangle on every call.
+int ptap_scene_pack_triangles(ptap_scene* s)
+{
+    if (!s || s->triangles.empty()) return PTAP_E_INVALID;
+    if (s->have_recs) return PTAP_OK;
+    for (const PtapTriangle& t : s->triangles)
+        for (int k = 0; k < 3; ++k)
+            if (t.v[k] < 0 || t.v[k] >= (int)s->vertices.size()) { s->err = "pack_triangles: vertex index out of range"; return PTAP_E_INVALID; }
+    std::vector<ptap::TriRec> recs(s->triangles.size());
+    ptap::makeTriRecs(s->vertices.data(), s->triangles.data(), (int)s->triangles.size(), recs.data());
+    if (!s->st_recs.fill(recs.data(), recs.size() * sizeof(ptap::TriRec))) { s->err = "pack_triangles: out of host memory"; return PTAP_E_NOMEM; }
+    s->have_recs = true;
     return PTAP_OK;
 }
 
@@ -771,8 +789,8 @@ int ptap_scene_view(const ptap_scene* s, PtapSceneView* out)
         out->bvh_tri_id = static_cast<const int32_t*>(s->st_tri_id.p); out->n_bvh_tris = (int)s->bvh.tri_id.size();
         out->bvh_mesh_root = s->bvh.mesh_root.data(); out->n_bvh_roots = (int)s->bvh.mesh_root.size();
         out->bvh_depth = s->bvh.max_depth + 1;
-        out->tri_recs = s->st_recs.p; out->n_tri_recs = (int)(s->st_recs.bytes / sizeof(ptap::TriRec));
     }
+    if (s->have_recs) { out->tri_recs = s->st_recs.p; out->n_tri_recs = (int)(s->st_recs.bytes / sizeof(ptap::TriRec)); }
     out->models = s->models.data(); out->nmodels = (int)s->models.size();
     out->meshes = s->meshes.data(); out->nmeshes = (int)s->meshes.size();
     out->vertices = s->vertices.data(); out->nvertices = (int)s->vertices.size();

@@ -115,6 +115,10 @@ class Scene:
         """One BVH per mesh, built on the host as part of scene construction (like addMeshesToGrid for the grid)."""
         self._check(N.lib().ptap_scene_build_bvh(self.h), "build_bvh")
 
+    def pack(self):
+        """The upload-bound triangle records in page-locked memory, without a host BVH (for trees built on the GPU): uploads become copies."""
+        self._check(N.lib().ptap_scene_pack_triangles(self.h), "pack_triangles")
+
     def validate_bvh(self) -> tuple[int, int]:
         """(violations, depth) of the host-built BVH: 0 violations = every triangle's tolerance band lies inside every compressed box above it."""
         bad = C.c_int64(-1); depth = C.c_int32(0)
