@@ -14,7 +14,8 @@
 // Morton-sorted leaves are merged bottom-up, every cluster pairing with the neighbour (within kPlocRadius positions) whose union with it
 // has the smallest surface area whenever the choice is mutual; the surviving clusters are compacted and the round repeats until one is
 // left.  Boxes are made at the merges, no refit pass is needed, and the tree is close to a SAH tree where the radix tree is not.
-// PTAP_DEVICE_BUILDER=lbvh keeps the radix tree.
+// PTAP_DEVICE_BUILDER=lbvh keeps the radix tree.  PLOC stops at kPlocTop clusters; the levels above them come from a binned-SAH build on the
+// host over the cluster boxes (buildTopSah: under a millisecond), because merges that are local in Morton order are arbitrary near the root.
 //
 // The tree is a different one than the host builder's, so rays visit different boxes; hits are bit-identical all the same, because the
 // boxes are conservative for the reference's predicate and the triangle arithmetic is the exact one (tests/test_gpu_device_bvh.py).
