@@ -579,7 +579,7 @@ int ptap_create(int device, size_t arena_bytes, ptap_ctx** out)
         if (!ok) { ptap_destroy(ctx); return PTAP_E_NOMEM; }
     }      // measured slower on every workload (profiles/r01/README.md): opt-in
     ctx->trace_ctas = std::max(0, envInt("PTAP_TRACE_CTAS", 0));
-    ctx->emu_replay_ctas = std::max(1, envInt("PTAP_EMU_REPLAY_CTAS", 6));     // per SM: k_emu_replay / k_trace_grid in list mode (tuning only)
+    ctx->emu_replay_ctas = std::max(1, envInt("PTAP_EMU_REPLAY_CTAS", 6));     // CTAs per SM of k_emu_tail (k_emu_setup: twice as many); tuning only
     ctx->emu_walk_ctas = std::max(1, envInt("PTAP_EMU_WALK_CTAS", 2));
     ctx->sc.emu_refill = std::min(32, std::max(1, envInt("PTAP_EMU_REFILL", 8)));
     if (arena_bytes) {                                          // caller-sized arena: split 1/4 scene, 3/4 frame

@@ -113,14 +113,14 @@ struct SceneDev {
     int batch;                  // rays a warp takes from the work-stealing cursor per atomic (PTAP_BATCH)
     int shade_sort;             // k_shade regroups each block's slots by material class before shading (PTAP_SHADE_SORT=1; default off)
     int vote_grid;              // k_trace_grid: lanes that must wait in a state before its step runs (the most popular state always runs)
-    int emu_refill;             // k_emu_replay: free lanes of a warp that trigger the set-up of the next slots (PTAP_EMU_REFILL)
+    int emu_refill;             // k_emu_tail: free lanes of a warp that trigger the loading of the next queued replays (PTAP_EMU_REFILL)
     int vote_tri, vote_inst, vote_refill;   // lanes that must wait in a state before the warp runs that state's step (PTAP_VOTE_*)
     float c_pad;                // slack of the pruning bound for the residual of model_to_world * world_to_model - I
     float tie;                  // two instances' winners whose approximate world distances differ by less than this relative slack are compared exactly
     float prune;                // relative slack of cross-instance pruning (1.0001), +inf when some model's matrices are not inverses
 };
 
-// PTAP_ACCEL_GRID_EMULATED: what k_trace_emu hands to k_emu_replay for every wavefront slot, and the list of slots for the walk itself
+// PTAP_ACCEL_GRID_EMULATED (trace_emu.cu): what k_trace_emu hands to the replay kernels for every wavefront slot, their queue, and the lists
 struct EmuBuf {
     int* n;                     // [slot] hits of the ray in its nearest model (> kEmuHits: not all kept - the walk answers that ray)
     int* id;                    // [hit][slot] their global triangle ids (stride slots per hit)

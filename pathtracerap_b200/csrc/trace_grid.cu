@@ -71,7 +71,7 @@ k_trace_grid(SceneDev sc, const float4* __restrict__ O, const float4* __restrict
              const int* __restrict__ list)
 {
     constexpr unsigned kFull = 0xffffffffu;
-    // list != null: the second launch of PTAP_ACCEL_GRID_EMULATED - only the slots k_trace_emu (trace_emu.cu) handed over are walked
+    // list != null: the last launch of PTAP_ACCEL_GRID_EMULATED - only the slots k_emu_full (trace_emu.cu) handed over are walked
     const int n = list ? (int)st->n_walk[round] : n_fixed >= 0 ? n_fixed : st->n_active[round];
     if (blockIdx.x == 0 && threadIdx.x == 0 && n_fixed < 0 && !list) st->rays_traced += (unsigned long long)n;
     if (blockIdx.x == 0 && threadIdx.x == 0 && list) st->rays_walked += (unsigned long long)n;
