@@ -28,26 +28,30 @@ def _reference_frame(arrays, W, H, depth, iters):
     return film, counts, "port"
 
 
-def test_config0_cornell_512x512_16spp_depth8(libptap):
+@pytest.mark.parametrize("accel_name", ["emulated", "walked"])
+def test_config0_cornell_512x512_16spp_depth8(libptap, accel_name):
     """configs[0]: Cornell box from Input data, 512 x 512, 16 spp, depth 8, diffuse only, golden image from the reference's host-compiled
-    path - produced live here (15.5 M rays on the host).  The drop-in default (grid walk, R0) must match it within RMSE <= 0.5 % of the
-    mean, PSNR >= 40 dB, > 97 % bit-equal pixels; iteration-0 active counts are SURVEY Appendix A.3b's checkpoints."""
+    path - produced live here (15.5 M rays on the host).  The drop-in default (the grid walk's results through the BVH, R0) and the walk
+    itself must match it within RMSE <= 0.5 % of the mean, PSNR >= 40 dB, > 97 % bit-equal pixels; iteration-0 active counts are SURVEY
+    Appendix A.3b's checkpoints."""
     import bench
-    from pathtracerap_b200 import ACCEL_GRID_COMPAT, Renderer
+    from pathtracerap_b200 import ACCEL_GRID_COMPAT, ACCEL_GRID_EMULATED, Renderer
+    accel = {"emulated": ACCEL_GRID_EMULATED, "walked": ACCEL_GRID_COMPAT}[accel_name]
     scene, arrays = bench.build_scene("cornell")
     scene.build_grids(25, 25, 25)
     W, H, iters, depth = 512, 512, 16, 8
     want, counts, kind = _reference_frame(arrays, W, H, depth, iters)
     assert counts[0] == [262144, 232245, 153987, 111947, 80385, 59065, 43551, 32384]
-    r = Renderer(width=W, height=H, depth=depth, accel=ACCEL_GRID_COMPAT, first_hit_cache=True)
+    r = Renderer(width=W, height=H, depth=depth, accel=accel, first_hit_cache=True)
     r.allocateOnGPU(scene)
+    assert r.accel == accel
     r.render(0, iters)
     film = r.film()
     st = r.stats()
     rmse = float(np.sqrt(np.mean((film - want) ** 2)))
     psnr = 20 * np.log10(float(want.max()) / max(rmse, 1e-12))
     exact = float(np.mean(film == want))
-    print(f"cornell 512x512x16 d8 vs {kind}: rmse={rmse:.3e} mean={want.mean():.3f} psnr={psnr:.1f} dB bit-equal pixels={exact:.4f}")
+    print(f"cornell 512x512x16 d8 ({accel_name}) vs {kind}: rmse={rmse:.3e} mean={want.mean():.3f} psnr={psnr:.1f} dB bit-equal pixels={exact:.4f}")
     assert rmse <= 0.005 * want.mean() and psnr >= 40.0 and exact > 0.97
     got = np.array(st["active_per_round"][:depth])
     assert got[0] == counts[-1][0] and got[1] == counts[-1][1]
@@ -62,10 +66,10 @@ def test_bundled_1000x800_iteration0_checkpoints(gpu_scene, oracle_scene):
     (tests/golden/trace_bundled.npz carries the same numbers): active rays per bounce 800000 / 708894 / 474310 /
     348742 / 254855 and hits 800000 / 574891 / 409613 / 300967 / 223986.  Rounds 0 and 1 are exact arithmetic end to end; later rounds
     inherit last-ulp differences of the sampled directions (libdevice vs glibc sinf/cosf/powf) and may drift by a few rays."""
-    from pathtracerap_b200 import ACCEL_GRID_COMPAT, Renderer
+    from pathtracerap_b200 import ACCEL_GRID_EMULATED, Renderer
     active = [800000, 708894, 474310, 348742, 254855]
     hits_want = [800000, 574891, 409613, 300967, 223986]
-    r = Renderer(width=1000, height=800, depth=5, accel=ACCEL_GRID_COMPAT, first_hit_cache=False)
+    r = Renderer(width=1000, height=800, depth=5, accel=ACCEL_GRID_EMULATED, first_hit_cache=False)       # the drop-in default
     r.allocateOnGPU(gpu_scene)
     n_got, h_got = [], []
     for rnd in range(5):
